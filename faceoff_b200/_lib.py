@@ -1,0 +1,125 @@
+"""ctypes binding of libfaceoff_b200.so (C ABI in include/faceoff_b200.h).
+
+The product path has NO fallback: if the shared library is missing or no sm_100 GPU is present,
+every op raises.  ``build()`` compiles the library in-tree with nvcc for sm_100a.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libfaceoff_b200.so")
+_lock = threading.Lock()
+_lib = None
+
+FORM_S1, FORM_S1_DGRAD, FORM_DOWN, FORM_UP = 0, 1, 2, 3
+
+
+class FaceoffB200Error(RuntimeError):
+    pass
+
+
+class Src(C.Structure):
+    _fields_ = [("ptr", C.c_void_p), ("c", C.c_int), ("cs", C.c_int), ("c_off", C.c_int)]
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("form", C.c_int), ("ndim", C.c_int), ("ksize", C.c_int),
+        ("n", C.c_int), ("d", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("n_src", C.c_int), ("src", Src * 2), ("cout", C.c_int),
+        ("wpacked", C.c_void_p), ("bias", C.c_void_p), ("mask", C.c_void_p), ("addend", C.c_void_p),
+        ("out_bf16", C.c_void_p), ("out_relu", C.c_void_p), ("out_f32", C.c_void_p),
+        ("out_cs", C.c_int), ("out_f32_nchw", C.c_int), ("relu_f32", C.c_int),
+    ]
+
+
+class WgradDesc(C.Structure):
+    _fields_ = [
+        ("form", C.c_int), ("ndim", C.c_int), ("ksize", C.c_int),
+        ("n", C.c_int), ("d", C.c_int), ("h", C.c_int), ("w", C.c_int),
+        ("p", Src), ("q", Src), ("dweight", C.c_void_p), ("dimA", C.c_int), ("dimB", C.c_int),
+        ("m_axis", C.c_int), ("q_w_off", C.c_int), ("accumulate", C.c_int),
+        ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+    ]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile libfaceoff_b200.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+    if res.returncode != 0:
+        raise FaceoffB200Error("building libfaceoff_b200.so failed")
+    return _SO
+
+
+_SIGS = {
+    "fo_last_error": (C.c_char_p, []),
+    "fo_version": (C.c_int, []),
+    "fo_init": (C.c_int, []),
+    "fo_conv_wpacked_bytes": (C.c_size_t, [C.POINTER(ConvDesc)]),
+    "fo_conv_pack_weights": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_void_p]),
+    "fo_conv_run": (C.c_int, [C.POINTER(ConvDesc), C.c_void_p]),
+    "fo_wgrad_workspace_bytes": (C.c_size_t, [C.POINTER(WgradDesc)]),
+    "fo_wgrad_run": (C.c_int, [C.POINTER(WgradDesc), C.c_void_p]),
+    "fo_pack_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                               C.c_void_p]),
+    "fo_unpack_nchw": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fo_relu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "fo_colsum": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p,
+                            C.c_size_t, C.c_void_p]),
+    "fo_colsum_workspace_bytes": (C.c_size_t, [C.c_int]),
+    "fo_maxpool2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fo_maxpool2_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_void_p]),
+    "fo_vq_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_vq_assign_workspace_bytes": (C.c_size_t, [C.c_size_t, C.c_int]),
+    "fo_vq_assign": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    "fo_vq_gather_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_vq_ema": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_float,
+                            C.c_float, C.c_void_p]),
+    "fo_vq_backward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_lpips_tap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "fo_lpips_tap_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGS)
+
+
+def load(init: bool = True):
+    """Load the shared library (and, with ``init``, require an sm_100 device)."""
+    global _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(_SO):
+                raise FaceoffB200Error(
+                    f"{_SO} not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                    "(faceoff_b200 has no CPU/PyTorch fallback)")
+            lib = C.CDLL(_SO)
+            for name, (res, args) in _SIGS.items():
+                fn = getattr(lib, name)
+                fn.restype = res
+                fn.argtypes = args
+            _lib = lib
+    if init:
+        rc = _lib.fo_init()
+        if rc != 0:
+            raise FaceoffB200Error(f"fo_init failed ({rc}): {_lib.fo_last_error().decode()}")
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = _lib.fo_last_error().decode() if _lib is not None else "library not loaded"
+        raise FaceoffB200Error(f"{what} failed ({rc}): {msg}")

@@ -1,0 +1,639 @@
+// C ABI (include/faceoff_b200.h) + host-side planners that turn a convolution description into the generic
+// implicit-GEMM launch (tile boxes, K-step table, TMA tensor maps, packed-weight order).
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <mutex>
+
+#include "../../include/faceoff_b200.h"
+#include "kernels.h"
+
+using namespace fo;
+
+// ------------------------------------------------------------------------------------------ errors / init
+static thread_local char g_err[512] = "";
+static int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+#define CUDA_TRY(expr)                                                                      \
+  do {                                                                                      \
+    cudaError_t _e = (expr);                                                                \
+    if (_e != cudaSuccess) return fail(FO_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static int g_num_sms = 0;
+static std::once_flag g_once;
+static int g_init_rc = FO_ERR_NO_DEVICE;
+static char g_init_err[512] = "fo_init not called";
+
+static void do_init() {
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    snprintf(g_init_err, sizeof(g_init_err), "no CUDA device: faceoff_b200 has no CPU path");
+    g_init_rc = FO_ERR_NO_DEVICE;
+    return;
+  }
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, dev);
+  if (prop.major != 10) {
+    snprintf(g_init_err, sizeof(g_init_err), "device %s is sm_%d%d; kernels are built for sm_100a only", prop.name,
+             prop.major, prop.minor);
+    g_init_rc = FO_ERR_NO_DEVICE;
+    return;
+  }
+  g_num_sms = prop.multiProcessorCount;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || fn == nullptr || qres != cudaDriverEntryPointSuccess) {
+    snprintf(g_init_err, sizeof(g_init_err), "cuTensorMapEncodeTiled not available: %s", cudaGetErrorString(e));
+    g_init_rc = FO_ERR_CUDA;
+    return;
+  }
+  g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  if ((e = init_conv_igemm()) != cudaSuccess || (e = init_wgrad_igemm()) != cudaSuccess ||
+      (e = init_vq()) != cudaSuccess) {
+    snprintf(g_init_err, sizeof(g_init_err), "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    g_init_rc = FO_ERR_CUDA;
+    return;
+  }
+  g_init_rc = FO_OK;
+  g_init_err[0] = 0;
+}
+
+extern "C" const char* fo_last_error(void) { return g_err; }
+extern "C" int fo_version(void) { return 100; }
+extern "C" int fo_init(void) {
+  std::call_once(g_once, do_init);
+  if (g_init_rc != FO_OK) return fail(g_init_rc, "%s", g_init_err);
+  return FO_OK;
+}
+#define REQUIRE_INIT()                       \
+  do {                                       \
+    int _rc = fo_init();                     \
+    if (_rc != FO_OK) return _rc;            \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ tensor maps
+static CUtensorMapSwizzle swizzle_for(int rowb) {
+  return rowb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : rowb == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B;
+}
+// bf16 tensor, `rank` dims (dim 0 contiguous), strides in elements for dims 1..rank-1
+static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t* dims, const uint64_t* strides_el,
+                      const uint32_t* box, int rowb) {
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gd[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+    if (i > 0) gs[i - 1] = strides_el[i] * 2;
+    if (box[i] > 256 || box[i] == 0) return fail(FO_ERR_INVALID, "TMA box dim %d = %u out of range", i, box[i]);
+  }
+  if ((reinterpret_cast<uintptr_t>(ptr) & 15) != 0) return fail(FO_ERR_INVALID, "tensor base not 16-byte aligned");
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gs[i] % 16 != 0) return fail(FO_ERR_INVALID, "TMA stride %d (%llu B) not a multiple of 16", i, (unsigned long long)gs[i]);
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(ptr), gd, gs, bx, es,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(rowb), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    return fail(FO_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d): rank %d dims [%llu %llu %llu %llu %llu] box [%u %u %u %u %u]",
+                (int)r, rank, (unsigned long long)gd[0], (unsigned long long)(rank > 1 ? gd[1] : 0),
+                (unsigned long long)(rank > 2 ? gd[2] : 0), (unsigned long long)(rank > 3 ? gd[3] : 0),
+                (unsigned long long)(rank > 4 ? gd[4] : 0), bx[0], rank > 1 ? bx[1] : 0, rank > 2 ? bx[2] : 0,
+                rank > 3 ? bx[3] : 0, rank > 4 ? bx[4] : 0);
+  }
+  return FO_OK;
+}
+
+// ------------------------------------------------------------------------------------------ tile boxes
+static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
+static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
+// choose box extents (powers of two, product == positions) over the tile domain ext[0..3]
+static void choose_box(const int ext[4], int positions, int box[4]) {
+  int rem = positions;
+  int last_used = 0;
+  for (int d = 0; d < 4; ++d) {
+    int b = 1;
+    if (ext[d] > 1 && rem > 1) {
+      const int pf = pow2_floor(ext[d]);
+      b = (ext[d] % pf == 0) ? pf : pow2_ceil(ext[d]);
+      if (b > rem) b = rem;
+      last_used = d;
+    }
+    box[d] = b;
+    rem /= b;
+  }
+  if (rem > 1) box[last_used] *= rem;  // tiny tensors: over-size the box, TMA zero-fills / stores are predicated
+}
+
+static const int kDownD[4] = {-1, 0, 0, 1};   // 4x4 s2 p1: input index 2*o + k - 1  ->  half-res offset
+static const int kDownPar[4] = {1, 0, 1, 0};  //                                        and parity
+
+// ------------------------------------------------------------------------------------------ conv planner
+struct ConvPlan {
+  ConvParams p;
+  ConvMaps maps;
+  PackParams pack;
+  int npad, ktot;
+};
+
+static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
+  ConvParams& p = out->p;
+  memset(&p, 0, sizeof(p));
+  memset(&out->pack, 0, sizeof(out->pack));
+  if (c->n_src < 1 || c->n_src > 2) return fail(FO_ERR_INVALID, "n_src must be 1 or 2");
+  const bool s1 = c->form == FO_FORM_S1 || c->form == FO_FORM_S1_DGRAD;
+  if (!s1 && c->form != FO_FORM_DOWN && c->form != FO_FORM_UP) return fail(FO_ERR_INVALID, "bad form %d", c->form);
+  if (c->ndim != 2 && !(c->ndim == 3 && s1)) return fail(FO_ERR_INVALID, "ndim %d unsupported for form %d", c->ndim, c->form);
+  if (s1 && c->ksize != 1 && c->ksize != 3) return fail(FO_ERR_INVALID, "ksize %d unsupported", c->ksize);
+  if (c->form == FO_FORM_DOWN && ((c->h | c->w) & 1)) return fail(FO_ERR_INVALID, "stride-2 conv needs even h, w");
+  // K chunk
+  int kc = 64;
+  for (int s = 0; s < c->n_src; ++s) {
+    const fo_src_t& src = c->src[s];
+    if (src.cs % 8 != 0 || src.c_off % 8 != 0) return fail(FO_ERR_INVALID, "source storage channels must be multiples of 8");
+    const int cpad = (src.c + 15) / 16 * 16;
+    if (src.c_off + cpad > src.cs) return fail(FO_ERR_INVALID, "source slice [%d,+%d) exceeds storage %d", src.c_off, cpad, src.cs);
+    while (cpad % kc != 0) kc /= 2;
+  }
+  if (kc < 16) return fail(FO_ERR_INVALID, "channel counts must be multiples of 16 after padding");
+  p.KC = kc;
+  const int rowb = kc * 2;
+  // N tiling
+  const int cout_pad = (c->cout + 15) / 16 * 16;
+  if (cout_pad <= 256) { p.NT = cout_pad; p.n_tiles = 1; }
+  else if (cout_pad % 256 == 0) { p.NT = 256; p.n_tiles = cout_pad / 256; }
+  else if (cout_pad % 128 == 0) { p.NT = 128; p.n_tiles = cout_pad / 128; }
+  else return fail(FO_ERR_INVALID, "cout %d unsupported", c->cout);
+  out->npad = p.NT * p.n_tiles;
+
+  // tile domain (map dims 1..4) and output addressing
+  int ext[4];
+  const long long ocs = c->out_cs;
+  const bool nchw = c->out_f32 != nullptr && c->out_f32_nchw;
+  if (nchw && (c->out_bf16 || c->out_relu || c->mask || c->addend || c->ndim != 2))
+    return fail(FO_ERR_INVALID, "NCHW fp32 output cannot be combined with channels-last outputs");
+  p.groups = 1;
+  if (s1 || c->form == FO_FORM_UP) {
+    if (c->ndim == 3) { ext[0] = c->w; ext[1] = c->h; ext[2] = c->d; ext[3] = c->n; }
+    else { ext[0] = c->w; ext[1] = c->h; ext[2] = c->n; ext[3] = 1; }
+  } else {  // DOWN: (wx, py, hy, f)
+    ext[0] = c->w / 2; ext[1] = 1; ext[2] = c->h / 2; ext[3] = c->n;
+  }
+  int box[4];
+  choose_box(ext, 128, box);
+  for (int d = 0; d < 4; ++d) {
+    p.box[d] = box[d];
+    p.tile_step[d] = box[d];
+    p.tile_cnt[d] = (ext[d] + box[d] - 1) / box[d];
+    p.lim[d] = ext[d];
+  }
+  if (s1) {
+    const long long W = c->w, H = c->h, D = c->d;
+    if (c->ndim == 3) {
+      p.out_stride[0] = ocs; p.out_stride[1] = W * ocs; p.out_stride[2] = H * W * ocs; p.out_stride[3] = D * H * W * ocs;
+    } else if (!nchw) {
+      p.out_stride[0] = ocs; p.out_stride[1] = W * ocs; p.out_stride[2] = H * W * ocs; p.out_stride[3] = 0;
+    } else {
+      p.out_stride[0] = 1; p.out_stride[1] = W; p.out_stride[2] = (long long)c->cout * H * W; p.out_stride[3] = 0;
+      p.out_cstride = (int)(H * W);
+    }
+  } else if (c->form == FO_FORM_DOWN) {
+    const long long Wo = c->w / 2, Ho = c->h / 2;
+    if (!nchw) { p.out_stride[0] = ocs; p.out_stride[1] = 0; p.out_stride[2] = Wo * ocs; p.out_stride[3] = Ho * Wo * ocs; }
+    else { p.out_stride[0] = 1; p.out_stride[1] = 0; p.out_stride[2] = Wo; p.out_stride[3] = (long long)c->cout * Ho * Wo; p.out_cstride = (int)(Ho * Wo); }
+  } else {  // UP
+    const long long Wo = 2LL * c->w, Ho = 2LL * c->h;
+    p.groups = 4;
+    if (!nchw) {
+      p.out_stride[0] = 2 * ocs; p.out_stride[1] = 2 * Wo * ocs; p.out_stride[2] = Ho * Wo * ocs; p.out_stride[3] = 0;
+      for (int g = 0; g < 4; ++g) p.out_off[g] = ((g >> 1) * Wo + (g & 1)) * ocs;
+    } else {
+      p.out_stride[0] = 2; p.out_stride[1] = 2 * Wo; p.out_stride[2] = (long long)c->cout * Ho * Wo; p.out_stride[3] = 0;
+      for (int g = 0; g < 4; ++g) p.out_off[g] = (g >> 1) * Wo + (g & 1);
+      p.out_cstride = (int)(Ho * Wo);
+    }
+  }
+  if (!nchw) p.out_cstride = 1;
+  p.c_store = nchw ? c->cout : (int)(ocs < out->npad ? ocs : out->npad);
+  if (!nchw && (c->out_bf16 || c->out_relu || c->out_f32) && (ocs % 8 != 0))
+    return fail(FO_ERR_INVALID, "out_cs must be a multiple of 8");
+
+  // K steps
+  int nk = 0;  // per group
+  KStep* ks = p.ksteps;
+  PackStep* ps = out->pack.steps;
+  int total = 0;
+  auto push = [&](int map, int c0, int d1, int d2, int d3, int tap, int wk0, int valid) -> bool {
+    if (total >= kMaxKSteps) return false;
+    ks[total].c0 = (int16_t)c0; ks[total].d1 = (int8_t)d1; ks[total].d2 = (int8_t)d2; ks[total].d3 = (int8_t)d3;
+    ks[total].map = (uint8_t)map; ks[total].pad = 0;
+    ps[total].tap = (int16_t)tap; ps[total].wk0 = (int16_t)wk0; ps[total].valid = (int16_t)valid; ps[total].pad = 0;
+    ++total;
+    return true;
+  };
+  bool ok = true;
+  auto chunks = [&](int map, int pix_c0, int d1, int d2, int d3, int tap) {
+    // all channel chunks of source `map` for one tap
+    const fo_src_t& src = c->src[map];
+    int wbase = 0;
+    for (int s = 0; s < map; ++s) wbase += c->src[s].c;
+    const int cpad = (src.c + 15) / 16 * 16;
+    for (int ch = 0; ch < cpad; ch += kc) {
+      const int valid = src.c - ch < kc ? src.c - ch : kc;
+      ok = ok && push(map, pix_c0 + src.c_off + ch, d1, d2, d3, tap, wbase + ch, valid);
+    }
+  };
+  if (s1) {
+    const int k = c->ksize, pad = (k - 1) / 2;
+    const int kd_n = c->ndim == 3 ? k : 1;
+    const int sign = c->form == FO_FORM_S1 ? 1 : -1;
+    for (int kd = 0; kd < kd_n; ++kd)
+      for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) {
+          const int tap = (kd * k + kh) * k + kw;
+          const int dw = sign * (kw - pad), dh = sign * (kh - pad), dd = c->ndim == 3 ? sign * (kd - pad) : 0;
+          for (int s = 0; s < c->n_src; ++s) chunks(s, 0, dw, dh, dd, tap);
+        }
+    nk = total;
+  } else if (c->form == FO_FORM_DOWN) {
+    for (int ky = 0; ky < 4; ++ky)
+      for (int kx = 0; kx < 4; ++kx)
+        for (int s = 0; s < c->n_src; ++s)
+          chunks(s, kDownPar[kx] * c->src[s].cs, kDownD[kx], kDownPar[ky], kDownD[ky], ky * 4 + kx);
+    nk = total;
+  } else {  // UP: out[2i-1+k] += in[i] w[k]; output parity p: k in {1,3} (p=0: i = h, h-1) or {0,2} (p=1: i = h+1, h)
+    static const int kk[2][2] = {{1, 3}, {0, 2}};
+    static const int dd[2][2] = {{0, -1}, {1, 0}};
+    for (int g = 0; g < 4; ++g) {
+      const int py = g >> 1, px = g & 1;
+      for (int a = 0; a < 2; ++a)
+        for (int b = 0; b < 2; ++b)
+          for (int s = 0; s < c->n_src; ++s)
+            chunks(s, 0, dd[px][b], dd[py][a], 0, kk[py][a] * 4 + kk[px][b]);
+      if (g == 0) nk = total;
+    }
+  }
+  if (!ok) return fail(FO_ERR_INVALID, "too many K steps (> %d)", kMaxKSteps);
+  p.num_ksteps = nk;
+  out->ktot = total * kc;
+  const int stage_bytes = (128 * rowb + p.NT * rowb + 1023) & ~1023;
+  int stages = (kMaxDynSmem - 2048) / stage_bytes;
+  if (stages > 8) stages = 8;
+  if (stages < 2) return fail(FO_ERR_INVALID, "tile does not fit in shared memory");
+  p.stages = stages;
+  p.total_tiles = p.groups * p.n_tiles * p.tile_cnt[0] * p.tile_cnt[1] * p.tile_cnt[2] * p.tile_cnt[3];
+
+  // weight pack description
+  PackParams& pk = out->pack;
+  pk.npad = out->npad; pk.ktot = out->ktot; pk.kc = kc; pk.cout = c->cout;
+  pk.taps = s1 ? (c->ndim == 3 ? c->ksize * c->ksize * c->ksize : c->ksize * c->ksize) : 16;
+
+  // epilogue pointers
+  p.bias = c->bias;
+  p.mask = (const __nv_bfloat16*)c->mask;
+  p.addend = (const __nv_bfloat16*)c->addend;
+  p.out_bf16 = (__nv_bfloat16*)c->out_bf16;
+  p.out_relu = (__nv_bfloat16*)c->out_relu;
+  p.out_f32 = c->out_f32;
+  p.relu_f32 = c->relu_f32;
+
+  if (!need_maps) return FO_OK;
+  // tensor maps
+  for (int s = 0; s < c->n_src; ++s) {
+    const fo_src_t& src = c->src[s];
+    uint64_t dims[5], str[5];
+    uint32_t bx[5];
+    const uint64_t cs = src.cs;
+    if (c->form == FO_FORM_DOWN) {
+      dims[0] = 2 * cs; dims[1] = c->w / 2; dims[2] = 2; dims[3] = c->h / 2; dims[4] = c->n;
+      str[0] = 1; str[1] = 2 * cs; str[2] = (uint64_t)c->w * cs; str[3] = 2ULL * c->w * cs; str[4] = (uint64_t)c->h * c->w * cs;
+    } else if (c->ndim == 3) {
+      dims[0] = cs; dims[1] = c->w; dims[2] = c->h; dims[3] = c->d; dims[4] = c->n;
+      str[0] = 1; str[1] = cs; str[2] = (uint64_t)c->w * cs; str[3] = (uint64_t)c->h * c->w * cs; str[4] = (uint64_t)c->d * c->h * c->w * cs;
+    } else {
+      dims[0] = cs; dims[1] = c->w; dims[2] = c->h; dims[3] = c->n; dims[4] = 1;
+      str[0] = 1; str[1] = cs; str[2] = (uint64_t)c->w * cs; str[3] = (uint64_t)c->h * c->w * cs; str[4] = (uint64_t)c->n * c->h * c->w * cs;
+    }
+    bx[0] = kc; bx[1] = box[0]; bx[2] = box[1]; bx[3] = box[2]; bx[4] = box[3];
+    int rc = encode_map(&out->maps.a[s], src.ptr, 5, dims, str, bx, rowb);
+    if (rc != FO_OK) return rc;
+  }
+  for (int s = c->n_src; s < kMaxAMaps; ++s) out->maps.a[s] = out->maps.a[0];
+  {
+    uint64_t dims[2] = {(uint64_t)out->ktot, (uint64_t)out->npad};
+    uint64_t str[2] = {1, (uint64_t)out->ktot};
+    uint32_t bx[2] = {(uint32_t)kc, (uint32_t)p.NT};
+    int rc = encode_map(&out->maps.b, c->wpacked, 2, dims, str, bx, rowb);
+    if (rc != FO_OK) return rc;
+  }
+  return FO_OK;
+}
+
+extern "C" size_t fo_conv_wpacked_bytes(const fo_conv_t* c) {
+  static thread_local ConvPlan plan;
+  if (plan_conv(c, &plan, false) != FO_OK) return 0;
+  return (size_t)plan.npad * plan.ktot * 2;
+}
+
+extern "C" int fo_conv_pack_weights(const fo_conv_t* c, const float* weight, int dimA, int dimB, int n_axis,
+                                    const float* n_scale, void* wpacked, fo_stream_t stream) {
+  REQUIRE_INIT();
+  static thread_local ConvPlan plan;
+  int rc = plan_conv(c, &plan, false);
+  if (rc != FO_OK) return rc;
+  (void)dimA;
+  plan.pack.dimB = dimB;
+  plan.pack.n_axis = n_axis;
+  plan.pack.n_scale = n_scale;
+  CUDA_TRY(launch_pack_weights(weight, wpacked, plan.pack, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+
+extern "C" int fo_conv_run(const fo_conv_t* c, fo_stream_t stream) {
+  REQUIRE_INIT();
+  static thread_local ConvPlan plan;
+  int rc = plan_conv(c, &plan, true);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_conv_igemm(plan.p, plan.maps, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+
+// ------------------------------------------------------------------------------------------ wgrad planner
+struct WgradPlan {
+  WgradParams p;
+  WgradMaps maps;
+  FinalizeParams fin;
+  int taps;
+};
+
+static int side_geometry(int c, int* rowb, int* chunks) {
+  const int cpad = (c + 15) / 16 * 16;
+  if (cpad == 16) { *rowb = 32; *chunks = 1; }
+  else if (cpad == 32) { *rowb = 64; *chunks = 1; }
+  else if (cpad == 64) { *rowb = 128; *chunks = 1; }
+  else if (cpad == 128) { *rowb = 128; *chunks = 2; }
+  else return -1;
+  return cpad;
+}
+
+static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
+  WgradParams& p = out->p;
+  memset(&p, 0, sizeof(p));
+  if (g->form != FO_FORM_S1 && g->form != FO_FORM_DOWN) return fail(FO_ERR_INVALID, "wgrad form must be S1 or DOWN");
+  const bool s1 = g->form == FO_FORM_S1;
+  if (g->ndim != 2 && !(g->ndim == 3 && s1)) return fail(FO_ERR_INVALID, "wgrad ndim unsupported");
+  const int mc = side_geometry(g->p.c, &p.p_rowb, &p.p_chunks);
+  const int nc = side_geometry(g->q.c, &p.q_rowb, &p.q_chunks);
+  if (mc < 0 || nc < 0) return fail(FO_ERR_INVALID, "wgrad channel counts must pad to 16/32/64/128 (got %d, %d)", g->p.c, g->q.c);
+  if (g->p.c_off + mc > g->p.cs || g->q.c_off + nc > g->q.cs) return fail(FO_ERR_INVALID, "wgrad slice exceeds storage");
+  p.MC = mc; p.NC = nc; p.p_c0 = g->p.c_off;
+  int ext[4];
+  if (s1 && g->ndim == 3) { ext[0] = g->w; ext[1] = g->h; ext[2] = g->d; ext[3] = g->n; }
+  else if (s1) { ext[0] = g->w; ext[1] = g->h; ext[2] = g->n; ext[3] = 1; }
+  else { ext[0] = g->w; ext[1] = 1; ext[2] = g->h; ext[3] = g->n; }  // P low-res (w,h) with a dummy parity dim
+  int box[4];
+  choose_box(ext, 64, box);
+  p.total_ptiles = 1;
+  for (int d = 0; d < 4; ++d) {
+    p.tile_step[d] = box[d];
+    p.tile_cnt[d] = (ext[d] + box[d] - 1) / box[d];
+    p.total_ptiles *= p.tile_cnt[d];
+    if (d < 3) p.box[d] = box[d];
+  }
+  if (box[3] != 1) return fail(FO_ERR_INVALID, "wgrad: tensor too small for a 64-pixel tile");
+  // taps
+  int nt = 0;
+  if (s1) {
+    const int k = g->ksize, pad = (k - 1) / 2;
+    if (k != 1 && k != 3) return fail(FO_ERR_INVALID, "wgrad ksize unsupported");
+    const int kd_n = g->ndim == 3 ? k : 1;
+    for (int kd = 0; kd < kd_n; ++kd)
+      for (int kh = 0; kh < k; ++kh)
+        for (int kw = 0; kw < k; ++kw) {
+          WgTap& t = p.taps[nt++];
+          t.c0 = (int16_t)g->q.c_off; t.d1 = (int8_t)(kw - pad); t.d2 = (int8_t)(kh - pad);
+          t.d3 = (int8_t)(g->ndim == 3 ? kd - pad : 0); t.map = 0; t.pad = 0;
+        }
+    p.taps_per_pass = k == 1 ? 1 : 3;
+  } else {
+    for (int ky = 0; ky < 4; ++ky)
+      for (int kx = 0; kx < 4; ++kx) {
+        WgTap& t = p.taps[nt++];
+        t.c0 = (int16_t)(kDownPar[kx] * g->q.cs + g->q.c_off); t.d1 = (int8_t)kDownD[kx]; t.d2 = (int8_t)kDownPar[ky];
+        t.d3 = (int8_t)kDownD[ky]; t.map = 0; t.pad = 0;
+      }
+    p.taps_per_pass = 4;
+  }
+  out->taps = nt;
+  p.passes = nt / p.taps_per_pass;
+  const int p_bytes = p.p_chunks * 64 * p.p_rowb, q_bytes = p.q_chunks * 64 * p.q_rowb;
+  const int stage_bytes = (p_bytes + p.taps_per_pass * q_bytes + 1023) & ~1023;
+  int stages = (kMaxDynSmem - 2048) / stage_bytes;
+  if (stages > 6) stages = 6;
+  if (stages < 2) return fail(FO_ERR_INVALID, "wgrad stage does not fit");
+  p.stages = stages;
+  int splits = (g_num_sms > 0 ? g_num_sms : 148) / p.passes;
+  if (splits < 1) splits = 1;
+  if (splits > p.total_ptiles) splits = p.total_ptiles;
+  p.splits = splits;
+  p.partial = (float*)g->workspace;
+
+  FinalizeParams& f = out->fin;
+  f.partial = p.partial; f.dweight = g->dweight; f.splits = splits; f.taps = nt; f.MC = mc; f.NC = nc;
+  f.m_real = g->p.c; f.n_real = g->q.c; f.dimB = g->dimB; f.m_axis = g->m_axis; f.q_w_off = g->q_w_off;
+  f.accumulate = g->accumulate;
+  if (!need_maps) return FO_OK;
+
+  uint64_t dims[5], str[5];
+  uint32_t bx[5];
+  // P map
+  {
+    const uint64_t cs = g->p.cs;
+    if (s1 && g->ndim == 3) {
+      dims[0] = cs; dims[1] = g->w; dims[2] = g->h; dims[3] = g->d; dims[4] = g->n;
+      str[0] = 1; str[1] = cs; str[2] = (uint64_t)g->w * cs; str[3] = (uint64_t)g->h * g->w * cs; str[4] = (uint64_t)g->d * g->h * g->w * cs;
+    } else if (s1) {
+      dims[0] = cs; dims[1] = g->w; dims[2] = g->h; dims[3] = g->n; dims[4] = 1;
+      str[0] = 1; str[1] = cs; str[2] = (uint64_t)g->w * cs; str[3] = (uint64_t)g->h * g->w * cs; str[4] = (uint64_t)g->n * g->h * g->w * cs;
+    } else {
+      dims[0] = cs; dims[1] = g->w; dims[2] = 1; dims[3] = g->h; dims[4] = g->n;
+      str[0] = 1; str[1] = cs; str[2] = (uint64_t)g->w * cs; str[3] = (uint64_t)g->w * cs; str[4] = (uint64_t)g->h * g->w * cs;
+    }
+    bx[0] = p.p_rowb / 2; bx[1] = box[0]; bx[2] = box[1]; bx[3] = box[2]; bx[4] = 1;
+    int rc = encode_map(&out->maps.p, g->p.ptr, 5, dims, str, bx, p.p_rowb);
+    if (rc != FO_OK) return rc;
+  }
+  {
+    const uint64_t cs = g->q.cs;
+    if (s1 && g->ndim == 3) {
+      dims[0] = cs; dims[1] = g->w; dims[2] = g->h; dims[3] = g->d; dims[4] = g->n;
+      str[0] = 1; str[1] = cs; str[2] = (uint64_t)g->w * cs; str[3] = (uint64_t)g->h * g->w * cs; str[4] = (uint64_t)g->d * g->h * g->w * cs;
+    } else if (s1) {
+      dims[0] = cs; dims[1] = g->w; dims[2] = g->h; dims[3] = g->n; dims[4] = 1;
+      str[0] = 1; str[1] = cs; str[2] = (uint64_t)g->w * cs; str[3] = (uint64_t)g->h * g->w * cs; str[4] = (uint64_t)g->n * g->h * g->w * cs;
+    } else {  // Q is the hi-res tensor [n, 2h, 2w, cs] in parity view
+      const uint64_t W2 = 2ULL * g->w, H2 = 2ULL * g->h;
+      dims[0] = 2 * cs; dims[1] = g->w; dims[2] = 2; dims[3] = g->h; dims[4] = g->n;
+      str[0] = 1; str[1] = 2 * cs; str[2] = W2 * cs; str[3] = 2 * W2 * cs; str[4] = H2 * W2 * cs;
+    }
+    bx[0] = p.q_rowb / 2; bx[1] = box[0]; bx[2] = box[1]; bx[3] = box[2]; bx[4] = 1;
+    int rc = encode_map(&out->maps.q[0], g->q.ptr, 5, dims, str, bx, p.q_rowb);
+    if (rc != FO_OK) return rc;
+    for (int i = 1; i < kMaxAMaps; ++i) out->maps.q[i] = out->maps.q[0];
+  }
+  return FO_OK;
+}
+
+extern "C" size_t fo_wgrad_workspace_bytes(const fo_wgrad_t* g) {
+  if (fo_init() != FO_OK) return 0;
+  static thread_local WgradPlan plan;
+  if (plan_wgrad(g, &plan, false) != FO_OK) return 0;
+  return (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float);
+}
+
+extern "C" int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream) {
+  REQUIRE_INIT();
+  static thread_local WgradPlan plan;
+  int rc = plan_wgrad(g, &plan, true);
+  if (rc != FO_OK) return rc;
+  const size_t need = (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float);
+  if (g->workspace == nullptr || g->workspace_bytes < need)
+    return fail(FO_ERR_INVALID, "wgrad workspace too small: %zu < %zu", g->workspace_bytes, need);
+  CUDA_TRY(launch_wgrad_igemm(plan.p, plan.maps, (cudaStream_t)stream));
+  CUDA_TRY(launch_wgrad_finalize(plan.fin, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+
+// ------------------------------------------------------------------------------------------ elementwise
+extern "C" int fo_pack_nchw(const float* x, void* out, int n, int c, int hw, int cs, const float* shift,
+                            const float* scale, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (cs % 8 != 0 || c > cs) return fail(FO_ERR_INVALID, "pack: bad channel counts %d/%d", c, cs);
+  if (cs > 32 && shift != nullptr) return fail(FO_ERR_INVALID, "pack: shift/scale only for cs <= 32");
+  CUDA_TRY(launch_pack_nchw(x, out, n, c, hw, cs, shift, scale, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_unpack_nchw(const void* x, float* out, int n, int c, int hw, int cs, fo_stream_t stream) {
+  REQUIRE_INIT();
+  CUDA_TRY(launch_unpack_nchw(x, out, n, c, hw, cs, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_relu(const void* x, void* y, size_t numel, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (numel % 8 != 0) return fail(FO_ERR_INVALID, "relu: numel must be a multiple of 8");
+  CUDA_TRY(launch_relu(x, y, numel, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" size_t fo_colsum_workspace_bytes(int cs) {
+  if (fo_init() != FO_OK) return 0;
+  return (size_t)colsum_blocks(g_num_sms) * cs * sizeof(float);
+}
+extern "C" int fo_colsum(const void* x, size_t rows, int cs, int c_off, int c, float* out, int accumulate,
+                         void* workspace, size_t workspace_bytes, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (cs % 8 != 0 || cs > 2048) return fail(FO_ERR_INVALID, "colsum: cs must be a multiple of 8");
+  if (workspace_bytes < fo_colsum_workspace_bytes(cs)) return fail(FO_ERR_INVALID, "colsum workspace too small");
+  CUDA_TRY(launch_colsum(x, rows, cs, c_off, c, out, accumulate, (float*)workspace, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_maxpool2(const void* x, void* y, int n, int h, int w, int cs, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if ((h | w) & 1 || cs % 8) return fail(FO_ERR_INVALID, "maxpool2: even h, w and cs %% 8 == 0 required");
+  CUDA_TRY(launch_maxpool2(x, y, n, h, w, cs, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int cs,
+                               fo_stream_t stream) {
+  REQUIRE_INIT();
+  CUDA_TRY(launch_maxpool2_bwd(x, y, dy, dx, n, h, w, cs, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+
+// ------------------------------------------------------------------------------------------ VQ
+extern "C" int fo_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
+                          fo_stream_t stream) {
+  REQUIRE_INIT();
+  CUDA_TRY(launch_vq_prep(embed, dim, n_embed, e_split, e_t, e_norm2, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" size_t fo_vq_assign_workspace_bytes(size_t rows, int dim) { return vq_assign_workspace_bytes(rows, dim); }
+extern "C" int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* embed, const void* e_split,
+                            const float* e_norm2, int64_t* embed_ind, int* n_flagged, void* workspace,
+                            size_t workspace_bytes, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (dim != 64 && dim != 128) return fail(FO_ERR_INVALID, "vq_assign: dim must be 64 or 128 (got %d)", dim);
+  if (n_embed % 16 != 0 || n_embed > 8192) return fail(FO_ERR_INVALID, "vq_assign: n_embed must be a multiple of 16, <= 8192");
+  if (workspace_bytes < vq_assign_workspace_bytes(rows, dim)) return fail(FO_ERR_INVALID, "vq_assign workspace too small");
+  if (rows == 0) return FO_OK;
+  CUtensorMap map_e;
+  uint64_t dims[2] = {(uint64_t)2 * dim, (uint64_t)n_embed};
+  uint64_t str[2] = {1, (uint64_t)2 * dim};
+  uint32_t bx[2] = {64, 256};
+  int rc = encode_map(&map_e, e_split, 2, dims, str, bx, 128);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_vq_assign(x, rows, dim, n_embed, embed, e_split, e_norm2, embed_ind, n_flagged, workspace, &map_e,
+                            g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_vq_gather_stats(const float* x, const int64_t* embed_ind, size_t rows, int dim, int n_embed,
+                                  const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
+                                  float* embed_sum, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (dim % 4 != 0) return fail(FO_ERR_INVALID, "vq: dim must be a multiple of 4");
+  if (rows == 0) return FO_OK;
+  CUDA_TRY(launch_vq_gather_stats(x, embed_ind, rows, dim, n_embed, e_t, q_f32, q_bf16, diff_sum, counts, embed_sum,
+                                  g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts,
+                         const float* embed_sum, int dim, int n_embed, float decay, float eps, fo_stream_t stream) {
+  REQUIRE_INIT();
+  CUDA_TRY(launch_vq_ema(embed, cluster_size, embed_avg, counts, embed_sum, dim, n_embed, decay, eps,
+                         (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_vq_backward(const void* g_q, int g_q_is_bf16, int g_cs, int g_c_off, const float* g_diff,
+                              const float* x, const int64_t* embed_ind, const float* e_t, size_t rows, int dim,
+                              int n_embed, float* gx_f32, void* gx_bf16, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (rows == 0) return FO_OK;
+  CUDA_TRY(launch_vq_backward(g_q, g_q_is_bf16, g_cs, g_c_off, g_diff, x, embed_ind, e_t, rows, dim, n_embed, gx_f32,
+                              gx_bf16, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+
+// ------------------------------------------------------------------------------------------ LPIPS / MSE
+extern "C" int fo_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out,
+                            fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (c % 64 != 0 || c > 512) return fail(FO_ERR_INVALID, "lpips_tap: c must be 64..512, multiple of 64");
+  CUDA_TRY(launch_lpips_tap(f0, f1, w, n, hw, c, out, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
+                                void* d_f0, const void* addend, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (c % 64 != 0 || c > 512) return fail(FO_ERR_INVALID, "lpips_tap_bwd: c must be 64..512, multiple of 64");
+  CUDA_TRY(launch_lpips_tap_bwd(f0, f1, w, g, n, hw, c, d_f0, addend, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, fo_stream_t stream) {
+  REQUIRE_INIT();
+  CUDA_TRY(launch_mse(a, b, n, ca, c, hw, sum_out, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}

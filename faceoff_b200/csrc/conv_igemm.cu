@@ -1,0 +1,289 @@
+// Implicit-GEMM convolution for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+// One kernel covers every forward / data-gradient convolution on the FaceOff hot path
+// (reference models/vqvae_conv3d_latent.py:86-190 Conv2d k1/k3/k4s2, ConvTranspose2d k4s2, Conv3d k3;
+// models/lpips.py:115-152 VGG16 3x3).  The kernel knows nothing about convolutions: the host planner
+// (api.cu) describes the op as
+//   * an M tiling of the output into boxes of 128 positions on a <=5-D channels-last tensor map,
+//   * a list of K steps (tensor map, channel chunk, spatial shift).  Out-of-range coordinates are
+//     zero-filled by TMA, which implements the conv padding; stride-2 convs address a parity
+//     (space-to-depth) view of the same memory; torch.cat inputs are just K steps on another map,
+//   * a packed bf16 weight matrix [Cout][K steps * KC] in the same K-step order.
+//
+// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+//   warp 0      TMA producer      (A box [128 x KC] + B box [NT x KC] per stage, 128B/64B/32B swizzle)
+//   warp 1      MMA issuer        (lane 0 issues tcgen05.mma kind::f16 BF16xBF16->FP32, M=128, N=NT)
+//   warps 2..5  epilogue          (tcgen05.ld -> +bias -> *mask -> +addend -> relu -> bf16/fp32 stores)
+// TMEM holds two accumulators (2 x NT columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+#include "common.cuh"
+#include "igemm.cuh"
+
+namespace fo {
+
+constexpr int kConvThreads = 192;
+
+__device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& g, int& nt, int (&base)[4]) {
+  // n-tile fastest so CTAs that share an A tile run concurrently and hit L2
+  nt = tile % p.n_tiles;
+  int t = tile / p.n_tiles;
+#pragma unroll
+  for (int d = 0; d < 4; ++d) {
+    int c = p.tile_cnt[d];
+    int i = t % c;
+    t /= c;
+    base[d] = i * p.tile_step[d];
+  }
+  g = t;
+}
+
+template <int NCH>
+__device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32_t (&v)[NCH], int col0, bool valid,
+                                               long long off) {
+  // col0: first output channel of this chunk (global channel index); off: element offset of channel 0
+  float f[NCH];
+#pragma unroll
+  for (int j = 0; j < NCH; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) f[j] += __ldg(p.bias + col0 + j);
+  }
+  if (!valid) return;
+  const bool full = (col0 + NCH <= p.c_store);
+  if (p.mask != nullptr && full) {
+    const uint4* mp = reinterpret_cast<const uint4*>(p.mask + off + col0);
+#pragma unroll
+    for (int q = 0; q < NCH / 8; ++q) {
+      uint4 m = __ldg(mp + q);
+      uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (!(bf16lo(w[e]) > 0.f)) f[q * 8 + 2 * e] = 0.f;
+        if (!(bf16hi(w[e]) > 0.f)) f[q * 8 + 2 * e + 1] = 0.f;
+      }
+    }
+  }
+  if (p.addend != nullptr && full) {
+    const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + col0);
+#pragma unroll
+    for (int q = 0; q < NCH / 8; ++q) {
+      uint4 m = __ldg(ap + q);
+      uint32_t w[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        f[q * 8 + 2 * e] += bf16lo(w[e]);
+        f[q * 8 + 2 * e + 1] += bf16hi(w[e]);
+      }
+    }
+  }
+  if (p.out_f32 != nullptr) {
+    if (p.out_cstride == 1 && full) {
+      float4* op = reinterpret_cast<float4*>(p.out_f32 + off + col0);
+#pragma unroll
+      for (int q = 0; q < NCH / 4; ++q) {
+        float4 o = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        if (p.relu_f32) {
+          o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+        }
+        op[q] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        if (col0 + j < p.c_store) {
+          float o = p.relu_f32 ? fmaxf(f[j], 0.f) : f[j];
+          p.out_f32[off + (long long)(col0 + j) * p.out_cstride] = o;
+        }
+      }
+    }
+  }
+  if (full) {
+    if (p.out_bf16 != nullptr) {
+      uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + off + col0);
+#pragma unroll
+      for (int q = 0; q < NCH / 8; ++q) {
+        uint4 o;
+        o.x = pack_bf16x2(f[8 * q + 0], f[8 * q + 1]);
+        o.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
+        o.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
+        o.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
+        op[q] = o;
+      }
+    }
+    if (p.out_relu != nullptr) {
+      uint4* op = reinterpret_cast<uint4*>(p.out_relu + off + col0);
+#pragma unroll
+      for (int q = 0; q < NCH / 8; ++q) {
+        uint4 o;
+        o.x = pack_bf16x2(fmaxf(f[8 * q + 0], 0.f), fmaxf(f[8 * q + 1], 0.f));
+        o.y = pack_bf16x2(fmaxf(f[8 * q + 2], 0.f), fmaxf(f[8 * q + 3], 0.f));
+        o.z = pack_bf16x2(fmaxf(f[8 * q + 4], 0.f), fmaxf(f[8 * q + 5], 0.f));
+        o.w = pack_bf16x2(fmaxf(f[8 * q + 6], 0.f), fmaxf(f[8 * q + 7], 0.f));
+        op[q] = o;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kConvThreads, 1)
+conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ ConvMaps maps) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages x (A tile | B tile)] | barriers | tmem ptr
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int rowb = p.KC * 2;
+  const int a_bytes = 128 * rowb;
+  const int b_bytes = p.NT * rowb;
+  const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;                  // [stages]
+  uint64_t* empty_bar = bars + p.stages;      // [stages]
+  uint64_t* tfull_bar = bars + 2 * p.stages;  // [2]
+  uint64_t* tempty_bar = tfull_bar + 2;       // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * p.NT) tmem_cols <<= 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&maps.a[i]);
+      tma_prefetch_desc(&maps.b);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);
+    }
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int g, nt, base[4];
+        decode_tile(p, tile, g, nt, base);
+        const KStep* ks = p.ksteps + g * p.num_ksteps;
+        const int kcol0 = g * p.num_ksteps * p.KC;
+        for (int k = 0; k < p.num_ksteps; ++k) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + (size_t)stage * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          const KStep s = ks[k];
+          tma_load_5d(sa, &maps.a[s.map], &full_bar[stage], s.c0, base[0] + s.d1, base[1] + s.d2, base[2] + s.d3,
+                      base[3]);
+          tma_load_2d(sb, &maps.b, &full_bar[stage], kcol0 + k * p.KC, nt * p.NT);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
+    int stage = 0;
+    uint32_t phase = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + buf * p.NT;
+      for (int k = 0; k < p.num_ksteps; ++k) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+          for (int kk = 0; kk < p.KC / 16; ++kk) {
+            const uint64_t ad = make_smem_desc(sa + kk * 32, rowb, 16);
+            const uint64_t bd = make_smem_desc(sb + kk * 32, rowb, 16);
+            umma_bf16(d_tmem, ad, bd, idesc, (k | kk) != 0);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (k == p.num_ksteps - 1) umma_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+    const int row = quarter * 32 + lane;    // pixel row inside the tile
+    const int b1 = row % p.box[0];
+    const int b2 = (row / p.box[0]) % p.box[1];
+    const int b3 = (row / (p.box[0] * p.box[1])) % p.box[2];
+    const int b4 = row / (p.box[0] * p.box[1] * p.box[2]);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      int g, nt, base[4];
+      decode_tile(p, tile, g, nt, base);
+      const int c1 = base[0] + b1, c2 = base[1] + b2, c3 = base[2] + b3, c4 = base[3] + b4;
+      const bool valid = (c1 < p.lim[0]) && (c2 < p.lim[1]) && (c3 < p.lim[2]) && (c4 < p.lim[3]);
+      const long long off = p.out_off[g] + c1 * p.out_stride[0] + c2 * p.out_stride[1] + c3 * p.out_stride[2] +
+                            c4 * p.out_stride[3];
+      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * p.NT;
+      const int ncol0 = nt * p.NT;
+      int c = 0;
+      for (; c + 32 <= p.NT; c += 32) {
+        uint32_t v[32];
+        tmem_ld32(taddr + c, v);
+        tmem_ld_wait();
+        epilogue_chunk<32>(p, v, ncol0 + c, valid, off);
+      }
+      for (; c + 16 <= p.NT; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(taddr + c, v);
+        tmem_ld_wait();
+        epilogue_chunk<16>(p, v, ncol0 + c, valid, off);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+size_t conv_smem_bytes(const ConvParams& p) {
+  const int rowb = p.KC * 2;
+  const int stage_bytes = (128 * rowb + p.NT * rowb + 1023) & ~1023;
+  return (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024;
+}
+
+cudaError_t launch_conv_igemm(const ConvParams& p, const ConvMaps& maps, int num_sms, cudaStream_t stream) {
+  const size_t smem = conv_smem_bytes(p);
+  int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
+  conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p, maps);
+  return cudaGetLastError();
+}
+
+cudaError_t init_conv_igemm() {
+  return cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+}
+
+}  // namespace fo

@@ -1,0 +1,88 @@
+// Parameter blocks shared by the host planners (api.cu) and the tcgen05 implicit-GEMM kernels.
+#pragma once
+#include <cuda.h>
+#include <stdint.h>
+
+namespace fo {
+
+constexpr int kMaxKSteps = 160;   // 27 taps x 4 channel chunks, VGG 9 x 8, ...
+constexpr int kMaxAMaps = 3;
+constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
+constexpr int kMaxGroups = 4;     // sub-pixel (parity) classes of a stride-2 transposed conv
+
+// One K step of the implicit GEMM: which activation map, which channel chunk, which spatial shift.
+struct KStep {
+  int16_t c0;      // coordinate on map dim 0 (channels)
+  int8_t d1, d2, d3;  // coordinate deltas on map dims 1..3
+  uint8_t map;     // A-operand tensor map index
+  int16_t pad;
+};
+
+// conv_igemm: D[128 pixels, NT] = sum_k A_k[128, KC] * W_k[NT, KC]^T   (+ fused epilogue)
+struct ConvParams {
+  // M tiling: a tile is a box of box[0] x box[1] x box[2] x box[3] positions on map dims 1..4, product 128
+  int tile_cnt[4];    // tiles along map dims 1..4 (dim 1 fastest)
+  int tile_step[4];   // coordinate step per tile on dims 1..4
+  int box[4];         // in-tile extents on dims 1..4
+  int lim[4];         // valid output extents on dims 1..4 (partial tiles are predicated)
+  int n_tiles;        // N tiles of width NT
+  int NT;             // columns per N tile (multiple of 16, <= 256)
+  int KC;             // channels per K step: 16 / 32 / 64  (row bytes 32 / 64 / 128 = swizzle mode)
+  int num_ksteps;     // per group
+  int groups;
+  int stages;
+  int total_tiles;    // groups * n_tiles * prod(tile_cnt)
+  // epilogue
+  long long out_stride[4];       // element strides of dims 1..4 in the output tensors
+  long long out_off[kMaxGroups]; // per-group element offset
+  int out_cstride;               // channel stride of out_f32 (1 = channels-last)
+  int c_store;                   // channels actually stored (<= n_tiles*NT)
+  const float* bias;             // [>= n_tiles*NT] or null
+  const __nv_bfloat16* mask;     // zero the result where mask <= 0 (same layout as out_bf16) or null
+  const __nv_bfloat16* addend;   // added after masking (same layout) or null
+  __nv_bfloat16* out_bf16;       // raw result or null
+  __nv_bfloat16* out_relu;       // relu(result) or null
+  float* out_f32;                // raw result in fp32 (channel stride out_cstride) or null
+  int relu_f32;                  // apply relu to out_f32 too
+  KStep ksteps[kMaxKSteps];
+};
+
+struct ConvMaps {
+  CUtensorMap a[kMaxAMaps];
+  CUtensorMap b;
+};
+
+// wgrad_igemm: dW[g][m][n] = sum_pixels P[pix][m] * Q[pix (+) shift_g][n]; both operands MN-major.
+constexpr int kMaxWgTaps = 4;  // accumulators resident in TMEM per CTA pass (4 x 128 columns)
+struct WgTap {
+  int16_t c0;
+  int8_t d1, d2, d3;
+  uint8_t map;
+  int16_t pad;
+};
+struct WgradParams {
+  int tile_cnt[4];
+  int tile_step[4];
+  int box[3];            // product = pixels per K step (64)
+  int MC;                // P-side channels (rows of dW tile): 64 or 128 (UMMA M)
+  int p_chunks;          // TMA boxes on the P side (MC/chunk width)
+  int p_rowb;            // bytes per pixel row in a P box (32/64/128)
+  int NC;                // Q-side channels per tap (UMMA N), multiple of 16, <= 128
+  int q_chunks;
+  int q_rowb;
+  int taps_per_pass;     // <= kMaxWgTaps
+  int passes;
+  int splits;            // split-K factor over pixel tiles
+  int total_ptiles;      // prod(tile_cnt)
+  int stages;
+  int p_c0;              // channel offset of the P side inside its map
+  int p_map_is_a0;       // unused, reserved
+  float* partial;        // [splits][passes*taps_per_pass][MC][NC] fp32
+  WgTap taps[64];        // passes * taps_per_pass entries (padded entries have map = 255)
+};
+struct WgradMaps {
+  CUtensorMap p;
+  CUtensorMap q[kMaxAMaps];
+};
+
+}  // namespace fo

@@ -1,0 +1,78 @@
+// Internal launcher declarations shared between the .cu translation units and api.cu.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "igemm.cuh"
+
+namespace fo {
+
+struct PackStep {
+  int16_t tap;    // linear filter-tap index in the PyTorch weight
+  int16_t wk0;    // first index on the weight's K axis
+  int16_t valid;  // valid channels in this chunk (rest are zero)
+  int16_t pad;
+};
+struct PackParams {
+  int npad, ktot, kc, cout;
+  int dimB, taps, n_axis;
+  const float* n_scale;
+  PackStep steps[kMaxKSteps];
+};
+struct FinalizeParams {
+  const float* partial;
+  float* dweight;
+  int splits, taps, MC, NC, m_real, n_real;
+  int dimB, m_axis, q_w_off, accumulate;
+};
+
+// conv_igemm.cu / wgrad_igemm.cu
+size_t conv_smem_bytes(const ConvParams& p);
+cudaError_t launch_conv_igemm(const ConvParams& p, const ConvMaps& maps, int num_sms, cudaStream_t stream);
+cudaError_t init_conv_igemm();
+size_t wgrad_smem_bytes(const WgradParams& p);
+cudaError_t launch_wgrad_igemm(const WgradParams& p, const WgradMaps& maps, cudaStream_t stream);
+cudaError_t init_wgrad_igemm();
+
+// elementwise.cu
+cudaError_t launch_pack_nchw(const float* x, void* out, int n, int c, int hw, int cs, const float* shift,
+                             const float* scale, int num_sms, cudaStream_t st);
+cudaError_t launch_unpack_nchw(const void* x, float* out, int n, int c, int hw, int cs, cudaStream_t st);
+cudaError_t launch_relu(const void* x, void* y, size_t numel, int num_sms, cudaStream_t st);
+cudaError_t launch_pack_weights(const float* w, void* out, const PackParams& pp, int num_sms, cudaStream_t st);
+cudaError_t launch_wgrad_finalize(const FinalizeParams& fp, int num_sms, cudaStream_t st);
+int colsum_blocks(int num_sms);
+cudaError_t launch_colsum(const void* x, size_t rows, int cs, int c_off, int c, float* out, int accumulate,
+                          float* workspace, int num_sms, cudaStream_t st);
+cudaError_t launch_maxpool2(const void* x, void* y, int n, int h, int w, int cs, int num_sms, cudaStream_t st);
+cudaError_t launch_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int cs,
+                                int num_sms, cudaStream_t st);
+
+// vq.cu
+cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
+                           cudaStream_t st);
+size_t vq_assign_workspace_bytes(size_t rows, int dim);
+cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* embed,
+                             const void* e_split, const float* e_norm2, int64_t* embed_ind, int* n_flagged,
+                             void* workspace, const CUtensorMap* map_e, int num_sms, cudaStream_t st);
+cudaError_t init_vq();
+cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t rows, int dim, int n_embed,
+                                   const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
+                                   float* embed_sum, int num_sms, cudaStream_t st);
+cudaError_t launch_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts,
+                          const float* embed_sum, int dim, int n_embed, float decay, float eps, cudaStream_t st);
+cudaError_t launch_vq_backward(const void* g_q, int g_q_is_bf16, int g_cs, int g_c_off, const float* g_diff,
+                               const float* x, const int64_t* ind, const float* e_t, size_t rows, int dim,
+                               int n_embed, float* gx_f32, void* gx_bf16, int num_sms, cudaStream_t st);
+
+// lpips.cu
+cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out,
+                             int num_sms, cudaStream_t st);
+cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
+                                 void* d_f0, const void* addend, int num_sms, cudaStream_t st);
+cudaError_t launch_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, int num_sms,
+                       cudaStream_t st);
+
+}  // namespace fo

@@ -1,0 +1,222 @@
+// LPIPS head (reference models/lpips.py:80-93,155-161): per tap, channel-normalise both feature maps, squared
+// difference, 1x1 "lin" conv to one channel, spatial mean -- fused into ONE bandwidth-bound pass that reads
+// f0 and f1 exactly once (bf16 channels-last) and emits a scalar per image.  The reference materialises >= 10
+// full-size temporaries per tap.
+#include "common.cuh"
+#include "kernels.h"
+
+namespace fo {
+
+constexpr float kLpipsEps = 1e-10f;  // models/lpips.py:155 -- added to the norm, outside the sqrt
+
+// LPP lanes cooperate on one pixel; each lane holds VPL 16-byte vectors (8 channels) of f0 and f1.
+template <int VPL>
+__device__ __forceinline__ void load_pix(const __nv_bfloat16* p, int lpp, int sub, float (&v)[VPL * 8]) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const uint4 u = __ldg(q + i * lpp + sub);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      v[i * 8 + 2 * e] = bf16lo(w[e]);
+      v[i * 8 + 2 * e + 1] = bf16hi(w[e]);
+    }
+  }
+}
+__device__ __forceinline__ float group_sum(float s, int lpp) {
+  for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  return s;
+}
+
+template <int VPL>
+__global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
+                                 const float* __restrict__ w, int hw, int c, int lpp, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int n = blockIdx.y;
+  const int ppw = 32 / lpp;                        // pixels per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % lpp, pw = lane / lpp;
+  float wv[VPL * 8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wv[i * 8 + e] = __ldg(w + (i * lpp + sub) * 8 + e);
+  float acc = 0.f;
+  const int pix_per_block = (blockDim.x >> 5) * ppw;
+  for (int p0 = blockIdx.x * pix_per_block; p0 < hw; p0 += gridDim.x * pix_per_block) {
+    const int pix = p0 + warp * ppw + pw;
+    const bool ok = pix < hw;
+    float a[VPL * 8], b[VPL * 8];
+    const size_t off = ((size_t)n * hw + (ok ? pix : 0)) * c;
+    load_pix<VPL>(f0 + off, lpp, sub, a);
+    load_pix<VPL>(f1 + off, lpp, sub, b);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL * 8; ++j) { s0 += a[j] * a[j]; s1 += b[j] * b[j]; }
+    s0 = group_sum(s0, lpp);
+    s1 = group_sum(s1, lpp);
+    const float i0 = 1.f / (sqrtf(s0) + kLpipsEps), i1 = 1.f / (sqrtf(s1) + kLpipsEps);
+    float d = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL * 8; ++j) {
+      const float t = a[j] * i0 - b[j] * i1;
+      d += wv[j] * t * t;
+    }
+    if (ok) acc += d;
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(out + n, s / (float)hw);
+  }
+}
+
+// d/df0 of the tap value, times g[n], gated by the ReLU that produced f0, plus optional addend (pool gradient).
+//   a = f0/n0, n0 = |f0| + eps ;  u_c = (2/hw) w_c (a_c - b_c)
+//   dL/df0_j = u_j / n0 - (sum_c u_c f0_c) f0_j / (n0^2 |f0|)
+template <int VPL>
+__global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
+                                     const float* __restrict__ w, const float* __restrict__ g, int hw, int c, int lpp,
+                                     __nv_bfloat16* __restrict__ d_f0, const __nv_bfloat16* __restrict__ addend) {
+  const int n = blockIdx.y;
+  const int ppw = 32 / lpp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % lpp, pw = lane / lpp;
+  float wv[VPL * 8];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) wv[i * 8 + e] = __ldg(w + (i * lpp + sub) * 8 + e);
+  const float gn = g[n] * 2.f / (float)hw;
+  const int pix_per_block = (blockDim.x >> 5) * ppw;
+  for (int p0 = blockIdx.x * pix_per_block; p0 < hw; p0 += gridDim.x * pix_per_block) {
+    const int pix = p0 + warp * ppw + pw;
+    const bool ok = pix < hw;
+    float a[VPL * 8], b[VPL * 8];
+    const size_t off = ((size_t)n * hw + (ok ? pix : 0)) * c;
+    load_pix<VPL>(f0 + off, lpp, sub, a);
+    load_pix<VPL>(f1 + off, lpp, sub, b);
+    float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL * 8; ++j) { s0 += a[j] * a[j]; s1 += b[j] * b[j]; }
+    s0 = group_sum(s0, lpp);
+    s1 = group_sum(s1, lpp);
+    const float r0 = sqrtf(s0);
+    const float n0 = r0 + kLpipsEps;
+    const float i0 = 1.f / n0, i1 = 1.f / (sqrtf(s1) + kLpipsEps);
+    float u[VPL * 8];
+    float dot = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL * 8; ++j) {
+      u[j] = gn * wv[j] * (a[j] * i0 - b[j] * i1);
+      dot += u[j] * a[j];
+    }
+    dot = group_sum(dot, lpp);
+    const float k2 = r0 > 0.f ? dot * i0 * i0 / r0 : 0.f;
+    float ad[VPL * 8];
+    if (addend != nullptr) {
+      load_pix<VPL>(addend + off, lpp, sub, ad);
+    } else {
+#pragma unroll
+      for (int j = 0; j < VPL * 8; ++j) ad[j] = 0.f;
+    }
+    if (ok) {
+      uint4* dst = reinterpret_cast<uint4*>(d_f0 + off);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int j = i * 8 + e;
+          const float gr = u[j] * i0 - k2 * a[j];
+          o[e] = a[j] > 0.f ? gr + ad[j] : 0.f;   // ReLU gate of the tap (addend is already gated)
+        }
+        uint4 ov;
+        ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
+        ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
+        dst[i * lpp + sub] = ov;
+      }
+    }
+  }
+}
+
+static void lpips_geometry(int c, int& lpp, int& vpl) {
+  const int vecs = c / 8;
+  lpp = vecs < 32 ? vecs : 32;
+  vpl = vecs / lpp;
+}
+
+cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out,
+                             int num_sms, cudaStream_t st) {
+  int lpp, vpl;
+  lpips_geometry(c, lpp, vpl);
+  const int threads = 256;
+  const int pix_per_block = (threads / 32) * (32 / lpp);
+  int bx = (hw + pix_per_block - 1) / pix_per_block;
+  const int cap = (num_sms * 8 + n - 1) / n;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n);
+  const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
+  if (vpl == 1) lpips_tap_kernel<1><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  else if (vpl == 2) lpips_tap_kernel<2><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
+                                 void* d_f0, const void* addend, int num_sms, cudaStream_t st) {
+  int lpp, vpl;
+  lpips_geometry(c, lpp, vpl);
+  const int threads = 256;
+  const int pix_per_block = (threads / 32) * (32 / lpp);
+  int bx = (hw + pix_per_block - 1) / pix_per_block;
+  const int cap = (num_sms * 8 + n - 1) / n;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n);
+  const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
+  if (vpl == 1)
+    lpips_tap_bwd_kernel<1><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, (__nv_bfloat16*)d_f0,
+                                                      (const __nv_bfloat16*)addend);
+  else if (vpl == 2)
+    lpips_tap_bwd_kernel<2><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, (__nv_bfloat16*)d_f0,
+                                                      (const __nv_bfloat16*)addend);
+  else return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+// sum((a[:, :c] - b)^2), NCHW fp32
+__global__ void mse_kernel(const float* __restrict__ a, const float* __restrict__ b, int ca, int c, int hw, size_t total,
+                           float* __restrict__ out) {
+  __shared__ float red[32];
+  float acc = 0.f;
+  const size_t chw = (size_t)c * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / chw, r = i % chw;
+    const float d = a[n * (size_t)ca * hw + r] - b[i];
+    acc += d * d;
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(out, s);
+  }
+}
+cudaError_t launch_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, int num_sms,
+                       cudaStream_t st) {
+  const size_t total = (size_t)n * c * hw;
+  size_t blocks = (total + 255) / 256;
+  if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  mse_kernel<<<(int)blocks, 256, 0, st>>>(a, b, ca, c, hw, total, sum_out);
+  return cudaGetLastError();
+}
+
+}  // namespace fo

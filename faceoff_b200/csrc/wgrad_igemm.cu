@@ -1,0 +1,187 @@
+// Weight-gradient implicit GEMM for sm_100a (tcgen05 + TMA + TMEM), split-K over pixels.
+//
+//   dW[tap][m][n] = sum over pixels  P[pix][m] * Q[pix (+) shift_tap][n]
+//
+// P and Q are channels-last activations/gradients; the reduction (K) dimension is the pixel index,
+// so both operands are "MN-major" for the tensor core: a TMA box {channels<=64, 64 pixels} lands in
+// shared memory as 64 rows (pixels) of 32/64/128 B and is consumed directly through an MN-major UMMA
+// descriptor (LBO = distance between 64-channel boxes, SBO = 8 rows).  The spatial shift of Q per
+// filter tap is a TMA coordinate offset with hardware zero fill = the conv padding.
+// (reference autograd of nn.Conv2d / ConvTranspose2d / Conv3d in models/vqvae_conv3d_latent.py:86-190.)
+//
+// grid = (splits, passes).  A CTA owns `taps_per_pass` taps (one 128 x NC fp32 accumulator each, all
+// resident in TMEM) and a contiguous range of 64-pixel tiles; per tile it loads P once and Q once per
+// tap.  Partials go to partial[split][tap][m][n]; wgrad_finalize (elementwise.cu) reduces the splits in a
+// fixed order (deterministic) and scatters into the PyTorch weight layout.
+#include "common.cuh"
+#include "igemm.cuh"
+
+namespace fo {
+
+constexpr int kWgThreads = 192;
+constexpr int kWgPix = 64;  // pixels per K step
+
+__global__ void __launch_bounds__(kWgThreads, 1)
+wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ WgradMaps maps) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int p_chunk_bytes = kWgPix * p.p_rowb;
+  const int q_chunk_bytes = kWgPix * p.q_rowb;
+  const int p_bytes = p.p_chunks * p_chunk_bytes;
+  const int q_bytes = p.q_chunks * q_chunk_bytes;  // per tap
+  const int stage_bytes = (p_bytes + p.taps_per_pass * q_bytes + 1023) & ~1023;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + p.stages;
+  uint64_t* done_bar = bars + 2 * p.stages;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.taps_per_pass * p.NC) tmem_cols <<= 1;
+
+  const int split = blockIdx.x;
+  const int pass = blockIdx.y;
+  // contiguous range of pixel tiles for this split
+  const int per = (p.total_ptiles + p.splits - 1) / p.splits;
+  const int t_begin = split * per;
+  const int t_end = min(p.total_ptiles, t_begin + per);
+  const int n_my = max(0, t_end - t_begin);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      tma_prefetch_desc(&maps.p);
+      for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&maps.q[i]);
+    }
+    __syncwarp();
+    tmem_alloc(tmem_ptr, tmem_cols);
+    tmem_relinquish();
+  } else if (warp == 1 && lane == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(done_bar, 1);
+    fence_mbar_init();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  const WgTap* taps = p.taps + pass * p.taps_per_pass;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int t = t_begin; t < t_end; ++t) {
+        int base[4];
+        int r = t;
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          int c = p.tile_cnt[d];
+          base[d] = (r % c) * p.tile_step[d];
+          r /= c;
+        }
+        mbar_wait(&empty_bar[stage], phase ^ 1);
+        uint8_t* sp = smem + (size_t)stage * stage_bytes;
+        mbar_expect_tx(&full_bar[stage], p_bytes + p.taps_per_pass * q_bytes);
+        const int p_cw = p.p_rowb / 2;
+        for (int c = 0; c < p.p_chunks; ++c)
+          tma_load_5d(sp + c * p_chunk_bytes, &maps.p, &full_bar[stage], p.p_c0 + c * p_cw, base[0], base[1], base[2],
+                      base[3]);
+        const int q_cw = p.q_rowb / 2;
+        for (int tp = 0; tp < p.taps_per_pass; ++tp) {
+          const WgTap w = taps[tp];
+          uint8_t* sq = sp + p_bytes + tp * q_bytes;
+          for (int c = 0; c < p.q_chunks; ++c)
+            tma_load_5d(sq + c * q_chunk_bytes, &maps.q[w.map], &full_bar[stage], w.c0 + c * q_cw, base[0] + w.d1,
+                        base[1] + w.d2, base[2] + w.d3, base[3]);
+        }
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    const uint32_t idesc = make_idesc_bf16(128, p.NC, 1, 1);
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int i = 0; i < n_my; ++i) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sp = smem_u32(smem + (size_t)stage * stage_bytes);
+        for (int tp = 0; tp < p.taps_per_pass; ++tp) {
+          const uint32_t sq = sp + p_bytes + tp * q_bytes;
+#pragma unroll
+          for (int kk = 0; kk < kWgPix / 16; ++kk) {
+            // 16 pixels = two 8-row swizzle groups
+            const uint64_t ad = make_smem_desc(sp + kk * 16 * p.p_rowb, p.p_rowb, p.p_chunks > 1 ? p_chunk_bytes : 0);
+            const uint64_t bd = make_smem_desc(sq + kk * 16 * p.q_rowb, p.q_rowb, p.q_chunks > 1 ? q_chunk_bytes : 0);
+            umma_bf16(tmem_base + tp * p.NC, ad, bd, idesc, (i | kk) != 0);
+          }
+        }
+        umma_commit(&empty_bar[stage]);
+        if (i == n_my - 1) umma_commit(done_bar);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1; }
+    }
+  } else {
+    // epilogue: TMEM -> partial[split][pass*tpp + tp][m][n]
+    const int quarter = warp & 3;
+    const int row = quarter * 32 + lane;
+    if (n_my > 0) {
+      mbar_wait(done_bar, 0);
+      tc_fence_after();
+    }
+    for (int tp = 0; tp < p.taps_per_pass; ++tp) {
+      const int tap = pass * p.taps_per_pass + tp;
+      float* dst = p.partial + (((size_t)split * (p.passes * p.taps_per_pass) + tap) * p.MC + row) * p.NC;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tp * p.NC;
+      for (int c = 0; c < p.NC; c += 16) {
+        uint32_t v[16];
+        if (n_my > 0) {
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = 0u;
+        }
+        if (row < p.MC) {
+          float4* o = reinterpret_cast<float4*>(dst + c);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            o[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]),
+                               __uint_as_float(v[4 * q + 3]));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+size_t wgrad_smem_bytes(const WgradParams& p) {
+  const int p_bytes = p.p_chunks * kWgPix * p.p_rowb;
+  const int q_bytes = p.q_chunks * kWgPix * p.q_rowb;
+  const int stage_bytes = (p_bytes + p.taps_per_pass * q_bytes + 1023) & ~1023;
+  return (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+}
+
+cudaError_t launch_wgrad_igemm(const WgradParams& p, const WgradMaps& maps, cudaStream_t stream) {
+  dim3 grid(p.splits, p.passes);
+  wgrad_igemm_kernel<<<grid, kWgThreads, wgrad_smem_bytes(p), stream>>>(p, maps);
+  return cudaGetLastError();
+}
+
+cudaError_t init_wgrad_igemm() {
+  return cudaFuncSetAttribute(wgrad_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+}
+
+}  // namespace fo

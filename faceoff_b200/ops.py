@@ -1,0 +1,317 @@
+"""Thin tensor-level wrappers over the C ABI (faceoff_b200/_lib.py).
+
+Activations are channels-last bf16 tensors shaped [N, H, W, Cs] (2-D) or [N, D, H, W, Cs] (3-D),
+contiguous, Cs a multiple of 16; logical channel counts are passed explicitly.  Everything here runs on the
+current CUDA stream and never synchronises the host.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib as L
+from ._lib import FORM_DOWN, FORM_S1, FORM_S1_DGRAD, FORM_UP, ConvDesc, Src, WgradDesc  # noqa: F401
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def pad16(c: int) -> int:
+    return (c + 15) // 16 * 16
+
+
+# ------------------------------------------------------------------------------------------------
+# workspaces (per device, grown on demand; all users are ordered on the current stream)
+# ------------------------------------------------------------------------------------------------
+_ws: Dict[Tuple[int, str], torch.Tensor] = {}
+
+
+def workspace(nbytes: int, device, tag: str = "main") -> torch.Tensor:
+    key = (torch.device(device).index or 0, tag)
+    t = _ws.get(key)
+    if t is None or t.numel() < nbytes:
+        t = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _ws[key] = t
+    return t
+
+
+# ------------------------------------------------------------------------------------------------
+# convolution family
+# ------------------------------------------------------------------------------------------------
+SrcT = Tuple[torch.Tensor, int, int]  # (tensor, logical channels, channel offset)
+
+_wcache: Dict[tuple, Tuple[int, torch.Tensor]] = {}
+
+
+def _fill_src(dst: Src, s: SrcT):
+    t, c, c_off = s
+    assert t.dtype == torch.bfloat16 and t.is_contiguous() and t.is_cuda, "activations must be contiguous bf16 CUDA"
+    dst.ptr, dst.c, dst.cs, dst.c_off = t.data_ptr(), c, t.shape[-1], c_off
+
+
+def _conv_desc(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], cout: int) -> ConvDesc:
+    d = ConvDesc()
+    t0 = srcs[0][0]
+    d.form, d.ndim, d.ksize = form, ndim, ksize
+    if ndim == 3:
+        d.n, d.d, d.h, d.w = t0.shape[0], t0.shape[1], t0.shape[2], t0.shape[3]
+    else:
+        d.n, d.d, d.h, d.w = t0.shape[0], 1, t0.shape[1], t0.shape[2]
+    d.n_src = len(srcs)
+    for i, s in enumerate(srcs):
+        assert s[0].shape[:-1] == t0.shape[:-1]
+        _fill_src(d.src[i], s)
+    d.cout = cout
+    return d
+
+
+def out_spatial(form: int, shape: Sequence[int]) -> Tuple[int, ...]:
+    """Leading (non-channel) output shape for an input of leading shape ``shape``."""
+    if form == FORM_DOWN:
+        return (shape[0], shape[1] // 2, shape[2] // 2)
+    if form == FORM_UP:
+        return (shape[0], shape[1] * 2, shape[2] * 2)
+    return tuple(shape)
+
+
+def packed_weights(desc: ConvDesc, weight: torch.Tensor, n_axis: int, n_scale: Optional[torch.Tensor], key_extra) -> torch.Tensor:
+    lib = L.load()
+    key = (weight.data_ptr(), desc.form, desc.ndim, desc.ksize, n_axis, key_extra, _p(n_scale))
+    ver = weight._version
+    hit = _wcache.get(key)
+    if hit is not None and hit[0] == ver:
+        return hit[1]
+    nbytes = lib.fo_conv_wpacked_bytes(C.byref(desc))
+    if nbytes == 0:
+        raise L.FaceoffB200Error("fo_conv_wpacked_bytes: " + lib.fo_last_error().decode())
+    wp = torch.empty(nbytes // 2, dtype=torch.bfloat16, device=weight.device)
+    assert weight.dtype == torch.float32 and weight.is_contiguous()
+    L.check(lib.fo_conv_pack_weights(C.byref(desc), weight.data_ptr(), weight.shape[0], weight.shape[1], n_axis,
+                                     _p(n_scale), wp.data_ptr(), _stream()), "fo_conv_pack_weights")
+    _wcache[key] = (ver, wp)
+    return wp
+
+
+def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.Tensor, n_axis: int, cout: int,
+         bias: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
+         addend: Optional[torch.Tensor] = None, want_raw: bool = True, want_relu: bool = False,
+         f32: Optional[str] = None, relu_f32: bool = False, n_scale: Optional[torch.Tensor] = None,
+         out_cs: Optional[int] = None, out_raw: Optional[torch.Tensor] = None):
+    """Run one implicit-GEMM convolution.  Returns (raw_bf16|None, relu_bf16|None, f32|None).
+
+    f32: None | 'cl' (channels-last fp32 [.., out_cs]) | 'nchw' (fp32 [N, cout, H, W]).
+    """
+    lib = L.load()
+    d = _conv_desc(form, ndim, ksize, srcs, cout)
+    key_extra = tuple((s[1], s[0].shape[-1], s[2]) for s in srcs) + (cout,)
+    wp = packed_weights(d, weight, n_axis, n_scale, key_extra)
+    d.wpacked = wp.data_ptr()
+    t0 = srcs[0][0]
+    lead = out_spatial(form, t0.shape[:-1])
+    ocs = out_cs if out_cs is not None else pad16(cout)
+    dev = t0.device
+    raw = relu = of32 = None
+    if f32 == "nchw":
+        of32 = torch.empty((lead[0], cout, lead[1], lead[2]), dtype=torch.float32, device=dev)
+        d.out_f32_nchw = 1
+    else:
+        if want_raw:
+            raw = out_raw if out_raw is not None else torch.empty((*lead, ocs), dtype=torch.bfloat16, device=dev)
+        if want_relu:
+            relu = torch.empty((*lead, ocs), dtype=torch.bfloat16, device=dev)
+        if f32 == "cl":
+            of32 = torch.empty((*lead, ocs), dtype=torch.float32, device=dev)
+    if ocs > pad16(cout):
+        # channels beyond the computed ones are never written by the kernel
+        for t in (raw, relu):
+            if t is not None and t is not out_raw:
+                t[..., pad16(cout):].zero_()
+    d.out_cs = ocs
+    d.bias = _p(bias)
+    d.mask = _p(mask)
+    d.addend = _p(addend)
+    d.out_bf16, d.out_relu, d.out_f32 = _p(raw), _p(relu), _p(of32)
+    d.relu_f32 = int(relu_f32)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= pad16(cout), "bias must be fp32 padded to 16"
+    for t in (mask, addend):
+        if t is not None:
+            assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape) == (*lead, ocs), (t.shape, lead, ocs)
+    L.check(lib.fo_conv_run(C.byref(d), _stream()), "fo_conv_run")
+    return raw, relu, of32
+
+
+def wgrad(form: int, ndim: int, ksize: int, p: SrcT, q: SrcT, dweight: torch.Tensor, m_axis: int, q_w_off: int = 0,
+          accumulate: bool = False):
+    """dweight (fp32, PyTorch layout) (+)= sum_pix P (x) Q.  form: FORM_S1 or FORM_DOWN (Q = hi-res side)."""
+    lib = L.load()
+    g = WgradDesc()
+    pt = p[0]
+    g.form, g.ndim, g.ksize = form, ndim, ksize
+    if ndim == 3:
+        g.n, g.d, g.h, g.w = pt.shape[0], pt.shape[1], pt.shape[2], pt.shape[3]
+    else:
+        g.n, g.d, g.h, g.w = pt.shape[0], 1, pt.shape[1], pt.shape[2]
+    _fill_src(g.p, p)
+    _fill_src(g.q, q)
+    assert dweight.dtype == torch.float32 and dweight.is_contiguous()
+    g.dweight, g.dimA, g.dimB = dweight.data_ptr(), dweight.shape[0], dweight.shape[1]
+    g.m_axis, g.q_w_off, g.accumulate = m_axis, q_w_off, int(accumulate)
+    need = lib.fo_wgrad_workspace_bytes(C.byref(g))
+    if need == 0:
+        raise L.FaceoffB200Error("fo_wgrad_workspace_bytes: " + lib.fo_last_error().decode())
+    ws = workspace(need, pt.device, "wgrad")
+    g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
+    L.check(lib.fo_wgrad_run(C.byref(g), _stream()), "fo_wgrad_run")
+
+
+def colsum(x: torch.Tensor, c: int, out: torch.Tensor, c_off: int = 0, accumulate: bool = False):
+    """out[:c] (+)= x.reshape(-1, Cs)[:, c_off:c_off+c].sum(0)   (bias gradient)."""
+    lib = L.load()
+    cs = x.shape[-1]
+    rows = x.numel() // cs
+    need = lib.fo_colsum_workspace_bytes(cs)
+    ws = workspace(need, x.device, "colsum")
+    L.check(lib.fo_colsum(x.data_ptr(), rows, cs, c_off, c, out.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel(),
+                          _stream()), "fo_colsum")
+
+
+def pack_nchw(x: torch.Tensor, cs: Optional[int] = None, shift: Optional[torch.Tensor] = None,
+              scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NCHW fp32 -> channels-last bf16 [N,H,W,cs] (zero padded channels)."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.dim() == 4
+    x = x.contiguous()
+    n, c, h, w = x.shape
+    cs = cs or pad16(c)
+    out = torch.empty((n, h, w, cs), dtype=torch.bfloat16, device=x.device)
+    L.check(lib.fo_pack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _p(shift), _p(scale), _stream()),
+            "fo_pack_nchw")
+    return out
+
+
+def unpack_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
+    """channels-last bf16 [N,H,W,cs] -> NCHW fp32 [N,c,H,W]."""
+    lib = L.load()
+    n, h, w, cs = x.shape
+    out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    L.check(lib.fo_unpack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _stream()), "fo_unpack_nchw")
+    return out
+
+
+def relu(x: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    y = torch.empty_like(x)
+    L.check(lib.fo_relu(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "fo_relu")
+    return y
+
+
+def maxpool2(x: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    n, h, w, cs = x.shape
+    y = torch.empty((n, h // 2, w // 2, cs), dtype=torch.bfloat16, device=x.device)
+    L.check(lib.fo_maxpool2(x.data_ptr(), y.data_ptr(), n, h, w, cs, _stream()), "fo_maxpool2")
+    return y
+
+
+def maxpool2_bwd(x: torch.Tensor, y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
+    lib = L.load()
+    n, h, w, cs = x.shape
+    dx = torch.empty_like(x)
+    L.check(lib.fo_maxpool2_bwd(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, cs, _stream()),
+            "fo_maxpool2_bwd")
+    return dx
+
+
+# ------------------------------------------------------------------------------------------------
+# vector quantiser
+# ------------------------------------------------------------------------------------------------
+def vq_prep(embed: torch.Tensor):
+    """embed fp32 [dim, n_embed] -> (e_split bf16 [n_embed, 2*dim], e_t fp32 [n_embed, dim], e_norm2 fp32 [n_embed+1])."""
+    lib = L.load()
+    dim, n_embed = embed.shape
+    dev = embed.device
+    e_split = torch.empty((n_embed, 2 * dim), dtype=torch.bfloat16, device=dev)
+    e_t = torch.empty((n_embed, dim), dtype=torch.float32, device=dev)
+    e_norm2 = torch.empty(n_embed + 1, dtype=torch.float32, device=dev)
+    L.check(lib.fo_vq_prep(embed.data_ptr(), dim, n_embed, e_split.data_ptr(), e_t.data_ptr(), e_norm2.data_ptr(),
+                           _stream()), "fo_vq_prep")
+    return e_split, e_t, e_norm2
+
+
+def vq_assign(x: torch.Tensor, embed: torch.Tensor, e_split: torch.Tensor, e_norm2: torch.Tensor,
+              n_flagged: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x fp32 [rows, dim] -> embed_ind int64 [rows]."""
+    lib = L.load()
+    rows, dim = x.shape
+    n_embed = embed.shape[1]
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    ind = torch.empty(rows, dtype=torch.int64, device=x.device)
+    need = lib.fo_vq_assign_workspace_bytes(rows, dim)
+    ws = workspace(need, x.device, "vq")
+    L.check(lib.fo_vq_assign(x.data_ptr(), rows, dim, n_embed, embed.data_ptr(), e_split.data_ptr(),
+                             e_norm2.data_ptr(), ind.data_ptr(), _p(n_flagged), ws.data_ptr(), ws.numel(), _stream()),
+            "fo_vq_assign")
+    return ind
+
+
+def vq_gather_stats(x: torch.Tensor, ind: torch.Tensor, e_t: torch.Tensor, diff_sum: torch.Tensor,
+                    counts: Optional[torch.Tensor], embed_sum: Optional[torch.Tensor], want_f32: bool = True,
+                    want_bf16: bool = False):
+    lib = L.load()
+    rows, dim = x.shape
+    n_embed = e_t.shape[0]
+    q32 = torch.empty_like(x) if want_f32 else None
+    q16 = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    L.check(lib.fo_vq_gather_stats(x.data_ptr(), ind.data_ptr(), rows, dim, n_embed, e_t.data_ptr(), _p(q32), _p(q16),
+                                   diff_sum.data_ptr(), _p(counts), _p(embed_sum), _stream()), "fo_vq_gather_stats")
+    return q32, q16
+
+
+def vq_ema(embed, cluster_size, embed_avg, counts, embed_sum, decay: float, eps: float):
+    lib = L.load()
+    dim, n_embed = embed.shape
+    L.check(lib.fo_vq_ema(embed.data_ptr(), cluster_size.data_ptr(), embed_avg.data_ptr(), counts.data_ptr(),
+                          embed_sum.data_ptr(), dim, n_embed, decay, eps, _stream()), "fo_vq_ema")
+
+
+def vq_backward(g_q: Optional[torch.Tensor], g_c_off: int, g_diff: Optional[torch.Tensor], x: torch.Tensor,
+                ind: torch.Tensor, e_t: torch.Tensor, want_f32: bool = True, want_bf16: bool = False):
+    lib = L.load()
+    rows, dim = x.shape
+    n_embed = e_t.shape[0]
+    g32 = torch.empty_like(x) if want_f32 else None
+    g16 = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    is_bf16 = int(g_q is not None and g_q.dtype == torch.bfloat16)
+    g_cs = g_q.shape[-1] if g_q is not None else dim
+    L.check(lib.fo_vq_backward(_p(g_q), is_bf16, g_cs, g_c_off, _p(g_diff), x.data_ptr(), ind.data_ptr(),
+                               e_t.data_ptr(), rows, dim, n_embed, _p(g32), _p(g16), _stream()), "fo_vq_backward")
+    return g32, g16
+
+
+# ------------------------------------------------------------------------------------------------
+# LPIPS head
+# ------------------------------------------------------------------------------------------------
+def lpips_tap(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, out: torch.Tensor):
+    """out[n] += mean_hw sum_c w_c (norm(f0) - norm(f1))^2 ; f0, f1 bf16 [N,H,W,C]."""
+    lib = L.load()
+    n, h, wd, c = f0.shape
+    L.check(lib.fo_lpips_tap(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), n, h * wd, c, out.data_ptr(), _stream()),
+            "fo_lpips_tap")
+
+
+def lpips_tap_bwd(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.Tensor,
+                  addend: Optional[torch.Tensor] = None) -> torch.Tensor:
+    lib = L.load()
+    n, h, wd, c = f0.shape
+    d = torch.empty_like(f0)
+    L.check(lib.fo_lpips_tap_bwd(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), g.data_ptr(), n, h * wd, c, d.data_ptr(),
+                                 _p(addend), _stream()), "fo_lpips_tap_bwd")
+    return d

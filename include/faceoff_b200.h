@@ -1,0 +1,183 @@
+/* faceoff_b200 -- C ABI of the B200-native FaceOff training-step hot path.
+ *
+ * The reference (skymanaditya1/FaceOff) is pure Python/PyTorch and has no FFI of its own; its "plugin
+ * boundary" for this path is the nn.Module surface of models/vqvae_conv3d_latent.py, models/lpips.py,
+ * loss.py:VQLPIPS and the distributed/ package.  the Python package faceoff_b200 re-implements that
+ * surface and calls ONLY the functions below (via ctypes): plain pointers, sizes and a cudaStream_t.
+ * PyTorch owns every buffer; nothing here allocates persistent device memory.
+ *
+ * All functions return 0 on success, else a non-zero code; fo_last_error() gives the message
+ * (thread-local).  There is no CPU fallback: every entry point fails with FO_ERR_NO_DEVICE when no
+ * sm_100 device is present.
+ *
+ * Layouts: activations are channels-last bf16: [N, (D,) H, W, Cs] with Cs (storage channels per pixel) a
+ * multiple of 16 (logical channels beyond C are zero).  Weights stay in the PyTorch fp32 layouts
+ * ([Cout,Cin,k..] for Conv, [Cin,Cout,kh,kw] for ConvTranspose2d) and are re-packed to bf16 K-step order by
+ * fo_conv_pack_weights into caller-provided workspace.
+ */
+#ifndef FACEOFF_B200_H
+#define FACEOFF_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void* fo_stream_t; /* cudaStream_t */
+
+enum {
+  FO_OK = 0,
+  FO_ERR_INVALID = 1,   /* bad argument / unsupported geometry */
+  FO_ERR_CUDA = 2,      /* CUDA runtime or driver error */
+  FO_ERR_NO_DEVICE = 3, /* no sm_100 GPU: there is no CPU path */
+};
+
+const char* fo_last_error(void);
+int fo_version(void);
+/* Must be called once per process after the CUDA context exists (sets kernel attributes, resolves
+ * cuTensorMapEncodeTiled). */
+int fo_init(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Convolution family (implicit GEMM on tcgen05).  Replaces, for this path, torch.nn.functional
+ * conv2d / conv_transpose2d / conv3d forward and their autograd (cuDNN fprop / dgrad / wgrad) as called
+ * from reference models/vqvae_conv3d_latent.py:86-190,208-217 and models/lpips.py:115-152.
+ * ------------------------------------------------------------------------------------------- */
+
+/* "form" of the implicit GEMM */
+enum {
+  FO_FORM_S1 = 0,      /* stride-1 conv, k in {1,3}, pad (k-1)/2, 2-D or 3-D              (Conv2d/Conv3d forward) */
+  FO_FORM_S1_DGRAD = 1,/* same geometry with mirrored taps                                 (their data gradient)   */
+  FO_FORM_DOWN = 2,    /* 4x4 stride-2 pad-1 gather form: out[o] = sum in[2o+k-1] w[k]     (Conv2d s2 forward, ConvTranspose2d dgrad) */
+  FO_FORM_UP = 3,      /* 4x4 stride-2 pad-1 scatter form: out[2i-1+k] += in[i] w[k]       (ConvTranspose2d forward, Conv2d s2 dgrad) */
+};
+
+typedef struct {
+  const void* ptr; /* bf16 channels-last */
+  int c;           /* logical channels taken from this source */
+  int cs;          /* storage channels per pixel */
+  int c_off;       /* first channel inside the pixel (for reading a slice of a wider tensor) */
+} fo_src_t;
+
+typedef struct {
+  int form;
+  int ndim;  /* 2 or 3 (3 only for FO_FORM_S1 / FO_FORM_S1_DGRAD) */
+  int ksize; /* 1 or 3 for S1 forms; ignored (4) for DOWN / UP */
+  /* input-side extents (the tensor the A operand is read from).  2-D: n = frames, d = 1. */
+  int n, d, h, w;
+  int n_src; /* 1 or 2: torch.cat([src0, src1], dim=1) folded into the K loop */
+  fo_src_t src[2];
+  int cout; /* logical output channels (N of the GEMM) */
+  /* packed weights produced by fo_conv_pack_weights for the SAME descriptor */
+  const void* wpacked;
+  /* fused epilogue: r = acc + bias; r = mask>0 ? r : 0; r += addend; outputs below (any subset) */
+  const float* bias;      /* [cout] fp32 or NULL */
+  const void* mask;       /* bf16, layout of out_bf16, or NULL */
+  const void* addend;     /* bf16, layout of out_bf16, or NULL */
+  void* out_bf16;         /* r            -> bf16 channels-last [.., out_cs] or NULL */
+  void* out_relu;         /* relu(r)      -> bf16 channels-last [.., out_cs] or NULL */
+  float* out_f32;         /* r (or relu)  -> fp32, channels-last [.., out_cs] (out_f32_nchw=0) or NCHW [n,cout,h,w] (=1) */
+  int out_cs;             /* storage channels of the channels-last outputs */
+  int out_f32_nchw;
+  int relu_f32;
+} fo_conv_t;
+
+/* Bytes of packed-weight workspace needed for this descriptor. */
+size_t fo_conv_wpacked_bytes(const fo_conv_t* c);
+/* Re-pack fp32 PyTorch-layout weights [A][B][taps] into bf16 K-step order.
+ * n_axis: which of the first two weight axes is the GEMM N (output) axis: Conv fwd 0, Conv dgrad 1,
+ * ConvTranspose fwd 1, ConvTranspose dgrad 0.  dimA/dimB are the sizes of those two axes.
+ * n_scale: optional fp32 [cout] multiplier per output channel (folds LPIPS' 1/scale into the first VGG dgrad). */
+int fo_conv_pack_weights(const fo_conv_t* c, const float* weight, int dimA, int dimB, int n_axis,
+                         const float* n_scale, void* wpacked, fo_stream_t stream);
+int fo_conv_run(const fo_conv_t* c, fo_stream_t stream);
+
+/* Weight gradient: dW[m][n][tap] = sum_pix P[pix][m] * Q[pix (+) tap][n].
+ * form FO_FORM_S1 (P = dy, Q = x), FO_FORM_DOWN (P = dy low-res, Q = x hi-res) -> Conv weight [m=cout][n=cin][taps];
+ * FO_FORM_UP (P = x low-res, Q = dy hi-res) -> ConvTranspose2d weight [m=cin][n=cout][taps]. */
+typedef struct {
+  int form;
+  int ndim, ksize;
+  int n, d, h, w;       /* extents of P (the non-shifted operand) */
+  fo_src_t p, q;
+  float* dweight;       /* fp32 PyTorch-layout gradient tensor (written, or accumulated if accumulate != 0) */
+  int dimA, dimB;       /* sizes of the first two axes of dweight */
+  int m_axis;           /* which weight axis the P channels index (0 or 1) */
+  int q_w_off;          /* channel offset of Q's channels on the other weight axis (torch.cat second source) */
+  int accumulate;
+  void* workspace;      /* split-K partials */
+  size_t workspace_bytes;
+} fo_wgrad_t;
+size_t fo_wgrad_workspace_bytes(const fo_wgrad_t* g);
+int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout / elementwise helpers
+ * ------------------------------------------------------------------------------------------- */
+/* NCHW fp32 -> channels-last bf16 [n, hw, cs]; channels >= c zero; optional per-channel (x - shift)/scale
+ * (LPIPS ScalingLayer, reference models/lpips.py:96-103). */
+int fo_pack_nchw(const float* x, void* out, int n, int c, int hw, int cs, const float* shift, const float* scale,
+                 fo_stream_t stream);
+/* channels-last bf16 [n, hw, cs] -> NCHW fp32 [n, c, hw] */
+int fo_unpack_nchw(const void* x, float* out, int n, int c, int hw, int cs, fo_stream_t stream);
+/* y = relu(x) on bf16 */
+int fo_relu(const void* x, void* y, size_t numel, fo_stream_t stream);
+/* out[c] (+)= sum_rows x[row][c_off + c], x bf16 [rows, cs]  (bias gradients) */
+int fo_colsum(const void* x, size_t rows, int cs, int c_off, int c, float* out, int accumulate, void* workspace,
+              size_t workspace_bytes, fo_stream_t stream);
+size_t fo_colsum_workspace_bytes(int cs);
+/* 2x2/2 max pool on channels-last bf16 [n,h,w,cs] and its gradient (reference VGG trunk models/lpips.py:115-152) */
+int fo_maxpool2(const void* x, void* y, int n, int h, int w, int cs, fo_stream_t stream);
+/* dx is the gradient w.r.t. the PRE-ReLU conv output feeding the pool (x is post-ReLU: x == 0 closes the gate). */
+int fo_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int cs,
+                    fo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Vector quantiser (reference models/vqvae_conv3d_latent.py:33-83)
+ * ------------------------------------------------------------------------------------------- */
+/* Codebook prep: embed fp32 [dim, n_embed] -> e_split bf16 [n_embed, 2*dim] (hi | lo halves, the GEMM B operand),
+ * e_t fp32 [n_embed, dim] (transposed copy: the gather operand; keep it for fo_vq_backward because the EMA
+ * update overwrites embed inside forward), e_norm2 fp32 [n_embed + 1] (|e_k|^2, then max_k |e_k|^2). */
+int fo_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
+               fo_stream_t stream);
+/* Nearest-code assignment (:48-54).  x fp32 [rows, dim].  embed_ind int64 [rows].
+ * Tensor-core distances (bf16 split, error-bounded) + exact fp32 re-evaluation of rows whose top-2 gap is
+ * inside the error band; n_flagged (device int32, optional) counts those rows. */
+int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* embed, const void* e_split,
+                 const float* e_norm2, int64_t* embed_ind, int* n_flagged, void* workspace, size_t workspace_bytes,
+                 fo_stream_t stream);
+size_t fo_vq_assign_workspace_bytes(size_t rows, int dim);
+/* Gather + straight-through + commitment loss + EMA statistics (:55-61,77-78), one pass:
+ *   quantize = x + (E[:, ind] - x)         -> q_f32 (optional) and q_bf16 (optional, channels-last copy)
+ *   diff_sum += sum (E[:, ind] - x)^2      (caller divides by rows*dim)
+ *   counts[k] += #rows assigned to k ; embed_sum[d][k] += sum of x rows assigned to k   (if counts != NULL) */
+int fo_vq_gather_stats(const float* x, const int64_t* embed_ind, size_t rows, int dim, int n_embed,
+                       const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
+                       float* embed_sum, fo_stream_t stream);
+/* EMA update + renormalisation (:66-75), in place on the three buffers; counts / embed_sum are the
+ * (all-reduced) statistics. */
+int fo_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts, const float* embed_sum,
+              int dim, int n_embed, float decay, float eps, fo_stream_t stream);
+/* Backward of :77-78: gx = g_q + g_diff * 2 (x - q) / (rows*dim).  g_q fp32 or bf16 (g_q_is_bf16). */
+int fo_vq_backward(const void* g_q, int g_q_is_bf16, int g_cs, int g_c_off, const float* g_diff, const float* x,
+                   const int64_t* embed_ind, const float* e_t, size_t rows, int dim, int n_embed, float* gx_f32,
+                   void* gx_bf16, fo_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * LPIPS head (reference models/lpips.py:80-93,155-161) and MSE (train_faceoff_perceptual.py:37-39)
+ * ------------------------------------------------------------------------------------------- */
+/* One tap: per image n, out[n] += (1/hw) * sum_pix sum_c w[c] * (f0/(|f0|+eps) - f1/(|f1|+eps))^2.
+ * f0, f1 channels-last bf16 [n, hw, c]. */
+int fo_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out, fo_stream_t stream);
+/* Gradient wrt f0: d_f0 (bf16, same layout), scaled by g[n] (fp32 per image), masked by f0 > 0 (ReLU tap). */
+int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c, void* d_f0,
+                     const void* addend, fo_stream_t stream);
+/* sum((a[:, :c] - b)^2) over NCHW fp32 a [n, ca, hw] and b [n, c, hw]; grad (optional) = gscale * 2 (a - b) into
+ * channels-last bf16 [n, hw, cs] (channels >= c zero). */
+int fo_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, fo_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FACEOFF_B200_H */
