@@ -457,7 +457,7 @@ cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t ro
     static bool configured = false;
     if (!configured) {
       cudaError_t e = cudaFuncSetAttribute(vq_gather_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           kMaxDynSmem);
+                                           kMaxDynSmem - 1024);  // the kernel also has 128 B of static smem
       if (e != cudaSuccess) return e;
       configured = true;
     }

@@ -1,0 +1,209 @@
+"""A minimal tape over the C-ABI ops: forward builds nodes + backward closures, backward replays the tape.
+
+Why not torch.autograd per op: the backward of every conv here is *fused* -- the data-gradient kernel applies
+the ReLU gate of the consumer's input and accumulates into an existing gradient in its epilogue, torch.cat
+gradients are channel slices of one wide tensor, and weight gradients go straight into fp32 PyTorch-layout
+buffers.  torch.autograd only sees one Function per module call (vqvae.py / lpips.py).
+
+A Node is one activation in channels-last bf16 ([F, H, W, Cs]):
+    raw  : pre-activation value (or None if never needed)
+    act  : relu(raw)            (or None)
+    g    : gradient w.r.t. *raw*, as (tensor, channel_offset); consumers of the relu view gate with act > 0.
+"""
+from __future__ import annotations
+
+from typing import Callable, Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import ops
+from .ops import FORM_DOWN, FORM_S1, FORM_S1_DGRAD, FORM_UP, pad16
+
+
+class Node:
+    __slots__ = ("raw", "act", "c", "g", "f32")
+
+    def __init__(self, c: int, raw=None, act=None, f32=None):
+        self.c = c
+        self.raw = raw
+        self.act = act
+        self.f32 = f32
+        self.g: Optional[Tuple[torch.Tensor, int]] = None
+
+    @property
+    def any(self) -> torch.Tensor:
+        return self.raw if self.raw is not None else self.act
+
+    @property
+    def cs(self) -> int:
+        return self.any.shape[-1]
+
+
+class View:
+    """A consumer's view of a node: the raw value or its ReLU."""
+    __slots__ = ("node", "relu")
+
+    def __init__(self, node: Node, relu: bool):
+        self.node = node
+        self.relu = relu
+
+    @property
+    def t(self) -> torch.Tensor:
+        t = self.node.act if self.relu else self.node.raw
+        assert t is not None, "requested view was not materialised"
+        return t
+
+
+class Tape:
+    def __init__(self, params: Dict[str, torch.Tensor], need_grad: bool):
+        self.params = params
+        self.need_grad = need_grad
+        self.grads: Dict[str, torch.Tensor] = {}
+        self._bwd: List[Callable[[], None]] = []
+        self.dp = None                 # optional FusedDataParallel: grads are born in its flat bucket
+        self._fresh: set = set()       # pre-allocated gradient buffers not written yet
+
+    def record(self, fn: Callable[[], None]):
+        if self.need_grad:
+            self._bwd.append(fn)
+
+    def backward(self):
+        for fn in reversed(self._bwd):
+            fn()
+        self._bwd.clear()
+
+    def grad_buffer(self, name: str) -> Tuple[torch.Tensor, bool]:
+        """fp32 gradient buffer for a parameter and whether to accumulate into it."""
+        g = self.grads.get(name)
+        if g is None:
+            g = torch.empty_like(self.params[name], dtype=torch.float32)
+            self.grads[name] = g
+            return g, False
+        if name in self._fresh:
+            self._fresh.discard(name)
+            return g, False
+        return g, True
+
+    def grad_ready(self, name: str):
+        if self.dp is not None:
+            self.dp.grad_ready(name)
+
+
+_DGRAD_FORM = {FORM_S1: FORM_S1_DGRAD, FORM_DOWN: FORM_UP, FORM_UP: FORM_DOWN}
+
+
+def _padded_bias(tape: Tape, name: str, cout: int) -> torch.Tensor:
+    b = tape.params[name]
+    if b.numel() == pad16(cout):
+        return b
+    key = ("bias_pad", name)
+    cache = tape.__dict__.setdefault("_cache", {})
+    hit = cache.get(key)
+    if hit is None:
+        hit = torch.zeros(pad16(cout), dtype=torch.float32, device=b.device)
+        hit[:cout] = b.detach()
+        cache[key] = hit
+    return hit
+
+
+def _as5(t: torch.Tensor, clips: int) -> torch.Tensor:
+    f = t.shape[0]
+    return t.view(clips, f // clips, *t.shape[1:])
+
+
+def conv_op(tape: Tape, form: int, ksize: int, srcs: Sequence[View], wname: str, cout: int, *, transposed: bool = False,
+            want_raw: bool = True, want_relu: bool = False, residual: Optional[Node] = None, f32: Optional[str] = None,
+            ndim: int = 2, clips: int = 1, input_needs_grad: bool = True, bias: bool = True,
+            param_grad: bool = True) -> Node:
+    """One convolution layer (forward now, backward recorded).
+
+    ``wname`` is the state-dict prefix ("enc_b.blocks.0"): weight = wname.weight, bias = wname.bias.
+    ``transposed``: the parameter is a ConvTranspose2d weight [Cin, Cout, 4, 4] (form must be FORM_UP).
+    ``residual``: node whose raw value is added to the output (ResBlock ``out += input``).
+    """
+    w = tape.params[wname + ".weight"]
+    b = _padded_bias(tape, wname + ".bias", cout) if bias else None
+    n_axis = 1 if transposed else 0
+
+    def shaped(t):
+        return _as5(t, clips) if ndim == 3 else t
+
+    src_list = [(shaped(v.t), v.node.c, 0) for v in srcs]
+    raw, relu, of32 = ops.conv(form, ndim, ksize, src_list, w, n_axis, cout, bias=b,
+                               addend=None if residual is None else shaped(residual.raw),
+                               want_raw=want_raw, want_relu=want_relu, f32=f32)
+
+    def flat(t):
+        return None if t is None else (t.view(-1, *t.shape[2:]) if ndim == 3 else t)
+
+    out = Node(cout, raw=flat(raw), act=flat(relu), f32=of32 if f32 == "nchw" else flat(of32))
+
+    def backward():
+        assert out.g is not None, f"no gradient reached {wname}"
+        gt, g_off = out.g
+        dy = (shaped(gt), cout, g_off)
+        # bias gradient
+        if bias and param_grad:
+            gb, acc = tape.grad_buffer(wname + ".bias")
+            ops.colsum(gt, cout, gb, c_off=g_off, accumulate=acc)
+        # weight gradient, one launch per concatenated source
+        gw, acc = tape.grad_buffer(wname + ".weight") if param_grad else (None, False)
+        w_off = 0
+        for v, s in zip(srcs, src_list):
+            if not param_grad:
+                break
+            if form == FORM_S1:
+                ops.wgrad(FORM_S1, ndim, ksize, dy, s, gw, m_axis=0, q_w_off=w_off, accumulate=acc)
+            elif form == FORM_DOWN:
+                ops.wgrad(FORM_DOWN, 2, 4, dy, s, gw, m_axis=0, q_w_off=w_off, accumulate=acc)
+            else:  # FORM_UP / ConvTranspose2d weight [cin, cout]: P = x (low res), Q = dy (hi res)
+                assert len(srcs) == 1
+                ops.wgrad(FORM_DOWN, 2, 4, s, dy, gw, m_axis=0, q_w_off=0, accumulate=acc)
+            w_off += v.node.c
+        if param_grad:
+            tape.grad_ready(wname + ".weight")
+            if bias:
+                tape.grad_ready(wname + ".bias")
+        # residual pass-through
+        if residual is not None:
+            assert g_off == 0
+            if residual.g is None:
+                residual.g = (gt, 0)
+            else:
+                residual.g = (residual.g[0] + gt, 0)
+        # data gradient
+        if not input_needs_grad:
+            return
+        cin_total = sum(v.node.c for v in srcs)
+        dform = _DGRAD_FORM[form]
+        dn_axis = 0 if transposed else 1
+        if len(srcs) == 1:
+            v = srcs[0]
+            nd = v.node
+            mask = shaped(nd.act) if v.relu else None
+            addend = None
+            if nd.g is not None:
+                assert nd.g[1] == 0 and nd.g[0].shape[-1] == nd.cs
+                addend = shaped(nd.g[0])
+            dx, _, _ = ops.conv(dform, ndim, ksize, [dy], w, dn_axis, cin_total, mask=mask, addend=addend,
+                                out_cs=nd.cs)
+            nd.g = (flat(dx), 0)
+        else:
+            dx, _, _ = ops.conv(dform, ndim, ksize, [dy], w, dn_axis, cin_total)
+            dx = flat(dx)
+            off = 0
+            for v in srcs:
+                assert v.node.g is None and not v.relu, "torch.cat sources must have a single consumer"
+                v.node.g = (dx, off)
+                off += v.node.c
+
+    tape.record(backward)
+    return out
+
+
+def resblock_op(tape: Tape, x: Node, prefix: str, channel: int, n_res_channel: int, last: bool) -> Node:
+    """ResBlock (reference models/vqvae_conv3d_latent.py:86-101): relu -> 3x3 -> relu -> 1x1 -> += input.
+    ``last``: the block is followed by the stack's final in-place ReLU, so only relu(out) is materialised."""
+    h = conv_op(tape, FORM_S1, 3, [View(x, True)], prefix + ".conv.1", n_res_channel, want_raw=False, want_relu=True)
+    return conv_op(tape, FORM_S1, 1, [View(h, True)], prefix + ".conv.3", channel, residual=x, want_raw=not last,
+                   want_relu=True)

@@ -1,0 +1,192 @@
+"""Drop-in replacements for the reference's models/lpips.py (LPIPS, ScalingLayer, NetLinLayer, vgg16) and
+loss.py:VQLPIPS.  Same constructor arguments, forward signatures and state-dict keys; the VGG16 trunk runs on
+the tcgen05 implicit-GEMM conv kernel, the LPIPS head is one fused bandwidth-bound reduction per tap
+(csrc/lpips.cu), and only the ``input`` side keeps activations for backward (all LPIPS parameters are frozen,
+reference models/lpips.py:63-64, so there is no weight gradient).
+"""
+from __future__ import annotations
+
+import os
+import warnings
+
+import torch
+from torch import nn
+
+from . import ops
+from .graph import FORM_S1, Node, Tape, View, conv_op
+from .vqvae import _GraphFn, _params_of
+
+_VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
+_SLICE_ENDS = [4, 9, 16, 23, 30]  # reference models/lpips.py:127-136
+
+
+class ScalingLayer(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.register_buffer("shift", torch.Tensor([-.030, -.088, -.188])[None, :, None, None])
+        self.register_buffer("scale", torch.Tensor([.458, .448, .450])[None, :, None, None])
+
+    def forward(self, inp):
+        return (inp - self.shift) / self.scale
+
+
+class NetLinLayer(nn.Module):
+    """A single linear layer which does a 1x1 conv (parameter holder; evaluated inside the fused tap kernel)."""
+
+    def __init__(self, chn_in, chn_out=1, use_dropout=False):
+        super().__init__()
+        layers = [nn.Dropout()] if use_dropout else []
+        layers += [nn.Conv2d(chn_in, chn_out, 1, stride=1, padding=0, bias=False)]
+        self.model = nn.Sequential(*layers)
+
+
+class vgg16(nn.Module):
+    """VGG16 feature trunk split in the 5 LPIPS slices; module indices follow torchvision's vgg16.features so
+    the state-dict keys (net.slice{k}.{idx}.weight) match the reference (models/lpips.py:115-136)."""
+
+    def __init__(self, requires_grad=False, pretrained=True):
+        super().__init__()
+        self.N_slices = 5
+        slices = [nn.Sequential() for _ in range(5)]
+        idx, cin, which = 0, 3, 0
+        self.layout = []  # (kind, key, cout)
+        for v in _VGG_CFG:
+            if v == "M":
+                if idx >= _SLICE_ENDS[which]:
+                    which += 1
+                slices[which].add_module(str(idx), nn.MaxPool2d(kernel_size=2, stride=2))
+                self.layout.append(("pool", None, cin))
+                idx += 1
+            else:
+                if idx >= _SLICE_ENDS[which]:
+                    which += 1
+                slices[which].add_module(str(idx), nn.Conv2d(cin, v, 3, padding=1))
+                slices[which].add_module(str(idx + 1), nn.ReLU(inplace=True))
+                self.layout.append(("conv", f"slice{which + 1}.{idx}", v))
+                idx += 2
+                cin = v
+            if idx in _SLICE_ENDS:
+                self.layout.append(("tap", None, cin))
+        self.slice1, self.slice2, self.slice3, self.slice4, self.slice5 = slices
+        if not requires_grad:
+            for p in self.parameters():
+                p.requires_grad = False
+
+
+def normalize_tensor(x, eps=1e-10):
+    norm_factor = torch.sqrt(torch.sum(x ** 2, dim=1, keepdim=True))
+    return x / (norm_factor + eps)
+
+
+def spatial_average(x, keepdim=True):
+    return x.mean([2, 3], keepdim=keepdim)
+
+
+class LPIPS(nn.Module):
+    """Learned perceptual metric.  forward(input, target) -> [N,1,1,1] (reference models/lpips.py:80-93)."""
+
+    def __init__(self, use_dropout=True):
+        super().__init__()
+        self.scaling_layer = ScalingLayer()
+        self.chns = [64, 128, 256, 512, 512]
+        self.net = vgg16(pretrained=True, requires_grad=False)
+        self.lin0 = NetLinLayer(self.chns[0], use_dropout=use_dropout)
+        self.lin1 = NetLinLayer(self.chns[1], use_dropout=use_dropout)
+        self.lin2 = NetLinLayer(self.chns[2], use_dropout=use_dropout)
+        self.lin3 = NetLinLayer(self.chns[3], use_dropout=use_dropout)
+        self.lin4 = NetLinLayer(self.chns[4], use_dropout=use_dropout)
+        self.load_from_pretrained()
+        for param in self.parameters():
+            param.requires_grad = False
+
+    def load_from_pretrained(self, name="vgg_lpips"):
+        """The reference downloads vgg.pth (models/lpips.py:66-69).  There is no network here: load the file if it
+        is already at the reference's relative path, otherwise keep the (random) initialisation."""
+        ckpt = os.path.join("taming/modules/autoencoder/lpips", "vgg.pth")
+        if os.path.exists(ckpt):
+            self.load_state_dict(torch.load(ckpt, map_location=torch.device("cpu")), strict=False)
+        else:
+            warnings.warn(f"LPIPS: {ckpt} not found and downloads are disabled; weights stay randomly initialised "
+                          "(load a state_dict explicitly)")
+
+    # ------------------------------------------------------------------------------------------
+    def _trunk(self, tape: Tape, x: torch.Tensor, tap_hook=None):
+        """Scaling layer + VGG16 trunk on channels-last bf16.  ``tap_hook(k, node)`` is called at each of the five
+        taps, at the tape position of the tap (so whatever it records is replayed after the following pool's
+        backward).  Returns (input node, tap nodes)."""
+        shift = self.scaling_layer.shift.reshape(-1).contiguous()
+        scale = self.scaling_layer.scale.reshape(-1).contiguous()
+        xin = Node(3, raw=ops.pack_nchw(x.to(torch.float32), shift=shift, scale=scale))
+        cur, cur_relu = xin, False
+        taps = []
+        for kind, key, ch in self.net.layout:
+            if kind == "conv":
+                cur = conv_op(tape, FORM_S1, 3, [View(cur, cur_relu)], "net." + key, ch, want_raw=False, want_relu=True,
+                              param_grad=False)
+                cur_relu = True
+            elif kind == "tap":
+                if tap_hook is not None:
+                    tap_hook(len(taps), cur)
+                taps.append(cur)
+            else:  # 2x2 max pool
+                src = cur
+                pooled = Node(ch, raw=ops.maxpool2(src.act))
+
+                def pool_bwd(src=src, pooled=pooled):
+                    assert src.g is None
+                    src.g = (ops.maxpool2_bwd(src.act, pooled.raw, pooled.g[0]), 0)
+
+                tape.record(pool_bwd)
+                cur, cur_relu = pooled, False
+        return xin, taps
+
+    def forward(self, input, target):
+        lins = [self.lin0, self.lin1, self.lin2, self.lin3, self.lin4]
+        ws = [l.model[-1].weight.reshape(-1).to(torch.float32).contiguous() for l in lins]
+        model = self
+
+        def runner(tape: Tape, x: torch.Tensor):
+            n = x.shape[0]
+            # target side: no gradient, nothing kept but the five taps
+            t_tape = Tape(tape.params, need_grad=False)
+            _, taps1 = model._trunk(t_tape, target.detach())
+            feats1 = [t.act for t in taps1]
+            val = torch.zeros(n, dtype=torch.float32, device=x.device)
+            g_holder = {}
+
+            def tap_hook(k, node):
+                f1, w = feats1[k], ws[k]
+                ops.lpips_tap(node.act, f1, w, val)
+
+                def tap_bwd():
+                    addend = node.g[0] if node.g is not None else None
+                    node.g = (ops.lpips_tap_bwd(node.act, f1, w, g_holder["g"], addend), 0)
+
+                tape.record(tap_bwd)
+
+            xin, _ = model._trunk(tape, x, tap_hook)
+
+            def seed(tape_, gouts):
+                g = gouts[0]
+                g_holder["g"] = (torch.zeros(n, device=x.device) if g is None else g.reshape(n).to(torch.float32).contiguous())
+
+            def input_grad():
+                if xin.g is None:
+                    return None
+                gx = ops.unpack_nchw(xin.g[0], 3)
+                return gx / model.scaling_layer.scale
+            return (val.view(n, 1, 1, 1),), {"seed": seed, "input_grad": input_grad}
+
+        ps = _params_of(self)
+        return _GraphFn.apply(runner, input, tuple(ps.keys()), *ps.values())[0]
+
+
+class VQLPIPS(nn.Module):
+    """reference loss.py:27-33"""
+
+    def __init__(self):
+        super().__init__()
+        self.perceptual_loss = LPIPS().eval()
+
+    def forward(self, targets, reconstructions):
+        return self.perceptual_loss(targets.contiguous(), reconstructions.contiguous()).mean()

@@ -1,0 +1,257 @@
+"""GPU parity tests (run on the B200 box: ``pytest -m gpu``).  Everything goes through the C ABI
+(faceoff_b200/libfaceoff_b200.so) and is compared with (a) the committed golden vectors produced by the
+UNMODIFIED reference (tests/golden/golden.pt) and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances (BASELINE.json north_star): fp32 path (Quantize) rtol 1e-5, indices bit-exact outside near-ties
+(relative gap < 1e-6); bf16 conv path rtol 2e-2 / atol 1e-2, checked as max-normalised error per tensor.
+"""
+import os
+import warnings
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "golden.pt")
+
+BF16_RTOL, BF16_ATOL = 2e-2, 1e-2
+
+
+def _golden():
+    return torch.load(GOLDEN, map_location="cpu")
+
+
+def _near_tie_rows(x, embed, thresh=1e-6):
+    """rows whose best / second-best distance gap is < thresh relative (fp64) -- excluded per north_star."""
+    x = x.double().reshape(-1, embed.shape[0])
+    d = x.pow(2).sum(1, keepdim=True) - 2 * x @ embed.double() + embed.double().pow(2).sum(0, keepdim=True)
+    s = d.sort(1).values
+    return ((s[:, 1] - s[:, 0]) / s[:, 0].abs()) < thresh
+
+
+def maxnorm_err(a, b):
+    return ((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12)).item()
+
+
+@pytest.mark.parametrize("tag", ["q_small", "q_d128"])
+def test_quantize_matches_reference_golden(tag):
+    from faceoff_b200.vqvae import Quantize
+
+    g = _golden()[tag]
+    D, K = g["embed0"].shape
+    q = Quantize(D, K).cuda()
+    q.embed.copy_(g["embed0"])
+    q.embed_avg.copy_(g["embed_avg0"])
+    q.cluster_size.copy_(g["cluster_size0"])
+    q.train()
+    q.n_flagged = torch.zeros(1, dtype=torch.int32, device="cuda")
+    x = g["x"].cuda().requires_grad_(True)
+    quant, diff, ind = q(x)
+    (quant * g["gq"].cuda()).sum().add(diff * 3.0).backward()
+    torch.cuda.synchronize()
+    assert ind.dtype == torch.int64 and ind.shape == g["embed_ind"].shape
+    tie = _near_tie_rows(g["x"], g["embed0"]).reshape(ind.shape)
+    mism = (ind.cpu() != g["embed_ind"]) & ~tie
+    assert mism.sum().item() == 0, f"{mism.sum().item()} index mismatches outside near-ties ({tie.sum().item()} near-ties)"
+    torch.testing.assert_close(quant.detach().cpu(), g["quantize"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(diff.detach().cpu(), g["diff"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(x.grad.cpu(), g["grad_x"], rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(q.cluster_size.cpu(), g["cluster_size1"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(q.embed_avg.cpu(), g["embed_avg1"], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(q.embed.cpu(), g["embed1"], rtol=1e-5, atol=1e-6)
+    print(f"{tag}: rows re-evaluated exactly: {q.n_flagged.item()} / {ind.numel()}")
+
+
+def test_quantize_eval_mode_leaves_buffers_untouched():
+    from faceoff_b200.vqvae import Quantize
+
+    torch.manual_seed(0)
+    q = Quantize(64, 512).cuda().eval()
+    e0, c0 = q.embed.clone(), q.cluster_size.clone()
+    out, diff, ind = q(torch.randn(2, 8, 8, 64, device="cuda"))
+    torch.cuda.synchronize()
+    assert torch.equal(q.embed, e0) and torch.equal(q.cluster_size, c0)
+    # quantize values are codebook rows (straight-through evaluated in fp32: x + (q - x))
+    ref = q.embed_code(ind)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("rows,dim,K", [(122880, 64, 512), (30720, 128, 2048), (1, 64, 512), (129, 64, 16)])
+def test_vq_assign_bit_exact_vs_fp64(rows, dim, K):
+    """Full config-4 style sizes: indices must equal the fp64 argmin (first minimum) outside near-ties."""
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(11)
+    x = torch.randn(rows, dim, generator=gen)
+    e = torch.randn(dim, K, generator=gen)
+    xs, es = x.cuda(), e.cuda()
+    e_split, e_t, e_n2 = ops.vq_prep(es)
+    ind = ops.vq_assign(xs, es, e_split, e_n2).cpu()
+    d = x.double().pow(2).sum(1, keepdim=True) - 2 * x.double() @ e.double() + e.double().pow(2).sum(0, keepdim=True)
+    ref = d.argmin(1)
+    assert torch.equal(ind, ref), f"{(ind != ref).sum().item()} mismatches"
+
+
+def _load_vqvae(p):
+    from faceoff_b200.vqvae import VQVAE
+
+    m = VQVAE(in_channel=6)
+    m.load_state_dict(p, strict=True)
+    return m.cuda().train()
+
+
+@pytest.mark.parametrize("tag", ["vqvae_1x4x64", "vqvae_2x3x64_lpips"])
+def test_vqvae_train_step_matches_reference_golden(tag):
+    from oracle import faceoff_oracle as O
+
+    g = _golden()[tag]
+    cfg = g["cfg"]
+    p = O.init_vqvae_params(seed=cfg["seed_params"])
+    img, gt = O.synthetic_clip(cfg["n_clips"], cfg["T"], cfg["H"], cfg["W"], seed=cfg["seed_data"])
+    model = _load_vqvae(p)
+    lp = None
+    if cfg["with_lpips"]:
+        from faceoff_b200.lpips import VQLPIPS
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            vql = VQLPIPS()
+        lp = O.init_lpips_params(seed=cfg["seed_lpips"])
+        vql.load_state_dict({"perceptual_loss." + k: v for k, v in lp.items()}, strict=True)
+        vql = vql.cuda()
+    x = img.cuda()
+    dec, diff, id_t, id_b = model.forward_with_ids(x, clips=cfg["n_clips"])
+    rec = dec[:, :3]
+    recon = torch.nn.functional.mse_loss(rec, gt.cuda())
+    latent = diff.mean()
+    loss = recon + latent
+    if lp is not None:
+        perc = vql(gt.cuda(), rec)
+        loss = loss + perc
+    loss.backward()
+    torch.cuda.synchronize()
+
+    # indices: the conv stack is bf16, so a few rows may legitimately flip; they must agree almost everywhere
+    agree_t = (id_t.cpu() == g["id_t"].long()).float().mean().item()
+    agree_b = (id_b.cpu() == g["id_b"].long()).float().mean().item()
+    print(f"{tag}: id agreement top {agree_t:.4f} bottom {agree_b:.4f}")
+    assert agree_t > 0.98 and agree_b > 0.98
+    assert maxnorm_err(dec[0].cpu(), g["dec_full0"]) < 3e-2
+    assert abs(recon.item() - g["recon_loss"].item()) <= BF16_RTOL * abs(g["recon_loss"].item()) + BF16_ATOL
+    assert abs(latent.item() - g["latent_loss"].item()) <= BF16_RTOL * abs(g["latent_loss"].item()) + BF16_ATOL
+    if lp is not None:
+        assert abs(perc.item() - g["perceptual_loss"].item()) <= BF16_RTOL * abs(g["perceptual_loss"].item()) + BF16_ATOL
+    # gradients: norm agreement for every parameter + max-normalised error on the stored slices
+    grads = {k: v.grad for k, v in model.named_parameters()}
+    worst = 0.0
+    for k, nref in g["grad_norms_ref"].items():
+        assert grads[k] is not None, k
+        n = grads[k].norm().item()
+        rel = abs(n - nref.item()) / (nref.item() + 1e-12)
+        worst = max(worst, rel)
+        assert rel < 6e-2, (k, n, nref.item())
+    for k, gref in g["grads_ref"].items():
+        got = grads[k].cpu()
+        got = got if got.numel() == gref.numel() else got[:8, :8]
+        err = maxnorm_err(got, gref)
+        assert err < 6e-2, (k, err)
+    print(f"{tag}: worst grad-norm rel err {worst:.3e}")
+    # EMA codebooks
+    for k, bref in g["buffers_ref"].items():
+        mod, name = k.split(".")
+        got = getattr(getattr(model, mod), name).cpu()
+        assert maxnorm_err(got, bref) < 2e-2, k
+
+
+def test_vqvae_forward_signature_and_eval():
+    from oracle import faceoff_oracle as O
+
+    p = O.init_vqvae_params(seed=0)
+    model = _load_vqvae(p).eval()
+    img, _ = O.synthetic_clip(1, 2, 64, 64)
+    with torch.no_grad():
+        dec, diff = model(img.cuda())
+    assert dec.shape == (2, 6, 64, 64) and dec.dtype == torch.float32 and diff.shape == (1,)
+    ref = O.vqvae_forward(p, img, n_clips=1, training=False)
+    assert maxnorm_err(dec.cpu(), ref["dec"]) < 3e-2
+    # eval must not touch the codebooks
+    torch.testing.assert_close(model.quantize_t.embed.cpu(), p["quantize_t.embed"])
+    # 5-D (batched clips) entry point
+    img2, _ = O.synthetic_clip(2, 2, 64, 64)
+    with torch.no_grad():
+        dec2, _ = model(img2.cuda().view(2, 2, 6, 64, 64))
+    assert dec2.shape == (2, 2, 6, 64, 64)
+
+
+def test_lpips_matches_reference_golden():
+    from faceoff_b200.lpips import LPIPS
+    from oracle import faceoff_oracle as O
+
+    g = _golden()["lpips_3x64"]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = LPIPS()
+    m.load_state_dict(O.init_lpips_params(seed=1), strict=True)
+    m = m.cuda().eval()
+    a = g["a"].cuda()
+    b = g["b"].cuda().requires_grad_(True)
+    val = m(a, b)
+    val.mean().backward()
+    torch.cuda.synchronize()
+    assert val.shape == (3, 1, 1, 1)
+    assert maxnorm_err(val.detach().cpu(), g["val"]) < BF16_RTOL * 2.5
+    assert maxnorm_err(b.grad.cpu(), g["grad_b"]) < 0.1
+    # symmetric in value (reference trainer passes (ground_truth, out))
+    val2 = m(b.detach(), a)
+    assert maxnorm_err(val2.cpu(), val.detach().cpu()) < 2e-2
+
+
+def test_submodules_drop_in():
+    """Encoder / Decoder / ResBlock / Conv3dLatentPostnet stand-alone against the oracle's functions."""
+    from faceoff_b200.vqvae import Conv3dLatentPostnet, Decoder, Encoder, ResBlock
+    from oracle import faceoff_oracle as O
+    import torch.nn.functional as F
+
+    torch.manual_seed(0)
+    enc = Encoder(6, 128, 2, 32, 4).cuda()
+    x = torch.rand(2, 6, 64, 64, device="cuda") * 2 - 1
+    y = enc(x)
+    p = {"e." + k: v.detach().cpu() for k, v in enc.state_dict().items()}
+    ref = O.encoder(p, "e", x.cpu(), 4)
+    assert y.shape == ref.shape and maxnorm_err(y.cpu(), ref) < 3e-2
+    dec = Decoder(64, 64, 128, 2, 32, 2).cuda()
+    z = torch.randn(2, 64, 8, 8, device="cuda", requires_grad=True)
+    out = dec(z)
+    p = {"d." + k: v.detach().cpu() for k, v in dec.state_dict().items()}
+    zc = z.detach().cpu().requires_grad_(True)
+    ref = O.decoder(p, "d", zc, 2)
+    assert maxnorm_err(out.detach().cpu(), ref) < 3e-2
+    go = torch.randn_like(out)
+    out.backward(go)
+    ref.backward(go.cpu())
+    assert maxnorm_err(z.grad.cpu(), zc.grad) < 5e-2
+    rb = ResBlock(128, 32).cuda()
+    h = torch.randn(2, 128, 16, 16, device="cuda")
+    p = {"r." + k: v.detach().cpu() for k, v in rb.state_dict().items()}
+    assert maxnorm_err(rb(h).cpu(), O.resblock(p, "r", h.cpu())) < 3e-2
+    c3 = Conv3dLatentPostnet(128).cuda()
+    v = torch.randn(1, 128, 3, 8, 8, device="cuda")
+    p = {"c." + k: t.detach().cpu() for k, t in c3.state_dict().items()}
+    assert maxnorm_err(c3(v).cpu(), O.conv3d_postnet(p, "c", v.cpu())) < 3e-2
+
+
+def test_clip_independence_property():
+    """Size-independent property: a batch of B clips == B single-clip calls (Conv3d must not mix clips)."""
+    from oracle import faceoff_oracle as O
+
+    p = O.init_vqvae_params(seed=0)
+    model = _load_vqvae(p).eval()
+    img, _ = O.synthetic_clip(2, 3, 64, 64, seed=3)
+    with torch.no_grad():
+        both, _ = model(img.cuda().view(2, 3, 6, 64, 64))
+        one0, _ = model(img[:3].cuda())
+        one1, _ = model(img[3:].cuda())
+    torch.testing.assert_close(both[0], one0, rtol=0, atol=0)
+    torch.testing.assert_close(both[1], one1, rtol=0, atol=0)
