@@ -15,6 +15,33 @@ from . import _lib as L
 from ._lib import FORM_DOWN, FORM_S1, FORM_S1_DGRAD, FORM_UP, ConvDesc, Src, WgradDesc  # noqa: F401
 
 
+# Instrumentation used by bench.py: when PROFILE is a dict, every tensor-core launch is bracketed by CUDA events on the
+# launching stream (name -> [(start, stop, algorithmic FLOPs)]); LAUNCHES counts kernels launched through this module.
+PROFILE: Optional[dict] = None
+LAUNCHES = 0
+
+
+def _count(n: int):
+    global LAUNCHES
+    LAUNCHES += n
+
+
+class _Timed:
+    def __init__(self, name: str, work: float):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if PROFILE is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.b = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+
+    def __exit__(self, *exc):
+        if PROFILE is not None:
+            self.b.record()
+            PROFILE.setdefault(self.name, []).append((self.a, self.b, self.work))
+
+
 def _stream() -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -95,6 +122,7 @@ def packed_weights(desc: ConvDesc, weight: torch.Tensor, n_axis: int, n_scale: O
     assert weight.dtype == torch.float32 and weight.is_contiguous()
     L.check(lib.fo_conv_pack_weights(C.byref(desc), weight.data_ptr(), weight.shape[0], weight.shape[1], n_axis,
                                      _p(n_scale), wp.data_ptr(), _stream()), "fo_conv_pack_weights")
+    _count(1)
     _wcache[key] = (ver, wp)
     return wp
 
@@ -144,7 +172,15 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
     for t in (mask, addend):
         if t is not None:
             assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape) == (*lead, ocs), (t.shape, lead, ocs)
-    L.check(lib.fo_conv_run(C.byref(d), _stream()), "fo_conv_run")
+    # algorithmic FLOPs: 2 * positions * cin * cout * taps (positions: outputs, or inputs for the scatter form)
+    cin = sum(s_[1] for s_ in srcs)
+    taps = 16 if form in (FORM_DOWN, FORM_UP) else ksize ** ndim
+    n_pos = 1
+    for v_ in (lead if form != FORM_UP else t0.shape[:-1]):
+        n_pos *= int(v_)
+    with _Timed("conv_igemm", 2.0 * n_pos * cin * cout * taps):
+        L.check(lib.fo_conv_run(C.byref(d), _stream()), "fo_conv_run")
+    _count(1)
     return raw, relu, of32
 
 
@@ -169,7 +205,13 @@ def wgrad(form: int, ndim: int, ksize: int, p: SrcT, q: SrcT, dweight: torch.Ten
         raise L.FaceoffB200Error("fo_wgrad_workspace_bytes: " + lib.fo_last_error().decode())
     ws = workspace(need, pt.device, "wgrad")
     g.workspace, g.workspace_bytes = ws.data_ptr(), ws.numel()
-    L.check(lib.fo_wgrad_run(C.byref(g), _stream()), "fo_wgrad_run")
+    taps = 16 if form == FORM_DOWN else ksize ** ndim
+    n_pos = 1
+    for v_ in pt.shape[:-1]:
+        n_pos *= int(v_)
+    with _Timed("wgrad_igemm", 2.0 * n_pos * p[1] * q[1] * taps):
+        L.check(lib.fo_wgrad_run(C.byref(g), _stream()), "fo_wgrad_run")
+    _count(2)
 
 
 def colsum(x: torch.Tensor, c: int, out: torch.Tensor, c_off: int = 0, accumulate: bool = False):
@@ -181,6 +223,7 @@ def colsum(x: torch.Tensor, c: int, out: torch.Tensor, c_off: int = 0, accumulat
     ws = workspace(need, x.device, "colsum")
     L.check(lib.fo_colsum(x.data_ptr(), rows, cs, c_off, c, out.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel(),
                           _stream()), "fo_colsum")
+    _count(2)
 
 
 def pack_nchw(x: torch.Tensor, cs: Optional[int] = None, shift: Optional[torch.Tensor] = None,
@@ -194,6 +237,7 @@ def pack_nchw(x: torch.Tensor, cs: Optional[int] = None, shift: Optional[torch.T
     out = torch.empty((n, h, w, cs), dtype=torch.bfloat16, device=x.device)
     L.check(lib.fo_pack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _p(shift), _p(scale), _stream()),
             "fo_pack_nchw")
+    _count(1)
     return out
 
 
@@ -203,6 +247,7 @@ def unpack_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
     n, h, w, cs = x.shape
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
     L.check(lib.fo_unpack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _stream()), "fo_unpack_nchw")
+    _count(1)
     return out
 
 
@@ -210,6 +255,7 @@ def relu(x: torch.Tensor) -> torch.Tensor:
     lib = L.load()
     y = torch.empty_like(x)
     L.check(lib.fo_relu(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "fo_relu")
+    _count(1)
     return y
 
 
@@ -218,6 +264,7 @@ def maxpool2(x: torch.Tensor) -> torch.Tensor:
     n, h, w, cs = x.shape
     y = torch.empty((n, h // 2, w // 2, cs), dtype=torch.bfloat16, device=x.device)
     L.check(lib.fo_maxpool2(x.data_ptr(), y.data_ptr(), n, h, w, cs, _stream()), "fo_maxpool2")
+    _count(1)
     return y
 
 
@@ -227,6 +274,7 @@ def maxpool2_bwd(x: torch.Tensor, y: torch.Tensor, dy: torch.Tensor) -> torch.Te
     dx = torch.empty_like(x)
     L.check(lib.fo_maxpool2_bwd(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, cs, _stream()),
             "fo_maxpool2_bwd")
+    _count(1)
     return dx
 
 
@@ -243,6 +291,7 @@ def vq_prep(embed: torch.Tensor):
     e_norm2 = torch.empty(n_embed + 1, dtype=torch.float32, device=dev)
     L.check(lib.fo_vq_prep(embed.data_ptr(), dim, n_embed, e_split.data_ptr(), e_t.data_ptr(), e_norm2.data_ptr(),
                            _stream()), "fo_vq_prep")
+    _count(2)
     return e_split, e_t, e_norm2
 
 
@@ -259,6 +308,7 @@ def vq_assign(x: torch.Tensor, embed: torch.Tensor, e_split: torch.Tensor, e_nor
     L.check(lib.fo_vq_assign(x.data_ptr(), rows, dim, n_embed, embed.data_ptr(), e_split.data_ptr(),
                              e_norm2.data_ptr(), ind.data_ptr(), _p(n_flagged), ws.data_ptr(), ws.numel(), _stream()),
             "fo_vq_assign")
+    _count(2)
     return ind
 
 
@@ -272,6 +322,7 @@ def vq_gather_stats(x: torch.Tensor, ind: torch.Tensor, e_t: torch.Tensor, diff_
     q16 = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     L.check(lib.fo_vq_gather_stats(x.data_ptr(), ind.data_ptr(), rows, dim, n_embed, e_t.data_ptr(), _p(q32), _p(q16),
                                    diff_sum.data_ptr(), _p(counts), _p(embed_sum), _stream()), "fo_vq_gather_stats")
+    _count(1)
     return q32, q16
 
 
@@ -280,6 +331,7 @@ def vq_ema(embed, cluster_size, embed_avg, counts, embed_sum, decay: float, eps:
     dim, n_embed = embed.shape
     L.check(lib.fo_vq_ema(embed.data_ptr(), cluster_size.data_ptr(), embed_avg.data_ptr(), counts.data_ptr(),
                           embed_sum.data_ptr(), dim, n_embed, decay, eps, _stream()), "fo_vq_ema")
+    _count(1)
 
 
 def vq_backward(g_q: Optional[torch.Tensor], g_c_off: int, g_diff: Optional[torch.Tensor], x: torch.Tensor,
@@ -293,6 +345,7 @@ def vq_backward(g_q: Optional[torch.Tensor], g_c_off: int, g_diff: Optional[torc
     g_cs = g_q.shape[-1] if g_q is not None else dim
     L.check(lib.fo_vq_backward(_p(g_q), is_bf16, g_cs, g_c_off, _p(g_diff), x.data_ptr(), ind.data_ptr(),
                                e_t.data_ptr(), rows, dim, n_embed, _p(g32), _p(g16), _stream()), "fo_vq_backward")
+    _count(1)
     return g32, g16
 
 
@@ -305,6 +358,7 @@ def lpips_tap(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, out: torch.Te
     n, h, wd, c = f0.shape
     L.check(lib.fo_lpips_tap(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), n, h * wd, c, out.data_ptr(), _stream()),
             "fo_lpips_tap")
+    _count(1)
 
 
 def lpips_tap_bwd(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.Tensor,
@@ -314,4 +368,5 @@ def lpips_tap_bwd(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.
     d = torch.empty_like(f0)
     L.check(lib.fo_lpips_tap_bwd(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), g.data_ptr(), n, h * wd, c, d.data_ptr(),
                                  _p(addend), _stream()), "fo_lpips_tap_bwd")
+    _count(1)
     return d
