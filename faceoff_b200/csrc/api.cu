@@ -524,7 +524,7 @@ extern "C" int fo_pack_nchw(const float* x, void* out, int n, int c, int hw, int
                             const float* scale, fo_stream_t stream) {
   REQUIRE_INIT();
   if (cs % 8 != 0 || c > cs) return fail(FO_ERR_INVALID, "pack: bad channel counts %d/%d", c, cs);
-  if (cs > 32 && shift != nullptr) return fail(FO_ERR_INVALID, "pack: shift/scale only for cs <= 32");
+  if (cs != 16 && cs != 32 && shift != nullptr) return fail(FO_ERR_INVALID, "pack: shift/scale only for cs 16 / 32");
   CUDA_TRY(launch_pack_nchw(x, out, n, c, hw, cs, shift, scale, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
@@ -561,6 +561,26 @@ extern "C" int fo_maxpool2_bwd(const void* x, const void* y, const void* dy, voi
                                fo_stream_t stream) {
   REQUIRE_INIT();
   CUDA_TRY(launch_maxpool2_bwd(x, y, dy, dx, n, h, w, cs, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+
+extern "C" int fo_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (c > 8 || c > ca || ((h | w) & 1)) return fail(FO_ERR_INVALID, "im2col4x4s2: need c <= 8, even h and w");
+  CUDA_TRY(launch_im2col4x4s2(x, out, n, ca, c, h, w, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi,
+                              fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (c > 8) return fail(FO_ERR_INVALID, "col2im4x4s2: need c <= 8");
+  CUDA_TRY(launch_col2im4x4s2(col, bias, out, n, c, hi, wi, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_chansum_nchw(const float* x, int n, int ca, int c, int hw, float* out, int accumulate,
+                               fo_stream_t stream) {
+  REQUIRE_INIT();
+  CUDA_TRY(launch_chansum_nchw(x, n, ca, c, hw, out, accumulate, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
 

@@ -7,26 +7,32 @@
 namespace fo {
 
 // ---------------------------------------------------------------- NCHW fp32 -> channels-last bf16
-// block handles 32 pixels of one image; smem transpose so both sides are coalesced.
-__global__ void pack_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, int hw, int cs,
-                                 const float* __restrict__ shift, const float* __restrict__ scale) {
-  __shared__ float tile[32][33];
-  const int n = blockIdx.y;
-  const int p0 = blockIdx.x * 32;
-  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
-  for (int cc = ty; cc < cs && cc < 32; cc += 8) {
-    float v = 0.f;
-    if (cc < c && p0 + tx < hw) {
-      v = x[((size_t)n * c + cc) * hw + p0 + tx];
-      if (shift != nullptr) v = (v - shift[cc]) / scale[cc];
+// one thread per pixel: per-plane reads are coalesced across the warp, each thread writes its CS channels as 16-byte
+// vectors (a warp writes 32*CS*2 contiguous bytes).
+template <int CS>
+__global__ void pack_nchw_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, int hw,
+                                 const float* __restrict__ shift, const float* __restrict__ scale, size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / hw, px = i % hw;
+    float v[CS];
+#pragma unroll
+    for (int cc = 0; cc < CS; ++cc) {
+      v[cc] = 0.f;
+      if (cc < c) {
+        v[cc] = __ldg(x + (n * c + cc) * hw + px);
+        if (shift != nullptr) v[cc] = (v[cc] - shift[cc]) / scale[cc];
+      }
     }
-    tile[cc][tx] = v;
-  }
-  __syncthreads();
-  // write: each pixel has cs (<=32) channels contiguous
-  for (int i = threadIdx.x; i < 32 * cs; i += blockDim.x) {
-    const int px = i / cs, cc = i % cs;
-    if (p0 + px < hw) out[((size_t)n * hw + p0 + px) * cs + cc] = __float2bfloat16(tile[cc][px]);
+    uint4* dst = reinterpret_cast<uint4*>(out + i * CS);
+#pragma unroll
+    for (int q = 0; q < CS / 8; ++q) {
+      uint4 o;
+      o.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+      o.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+      o.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+      o.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+      dst[q] = o;
+    }
   }
 }
 
@@ -209,6 +215,98 @@ __global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const _
   }
 }
 
+// ---------------------------------------------------------------- im2col / col2im for the 6-channel 4x4 stride-2 layers
+// The first Conv2d (6->64, k4 s2 p1) and the last ConvTranspose2d (64->6) have too few channels for an efficient
+// implicit GEMM (32-byte TMA rows, N=16 MMAs).  Their image-side operand is therefore laid out as an explicit
+// [pixels, 16 taps x 8 channels = 128] bf16 matrix so that the layer becomes a plain K=128 (or N=128) GEMM on the same
+// tcgen05 kernel.  k = (ky*4+kx)*8 + c, value = x[c][2*oy+ky-1][2*ox+kx-1] (zero outside / for c >= C).
+__global__ void im2col4x4s2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int ca, int c, int h,
+                                   int w) {
+  __shared__ float sm[8][4][68];  // [channel][input row][input col], cols 2*ox0-1 .. 2*ox0+64
+  const int wo = w / 2, ho = h / 2;
+  const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 32;
+  const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy - 1;
+  for (int i = threadIdx.x; i < 8 * 4 * 66; i += blockDim.x) {
+    const int col = i % 66, r = (i / 66) % 4, cc = i / (66 * 4);
+    const int iy = iy0 + r, ix = ix0 + col;
+    float v = 0.f;
+    if (cc < c && iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + (((size_t)n * ca + cc) * h + iy) * w + ix);
+    sm[cc][r][col] = v;
+  }
+  __syncthreads();
+  (void)ho;
+  for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
+    const int px = i >> 4, tap = i & 15;
+    const int ox = ox0 + px;
+    if (ox >= wo) continue;
+    const int ky = tap >> 2, kx = tap & 3;
+    const int col = 2 * px + kx;
+    uint4 o;
+    o.x = pack_bf16x2(sm[0][ky][col], sm[1][ky][col]);
+    o.y = pack_bf16x2(sm[2][ky][col], sm[3][ky][col]);
+    o.z = pack_bf16x2(sm[4][ky][col], sm[5][ky][col]);
+    o.w = pack_bf16x2(sm[6][ky][col], sm[7][ky][col]);
+    reinterpret_cast<uint4*>(out + (((size_t)n * (h / 2) + oy) * wo + ox) * 128)[tap] = o;
+  }
+}
+
+// out[n][co][oy][ox] = bias[co] + sum of the (up to) 4 col entries that map to this output pixel
+__global__ void col2im4x4s2_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias,
+                                   float* __restrict__ out, int c, int hi, int wi, size_t total) {
+  const int ho = 2 * hi, wo = 2 * wi;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % wo);
+    size_t r = i / wo;
+    const int oy = (int)(r % ho);
+    const size_t n = r / ho;
+    const int hy = oy >> 1, hx = ox >> 1;
+    // oy = 2*iy - 1 + ky : even oy -> (iy=hy, ky=1), (hy-1, 3) ; odd oy -> (hy+1, 0), (hy, 2)
+    const int iy_[2] = {(oy & 1) ? hy + 1 : hy, (oy & 1) ? hy : hy - 1};
+    const int ky_[2] = {(oy & 1) ? 0 : 1, (oy & 1) ? 2 : 3};
+    const int ix_[2] = {(ox & 1) ? hx + 1 : hx, (ox & 1) ? hx : hx - 1};
+    const int kx_[2] = {(ox & 1) ? 0 : 1, (ox & 1) ? 2 : 3};
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+#pragma unroll
+    for (int a = 0; a < 2; ++a) {
+      if (iy_[a] < 0 || iy_[a] >= hi) continue;
+#pragma unroll
+      for (int b = 0; b < 2; ++b) {
+        if (ix_[b] < 0 || ix_[b] >= wi) continue;
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(col + ((n * hi + iy_[a]) * wi + ix_[b]) * 128) +
+                              (ky_[a] * 4 + kx_[b]));
+        acc[0] += bf16lo(u.x); acc[1] += bf16hi(u.x); acc[2] += bf16lo(u.y); acc[3] += bf16hi(u.y);
+        acc[4] += bf16lo(u.z); acc[5] += bf16hi(u.z); acc[6] += bf16lo(u.w); acc[7] += bf16hi(u.w);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e)
+      if (e < c) out[((n * c + e) * ho + oy) * wo + ox] = acc[e] + (bias != nullptr ? bias[e] : 0.f);
+  }
+}
+
+// out[c] (+)= sum over n, hw of x[n][c][hw]   (bias gradient of the last layer, NCHW fp32 gradient)
+__global__ void chansum_nchw_kernel(const float* __restrict__ x, int n, int ca, int c, int hw, float* __restrict__ out) {
+  __shared__ float red[32];
+  const int cc = blockIdx.y;
+  float acc = 0.f;
+  const size_t total = (size_t)n * hw;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t nn = i / hw, p = i % hw;
+    acc += x[(nn * ca + cc) * hw + p];
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(out + cc, s);
+  }
+  (void)c;
+}
+
 // ---------------------------------------------------------------- launchers
 static inline int grid_for(size_t work_items, int threads, int num_sms, int per_sm = 8) {
   size_t blocks = (work_items + threads - 1) / threads;
@@ -220,9 +318,11 @@ static inline int grid_for(size_t work_items, int threads, int num_sms, int per_
 
 cudaError_t launch_pack_nchw(const float* x, void* out, int n, int c, int hw, int cs, const float* shift,
                              const float* scale, int num_sms, cudaStream_t st) {
-  if (cs <= 32) {
-    dim3 grid((hw + 31) / 32, n);
-    pack_nchw_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, c, hw, cs, shift, scale);
+  if (cs == 16 || cs == 32) {
+    const size_t total = (size_t)n * hw;
+    const int grid = grid_for(total, 256, num_sms, 16);
+    if (cs == 16) pack_nchw_kernel<16><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, c, hw, shift, scale, total);
+    else pack_nchw_kernel<32><<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, c, hw, shift, scale, total);
   } else {
     const size_t total = (size_t)n * hw * cs;
     pack_nchw_wide_kernel<<<grid_for(total, 256, num_sms), 256, 0, st>>>(x, (__nv_bfloat16*)out, c, hw, cs, total);
@@ -274,6 +374,29 @@ cudaError_t launch_maxpool2_bwd(const void* x, const void* y, const void* dy, vo
   const size_t total = (size_t)n * (h / 2) * (w / 2) * cs;
   maxpool2_bwd_kernel<<<grid_for(total, 256, num_sms), 256, 0, st>>>(
       (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, n, h, w, cs);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w, cudaStream_t st) {
+  dim3 grid((w / 2 + 31) / 32, h / 2, n);
+  im2col4x4s2_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, ca, c, h, w);
+  return cudaGetLastError();
+}
+cudaError_t launch_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, int num_sms,
+                               cudaStream_t st) {
+  const size_t total = (size_t)n * (2 * hi) * (2 * wi);
+  col2im4x4s2_kernel<<<grid_for(total, 256, num_sms, 16), 256, 0, st>>>((const __nv_bfloat16*)col, bias, out, c, hi, wi,
+                                                                       total);
+  return cudaGetLastError();
+}
+cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, float* out, int accumulate, int num_sms,
+                                cudaStream_t st) {
+  if (!accumulate) {
+    cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * c, st);
+    if (e != cudaSuccess) return e;
+  }
+  dim3 grid(num_sms * 2, c);
+  chansum_nchw_kernel<<<grid, 256, 0, st>>>(x, n, ca, c, hw, out);
   return cudaGetLastError();
 }
 

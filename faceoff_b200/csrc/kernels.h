@@ -50,6 +50,12 @@ cudaError_t launch_maxpool2(const void* x, void* y, int n, int h, int w, int cs,
 cudaError_t launch_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int cs,
                                 int num_sms, cudaStream_t st);
 
+cudaError_t launch_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w, cudaStream_t st);
+cudaError_t launch_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, int num_sms,
+                               cudaStream_t st);
+cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, float* out, int accumulate, int num_sms,
+                                cudaStream_t st);
+
 // vq.cu
 cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
                            cudaStream_t st);

@@ -59,7 +59,7 @@ cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_spl
 constexpr int kVqThreads = 32 * 10;  // warp0 TMA(B), warp1 MMA, warps 2-5 loader/convert, warps 6-9 epilogue
 constexpr int kVqNT = 256;           // codes per accumulator
 constexpr int kVqBStages = 4;        // ring of [256 x 64] bf16 B tiles (32 KB each)
-constexpr float kVqBand = 1.5e-4f;   // flag rows with gap <= kVqBand * |x| * max|e|   (3x the split-bf16 error bound)
+constexpr float kVqBand = 1.5e-4f;   // |error of dist_k| <= kVqBand * |x| * |e_k|  (2.5x the split-bf16 bound 2*3*2^-17)
 
 struct VqAssignParams {
   const float* x;
@@ -85,7 +85,8 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_bufs * a_buf_bytes;
   float* sE2 = reinterpret_cast<float*>(sB + (size_t)kVqBStages * b_tile);  // [n_tiles*256]
-  float* sX2 = sE2 + p.n_tiles * kVqNT;                                      // [4][128] (epilogue may lag the loader by 3 tiles)
+  float* sEN = sE2 + p.n_tiles * kVqNT;                                      // [n_tiles*256]  |e_k|
+  float* sX2 = sEN + p.n_tiles * kVqNT;                                      // [4][128] (epilogue may lag the loader by 3 tiles)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sX2 + 4 * 128);
   uint64_t* b_full = bars;                    // [kVqBStages]
   uint64_t* b_empty = b_full + kVqBStages;    // [kVqBStages]
@@ -117,13 +118,14 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     fence_mbar_init();
   }
   // |e|^2 to smem (padded codes get +inf so they never win)
-  for (int k = threadIdx.x; k < p.n_tiles * kVqNT; k += blockDim.x)
+  for (int k = threadIdx.x; k < p.n_tiles * kVqNT; k += blockDim.x) {
     sE2[k] = k < p.n_embed ? p.e_norm2[k] : __int_as_float(0x7f800000);
+    sEN[k] = k < p.n_embed ? sqrtf(p.e_norm2[k]) : 0.f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
-  const float e2max = p.e_norm2[p.n_embed];
 
   if (warp == 0) {
     // ---------------------------------------------------------------- B producer (codebook tiles via TMA)
@@ -243,16 +245,23 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     const float INF = __int_as_float(0x7f800000);
     int it = 0, acc_it = 0;
     for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, ++it) {
-      float best = INF, second = INF;
+      // best = smallest distance so far; other_lb = smallest LOWER bound among all other codes, where code k's
+      // distance is only known to +- kVqBand * |x| * |e_k| (split-bf16 product error, scaled per code so that dead
+      // codes with huge norms -- the EMA renormalisation blows unused codes up, reference :70-75 -- do not widen it)
+      float best = INF, best_err = 0.f, other_lb = INF;
       int besti = 0;
-      float x2 = 0.f;
+      float x2 = 0.f, cx = 0.f;
       for (int nt = 0; nt < p.n_tiles; ++nt, ++acc_it) {
         const int tb = acc_it & 1;
         mbar_wait(&t_full[tb], (acc_it >> 1) & 1);
         tc_fence_after();
-        if (nt == 0) x2 = sX2[(it & 3) * 128 + row];   // written before a_full, which precedes t_full
+        if (nt == 0) {
+          x2 = sX2[(it & 3) * 128 + row];   // written before a_full, which precedes t_full
+          cx = kVqBand * sqrtf(x2);
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tb * kVqNT;
         const float* e2 = sE2 + nt * kVqNT;
+        const float* en = sEN + nt * kVqNT;
 #pragma unroll 1
         for (int c = 0; c < kVqNT; c += 32) {
           uint32_t v[32];
@@ -262,12 +271,14 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
           for (int j = 0; j < 32; ++j) {
             // same association as the reference: (|x|^2 - 2 x.e) + |e|^2   (:49-53)
             const float d = (x2 - 2.f * __uint_as_float(v[j])) + e2[c + j];
+            const float err = cx * en[c + j];
             if (d < best) {
-              second = best;
+              other_lb = fminf(other_lb, best - best_err);
               best = d;
+              best_err = err;
               besti = nt * kVqNT + c + j;
-            } else if (d < second) {
-              second = d;
+            } else {
+              other_lb = fminf(other_lb, d - err);
             }
           }
         }
@@ -278,8 +289,7 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
       const size_t grow = (size_t)rt * 128 + row;
       if (grow < p.rows) {
         p.embed_ind[grow] = besti;
-        const float band = kVqBand * sqrtf(x2 * e2max) + 1e-30f;
-        if (!(second - best > band)) {   // also catches NaN
+        if (!(other_lb > best + best_err)) {   // ambiguous within the error bound (also catches NaN)
           const int slot = atomicAdd(p.flag_count, 1);
           p.flag_rows[slot] = (int)grow;   // capacity = rows
         }
@@ -334,7 +344,7 @@ size_t vq_assign_smem_bytes(int dim, int n_embed) {
   const int kchunks = dim / 64;
   const int a_bufs = dim <= 64 ? 2 : 1;
   const int n_tiles = (n_embed + kVqNT - 1) / kVqNT;
-  return (size_t)a_bufs * 2 * kchunks * 128 * 128 + (size_t)kVqBStages * kVqNT * 128 + (size_t)n_tiles * kVqNT * 4 +
+  return (size_t)a_bufs * 2 * kchunks * 128 * 128 + (size_t)kVqBStages * kVqNT * 128 + (size_t)n_tiles * kVqNT * 8 +
          4 * 128 * 4 + (2 * kVqBStages + 8) * 8 + 16 + 1024;
 }
 size_t vq_assign_workspace_bytes(size_t rows, int dim) { return 256 + rows * sizeof(int); }

@@ -21,7 +21,7 @@ from .ops import FORM_DOWN, FORM_S1, FORM_S1_DGRAD, FORM_UP, pad16
 
 
 class Node:
-    __slots__ = ("raw", "act", "c", "g", "f32")
+    __slots__ = ("raw", "act", "c", "g", "f32", "gdec")
 
     def __init__(self, c: int, raw=None, act=None, f32=None):
         self.c = c
@@ -196,6 +196,82 @@ def conv_op(tape: Tape, form: int, ksize: int, srcs: Sequence[View], wname: str,
                 assert v.node.g is None and not v.relu, "torch.cat sources must have a single consumer"
                 v.node.g = (dx, off)
                 off += v.node.c
+
+    tape.record(backward)
+    return out
+
+
+def first_conv_op(tape: Tape, x_nchw: torch.Tensor, wname: str, cin: int, cout: int) -> Node:
+    """Conv2d(cin<=8 -> cout, 4, stride 2, pad 1) + ReLU on the raw fp32 NCHW input (reference
+    models/vqvae_conv3d_latent.py:109): explicit im2col (K = 16 taps x 8 = 128) + a 1x1 GEMM on the tcgen05 kernel.
+    The input needs no gradient."""
+    w = tape.params[wname + ".weight"]          # [cout, cin, 4, 4]
+    b = _padded_bias(tape, wname + ".bias", cout)
+    col = ops.im2col4x4s2(x_nchw, cin)          # [F, H/2, W/2, 128]
+    w2 = torch.zeros(cout, 16, 8, dtype=torch.float32, device=w.device)
+    w2[:, :, :cin] = w.detach().reshape(cout, cin, 16).permute(0, 2, 1)
+    w2 = w2.view(cout, 128, 1, 1)
+    _, act, _ = ops.conv(FORM_S1, 2, 1, [(col, 128, 0)], w2, 0, cout, bias=b, want_raw=False, want_relu=True,
+                         wkey=(w, "im2col"))
+    out = Node(cout, act=act)
+
+    def backward():
+        gt, g_off = out.g
+        gb, acc = tape.grad_buffer(wname + ".bias")
+        ops.colsum(gt, cout, gb, c_off=g_off, accumulate=acc)
+        dw2 = torch.empty(cout, 128, 1, 1, dtype=torch.float32, device=w.device)
+        ops.wgrad(FORM_S1, 2, 1, (gt, cout, g_off), (col, 128, 0), dw2, m_axis=0)
+        gw, acc = tape.grad_buffer(wname + ".weight")
+        dw = dw2.view(cout, 16, 8)[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, 4, 4)
+        if acc:
+            gw.add_(dw)
+        else:
+            gw.copy_(dw)
+        tape.grad_ready(wname + ".weight")
+        tape.grad_ready(wname + ".bias")
+
+    tape.record(backward)
+    return out
+
+
+def last_convT_op(tape: Tape, src: View, wname: str, cout: int) -> Node:
+    """ConvTranspose2d(cin -> cout<=8, 4, stride 2, pad 1) producing the fp32 NCHW reconstruction (reference :154-156):
+    1x1 GEMM to the [pixels, 16 taps x 8] column matrix (bf16) + col2im scatter (+bias).  Backward: im2col of the
+    incoming NCHW gradient, then 1x1 data / weight gradients.  ``out.gdec`` must hold the fp32 NCHW gradient."""
+    w = tape.params[wname + ".weight"]          # [cin, cout, 4, 4]
+    b = tape.params[wname + ".bias"]
+    cin = w.shape[0]
+    w2 = torch.zeros(16, 8, cin, dtype=torch.float32, device=w.device)
+    w2[:, :cout] = w.detach().reshape(cin, cout, 16).permute(2, 1, 0)
+    w2 = w2.view(128, cin, 1, 1)                # Conv weight [Cout'=128, Cin]
+    x = src.t
+    col, _, _ = ops.conv(FORM_S1, 2, 1, [(x, cin, 0)], w2, 0, 128, wkey=(w, "col2im"))
+    dec = ops.col2im4x4s2(col, b.detach().contiguous(), cout)
+    del col
+    out = Node(cout, f32=dec)
+    out.gdec = None
+
+    def backward():
+        g = out.gdec
+        assert g is not None, "no gradient reached the reconstruction"
+        gb, acc = tape.grad_buffer(wname + ".bias")
+        ops.chansum_nchw(g, cout, gb, accumulate=acc)
+        dcol = ops.im2col4x4s2(g, cout)         # [F, h, w, 128]
+        dw2 = torch.empty(128, cin, 1, 1, dtype=torch.float32, device=w.device)
+        ops.wgrad(FORM_S1, 2, 1, (dcol, 128, 0), (x, cin, 0), dw2, m_axis=0)
+        gw, acc = tape.grad_buffer(wname + ".weight")
+        dw = dw2.view(16, 8, cin)[:, :cout].permute(2, 1, 0).reshape(cin, cout, 4, 4)
+        if acc:
+            gw.add_(dw)
+        else:
+            gw.copy_(dw)
+        tape.grad_ready(wname + ".weight")
+        tape.grad_ready(wname + ".bias")
+        nd = src.node
+        addend = nd.g[0] if nd.g is not None else None
+        dx, _, _ = ops.conv(FORM_S1_DGRAD, 2, 1, [(dcol, 128, 0)], w2, 1, cin, mask=nd.act if src.relu else None,
+                            addend=addend, out_cs=nd.cs, wkey=(w, "col2im"))
+        nd.g = (dx, 0)
 
     tape.record(backward)
     return out

@@ -141,15 +141,29 @@ class LPIPS(nn.Module):
         return xin, taps
 
     def forward(self, input, target):
+        """LPIPS distance [N,1,1,1].  The value is symmetric in (input, target); gradients flow to whichever side
+        requires them (the reference trainer passes (ground_truth, reconstruction), train_faceoff_perceptual.py:42)."""
+        gi = torch.is_grad_enabled() and input.requires_grad
+        gt_ = torch.is_grad_enabled() and target.requires_grad
+        if gt_ and not gi:
+            return self._distance(target, input)
+        if gi and gt_:
+            # d/d(input) with target fixed + d/d(target) with input fixed; the value is counted once
+            return (self._distance(input, target.detach()) + self._distance(target, input.detach())
+                    - self._distance(input.detach(), target.detach()))
+        return self._distance(input, target)
+
+    def _distance(self, diff_side, fixed_side):
+        """Differentiable w.r.t. ``diff_side`` only."""
         lins = [self.lin0, self.lin1, self.lin2, self.lin3, self.lin4]
         ws = [l.model[-1].weight.reshape(-1).to(torch.float32).contiguous() for l in lins]
         model = self
 
         def runner(tape: Tape, x: torch.Tensor):
             n = x.shape[0]
-            # target side: no gradient, nothing kept but the five taps
+            # fixed side: no gradient, nothing kept but the five taps
             t_tape = Tape(tape.params, need_grad=False)
-            _, taps1 = model._trunk(t_tape, target.detach())
+            _, taps1 = model._trunk(t_tape, fixed_side.detach())
             feats1 = [t.act for t in taps1]
             val = torch.zeros(n, dtype=torch.float32, device=x.device)
             g_holder = {}
@@ -168,17 +182,18 @@ class LPIPS(nn.Module):
 
             def seed(tape_, gouts):
                 g = gouts[0]
-                g_holder["g"] = (torch.zeros(n, device=x.device) if g is None else g.reshape(n).to(torch.float32).contiguous())
+                g_holder["g"] = (torch.zeros(n, device=x.device) if g is None
+                                 else g.reshape(n).to(torch.float32).contiguous())
 
             def input_grad():
                 if xin.g is None:
                     return None
-                gx = ops.unpack_nchw(xin.g[0], 3)
-                return gx / model.scaling_layer.scale
+                return ops.unpack_nchw(xin.g[0], 3) / model.scaling_layer.scale
+
             return (val.view(n, 1, 1, 1),), {"seed": seed, "input_grad": input_grad}
 
         ps = _params_of(self)
-        return _GraphFn.apply(runner, input, tuple(ps.keys()), *ps.values())[0]
+        return _GraphFn.apply(runner, diff_side, tuple(ps.keys()), *ps.values())[0]
 
 
 class VQLPIPS(nn.Module):

@@ -108,10 +108,15 @@ def out_spatial(form: int, shape: Sequence[int]) -> Tuple[int, ...]:
     return tuple(shape)
 
 
-def packed_weights(desc: ConvDesc, weight: torch.Tensor, n_axis: int, n_scale: Optional[torch.Tensor], key_extra) -> torch.Tensor:
+def packed_weights(desc: ConvDesc, weight: torch.Tensor, n_axis: int, n_scale: Optional[torch.Tensor], key_extra,
+                   wkey=None) -> torch.Tensor:
+    """bf16 K-step-ordered copy of ``weight``, cached per (parameter storage, version, role).  ``wkey`` =
+    (source parameter, tag) must be given when ``weight`` is a temporary derived from a parameter (its own
+    data_ptr/version say nothing about staleness)."""
     lib = L.load()
-    key = (weight.data_ptr(), desc.form, desc.ndim, desc.ksize, n_axis, key_extra, _p(n_scale))
-    ver = weight._version
+    src_t, tag = (weight, None) if wkey is None else wkey
+    key = (src_t.data_ptr(), tag, desc.form, desc.ndim, desc.ksize, n_axis, key_extra, _p(n_scale))
+    ver = src_t._version
     hit = _wcache.get(key)
     if hit is not None and hit[0] == ver:
         return hit[1]
@@ -131,7 +136,7 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
          bias: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
          addend: Optional[torch.Tensor] = None, want_raw: bool = True, want_relu: bool = False,
          f32: Optional[str] = None, relu_f32: bool = False, n_scale: Optional[torch.Tensor] = None,
-         out_cs: Optional[int] = None, out_raw: Optional[torch.Tensor] = None):
+         out_cs: Optional[int] = None, out_raw: Optional[torch.Tensor] = None, wkey=None):
     """Run one implicit-GEMM convolution.  Returns (raw_bf16|None, relu_bf16|None, f32|None).
 
     f32: None | 'cl' (channels-last fp32 [.., out_cs]) | 'nchw' (fp32 [N, cout, H, W]).
@@ -139,7 +144,7 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
     lib = L.load()
     d = _conv_desc(form, ndim, ksize, srcs, cout)
     key_extra = tuple((s[1], s[0].shape[-1], s[2]) for s in srcs) + (cout,)
-    wp = packed_weights(d, weight, n_axis, n_scale, key_extra)
+    wp = packed_weights(d, weight, n_axis, n_scale, key_extra, wkey)
     d.wpacked = wp.data_ptr()
     t0 = srcs[0][0]
     lead = out_spatial(form, t0.shape[:-1])
@@ -249,6 +254,38 @@ def unpack_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
     L.check(lib.fo_unpack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _stream()), "fo_unpack_nchw")
     _count(1)
     return out
+
+
+def im2col4x4s2(x: torch.Tensor, c: int) -> torch.Tensor:
+    """NCHW fp32 [N, Ca, H, W] (first c <= 8 channels) -> bf16 [N, H/2, W/2, 128], k = (ky*4+kx)*8 + ch."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
+    n, ca, h, w = x.shape
+    out = torch.empty((n, h // 2, w // 2, 128), dtype=torch.bfloat16, device=x.device)
+    L.check(lib.fo_im2col4x4s2(x.data_ptr(), out.data_ptr(), n, ca, c, h, w, _stream()), "fo_im2col4x4s2")
+    _count(1)
+    return out
+
+
+def col2im4x4s2(col: torch.Tensor, bias: Optional[torch.Tensor], c: int) -> torch.Tensor:
+    """bf16 [N, Hi, Wi, 128] (k = tap*8 + co) -> NCHW fp32 [N, c, 2Hi, 2Wi] (+ bias)."""
+    lib = L.load()
+    n, hi, wi, k = col.shape
+    assert k == 128 and col.dtype == torch.bfloat16 and col.is_contiguous()
+    out = torch.empty((n, c, 2 * hi, 2 * wi), dtype=torch.float32, device=col.device)
+    L.check(lib.fo_col2im4x4s2(col.data_ptr(), _p(bias), out.data_ptr(), n, c, hi, wi, _stream()), "fo_col2im4x4s2")
+    _count(1)
+    return out
+
+
+def chansum_nchw(x: torch.Tensor, c: int, out: torch.Tensor, accumulate: bool = False):
+    """out[:c] (+)= x[:, :c].sum((0, 2, 3)) for NCHW fp32 x."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, ca, h, w = x.shape
+    L.check(lib.fo_chansum_nchw(x.data_ptr(), n, ca, c, h * w, out.data_ptr(), int(accumulate), _stream()),
+            "fo_chansum_nchw")
+    _count(1)
 
 
 def relu(x: torch.Tensor) -> torch.Tensor:

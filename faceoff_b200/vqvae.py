@@ -16,7 +16,8 @@ from torch import nn
 
 from . import distributed as dist_fn
 from . import ops
-from .graph import FORM_DOWN, FORM_S1, FORM_UP, Node, Tape, View, conv_op, resblock_op
+from .graph import (FORM_DOWN, FORM_S1, FORM_UP, Node, Tape, View, conv_op, first_conv_op, last_convT_op,
+                    resblock_op)
 
 
 # ------------------------------------------------------------------------------------------------
@@ -197,12 +198,16 @@ class ResBlock(nn.Module):
         return _run_graph(self, _io_wrap(build, self.in_channel, None), input)[0]
 
 
-def _encoder_graph(tape: Tape, x: Node, prefix: str, channel: int, n_res_block: int, n_res_channel: int, stride: int,
+def _encoder_graph(tape: Tape, x, prefix: str, channel: int, n_res_block: int, n_res_channel: int, stride: int,
                    input_needs_grad: bool) -> Node:
-    """Encoder (reference :103-131).  Returns a node whose ``act`` is the encoder output (post final ReLU)."""
+    """Encoder (reference :103-131).  Returns a node whose ``act`` is the encoder output (post final ReLU).
+    ``x``: a Node, or (stride 4 only) the raw fp32 NCHW image with <= 8 channels (im2col first layer, no input grad)."""
     if stride == 4:
-        a = conv_op(tape, FORM_DOWN, 4, [View(x, x.raw is None)], prefix + "blocks.0", channel // 2, want_raw=False,
-                    want_relu=True, input_needs_grad=input_needs_grad)
+        if isinstance(x, torch.Tensor):
+            a = first_conv_op(tape, x, prefix + "blocks.0", x.shape[1], channel // 2)
+        else:
+            a = conv_op(tape, FORM_DOWN, 4, [View(x, x.raw is None)], prefix + "blocks.0", channel // 2,
+                        want_raw=False, want_relu=True, input_needs_grad=input_needs_grad)
         a = conv_op(tape, FORM_DOWN, 4, [View(a, True)], prefix + "blocks.2", channel, want_raw=False, want_relu=True)
         a = conv_op(tape, FORM_S1, 3, [View(a, True)], prefix + "blocks.4", channel, want_raw=True,
                     want_relu=True)
@@ -229,6 +234,8 @@ def _decoder_graph(tape: Tape, srcs, prefix: str, out_channel: int, channel: int
     if stride == 4:
         a = conv_op(tape, FORM_UP, 4, [View(a, True)], f"{prefix}blocks.{k}", channel // 2, transposed=True,
                     want_raw=False, want_relu=True)
+        if final_f32 == "nchw" and out_channel <= 8:
+            return last_convT_op(tape, View(a, True), f"{prefix}blocks.{k + 2}", out_channel)
         return conv_op(tape, FORM_UP, 4, [View(a, True)], f"{prefix}blocks.{k + 2}", out_channel, transposed=True,
                        want_raw=final_f32 is None, f32=final_f32)
     return conv_op(tape, FORM_UP, 4, [View(a, True)], f"{prefix}blocks.{k}", out_channel, transposed=True,
@@ -392,7 +399,8 @@ class VQVAE(nn.Module):
                 dp.begin_forward(tape.params, model.param_forward_order())
             else:
                 dp = None
-            xin = Node(cin, raw=ops.pack_nchw(x.to(torch.float32)))
+            x = x.to(torch.float32).contiguous()
+            xin = x if cin <= 8 else Node(cin, raw=ops.pack_nchw(x))
             enc_b = _encoder_graph(tape, xin, "enc_b.", ch, nrb, nrc, 4, input_needs_grad=False)
             enc_t = _encoder_graph(tape, enc_b, "enc_t.", ch, nrb, nrc, 2, input_needs_grad=True)
             eb_c = _conv3d_graph(tape, View(enc_b, True), "conv3d_encoded_b.", 128, clips)
@@ -429,11 +437,13 @@ class VQVAE(nn.Module):
             diff = rec_t["diff_sum"] / numel_t + rec_b["diff_sum"] / numel_b  # [1]  (:268,276,278)
             def seed(tape_, gouts):
                 g_dec, g_diff = gouts[0], gouts[1]
-                if g_dec is not None:
-                    out.g = (ops.pack_nchw(g_dec.to(torch.float32).contiguous()), 0)
+                if g_dec is None:
+                    g_dec = torch.zeros_like(dec)
+                g_dec = g_dec.to(torch.float32).contiguous()
+                if cin <= 8:
+                    out.gdec = g_dec
                 else:
-                    out.g = (torch.zeros((*dec.shape[0:1], dec.shape[2], dec.shape[3], 16), dtype=torch.bfloat16,
-                                         device=dec.device), 0)
+                    out.g = (ops.pack_nchw(g_dec), 0)
                 if g_diff is not None:
                     gdiff_holder["g"] = g_diff.reshape(1).to(torch.float32).contiguous()
 

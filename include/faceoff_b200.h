@@ -127,6 +127,16 @@ int fo_relu(const void* x, void* y, size_t numel, fo_stream_t stream);
 int fo_colsum(const void* x, size_t rows, int cs, int c_off, int c, float* out, int accumulate, void* workspace,
               size_t workspace_bytes, fo_stream_t stream);
 size_t fo_colsum_workspace_bytes(int cs);
+/* Explicit im2col of a k4 s2 p1 window for tiny channel counts (c <= 8): x NCHW fp32 [n, ca, h, w] (first c channels)
+ * -> bf16 [n, h/2, w/2, 128], k = (ky*4+kx)*8 + ch.  Turns the first Conv2d(6->64,4,2,1) (reference
+ * models/vqvae_conv3d_latent.py:109) and the gradient of the last ConvTranspose2d(64->6,4,2,1) (:154-156) into plain
+ * K=128 GEMMs on the tcgen05 kernel. */
+int fo_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w, fo_stream_t stream);
+/* Inverse scatter for the last ConvTranspose2d: col bf16 [n, hi, wi, 128] (k = tap*8 + co) + bias -> NCHW fp32
+ * [n, c, 2hi, 2wi]. */
+int fo_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, fo_stream_t stream);
+/* out[ch] (+)= sum_{n,hw} x[n][ch][hw] for ch < c, x NCHW fp32 [n, ca, hw] (bias gradient of the last layer) */
+int fo_chansum_nchw(const float* x, int n, int ca, int c, int hw, float* out, int accumulate, fo_stream_t stream);
 /* 2x2/2 max pool on channels-last bf16 [n,h,w,cs] and its gradient (reference VGG trunk models/lpips.py:115-152) */
 int fo_maxpool2(const void* x, void* y, int n, int h, int w, int cs, fo_stream_t stream);
 /* dx is the gradient w.r.t. the PRE-ReLU conv output feeding the pool (x is post-ReLU: x == 0 closes the gate). */
