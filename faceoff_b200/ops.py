@@ -7,6 +7,7 @@ current CUDA stream and never synchronises the host.
 from __future__ import annotations
 
 import ctypes as C
+import weakref
 from typing import Dict, Optional, Sequence, Tuple
 
 import torch
@@ -74,7 +75,7 @@ def workspace(nbytes: int, device, tag: str = "main") -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------
 SrcT = Tuple[torch.Tensor, int, int]  # (tensor, logical channels, channel offset)
 
-_wcache: Dict[tuple, Tuple[int, torch.Tensor]] = {}
+_wcache: Dict[tuple, tuple] = {}
 
 
 def _fill_src(dst: Src, s: SrcT):
@@ -118,7 +119,9 @@ def packed_weights(desc: ConvDesc, weight: torch.Tensor, n_axis: int, n_scale: O
     key = (src_t.data_ptr(), tag, desc.form, desc.ndim, desc.ksize, n_axis, key_extra, _p(n_scale))
     ver = src_t._version
     hit = _wcache.get(key)
-    if hit is not None and hit[0] == ver:
+    # the entry is only valid for the SAME live tensor object: addresses (and version counters) are recycled by the
+    # caching allocator once a parameter dies
+    if hit is not None and hit[0] == ver and hit[2]() is src_t:
         return hit[1]
     nbytes = lib.fo_conv_wpacked_bytes(C.byref(desc))
     if nbytes == 0:
@@ -128,7 +131,7 @@ def packed_weights(desc: ConvDesc, weight: torch.Tensor, n_axis: int, n_scale: O
     L.check(lib.fo_conv_pack_weights(C.byref(desc), weight.data_ptr(), weight.shape[0], weight.shape[1], n_axis,
                                      _p(n_scale), wp.data_ptr(), _stream()), "fo_conv_pack_weights")
     _count(1)
-    _wcache[key] = (ver, wp)
+    _wcache[key] = (ver, wp, weakref.ref(src_t))
     return wp
 
 

@@ -363,6 +363,45 @@ def case_lpips():
     return ok
 
 
+def case_lpips_trunk():
+    import warnings
+    from faceoff_b200 import ops
+    from faceoff_b200.graph import Tape
+    from faceoff_b200.lpips import LPIPS
+    from oracle import faceoff_oracle as O
+    ok = True
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "golden.pt"), map_location="cpu")["lpips_3x64"]
+    lp = O.init_lpips_params(seed=1)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = LPIPS()
+    m.load_state_dict(lp)
+    m = m.cuda().eval()
+    for name in ("a", "b"):
+        x = g[name]
+        s = (x - lp["scaling_layer.shift"]) / lp["scaling_layer.scale"]
+        ref = O.vgg_taps(lp, s)
+        tape = Tape({k: v for k, v in m.named_parameters()}, need_grad=False)
+        _, taps = m._trunk(tape, x.cuda())
+        torch.cuda.synchronize()
+        for k, (t, r) in enumerate(zip(taps, ref)):
+            ok &= report(f"trunk {name} tap{k} {tuple(r.shape)}", from_cl(t.act, r.shape[1]).cpu(), r, tol=3e-2)
+    a, b = g["a"].cuda(), g["b"].cuda()
+    val = m(a, b)
+    ok &= report("lpips value", val.cpu().flatten(), g["val"].flatten(), tol=3e-2)
+    # per-tap head on the oracle features (isolates fo_lpips_tap from the trunk)
+    sa = (g["a"] - lp["scaling_layer.shift"]) / lp["scaling_layer.scale"]
+    sb = (g["b"] - lp["scaling_layer.shift"]) / lp["scaling_layer.scale"]
+    ta, tb = O.vgg_taps(lp, sa), O.vgg_taps(lp, sb)
+    for k in range(5):
+        d = (O.normalize_tensor(ta[k]) - O.normalize_tensor(tb[k])) ** 2
+        r = F.conv2d(d, lp[f"lin{k}.model.1.weight"]).mean([2, 3]).flatten()
+        out = torch.zeros(3, device=dev)
+        ops.lpips_tap(to_cl(ta[k].cuda()), to_cl(tb[k].cuda()), lp[f"lin{k}.model.1.weight"].flatten().cuda().contiguous(), out)
+        ok &= report(f"head tap{k}", out.cpu(), r, tol=2e-2)
+    return ok
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 
