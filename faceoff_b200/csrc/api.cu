@@ -194,14 +194,43 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   } else {  // DOWN: (wx, py, hy, f)
     ext[0] = c->w / 2; ext[1] = 1; ext[2] = c->h / 2; ext[3] = c->n;
   }
+  // CTA tile: 128 positions, or 256 (two M=128 sub-tiles sharing every B tile) when the problem is large enough;
+  // 3x3(x3) stride-1 filters additionally read their three vertical taps from one halo'd A box (see conv_igemm.cu).
   int box[4];
   choose_box(ext, 128, box);
+  p.MT = 1;
+  p.TPS = 1;
+  bool halo = false;
+  if (p.n_tiles == 1 && p.NT <= 128) {
+    int b2[4];
+    choose_box(ext, 256, b2);
+    long long tiles256 = 1;
+    bool exact = true;
+    for (int d = 0; d < 4; ++d) {
+      tiles256 *= (ext[d] + b2[d] - 1) / b2[d];
+      if (b2[d] > 1 && b2[d] > pow2_ceil(ext[d])) exact = false;
+    }
+    const int sms = g_num_sms > 0 ? g_num_sms : 148;
+    if (exact && tiles256 >= 2LL * sms) {
+      p.MT = 2;
+      for (int d = 0; d < 4; ++d) box[d] = b2[d];
+      const int tap_off = box[0] * rowb;
+      if (s1 && c->ksize == 3 && box[2] == 1 && box[3] == 1 && box[0] * box[1] == 256 && tap_off % 1024 == 0 &&
+          box[1] + 2 <= 256) {
+        halo = true;
+        p.TPS = 3;
+      }
+    }
+  }
   for (int d = 0; d < 4; ++d) {
     p.box[d] = box[d];
     p.tile_step[d] = box[d];
     p.tile_cnt[d] = (ext[d] + box[d] - 1) / box[d];
     p.lim[d] = ext[d];
   }
+  p.sub_off = 128 * rowb;
+  p.tap_off = halo ? box[0] * rowb : 0;
+  p.a_bytes = (halo ? box[0] * (box[1] + 2) : 128 * p.MT) * rowb;
   if (s1) {
     const long long W = c->w, H = c->h, D = c->d;
     if (c->ndim == 3) {
@@ -233,29 +262,33 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   if (!nchw && (c->out_bf16 || c->out_relu || c->out_f32) && (ocs % 8 != 0))
     return fail(FO_ERR_INVALID, "out_cs must be a multiple of 8");
 
-  // K steps
-  int nk = 0;  // per group
+  // K steps (= pipeline stages) and the matching packed-weight column blocks (TPS per stage)
+  int nk = 0;  // stages per group
   KStep* ks = p.ksteps;
   PackStep* ps = out->pack.steps;
-  int total = 0;
-  auto push = [&](int map, int c0, int d1, int d2, int d3, int tap, int wk0, int valid) -> bool {
-    if (total >= kMaxKSteps) return false;
-    ks[total].c0 = (int16_t)c0; ks[total].d1 = (int8_t)d1; ks[total].d2 = (int8_t)d2; ks[total].d3 = (int8_t)d3;
-    ks[total].map = (uint8_t)map; ks[total].pad = 0;
-    ps[total].tap = (int16_t)tap; ps[total].wk0 = (int16_t)wk0; ps[total].valid = (int16_t)valid; ps[total].pad = 0;
-    ++total;
-    return true;
-  };
+  int n_stage = 0, n_pack = 0;
   bool ok = true;
-  auto chunks = [&](int map, int pix_c0, int d1, int d2, int d3, int tap) {
-    // all channel chunks of source `map` for one tap
+  auto push_stage = [&](int map, int c0, int d1, int d2, int d3) {
+    if (n_stage >= kMaxKSteps) { ok = false; return; }
+    ks[n_stage].c0 = (int16_t)c0; ks[n_stage].d1 = (int8_t)d1; ks[n_stage].d2 = (int8_t)d2; ks[n_stage].d3 = (int8_t)d3;
+    ks[n_stage].map = (uint8_t)map; ks[n_stage].pad = 0;
+    ++n_stage;
+  };
+  auto push_pack = [&](int tap, int wk0, int valid) {
+    if (n_pack >= kMaxKSteps) { ok = false; return; }
+    ps[n_pack].tap = (int16_t)tap; ps[n_pack].wk0 = (int16_t)wk0; ps[n_pack].valid = (int16_t)valid; ps[n_pack].pad = 0;
+    ++n_pack;
+  };
+  // all channel chunks of source `map` for one stage; taps[] lists the TPS filter taps served by the stage
+  auto chunks = [&](int map, int pix_c0, int d1, int d2, int d3, const int* taps) {
     const fo_src_t& src = c->src[map];
     int wbase = 0;
     for (int s = 0; s < map; ++s) wbase += c->src[s].c;
     const int cpad = (src.c + 15) / 16 * 16;
     for (int ch = 0; ch < cpad; ch += kc) {
       const int valid = src.c - ch < kc ? src.c - ch : kc;
-      ok = ok && push(map, pix_c0 + src.c_off + ch, d1, d2, d3, tap, wbase + ch, valid);
+      push_stage(map, pix_c0 + src.c_off + ch, d1, d2, d3);
+      for (int j = 0; j < p.TPS; ++j) push_pack(taps[j], wbase + ch, valid);
     }
   };
   if (s1) {
@@ -263,19 +296,28 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     const int kd_n = c->ndim == 3 ? k : 1;
     const int sign = c->form == FO_FORM_S1 ? 1 : -1;
     for (int kd = 0; kd < kd_n; ++kd)
-      for (int kh = 0; kh < k; ++kh)
+      for (int kh = 0; kh < (halo ? 1 : k); ++kh)
         for (int kw = 0; kw < k; ++kw) {
-          const int tap = (kd * k + kh) * k + kw;
-          const int dw = sign * (kw - pad), dh = sign * (kh - pad), dd = c->ndim == 3 ? sign * (kd - pad) : 0;
-          for (int s = 0; s < c->n_src; ++s) chunks(s, 0, dw, dh, dd, tap);
+          const int dw = sign * (kw - pad), dd = c->ndim == 3 ? sign * (kd - pad) : 0;
+          if (halo) {
+            // box starts one image row above the tile; sub-box j holds the rows for vertical offset j-1
+            int taps[3];
+            for (int j = 0; j < 3; ++j) taps[j] = (kd * k + (sign > 0 ? j : 2 - j)) * k + kw;
+            for (int s = 0; s < c->n_src; ++s) chunks(s, 0, dw, -1, dd, taps);
+          } else {
+            const int tap = (kd * k + kh) * k + kw;
+            for (int s = 0; s < c->n_src; ++s) chunks(s, 0, dw, sign * (kh - pad), dd, &tap);
+          }
         }
-    nk = total;
+    nk = n_stage;
   } else if (c->form == FO_FORM_DOWN) {
     for (int ky = 0; ky < 4; ++ky)
       for (int kx = 0; kx < 4; ++kx)
-        for (int s = 0; s < c->n_src; ++s)
-          chunks(s, kDownPar[kx] * c->src[s].cs, kDownD[kx], kDownPar[ky], kDownD[ky], ky * 4 + kx);
-    nk = total;
+        for (int s = 0; s < c->n_src; ++s) {
+          const int tap = ky * 4 + kx;
+          chunks(s, kDownPar[kx] * c->src[s].cs, kDownD[kx], kDownPar[ky], kDownD[ky], &tap);
+        }
+    nk = n_stage;
   } else {  // UP: out[2i-1+k] += in[i] w[k]; output parity p: k in {1,3} (p=0: i = h, h-1) or {0,2} (p=1: i = h+1, h)
     static const int kk[2][2] = {{1, 3}, {0, 2}};
     static const int dd[2][2] = {{0, -1}, {1, 0}};
@@ -283,15 +325,17 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
       const int py = g >> 1, px = g & 1;
       for (int a = 0; a < 2; ++a)
         for (int b = 0; b < 2; ++b)
-          for (int s = 0; s < c->n_src; ++s)
-            chunks(s, 0, dd[px][b], dd[py][a], 0, kk[py][a] * 4 + kk[px][b]);
-      if (g == 0) nk = total;
+          for (int s = 0; s < c->n_src; ++s) {
+            const int tap = kk[py][a] * 4 + kk[px][b];
+            chunks(s, 0, dd[px][b], dd[py][a], 0, &tap);
+          }
+      if (g == 0) nk = n_stage;
     }
   }
   if (!ok) return fail(FO_ERR_INVALID, "too many K steps (> %d)", kMaxKSteps);
   p.num_ksteps = nk;
-  out->ktot = total * kc;
-  const int stage_bytes = (128 * rowb + p.NT * rowb + 1023) & ~1023;
+  out->ktot = n_pack * kc;
+  const int stage_bytes = (p.a_bytes + p.TPS * p.NT * rowb + 1023) & ~1023;
   int stages = (kMaxDynSmem - 2048) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(FO_ERR_INVALID, "tile does not fit in shared memory");
@@ -329,7 +373,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
       dims[0] = cs; dims[1] = c->w; dims[2] = c->h; dims[3] = c->n; dims[4] = 1;
       str[0] = 1; str[1] = cs; str[2] = (uint64_t)c->w * cs; str[3] = (uint64_t)c->h * c->w * cs; str[4] = (uint64_t)c->n * c->h * c->w * cs;
     }
-    bx[0] = kc; bx[1] = box[0]; bx[2] = box[1]; bx[3] = box[2]; bx[4] = box[3];
+    bx[0] = kc; bx[1] = box[0]; bx[2] = box[1] + (halo ? 2 : 0); bx[3] = box[2]; bx[4] = box[3];
     int rc = encode_map(&out->maps.a[s], src.ptr, 5, dims, str, bx, rowb);
     if (rc != FO_OK) return rc;
   }

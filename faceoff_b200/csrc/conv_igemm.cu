@@ -11,10 +11,17 @@
 //   * a packed bf16 weight matrix [Cout][K steps * KC] in the same K-step order.
 //
 // Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
-//   warp 0      TMA producer      (A box [128 x KC] + B box [NT x KC] per stage, 128B/64B/32B swizzle)
+//   warp 0      TMA producer      (one A box + TPS B boxes [NT x KC] per stage, 128B/64B/32B swizzle)
 //   warp 1      MMA issuer        (lane 0 issues tcgen05.mma kind::f16 BF16xBF16->FP32, M=128, N=NT)
 //   warps 2..5  epilogue          (tcgen05.ld -> +bias -> *mask -> +addend -> relu -> bf16/fp32 stores)
-// TMEM holds two accumulators (2 x NT columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// TMEM holds two sets of accumulators (2 x MT x NT columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// The kernel is L2->SM bandwidth bound (about 32 B/clk/SM are available, a 128x128x64 MMA step wants 128 B/clk when A
+// and B are both streamed), so operand reuse is what matters:
+//   MT = 2   the CTA tile is 256 output positions = two M=128 MMAs per B tile (B traffic / 2);
+//   TPS = 3  "halo" stages for 3x3(x3) filters: the A box holds R+2 image rows; the three vertical taps are the SAME
+//            shared-memory box read through descriptors offset by one image row (S*rowb bytes, a multiple of the
+//            1024-byte swizzle atom), so A traffic drops by 3R/(R+2).
 #include "common.cuh"
 #include "igemm.cuh"
 
@@ -130,9 +137,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   // carve: [stages x (A tile | B tile)] | barriers | tmem ptr
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int rowb = p.KC * 2;
-  const int a_bytes = 128 * rowb;
+  const int a_bytes = p.a_bytes;
   const int b_bytes = p.NT * rowb;
-  const int stage_bytes = (a_bytes + b_bytes + 1023) & ~1023;
+  const int stage_bytes = (a_bytes + p.TPS * b_bytes + 1023) & ~1023;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full_bar = bars;                  // [stages]
   uint64_t* empty_bar = bars + p.stages;      // [stages]
@@ -143,7 +150,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * p.NT) tmem_cols <<= 1;
+  while ((int)tmem_cols < 2 * p.MT * p.NT) tmem_cols <<= 1;
 
   if (warp == 0) {
     if (lane == 0) {
@@ -178,16 +185,17 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
         int g, nt, base[4];
         decode_tile(p, tile, g, nt, base);
         const KStep* ks = p.ksteps + g * p.num_ksteps;
-        const int kcol0 = g * p.num_ksteps * p.KC;
+        const int kcol0 = g * p.num_ksteps * p.TPS * p.KC;
         for (int k = 0; k < p.num_ksteps; ++k) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full_bar[stage], a_bytes + b_bytes);
+          mbar_expect_tx(&full_bar[stage], a_bytes + p.TPS * b_bytes);
           const KStep s = ks[k];
           tma_load_5d(sa, &maps.a[s.map], &full_bar[stage], s.c0, base[0] + s.d1, base[1] + s.d2, base[2] + s.d3,
                       base[3]);
-          tma_load_2d(sb, &maps.b, &full_bar[stage], kcol0 + k * p.KC, nt * p.NT);
+          for (int j = 0; j < p.TPS; ++j)
+            tma_load_2d(sb + j * b_bytes, &maps.b, &full_bar[stage], kcol0 + (k * p.TPS + j) * p.KC, nt * p.NT);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -202,18 +210,20 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       const int buf = it & 1;
       mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + buf * p.NT;
+      const uint32_t d_tmem = tmem_base + buf * p.MT * p.NT;
       for (int k = 0; k < p.num_ksteps; ++k) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
           const uint32_t sb = sa + a_bytes;
-          for (int kk = 0; kk < p.KC / 16; ++kk) {
-            const uint64_t ad = make_smem_desc(sa + kk * 32, rowb, 16);
-            const uint64_t bd = make_smem_desc(sb + kk * 32, rowb, 16);
-            umma_bf16(d_tmem, ad, bd, idesc, (k | kk) != 0);
-          }
+          for (int j = 0; j < p.TPS; ++j)
+            for (int m = 0; m < p.MT; ++m)
+              for (int kk = 0; kk < p.KC / 16; ++kk) {
+                const uint64_t ad = make_smem_desc(sa + m * p.sub_off + j * p.tap_off + kk * 32, rowb, 16);
+                const uint64_t bd = make_smem_desc(sb + j * b_bytes + kk * 32, rowb, 16);
+                umma_bf16(d_tmem + m * p.NT, ad, bd, idesc, (k | j | kk) != 0);
+              }
           umma_commit(&empty_bar[stage]);
           if (k == p.num_ksteps - 1) umma_commit(&tfull_bar[buf]);
         }
@@ -224,36 +234,39 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
-    const int row = quarter * 32 + lane;    // pixel row inside the tile
-    const int b1 = row % p.box[0];
-    const int b2 = (row / p.box[0]) % p.box[1];
-    const int b3 = (row / (p.box[0] * p.box[1])) % p.box[2];
-    const int b4 = row / (p.box[0] * p.box[1] * p.box[2]);
+    const int row = quarter * 32 + lane;    // pixel row inside the 128-row sub-tile
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       int g, nt, base[4];
       decode_tile(p, tile, g, nt, base);
-      const int c1 = base[0] + b1, c2 = base[1] + b2, c3 = base[2] + b3, c4 = base[3] + b4;
-      const bool valid = (c1 < p.lim[0]) && (c2 < p.lim[1]) && (c3 < p.lim[2]) && (c4 < p.lim[3]);
-      const long long off = p.out_off[g] + c1 * p.out_stride[0] + c2 * p.out_stride[1] + c3 * p.out_stride[2] +
-                            c4 * p.out_stride[3];
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * p.NT;
       const int ncol0 = nt * p.NT;
-      int c = 0;
-      for (; c + 32 <= p.NT; c += 32) {
-        uint32_t v[32];
-        tmem_ld32(taddr + c, v);
-        tmem_ld_wait();
-        epilogue_chunk<32>(p, v, ncol0 + c, valid, off);
-      }
-      for (; c + 16 <= p.NT; c += 16) {
-        uint32_t v[16];
-        tmem_ld16(taddr + c, v);
-        tmem_ld_wait();
-        epilogue_chunk<16>(p, v, ncol0 + c, valid, off);
+      for (int m = 0; m < p.MT; ++m) {
+        const int rg = m * 128 + row;
+        const int b1 = rg % p.box[0];
+        const int b2 = (rg / p.box[0]) % p.box[1];
+        const int b3 = (rg / (p.box[0] * p.box[1])) % p.box[2];
+        const int b4 = rg / (p.box[0] * p.box[1] * p.box[2]);
+        const int c1 = base[0] + b1, c2 = base[1] + b2, c3 = base[2] + b3, c4 = base[3] + b4;
+        const bool valid = (c1 < p.lim[0]) && (c2 < p.lim[1]) && (c3 < p.lim[2]) && (c4 < p.lim[3]);
+        const long long off = p.out_off[g] + c1 * p.out_stride[0] + c2 * p.out_stride[1] + c3 * p.out_stride[2] +
+                              c4 * p.out_stride[3];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * p.MT + m) * p.NT;
+        int c = 0;
+        for (; c + 32 <= p.NT; c += 32) {
+          uint32_t v[32];
+          tmem_ld32(taddr + c, v);
+          tmem_ld_wait();
+          epilogue_chunk<32>(p, v, ncol0 + c, valid, off);
+        }
+        for (; c + 16 <= p.NT; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(taddr + c, v);
+          tmem_ld_wait();
+          epilogue_chunk<16>(p, v, ncol0 + c, valid, off);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -271,7 +284,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
 
 size_t conv_smem_bytes(const ConvParams& p) {
   const int rowb = p.KC * 2;
-  const int stage_bytes = (128 * rowb + p.NT * rowb + 1023) & ~1023;
+  const int stage_bytes = (p.a_bytes + p.TPS * p.NT * rowb + 1023) & ~1023;
   return (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024;
 }
 

@@ -20,11 +20,16 @@ struct KStep {
 
 // conv_igemm: D[128 pixels, NT] = sum_k A_k[128, KC] * W_k[NT, KC]^T   (+ fused epilogue)
 struct ConvParams {
-  // M tiling: a tile is a box of box[0] x box[1] x box[2] x box[3] positions on map dims 1..4, product 128
+  // M tiling: a tile is a box of box[0] x box[1] x box[2] x box[3] positions on map dims 1..4, product 128*MT
   int tile_cnt[4];    // tiles along map dims 1..4 (dim 1 fastest)
   int tile_step[4];   // coordinate step per tile on dims 1..4
   int box[4];         // in-tile extents on dims 1..4
   int lim[4];         // valid output extents on dims 1..4 (partial tiles are predicated)
+  int MT;             // M sub-tiles of 128 rows per CTA tile (1 or 2); they share every B tile
+  int TPS;            // filter taps per pipeline stage (1, or 3 = the three vertical taps read from ONE halo'd A box)
+  int a_bytes;        // bytes of the A box of one stage
+  int sub_off;        // byte offset of M sub-tile 1 inside the A box
+  int tap_off;        // byte offset between consecutive taps inside the A box (one image row)
   int n_tiles;        // N tiles of width NT
   int NT;             // columns per N tile (multiple of 16, <= 256)
   int KC;             // channels per K step: 16 / 32 / 64  (row bytes 32 / 64 / 128 = swizzle mode)

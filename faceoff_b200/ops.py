@@ -146,7 +146,8 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
     """
     lib = L.load()
     d = _conv_desc(form, ndim, ksize, srcs, cout)
-    key_extra = tuple((s[1], s[0].shape[-1], s[2]) for s in srcs) + (cout,)
+    # the packed column order depends on the planner's tiling mode, which depends on the geometry
+    key_extra = tuple((s[1], s[0].shape[-1], s[2]) for s in srcs) + (cout, d.n, d.d, d.h, d.w)
     wp = packed_weights(d, weight, n_axis, n_scale, key_extra, wkey)
     d.wpacked = wp.data_ptr()
     t0 = srcs[0][0]

@@ -402,6 +402,81 @@ def case_lpips_trunk():
     return ok
 
 
+class _RoundBF16(torch.autograd.Function):
+    """bf16 storage emulation: round values in forward and gradients in backward."""
+
+    @staticmethod
+    def forward(ctx, x):
+        return bf(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return bf(g)
+
+
+def case_lpips_grad():
+    """How much of the LPIPS input-gradient error is inherent to bf16 activation/gradient storage?"""
+    import warnings
+    from faceoff_b200.lpips import LPIPS
+    from oracle import faceoff_oracle as O
+    g = torch.load(os.path.join(ROOT, "tests", "golden", "golden.pt"), map_location="cpu")["lpips_3x64"]
+    lp = {k: v.cuda() for k, v in O.init_lpips_params(seed=1).items()}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = LPIPS()
+    m.load_state_dict(lp)
+    m = m.cuda().eval()
+    a = g["a"].cuda()
+    b = g["b"].cuda().requires_grad_(True)
+    m(a, b).mean().backward()
+    ours = b.grad.clone()
+
+    def emu_taps(x):
+        taps, ci, idx = [], 0, 0
+        x = _RoundBF16.apply(x)
+        for v in O.VGG_CFG:
+            if v == "M":
+                x = F.max_pool2d(x, 2, 2)
+                idx += 1
+            else:
+                k = O._vgg_key(O.VGG_CONV_IDX[ci])
+                x = _RoundBF16.apply(F.relu(F.conv2d(x, bf(lp[k + ".weight"]), lp[k + ".bias"], padding=1)))
+                ci += 1
+                idx += 2
+            if idx in O.VGG_SLICE_ENDS:
+                taps.append(x)
+        return taps
+
+    def lp_val(taps_fn, x0, x1):
+        s0 = (x0 - lp["scaling_layer.shift"]) / lp["scaling_layer.scale"]
+        s1 = (x1 - lp["scaling_layer.shift"]) / lp["scaling_layer.scale"]
+        t0, t1 = taps_fn(s0), taps_fn(s1)
+        val = 0
+        for k in range(5):
+            d = (O.normalize_tensor(t0[k]) - O.normalize_tensor(t1[k])) ** 2
+            val = val + F.conv2d(d, lp[f"lin{k}.model.1.weight"]).mean([2, 3], keepdim=True)
+        return val
+
+    b2 = g["b"].cuda().requires_grad_(True)
+    lp_val(lambda s: O.vgg_taps(lp, s), a, b2).mean().backward()
+    ref = b2.grad.clone()
+    b3 = g["b"].cuda().requires_grad_(True)
+    lp_val(emu_taps, a, b3).mean().backward()
+    emu = b3.grad.clone()
+
+    def stats(name, x, r):
+        nw = ((x - r).norm() / r.norm()).item()
+        mx = ((x - r).abs().max() / r.abs().max()).item()
+        cos = F.cosine_similarity(x.flatten(), r.flatten(), dim=0).item()
+        print(f"  {name}: normwise rel err {nw:.3e}  max-normalised {mx:.3e}  cosine {cos:.6f}", flush=True)
+        return nw
+
+    e1 = stats("ours vs fp32 reference", ours, ref)
+    e2 = stats("bf16-storage emulation (torch) vs fp32 reference", emu, ref)
+    stats("golden (CPU reference) vs GPU fp32 reference", g["grad_b"].cuda(), ref)
+    return e1 < max(2.0 * e2, 0.05)
+
+
 CASES = {k[5:]: v for k, v in list(globals().items()) if k.startswith("case_")}
 
 
