@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -231,6 +232,18 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   p.sub_off = 128 * rowb;
   p.tap_off = halo ? box[0] * rowb : 0;
   p.a_bytes = (halo ? box[0] * (box[1] + 2) : 128 * p.MT) * rowb;
+  // split the A box over dim 2 (image rows) into several TMA operations
+  const int a_rows = box[1] + (halo ? 2 : 0);
+  p.a_ops = 1;
+  {
+    const char* e = getenv("FO_A_OPS");
+    int want = e ? atoi(e) : 1;
+    if (want > 1 && a_rows % want == 0 && box[2] == 1 && box[3] == 1 && ((a_rows / want) * box[0] * rowb) % 1024 == 0)
+      p.a_ops = want;
+    const char* sk = getenv("FO_SKIP_MMA");
+    p.dbg_skip_mma = sk ? atoi(sk) : 0;
+  }
+  p.a_op_rows = a_rows / p.a_ops;
   if (s1) {
     const long long W = c->w, H = c->h, D = c->d;
     if (c->ndim == 3) {
@@ -373,7 +386,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
       dims[0] = cs; dims[1] = c->w; dims[2] = c->h; dims[3] = c->n; dims[4] = 1;
       str[0] = 1; str[1] = cs; str[2] = (uint64_t)c->w * cs; str[3] = (uint64_t)c->h * c->w * cs; str[4] = (uint64_t)c->n * c->h * c->w * cs;
     }
-    bx[0] = kc; bx[1] = box[0]; bx[2] = box[1] + (halo ? 2 : 0); bx[3] = box[2]; bx[4] = box[3];
+    bx[0] = kc; bx[1] = box[0]; bx[2] = p.a_op_rows; bx[3] = box[2]; bx[4] = box[3];
     int rc = encode_map(&out->maps.a[s], src.ptr, 5, dims, str, bx, rowb);
     if (rc != FO_OK) return rc;
   }

@@ -174,7 +174,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  // warp-uniform copy (the shuffle lets the compiler keep MMA operands in uniform registers)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -192,8 +193,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
           uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&full_bar[stage], a_bytes + p.TPS * b_bytes);
           const KStep s = ks[k];
-          tma_load_5d(sa, &maps.a[s.map], &full_bar[stage], s.c0, base[0] + s.d1, base[1] + s.d2, base[2] + s.d3,
-                      base[3]);
+          const int a_op_bytes = a_bytes / p.a_ops;
+          for (int o = 0; o < p.a_ops; ++o)
+            tma_load_5d(sa + o * a_op_bytes, &maps.a[s.map], &full_bar[stage], s.c0, base[0] + s.d1,
+                        base[1] + s.d2 + o * p.a_op_rows, base[2] + s.d3, base[3]);
           for (int j = 0; j < p.TPS; ++j)
             tma_load_2d(sb + j * b_bytes, &maps.b, &full_bar[stage], kcol0 + (k * p.TPS + j) * p.KC, nt * p.NT);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -203,6 +206,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
     const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
+    const uint64_t desc_base = make_smem_desc(0, rowb, 16);   // start-address field left at 0
+    const int n_taps = p.dbg_skip_mma ? 0 : p.TPS;
+    const int kk_n = p.KC / 16;
+    const int b_step16 = b_bytes >> 4, sub16 = p.sub_off >> 4, tap16 = p.tap_off >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
@@ -215,15 +222,29 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
         if (lane == 0) {
+          // The single issuing thread must stay well under one MMA time (64 cycles at N=128) per instruction, so
+          // descriptors are formed by adding a pre-shifted byte offset to a per-stage base instead of re-encoding.
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          for (int j = 0; j < p.TPS; ++j)
-            for (int m = 0; m < p.MT; ++m)
-              for (int kk = 0; kk < p.KC / 16; ++kk) {
-                const uint64_t ad = make_smem_desc(sa + m * p.sub_off + j * p.tap_off + kk * 32, rowb, 16);
-                const uint64_t bd = make_smem_desc(sb + j * b_bytes + kk * 32, rowb, 16);
-                umma_bf16(d_tmem + m * p.NT, ad, bd, idesc, (k | j | kk) != 0);
+          const uint64_t a_base = desc_base + ((sa & 0x3FFFF) >> 4);
+          const uint64_t b_base = a_base + (a_bytes >> 4);
+          for (int j = 0; j < n_taps; ++j) {
+            const uint64_t bj = b_base + (uint32_t)(j * b_step16);
+            for (int m = 0; m < p.MT; ++m) {
+              const uint64_t am = a_base + (uint32_t)(m * sub16 + j * tap16);
+              const uint32_t dm = d_tmem + m * p.NT;
+              if (kk_n == 4) {
+                umma_bf16(dm, am, bj, idesc, (k | j) != 0);
+                umma_bf16(dm, am + 2, bj + 2, idesc, 1);
+                umma_bf16(dm, am + 4, bj + 4, idesc, 1);
+                umma_bf16(dm, am + 6, bj + 6, idesc, 1);
+              } else if (kk_n == 2) {
+                umma_bf16(dm, am, bj, idesc, (k | j) != 0);
+                umma_bf16(dm, am + 2, bj + 2, idesc, 1);
+              } else {
+                umma_bf16(dm, am, bj, idesc, (k | j) != 0);
               }
+            }
+          }
           umma_commit(&empty_bar[stage]);
           if (k == p.num_ksteps - 1) umma_commit(&tfull_bar[buf]);
         }

@@ -30,6 +30,9 @@ struct ConvParams {
   int a_bytes;        // bytes of the A box of one stage
   int sub_off;        // byte offset of M sub-tile 1 inside the A box
   int tap_off;        // byte offset between consecutive taps inside the A box (one image row)
+  int a_ops;          // the A box is fetched by a_ops TMA operations of a_op_rows image rows each (more ops in flight)
+  int a_op_rows;
+  int dbg_skip_mma;   // debug: do not issue MMAs (measures the pure TMA streaming rate)
   int n_tiles;        // N tiles of width NT
   int NT;             // columns per N tile (multiple of 16, <= 256)
   int KC;             // channels per K step: 16 / 32 / 64  (row bytes 32 / 64 / 128 = swizzle mode)

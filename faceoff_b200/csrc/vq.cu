@@ -125,7 +125,8 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  // warp-uniform copy (the shuffle lets the compiler keep MMA operands in uniform registers)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
 
   if (warp == 0) {
     // ---------------------------------------------------------------- B producer (codebook tiles via TMA)
@@ -146,6 +147,7 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = make_idesc_bf16(128, kVqNT, 0, 0);
+    const uint64_t desc_base = make_smem_desc(0, 128, 16);
     int stage = 0;
     uint32_t phase = 0;
     int it = 0, acc_it = 0;
@@ -160,21 +162,17 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + tb * kVqNT;
         for (int kc = 0; kc < p.kchunks; ++kc) {
-          const uint32_t a_hi = a_base + kc * a_sub;
-          const uint32_t a_lo = a_base + (p.kchunks + kc) * a_sub;
+          const uint64_t a_hi = desc_base + (((a_base + kc * a_sub) & 0x3FFFF) >> 4);
+          const uint64_t a_lo = desc_base + (((a_base + (p.kchunks + kc) * a_sub) & 0x3FFFF) >> 4);
           // B hi tile: hi*hi and lo*hi
           mbar_wait(&b_full[stage], phase);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t sb = smem_u32(sB + (size_t)stage * b_tile);
+            const uint64_t sb = desc_base + ((smem_u32(sB + (size_t)stage * b_tile) & 0x3FFFF) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(d_tmem, make_smem_desc(a_hi + kk * 32, 128, 16), make_smem_desc(sb + kk * 32, 128, 16), idesc,
-                        (kc | kk) != 0);
+            for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, a_hi + 2 * kk, sb + 2 * kk, idesc, (kc | kk) != 0);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(d_tmem, make_smem_desc(a_lo + kk * 32, 128, 16), make_smem_desc(sb + kk * 32, 128, 16), idesc,
-                        1);
+            for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, a_lo + 2 * kk, sb + 2 * kk, idesc, 1);
             umma_commit(&b_empty[stage]);
           }
           __syncwarp();
@@ -183,11 +181,9 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
           mbar_wait(&b_full[stage], phase);
           tc_fence_after();
           if (lane == 0) {
-            const uint32_t sb = smem_u32(sB + (size_t)stage * b_tile);
+            const uint64_t sb = desc_base + ((smem_u32(sB + (size_t)stage * b_tile) & 0x3FFFF) >> 4);
 #pragma unroll
-            for (int kk = 0; kk < 4; ++kk)
-              umma_bf16(d_tmem, make_smem_desc(a_hi + kk * 32, 128, 16), make_smem_desc(sb + kk * 32, 128, 16), idesc,
-                        1);
+            for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, a_hi + 2 * kk, sb + 2 * kk, idesc, 1);
             umma_commit(&b_empty[stage]);
           }
           __syncwarp();

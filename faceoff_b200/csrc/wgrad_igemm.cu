@@ -68,7 +68,8 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
+  // warp-uniform copy (the shuffle lets the compiler keep MMA operands in uniform registers)
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   const WgTap* taps = p.taps + pass * p.taps_per_pass;
 
   if (warp == 0) {
@@ -104,6 +105,9 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
     }
   } else if (warp == 1) {
     const uint32_t idesc = make_idesc_bf16(128, p.NC, 1, 1);
+    const uint64_t a_desc_base = make_smem_desc(0, p.p_rowb, p.p_chunks > 1 ? p_chunk_bytes : 0);
+    const uint64_t b_desc_base = make_smem_desc(0, p.q_rowb, p.q_chunks > 1 ? q_chunk_bytes : 0);
+    const uint32_t q16 = q_bytes >> 4, pk16 = (16 * p.p_rowb) >> 4, qk16 = (16 * p.q_rowb) >> 4;
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_my; ++i) {
@@ -111,15 +115,16 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
       tc_fence_after();
       if (lane == 0) {
         const uint32_t sp = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint64_t a0 = a_desc_base + ((sp & 0x3FFFF) >> 4);
+        const uint64_t b0 = b_desc_base + (((sp + p_bytes) & 0x3FFFF) >> 4);
         for (int tp = 0; tp < p.taps_per_pass; ++tp) {
-          const uint32_t sq = sp + p_bytes + tp * q_bytes;
-#pragma unroll
-          for (int kk = 0; kk < kWgPix / 16; ++kk) {
-            // 16 pixels = two 8-row swizzle groups
-            const uint64_t ad = make_smem_desc(sp + kk * 16 * p.p_rowb, p.p_rowb, p.p_chunks > 1 ? p_chunk_bytes : 0);
-            const uint64_t bd = make_smem_desc(sq + kk * 16 * p.q_rowb, p.q_rowb, p.q_chunks > 1 ? q_chunk_bytes : 0);
-            umma_bf16(tmem_base + tp * p.NC, ad, bd, idesc, (i | kk) != 0);
-          }
+          const uint64_t bt = b0 + (uint32_t)(tp * q16);
+          const uint32_t dt = tmem_base + tp * p.NC;
+          // 64 pixels = four K=16 MMAs; 16 pixels = two 8-row swizzle groups = 16 * rowb bytes
+          umma_bf16(dt, a0, bt, idesc, i != 0);
+          umma_bf16(dt, a0 + pk16, bt + qk16, idesc, 1);
+          umma_bf16(dt, a0 + 2 * pk16, bt + 2 * qk16, idesc, 1);
+          umma_bf16(dt, a0 + 3 * pk16, bt + 3 * qk16, idesc, 1);
         }
         umma_commit(&empty_bar[stage]);
         if (i == n_my - 1) umma_commit(done_bar);

@@ -1,0 +1,79 @@
+"""Stand-alone launches of the hot conv / wgrad kernels at production shapes, for ncu captures and A/B timing.
+
+    python tests/gpu_profile_conv.py [conv3d|conv3x3|wgrad3d|all] [clips]
+"""
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from faceoff_b200 import ops  # noqa: E402
+
+
+def timeit(fn, n=10):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+def main():
+    which = sys.argv[1] if len(sys.argv) > 1 else "all"
+    clips = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+    T = 30
+    dev = "cuda"
+    torch.manual_seed(0)
+    if which in ("conv3d", "all"):
+        x = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)
+        w = torch.randn(128, 128, 3, 3, 3, device=dev) * 0.02
+        b = torch.zeros(128, device=dev)
+        fl = 2.0 * clips * T * 64 * 64 * 128 * 128 * 27
+        ms = timeit(lambda: ops.conv(ops.FORM_S1, 3, 3, [(x, 128, 0)], w, 0, 128, bias=b, want_raw=False, want_relu=True))
+        print(f"conv3d fwd  [{clips}x{T}x64x64x128]: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: ops.conv(ops.FORM_S1_DGRAD, 3, 3, [(x, 128, 0)], w, 1, 128, mask=x, addend=x))
+        print(f"conv3d dgrad(+mask+addend): {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    if which in ("conv3x3", "all"):
+        F_ = clips * T
+        x = torch.randn(F_, 64, 64, 128, device=dev).to(torch.bfloat16)
+        w = torch.randn(128, 128, 3, 3, device=dev) * 0.03
+        b = torch.zeros(128, device=dev)
+        fl = 2.0 * F_ * 64 * 64 * 128 * 128 * 9
+        ms = timeit(lambda: ops.conv(ops.FORM_S1, 2, 3, [(x, 128, 0)], w, 0, 128, bias=b, want_raw=True, want_relu=True))
+        print(f"conv3x3 128->128 @64 fwd: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        w32 = torch.randn(32, 128, 3, 3, device=dev) * 0.03
+        fl32 = fl / 4
+        ms = timeit(lambda: ops.conv(ops.FORM_S1, 2, 3, [(x, 128, 0)], w32, 0, 32, bias=b, want_raw=False, want_relu=True))
+        print(f"conv3x3 128->32 @64 fwd: {ms:.3f} ms  {fl32 / ms / 1e9:.1f} TFLOP/s")
+        w1 = torch.randn(128, 32, 1, 1, device=dev) * 0.1
+        h = torch.randn(F_, 64, 64, 32, device=dev).to(torch.bfloat16)
+        ms = timeit(lambda: ops.conv(ops.FORM_S1, 2, 1, [(h, 32, 0)], w1, 0, 128, bias=b, addend=x, want_raw=True, want_relu=True))
+        gb = (h.numel() + 3 * x.numel()) * 2 / 1e9
+        print(f"conv1x1 32->128 (+res, raw+relu) @64: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        wd = torch.randn(128, 64, 4, 4, device=dev) * 0.03
+        xd = torch.randn(F_, 128, 128, 64, device=dev).to(torch.bfloat16)
+        fld = 2.0 * F_ * 64 * 64 * 128 * 64 * 16
+        ms = timeit(lambda: ops.conv(ops.FORM_DOWN, 2, 4, [(xd, 64, 0)], wd, 0, 128, bias=b, want_raw=False, want_relu=True))
+        print(f"conv4x4s2 64->128 (DOWN) : {ms:.3f} ms  {fld / ms / 1e9:.1f} TFLOP/s")
+        wu = torch.randn(128, 64, 4, 4, device=dev) * 0.03
+        ms = timeit(lambda: ops.conv(ops.FORM_UP, 2, 4, [(x, 128, 0)], wu, 1, 64, bias=b, want_raw=False, want_relu=True))
+        print(f"convT4x4s2 128->64 (UP)  : {ms:.3f} ms  {fld / ms / 1e9:.1f} TFLOP/s")
+    if which in ("wgrad3d", "all"):
+        x = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)
+        dy = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)
+        dw = torch.empty(128, 128, 3, 3, 3, device=dev)
+        fl = 2.0 * clips * T * 64 * 64 * 128 * 128 * 27
+        ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 3, 3, (dy, 128, 0), (x, 128, 0), dw, m_axis=0))
+        print(f"conv3d wgrad: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+
+
+if __name__ == "__main__":
+    main()
