@@ -463,8 +463,22 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
   if (s1 && g->ndim == 3) { ext[0] = g->w; ext[1] = g->h; ext[2] = g->d; ext[3] = g->n; }
   else if (s1) { ext[0] = g->w; ext[1] = g->h; ext[2] = g->n; ext[3] = 1; }
   else { ext[0] = g->w; ext[1] = 1; ext[2] = g->h; ext[3] = g->n; }  // P low-res (w,h) with a dummy parity dim
+  // pixels per stage: 128 (= 8 MMAs per tap) with a halo'd Q box for 3x3(x3) filters when a 128-pixel tile fits in one
+  // image, else 64
   int box[4];
-  choose_box(ext, 64, box);
+  p.kpix = 64;
+  p.halo = 0;
+  if (s1 && g->ksize == 3) {
+    int b2[4];
+    choose_box(ext, 128, b2);
+    if (b2[2] == 1 && b2[3] == 1 && b2[0] * b2[1] == 128 && b2[0] <= ext[0] && b2[1] <= ext[1] &&
+        (b2[0] * p.q_rowb) % 1024 == 0 && (b2[0] * p.p_rowb) % 1024 == 0) {
+      p.kpix = 128;
+      p.halo = 1;
+      for (int d = 0; d < 4; ++d) box[d] = b2[d];
+    }
+  }
+  if (!p.halo) choose_box(ext, 64, box);
   p.total_ptiles = 1;
   for (int d = 0; d < 4; ++d) {
     p.tile_step[d] = box[d];
@@ -473,33 +487,53 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
     if (d < 3) p.box[d] = box[d];
   }
   if (box[3] != 1) return fail(FO_ERR_INVALID, "wgrad: tensor too small for a 64-pixel tile");
-  // taps
+  p.q_tap_off = p.halo ? box[0] * p.q_rowb : 0;
+  p.q_box_bytes = (p.halo ? box[0] * (box[1] + 2) : p.kpix) * p.q_rowb;
+  // taps; slot order = pass-major.  tap_index maps a slot to the PyTorch filter tap.
   int nt = 0;
+  FinalizeParams& f = out->fin;
   if (s1) {
     const int k = g->ksize, pad = (k - 1) / 2;
     if (k != 1 && k != 3) return fail(FO_ERR_INVALID, "wgrad ksize unsupported");
     const int kd_n = g->ndim == 3 ? k : 1;
-    for (int kd = 0; kd < kd_n; ++kd)
-      for (int kh = 0; kh < k; ++kh)
-        for (int kw = 0; kw < k; ++kw) {
-          WgTap& t = p.taps[nt++];
-          t.c0 = (int16_t)g->q.c_off; t.d1 = (int8_t)(kw - pad); t.d2 = (int8_t)(kh - pad);
-          t.d3 = (int8_t)(g->ndim == 3 ? kd - pad : 0); t.map = 0; t.pad = 0;
-        }
+    if (p.halo) {
+      // pass = (kd, kw); the three slots of a pass are kh = 0, 1, 2 read from one box starting one row above
+      for (int kd = 0; kd < kd_n; ++kd)
+        for (int kw = 0; kw < k; ++kw)
+          for (int kh = 0; kh < k; ++kh) {
+            WgTap& t = p.taps[nt];
+            t.c0 = (int16_t)g->q.c_off; t.d1 = (int8_t)(kw - pad); t.d2 = (int8_t)(-1);
+            t.d3 = (int8_t)(g->ndim == 3 ? kd - pad : 0); t.map = 0; t.pad = 0;
+            f.tap_index[nt] = (int8_t)((kd * k + kh) * k + kw);
+            ++nt;
+          }
+    } else {
+      for (int kd = 0; kd < kd_n; ++kd)
+        for (int kh = 0; kh < k; ++kh)
+          for (int kw = 0; kw < k; ++kw) {
+            WgTap& t = p.taps[nt];
+            t.c0 = (int16_t)g->q.c_off; t.d1 = (int8_t)(kw - pad); t.d2 = (int8_t)(kh - pad);
+            t.d3 = (int8_t)(g->ndim == 3 ? kd - pad : 0); t.map = 0; t.pad = 0;
+            f.tap_index[nt] = (int8_t)nt;
+            ++nt;
+          }
+    }
     p.taps_per_pass = k == 1 ? 1 : 3;
   } else {
     for (int ky = 0; ky < 4; ++ky)
       for (int kx = 0; kx < 4; ++kx) {
-        WgTap& t = p.taps[nt++];
+        WgTap& t = p.taps[nt];
         t.c0 = (int16_t)(kDownPar[kx] * g->q.cs + g->q.c_off); t.d1 = (int8_t)kDownD[kx]; t.d2 = (int8_t)kDownPar[ky];
         t.d3 = (int8_t)kDownD[ky]; t.map = 0; t.pad = 0;
+        f.tap_index[nt] = (int8_t)nt;
+        ++nt;
       }
     p.taps_per_pass = 4;
   }
   out->taps = nt;
   p.passes = nt / p.taps_per_pass;
-  const int p_bytes = p.p_chunks * 64 * p.p_rowb, q_bytes = p.q_chunks * 64 * p.q_rowb;
-  const int stage_bytes = (p_bytes + p.taps_per_pass * q_bytes + 1023) & ~1023;
+  const int p_bytes = p.p_chunks * p.kpix * p.p_rowb, q_bytes = p.q_chunks * p.q_box_bytes;
+  const int stage_bytes = (p_bytes + (p.halo ? 1 : p.taps_per_pass) * q_bytes + 1023) & ~1023;
   int stages = (kMaxDynSmem - 2048) / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages < 2) return fail(FO_ERR_INVALID, "wgrad stage does not fit");
@@ -509,8 +543,13 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
   if (splits > p.total_ptiles) splits = p.total_ptiles;
   p.splits = splits;
   p.partial = (float*)g->workspace;
+  {
+    const char* sk = getenv("FO_SKIP_MMA");
+    p.dbg_skip_mma = sk ? atoi(sk) : 0;
+    const char* st = getenv("FO_WG_STAGES");
+    if (st && atoi(st) >= 2 && atoi(st) <= p.stages) p.stages = atoi(st);
+  }
 
-  FinalizeParams& f = out->fin;
   f.partial = p.partial; f.dweight = g->dweight; f.splits = splits; f.taps = nt; f.MC = mc; f.NC = nc;
   f.m_real = g->p.c; f.n_real = g->q.c; f.dimB = g->dimB; f.m_axis = g->m_axis; f.q_w_off = g->q_w_off;
   f.accumulate = g->accumulate;
@@ -548,7 +587,7 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
       dims[0] = 2 * cs; dims[1] = g->w; dims[2] = 2; dims[3] = g->h; dims[4] = g->n;
       str[0] = 1; str[1] = 2 * cs; str[2] = W2 * cs; str[3] = 2 * W2 * cs; str[4] = H2 * W2 * cs;
     }
-    bx[0] = p.q_rowb / 2; bx[1] = box[0]; bx[2] = box[1]; bx[3] = box[2]; bx[4] = 1;
+    bx[0] = p.q_rowb / 2; bx[1] = box[0]; bx[2] = box[1] + (p.halo ? 2 : 0); bx[3] = box[2]; bx[4] = 1;
     int rc = encode_map(&out->maps.q[0], g->q.ptr, 5, dims, str, bx, p.q_rowb);
     if (rc != FO_OK) return rc;
     for (int i = 1; i < kMaxAMaps; ++i) out->maps.q[i] = out->maps.q[0];

@@ -118,8 +118,9 @@ __global__ void wgrad_finalize_kernel(FinalizeParams fp) {
     const float* src = fp.partial + (size_t)tap * per_tap + (size_t)m * fp.NC + n;
     float acc = 0.f;
     for (int s = 0; s < fp.splits; ++s) acc += src[(size_t)s * fp.taps * per_tap];
-    const size_t idx = fp.m_axis == 0 ? ((size_t)m * fp.dimB + (fp.q_w_off + n)) * fp.taps + tap
-                                      : ((size_t)(fp.q_w_off + n) * fp.dimB + m) * fp.taps + tap;
+    const int wt = fp.tap_index[tap];
+    const size_t idx = fp.m_axis == 0 ? ((size_t)m * fp.dimB + (fp.q_w_off + n)) * fp.taps + wt
+                                      : ((size_t)(fp.q_w_off + n) * fp.dimB + m) * fp.taps + wt;
     if (fp.accumulate) fp.dweight[idx] += acc; else fp.dweight[idx] = acc;
   }
 }

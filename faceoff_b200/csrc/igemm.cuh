@@ -78,13 +78,17 @@ struct WgradParams {
   int NC;                // Q-side channels per tap (UMMA N), multiple of 16, <= 128
   int q_chunks;
   int q_rowb;
+  int kpix;              // pixels per pipeline stage (64 or 128); kpix/16 MMAs per tap
+  int halo;              // 1: the taps of a pass are the 3 vertical taps read from ONE Q box of R+2 image rows
+  int q_tap_off;         // halo: byte offset between consecutive taps inside the Q box (one image row)
+  int q_box_bytes;       // bytes of one Q chunk box
   int taps_per_pass;     // <= kMaxWgTaps
   int passes;
   int splits;            // split-K factor over pixel tiles
   int total_ptiles;      // prod(tile_cnt)
   int stages;
   int p_c0;              // channel offset of the P side inside its map
-  int p_map_is_a0;       // unused, reserved
+  int dbg_skip_mma;      // debug: do not issue MMAs (pure TMA streaming rate)
   float* partial;        // [splits][passes*taps_per_pass][MC][NC] fp32
   WgTap taps[64];        // passes * taps_per_pass entries (padded entries have map = 255)
 };

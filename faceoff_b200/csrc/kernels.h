@@ -26,6 +26,7 @@ struct FinalizeParams {
   float* dweight;
   int splits, taps, MC, NC, m_real, n_real;
   int dimB, m_axis, q_w_off, accumulate;
+  int8_t tap_index[64];  // partial slot -> filter tap index in the PyTorch weight
 };
 
 // conv_igemm.cu / wgrad_igemm.cu

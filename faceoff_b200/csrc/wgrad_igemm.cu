@@ -10,26 +10,28 @@
 // (reference autograd of nn.Conv2d / ConvTranspose2d / Conv3d in models/vqvae_conv3d_latent.py:86-190.)
 //
 // grid = (splits, passes).  A CTA owns `taps_per_pass` taps (one 128 x NC fp32 accumulator each, all
-// resident in TMEM) and a contiguous range of 64-pixel tiles; per tile it loads P once and Q once per
-// tap.  Partials go to partial[split][tap][m][n]; wgrad_finalize (elementwise.cu) reduces the splits in a
-// fixed order (deterministic) and scatters into the PyTorch weight layout.
+// resident in TMEM) and a contiguous range of kpix-pixel tiles; per tile it loads P once and Q either once per
+// tap, or (3x3(x3) filters, "halo") ONCE as a box of R+2 image rows whose three vertical taps are read through
+// descriptors offset by one image row -- the same operand-reuse trick as conv_igemm.cu, which turns the kernel from
+// TMA-bound into MMA-bound.  Partials go to partial[split][slot][m][n]; wgrad_finalize (elementwise.cu) reduces the
+// splits in a fixed order (deterministic) and scatters into the PyTorch weight layout.
 #include "common.cuh"
 #include "igemm.cuh"
 
 namespace fo {
 
 constexpr int kWgThreads = 192;
-constexpr int kWgPix = 64;  // pixels per K step
 
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ WgradMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int p_chunk_bytes = kWgPix * p.p_rowb;
-  const int q_chunk_bytes = kWgPix * p.q_rowb;
+  const int p_chunk_bytes = p.kpix * p.p_rowb;
+  const int q_chunk_bytes = p.q_box_bytes;
   const int p_bytes = p.p_chunks * p_chunk_bytes;
-  const int q_bytes = p.q_chunks * q_chunk_bytes;  // per tap
-  const int stage_bytes = (p_bytes + p.taps_per_pass * q_bytes + 1023) & ~1023;
+  const int q_bytes = p.q_chunks * q_chunk_bytes;  // per Q load group (per tap, or per stage with halo)
+  const int q_loads = p.halo ? 1 : p.taps_per_pass;
+  const int stage_bytes = (p_bytes + q_loads * q_bytes + 1023) & ~1023;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + p.stages;
@@ -87,13 +89,13 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
         }
         mbar_wait(&empty_bar[stage], phase ^ 1);
         uint8_t* sp = smem + (size_t)stage * stage_bytes;
-        mbar_expect_tx(&full_bar[stage], p_bytes + p.taps_per_pass * q_bytes);
+        mbar_expect_tx(&full_bar[stage], p_bytes + q_loads * q_bytes);
         const int p_cw = p.p_rowb / 2;
         for (int c = 0; c < p.p_chunks; ++c)
           tma_load_5d(sp + c * p_chunk_bytes, &maps.p, &full_bar[stage], p.p_c0 + c * p_cw, base[0], base[1], base[2],
                       base[3]);
         const int q_cw = p.q_rowb / 2;
-        for (int tp = 0; tp < p.taps_per_pass; ++tp) {
+        for (int tp = 0; tp < q_loads; ++tp) {
           const WgTap w = taps[tp];
           uint8_t* sq = sp + p_bytes + tp * q_bytes;
           for (int c = 0; c < p.q_chunks; ++c)
@@ -107,7 +109,9 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
     const uint32_t idesc = make_idesc_bf16(128, p.NC, 1, 1);
     const uint64_t a_desc_base = make_smem_desc(0, p.p_rowb, p.p_chunks > 1 ? p_chunk_bytes : 0);
     const uint64_t b_desc_base = make_smem_desc(0, p.q_rowb, p.q_chunks > 1 ? q_chunk_bytes : 0);
-    const uint32_t q16 = q_bytes >> 4, pk16 = (16 * p.p_rowb) >> 4, qk16 = (16 * p.q_rowb) >> 4;
+    const uint32_t q16 = (p.halo ? p.q_tap_off : q_bytes) >> 4, pk16 = (16 * p.p_rowb) >> 4, qk16 = (16 * p.q_rowb) >> 4;
+    const int n_taps = p.dbg_skip_mma ? 0 : p.taps_per_pass;
+    const int kk_n = p.kpix / 16;
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_my; ++i) {
@@ -117,14 +121,20 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
         const uint32_t sp = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint64_t a0 = a_desc_base + ((sp & 0x3FFFF) >> 4);
         const uint64_t b0 = b_desc_base + (((sp + p_bytes) & 0x3FFFF) >> 4);
-        for (int tp = 0; tp < p.taps_per_pass; ++tp) {
+        for (int tp = 0; tp < n_taps; ++tp) {
           const uint64_t bt = b0 + (uint32_t)(tp * q16);
           const uint32_t dt = tmem_base + tp * p.NC;
-          // 64 pixels = four K=16 MMAs; 16 pixels = two 8-row swizzle groups = 16 * rowb bytes
+          // 16 pixels per MMA = two 8-row swizzle groups = 16 * rowb bytes
           umma_bf16(dt, a0, bt, idesc, i != 0);
           umma_bf16(dt, a0 + pk16, bt + qk16, idesc, 1);
           umma_bf16(dt, a0 + 2 * pk16, bt + 2 * qk16, idesc, 1);
           umma_bf16(dt, a0 + 3 * pk16, bt + 3 * qk16, idesc, 1);
+          if (kk_n == 8) {
+            umma_bf16(dt, a0 + 4 * pk16, bt + 4 * qk16, idesc, 1);
+            umma_bf16(dt, a0 + 5 * pk16, bt + 5 * qk16, idesc, 1);
+            umma_bf16(dt, a0 + 6 * pk16, bt + 6 * qk16, idesc, 1);
+            umma_bf16(dt, a0 + 7 * pk16, bt + 7 * qk16, idesc, 1);
+          }
         }
         umma_commit(&empty_bar[stage]);
         if (i == n_my - 1) umma_commit(done_bar);
@@ -173,9 +183,9 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
 }
 
 size_t wgrad_smem_bytes(const WgradParams& p) {
-  const int p_bytes = p.p_chunks * kWgPix * p.p_rowb;
-  const int q_bytes = p.q_chunks * kWgPix * p.q_rowb;
-  const int stage_bytes = (p_bytes + p.taps_per_pass * q_bytes + 1023) & ~1023;
+  const int p_bytes = p.p_chunks * p.kpix * p.p_rowb;
+  const int q_bytes = p.q_chunks * p.q_box_bytes;
+  const int stage_bytes = (p_bytes + (p.halo ? 1 : p.taps_per_pass) * q_bytes + 1023) & ~1023;
   return (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
 }
 
