@@ -349,7 +349,15 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   p.num_ksteps = nk;
   out->ktot = n_pack * kc;
   const int stage_bytes = (p.a_bytes + p.TPS * p.NT * rowb + 1023) & ~1023;
-  int stages = (kMaxDynSmem - 2048) / stage_bytes;
+  // shared memory: pipeline stages + (optionally) the epilogue's prefetched mask / addend rows
+  const int avail = kMaxDynSmem - 2048 - 1024 - 8 * 32 * 80;
+  const int n_e = (c->mask != nullptr ? 1 : 0) + (c->addend != nullptr ? 1 : 0);
+  const int e_one = n_e * 128 * (p.NT * 2 + 16);
+  p.e_bufs = 0;
+  if (n_e > 0 && !nchw && c->out_f32 == nullptr && p.NT % 32 == 0 && p.n_tiles == 1) {
+    if ((avail - p.MT * e_one) / stage_bytes >= 2) p.e_bufs = p.MT;   // one buffer set per M sub-tile (warp group)
+  }
+  int stages = (avail - p.e_bufs * e_one) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(FO_ERR_INVALID, "tile does not fit in shared memory");
   p.stages = stages;

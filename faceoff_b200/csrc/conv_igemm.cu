@@ -10,10 +10,11 @@
 //     (space-to-depth) view of the same memory; torch.cat inputs are just K steps on another map,
 //   * a packed bf16 weight matrix [Cout][K steps * KC] in the same K-step order.
 //
-// Warp roles (192 threads, 1 CTA / SM, persistent over tiles):
+// Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0      TMA producer      (one A box + TPS B boxes [NT x KC] per stage, 128B/64B/32B swizzle)
 //   warp 1      MMA issuer        (lane 0 issues tcgen05.mma kind::f16 BF16xBF16->FP32, M=128, N=NT)
-//   warps 2..5  epilogue          (tcgen05.ld -> +bias -> *mask -> +addend -> relu -> bf16/fp32 stores)
+//   warps 2..9  epilogue          (tcgen05.ld -> +bias -> *mask -> +addend -> relu -> bf16/fp32 stores); warps 2-5 own
+//                                 M sub-tile 0, warps 6-9 sub-tile 1 (two warps per scheduler hide each other's latency)
 // TMEM holds two sets of accumulators (2 x MT x NT columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
 // The kernel is L2->SM bandwidth bound (about 32 B/clk/SM are available, a 128x128x64 MMA step wants 128 B/clk when A
@@ -27,7 +28,7 @@
 
 namespace fo {
 
-constexpr int kConvThreads = 192;
+constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of sub-tile 0, warps 6-9 of sub-tile 1
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& g, int& nt, int (&base)[4]) {
   // n-tile fastest so CTAs that share an A tile run concurrently and hit L2
@@ -131,6 +132,103 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
   }
 }
 
+// Coalesced variant for full 32-column chunks of channels-last bf16 tensors.  TMEM gives each lane one pixel row, but
+// a pixel's channels are contiguous in memory, so lane-per-row accesses touch 32 different lines per instruction.
+// Every tensor access therefore goes through a per-warp shared-memory transpose: 8 rows x 64 B per instruction
+// (full 32-byte sectors, 4 lanes per row).  stg: this warp's staging buffer, 32 rows x 80 B (16 B pad: conflict-free).
+// roff / rvalid: element offset and validity of row i*8 + lane/4 (i = 0..3), shuffled once per tile.
+constexpr int kStgPitch = 80;
+__device__ __forceinline__ void stage_load_rows(const __nv_bfloat16* src, int col0, const long long (&roff)[4],
+                                                const bool (&rvalid)[4], uint8_t* stg, int lane, uint32_t (&w)[16]) {
+  const int piece = lane & 3, r0 = lane >> 2;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (rvalid[i]) v = __ldg(reinterpret_cast<const uint4*>(src + roff[i] + col0) + piece);
+    *reinterpret_cast<uint4*>(stg + (i * 8 + r0) * kStgPitch + piece * 16) = v;
+  }
+  __syncwarp();
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + lane * kStgPitch + q * 16);
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ void stage_store_rows(__nv_bfloat16* dst, int col0, const long long (&roff)[4],
+                                                 const bool (&rvalid)[4], uint8_t* stg, int lane,
+                                                 const uint32_t (&w)[16]) {
+  const int piece = lane & 3, r0 = lane >> 2;
+#pragma unroll
+  for (int q = 0; q < 4; ++q)
+    *reinterpret_cast<uint4*>(stg + lane * kStgPitch + q * 16) = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint4 v = *reinterpret_cast<const uint4*>(stg + (i * 8 + r0) * kStgPitch + piece * 16);
+    if (rvalid[i]) *(reinterpret_cast<uint4*>(dst + roff[i] + col0) + piece) = v;
+  }
+  __syncwarp();
+}
+
+__device__ __forceinline__ void load_prefetched(const uint8_t* erow, int cbytes, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const uint4 v = *reinterpret_cast<const uint4*>(erow + cbytes + q * 16);
+    w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+  }
+}
+
+// e_mask / e_add: this lane's row in the prefetched (cp.async) copies of the mask / addend tile, or null.
+__device__ __forceinline__ void epilogue_chunk32_coalesced(const ConvParams& p, const uint32_t (&v)[32], int col0,
+                                                           int ccol, const long long (&roff)[4],
+                                                           const bool (&rvalid)[4], uint8_t* stg, int lane,
+                                                           const uint8_t* e_mask, const uint8_t* e_add,
+                                                           const float* s_bias) {
+  float f[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+  if (s_bias != nullptr) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const float4 b = *reinterpret_cast<const float4*>(s_bias + ccol + 4 * q);
+      f[4 * q] += b.x; f[4 * q + 1] += b.y; f[4 * q + 2] += b.z; f[4 * q + 3] += b.w;
+    }
+  } else if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) f[j] += __ldg(p.bias + col0 + j);
+  }
+  uint32_t w[16];
+  if (p.mask != nullptr) {
+    if (e_mask != nullptr) load_prefetched(e_mask, ccol * 2, w);
+    else stage_load_rows(p.mask, col0, roff, rvalid, stg, lane, w);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      if (!(bf16lo(w[e]) > 0.f)) f[2 * e] = 0.f;
+      if (!(bf16hi(w[e]) > 0.f)) f[2 * e + 1] = 0.f;
+    }
+  }
+  if (p.addend != nullptr) {
+    if (e_add != nullptr) load_prefetched(e_add, ccol * 2, w);
+    else stage_load_rows(p.addend, col0, roff, rvalid, stg, lane, w);
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      f[2 * e] += bf16lo(w[e]);
+      f[2 * e + 1] += bf16hi(w[e]);
+    }
+  }
+  if (p.out_bf16 != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(f[2 * e], f[2 * e + 1]);
+    stage_store_rows(p.out_bf16, col0, roff, rvalid, stg, lane, w);
+  }
+  if (p.out_relu != nullptr) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) w[e] = pack_bf16x2(fmaxf(f[2 * e], 0.f), fmaxf(f[2 * e + 1], 0.f));
+    stage_store_rows(p.out_relu, col0, roff, rvalid, stg, lane, w);
+  }
+}
+
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ ConvMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -146,6 +244,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   uint64_t* tfull_bar = bars + 2 * p.stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);        // [256] bias of the (single) N tile
+  uint8_t* stg_all = reinterpret_cast<uint8_t*>(s_bias + 256);   // 8 epilogue warps x 32 rows x 80 B
+  uint8_t* e_all = stg_all + 8 * 32 * kStgPitch;                // prefetched mask / addend rows (see epilogue)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -167,10 +268,13 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4);
+      mbar_init(&tempty_bar[b], 4 * p.MT);
     }
     fence_mbar_init();
   }
+  const bool bias_in_smem = p.bias != nullptr && p.n_tiles == 1;
+  if (bias_in_smem)
+    for (int i = threadIdx.x; i < p.NT; i += blockDim.x) s_bias[i] = p.bias[i];
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -252,35 +356,99 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
     }
-  } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+  } else if (warp - 2 < 4 * p.MT) {
+    // ------------------------------------------------------------------ epilogue (warps 2..5: sub-tile 0, 6..9: 1)
+    const int my_m = (warp - 2) >> 2;       // M sub-tile owned by this warp
     const int quarter = warp & 3;           // TMEM lane quarter this warp may access
     const int row = quarter * 32 + lane;    // pixel row inside the 128-row sub-tile
+    uint8_t* stg = stg_all + (warp - 2) * (32 * kStgPitch);
+    // bf16 channels-last tensors only (fp32 outputs keep the per-lane path)
+    const bool coalesced = p.out_f32 == nullptr && p.out_cstride == 1;
+    // Epilogue operand prefetch.  The mask / addend tiles are the only *loads* of the epilogue; with 4 warps of
+    // dependent load->use chains they would be latency bound (~8 KB in flight per SM).  Each warp therefore copies its 32
+    // rows of every such tile into shared memory with cp.async BEFORE waiting for the accumulator, i.e. overlapped with
+    // the MMAs of the tile (fully coalesced: 16 lanes x 16 B per row), and later reads its own row back (pitch
+    // NT*2+16 B: conflict-free).
+    const int e_pitch = p.NT * 2 + 16;
+    const int e_warp_bytes = 32 * e_pitch;
+    const int n_e = (p.mask != nullptr ? 1 : 0) + (p.addend != nullptr ? 1 : 0);
+    const bool prefetch = coalesced && p.e_bufs > 0 && n_e > 0;
+    // layout: [e_buf][tensor][warp quarter][32 rows][pitch]
+    auto e_ptr = [&](int ebuf, int tensor) -> uint8_t* {
+      return e_all + ((size_t)(ebuf * n_e + tensor) * 4 + quarter) * e_warp_bytes;
+    };
+    const int pieces = p.NT * 2 / 16;            // 16-byte pieces per row
+    auto issue_prefetch = [&](int ebuf, long long my_off, bool my_valid, int ncol0) {
+      // lane L owns row L of this warp; rows are fetched cooperatively, 32/pieces... rows per instruction
+      for (int idx = lane; idx < 32 * pieces; idx += 32) {
+        const int r = idx / pieces, pc = idx % pieces;
+        const long long o = __shfl_sync(0xffffffffu, my_off, r);
+        const bool ok = __shfl_sync(0xffffffffu, (int)my_valid, r) != 0;
+        int t = 0;
+        if (p.mask != nullptr) {
+          if (ok) cp_async16(e_ptr(ebuf, t) + r * e_pitch + pc * 16, p.mask + o + ncol0 + pc * 8);
+          ++t;
+        }
+        if (p.addend != nullptr) {
+          if (ok) cp_async16(e_ptr(ebuf, t) + r * e_pitch + pc * 16, p.addend + o + ncol0 + pc * 8);
+        }
+      }
+      cp_async_commit();
+    };
+    auto row_geometry = [&](const int (&base)[4], int g, int m, long long& off, bool& valid) {
+      const int rg = m * 128 + row;
+      const int b1 = rg % p.box[0];
+      const int b2 = (rg / p.box[0]) % p.box[1];
+      const int b3 = (rg / (p.box[0] * p.box[1])) % p.box[2];
+      const int b4 = rg / (p.box[0] * p.box[1] * p.box[2]);
+      const int c1 = base[0] + b1, c2 = base[1] + b2, c3 = base[2] + b3, c4 = base[3] + b4;
+      valid = (c1 < p.lim[0]) && (c2 < p.lim[1]) && (c3 < p.lim[2]) && (c4 < p.lim[3]);
+      off = p.out_off[g] + c1 * p.out_stride[0] + c2 * p.out_stride[1] + c3 * p.out_stride[2] + c4 * p.out_stride[3];
+    };
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       int g, nt, base[4];
       decode_tile(p, tile, g, nt, base);
+      const int ncol0 = nt * p.NT;
+      long long off;
+      bool valid;
+      row_geometry(base, g, my_m, off, valid);
+      const int ebuf = my_m;
+      if (prefetch) issue_prefetch(ebuf, off, valid, ncol0);   // buffer was last read by this warp in the previous tile
       mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
       tc_fence_after();
-      const int ncol0 = nt * p.NT;
-      for (int m = 0; m < p.MT; ++m) {
-        const int rg = m * 128 + row;
-        const int b1 = rg % p.box[0];
-        const int b2 = (rg / p.box[0]) % p.box[1];
-        const int b3 = (rg / (p.box[0] * p.box[1])) % p.box[2];
-        const int b4 = rg / (p.box[0] * p.box[1] * p.box[2]);
-        const int c1 = base[0] + b1, c2 = base[1] + b2, c3 = base[2] + b3, c4 = base[3] + b4;
-        const bool valid = (c1 < p.lim[0]) && (c2 < p.lim[1]) && (c3 < p.lim[2]) && (c4 < p.lim[3]);
-        const long long off = p.out_off[g] + c1 * p.out_stride[0] + c2 * p.out_stride[1] + c3 * p.out_stride[2] +
-                              c4 * p.out_stride[3];
+      {
+        const int m = my_m;
+        if (prefetch) {
+          cp_async_wait_all();
+          __syncwarp();
+        }
+        const uint8_t* e_mask = nullptr;
+        const uint8_t* e_add = nullptr;
+        if (prefetch) {
+          int t = 0;
+          if (p.mask != nullptr) e_mask = e_ptr(ebuf, t++) + lane * e_pitch;
+          if (p.addend != nullptr) e_add = e_ptr(ebuf, t) + lane * e_pitch;
+        }
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * p.MT + m) * p.NT;
+        // rows handled by this lane in the transposed (coalesced) accesses
+        long long roff[4];
+        bool rvalid[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          roff[i] = __shfl_sync(0xffffffffu, off, i * 8 + (lane >> 2));
+          rvalid[i] = __shfl_sync(0xffffffffu, (int)valid, i * 8 + (lane >> 2)) != 0;
+        }
         int c = 0;
         for (; c + 32 <= p.NT; c += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c, v);
           tmem_ld_wait();
-          epilogue_chunk<32>(p, v, ncol0 + c, valid, off);
+          if (coalesced && ncol0 + c + 32 <= p.c_store)
+            epilogue_chunk32_coalesced(p, v, ncol0 + c, c, roff, rvalid, stg, lane, e_mask, e_add,
+                                       bias_in_smem ? s_bias : nullptr);
+          else epilogue_chunk<32>(p, v, ncol0 + c, valid, off);
         }
         for (; c + 16 <= p.NT; c += 16) {
           uint32_t v[16];
@@ -306,7 +474,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
 size_t conv_smem_bytes(const ConvParams& p) {
   const int rowb = p.KC * 2;
   const int stage_bytes = (p.a_bytes + p.TPS * p.NT * rowb + 1023) & ~1023;
-  return (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024;
+  const int n_e = (p.mask != nullptr ? 1 : 0) + (p.addend != nullptr ? 1 : 0);
+  return (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024 + 8 * 32 * 80 +
+         (size_t)p.e_bufs * n_e * 128 * (p.NT * 2 + 16) + 1024;
 }
 
 cudaError_t launch_conv_igemm(const ConvParams& p, const ConvMaps& maps, int num_sms, cudaStream_t stream) {
