@@ -542,7 +542,7 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
   p.passes = nt / p.taps_per_pass;
   const int p_bytes = p.p_chunks * p.kpix * p.p_rowb, q_bytes = p.q_chunks * p.q_box_bytes;
   const int stage_bytes = (p_bytes + (p.halo ? 1 : p.taps_per_pass) * q_bytes + 1023) & ~1023;
-  int stages = (kMaxDynSmem - 2048) / stage_bytes;
+  int stages = (kMaxDynSmem - 2048 - 8192) / stage_bytes;   // 8 KB: all-ones tile of the fused bias gradient + alignment
   if (stages > 6) stages = 6;
   if (stages < 2) return fail(FO_ERR_INVALID, "wgrad stage does not fit");
   p.stages = stages;
@@ -607,7 +607,8 @@ extern "C" size_t fo_wgrad_workspace_bytes(const fo_wgrad_t* g) {
   if (fo_init() != FO_OK) return 0;
   static thread_local WgradPlan plan;
   if (plan_wgrad(g, &plan, false) != FO_OK) return 0;
-  return (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float);
+  return (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float) +
+         (size_t)plan.p.passes * plan.p.splits * plan.p.MC * sizeof(float);
 }
 
 extern "C" int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream) {
@@ -615,11 +616,20 @@ extern "C" int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream) {
   static thread_local WgradPlan plan;
   int rc = plan_wgrad(g, &plan, true);
   if (rc != FO_OK) return rc;
-  const size_t need = (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float);
+  const size_t main_bytes = (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float);
+  const size_t need = main_bytes + (size_t)plan.p.passes * plan.p.splits * plan.p.MC * sizeof(float);
   if (g->workspace == nullptr || g->workspace_bytes < need)
     return fail(FO_ERR_INVALID, "wgrad workspace too small: %zu < %zu", g->workspace_bytes, need);
+  plan.p.bias_partial = nullptr;
+  if (g->dbias != nullptr) {
+    if (plan.p.taps_per_pass * plan.p.NC + 16 > 512) return fail(FO_ERR_INVALID, "wgrad: no TMEM room for the fused bias gradient");
+    plan.p.bias_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g->workspace) + main_bytes);
+  }
   CUDA_TRY(launch_wgrad_igemm(plan.p, plan.maps, (cudaStream_t)stream));
   CUDA_TRY(launch_wgrad_finalize(plan.fin, g_num_sms, (cudaStream_t)stream));
+  if (g->dbias != nullptr)
+    CUDA_TRY(launch_bias_finalize(plan.p.bias_partial, plan.p.passes * plan.p.splits, plan.p.MC, g->p.c, g->dbias, g->dbias_accumulate,
+                                  (cudaStream_t)stream));
   return FO_OK;
 }
 

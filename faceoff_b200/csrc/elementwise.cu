@@ -125,6 +125,16 @@ __global__ void wgrad_finalize_kernel(FinalizeParams fp) {
   }
 }
 
+// bias gradient from the wgrad kernel's column-sum partials: out[c] (+)= sum_splits part[s][c]
+__global__ void bias_finalize_kernel(const float* __restrict__ part, int splits, int mc, int c, float* __restrict__ out,
+                                     int accumulate) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= c) return;
+  float s = 0.f;
+  for (int k = 0; k < splits; ++k) s += part[(size_t)k * mc + i];
+  if (accumulate) out[i] += s; else out[i] = s;
+}
+
 // ---------------------------------------------------------------- column sums (bias gradients)
 // x bf16 [rows, cs]; each block strides over rows; thread owns an 8-channel vector lane.
 __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, size_t rows, int cs, float* __restrict__ part) {
@@ -348,6 +358,11 @@ cudaError_t launch_pack_weights(const float* w, void* out, const PackParams& pp,
 cudaError_t launch_wgrad_finalize(const FinalizeParams& fp, int num_sms, cudaStream_t st) {
   const size_t total = (size_t)fp.taps * fp.m_real * fp.n_real;
   wgrad_finalize_kernel<<<grid_for(total, 256, num_sms), 256, 0, st>>>(fp);
+  return cudaGetLastError();
+}
+cudaError_t launch_bias_finalize(const float* part, int splits, int mc, int c, float* out, int accumulate,
+                                 cudaStream_t st) {
+  bias_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(part, splits, mc, c, out, accumulate);
   return cudaGetLastError();
 }
 int colsum_blocks(int num_sms) { return num_sms * 4; }

@@ -91,6 +91,7 @@ struct WgradParams {
   int p_c0;              // channel offset of the P side inside its map
   int dbg_skip_mma;      // debug: do not issue MMAs (pure TMA streaming rate)
   float* partial;        // [splits][passes*taps_per_pass][MC][NC] fp32
+  float* bias_partial;   // [passes][splits][MC] partial column sums of P (= bias gradient) or null
   WgTap taps[64];        // passes * taps_per_pass entries (padded entries have map = 255)
 };
 struct WgradMaps {

@@ -44,6 +44,8 @@ cudaError_t launch_unpack_nchw(const void* x, float* out, int n, int c, int hw, 
 cudaError_t launch_relu(const void* x, void* y, size_t numel, int num_sms, cudaStream_t st);
 cudaError_t launch_pack_weights(const float* w, void* out, const PackParams& pp, int num_sms, cudaStream_t st);
 cudaError_t launch_wgrad_finalize(const FinalizeParams& fp, int num_sms, cudaStream_t st);
+cudaError_t launch_bias_finalize(const float* part, int splits, int mc, int c, float* out, int accumulate,
+                                 cudaStream_t st);
 int colsum_blocks(int num_sms);
 cudaError_t launch_colsum(const void* x, size_t rows, int cs, int c_off, int c, float* out, int accumulate,
                           float* workspace, int num_sms, cudaStream_t st);

@@ -37,14 +37,28 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
   uint64_t* empty_bar = bars + p.stages;
   uint64_t* done_bar = bars + 2 * p.stages;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done_bar + 1);
+  // all-ones MN-major B tile [kpix pixels x 16] (32-byte rows): one extra N=16 MMA per K step turns the tensor core
+  // into a column-sum unit, so the bias gradient sum_pix dy[pix][m] comes for free with the weight gradient
+  uint8_t* ones_tile = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(tmem_ptr + 4) + 1023) & ~uintptr_t(1023));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.taps_per_pass * p.NC) tmem_cols <<= 1;
+  while ((int)tmem_cols < p.taps_per_pass * p.NC + (p.bias_partial != nullptr ? 16 : 0)) tmem_cols <<= 1;
 
   const int split = blockIdx.x;
   const int pass = blockIdx.y;
+  // the column-sum MMAs are spread round-robin over the passes (pass p takes pixel tiles i with i % passes == p) so no
+  // CTA becomes a straggler
+  const bool do_bias = p.bias_partial != nullptr;
+  const int bias_col = p.taps_per_pass * p.NC;   // TMEM column of the bias accumulator
+  if (do_bias) {
+    const uint32_t one2 = 0x3F803F80u;  // bf16 (1.0, 1.0)
+    for (int i = threadIdx.x; i < p.kpix * 32 / 16; i += blockDim.x)
+      reinterpret_cast<uint4*>(ones_tile)[i] = make_uint4(one2, one2, one2, one2);
+    fence_proxy_async();
+  }
   // contiguous range of pixel tiles for this split
   const int per = (p.total_ptiles + p.splits - 1) / p.splits;
   const int t_begin = split * per;
@@ -112,6 +126,8 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
     const uint32_t q16 = (p.halo ? p.q_tap_off : q_bytes) >> 4, pk16 = (16 * p.p_rowb) >> 4, qk16 = (16 * p.q_rowb) >> 4;
     const int n_taps = p.dbg_skip_mma ? 0 : p.taps_per_pass;
     const int kk_n = p.kpix / 16;
+    const uint32_t idesc_bias = make_idesc_bf16(128, 16, 1, 1);
+    const uint64_t ones_desc = make_smem_desc(smem_u32(ones_tile), 32, 0);
     int stage = 0;
     uint32_t phase = 0;
     for (int i = 0; i < n_my; ++i) {
@@ -135,6 +151,10 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
             umma_bf16(dt, a0 + 6 * pk16, bt + 6 * qk16, idesc, 1);
             umma_bf16(dt, a0 + 7 * pk16, bt + 7 * qk16, idesc, 1);
           }
+        }
+        if (do_bias && (i % p.passes) == pass) {
+          for (int kk = 0; kk < kk_n; ++kk)
+            umma_bf16(tmem_base + bias_col, a0 + kk * pk16, ones_desc + kk * 32, idesc_bias, (i >= p.passes) | (kk != 0));
         }
         umma_commit(&empty_bar[stage]);
         if (i == n_my - 1) umma_commit(done_bar);
@@ -172,6 +192,16 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
         }
       }
     }
+    if (do_bias) {
+      uint32_t v[16];
+      if (n_my > pass) {   // this CTA issued at least one column-sum MMA
+        tmem_ld16(tmem_base + ((uint32_t)(quarter * 32) << 16) + bias_col, v);
+        tmem_ld_wait();
+      } else {
+        v[0] = 0u;
+      }
+      if (row < p.MC) p.bias_partial[((size_t)pass * p.splits + split) * p.MC + row] = __uint_as_float(v[0]);
+    }
   }
 
   tc_fence_before();
@@ -186,7 +216,7 @@ size_t wgrad_smem_bytes(const WgradParams& p) {
   const int p_bytes = p.p_chunks * p.kpix * p.p_rowb;
   const int q_bytes = p.q_chunks * p.q_box_bytes;
   const int stage_bytes = (p_bytes + (p.halo ? 1 : p.taps_per_pass) * q_bytes + 1023) & ~1023;
-  return (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024;
+  return (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024 + 1024 + 128 * 32;
 }
 
 cudaError_t launch_wgrad_igemm(const WgradParams& p, const WgradMaps& maps, cudaStream_t stream) {

@@ -142,23 +142,28 @@ def conv_op(tape: Tape, form: int, ksize: int, srcs: Sequence[View], wname: str,
         assert out.g is not None, f"no gradient reached {wname}"
         gt, g_off = out.g
         dy = (shaped(gt), cout, g_off)
-        # bias gradient
-        if bias and param_grad:
-            gb, acc = tape.grad_buffer(wname + ".bias")
-            ops.colsum(gt, cout, gb, c_off=g_off, accumulate=acc)
-        # weight gradient, one launch per concatenated source
+        # weight gradient (one launch per concatenated source) with the bias gradient fused into the first launch when
+        # P = dy (the tensor core sums dy's columns with an all-ones operand); ConvTranspose2d keeps the column-sum kernel
         gw, acc = tape.grad_buffer(wname + ".weight") if param_grad else (None, False)
+        gb, bacc = tape.grad_buffer(wname + ".bias") if (bias and param_grad) else (None, False)
+        fused_bias_ok = form == FORM_S1 or (form == FORM_DOWN and 4 * pad16(srcs[0].node.c) + 16 <= 512)
+        if gb is not None and not fused_bias_ok:
+            ops.colsum(gt, cout, gb, c_off=g_off, accumulate=bacc)
+            gb = None
         w_off = 0
         for v, s in zip(srcs, src_list):
             if not param_grad:
                 break
             if form == FORM_S1:
-                ops.wgrad(FORM_S1, ndim, ksize, dy, s, gw, m_axis=0, q_w_off=w_off, accumulate=acc)
+                ops.wgrad(FORM_S1, ndim, ksize, dy, s, gw, m_axis=0, q_w_off=w_off, accumulate=acc, dbias=gb,
+                          dbias_accumulate=bacc)
             elif form == FORM_DOWN:
-                ops.wgrad(FORM_DOWN, 2, 4, dy, s, gw, m_axis=0, q_w_off=w_off, accumulate=acc)
+                ops.wgrad(FORM_DOWN, 2, 4, dy, s, gw, m_axis=0, q_w_off=w_off, accumulate=acc, dbias=gb,
+                          dbias_accumulate=bacc)
             else:  # FORM_UP / ConvTranspose2d weight [cin, cout]: P = x (low res), Q = dy (hi res)
                 assert len(srcs) == 1
                 ops.wgrad(FORM_DOWN, 2, 4, s, dy, gw, m_axis=0, q_w_off=0, accumulate=acc)
+            gb = None
             w_off += v.node.c
         if param_grad:
             tape.grad_ready(wname + ".weight")

@@ -106,6 +106,8 @@ typedef struct {
   int m_axis;           /* which weight axis the P channels index (0 or 1) */
   int q_w_off;          /* channel offset of Q's channels on the other weight axis (torch.cat second source) */
   int accumulate;
+  float* dbias;         /* optional: fp32 [p.c] bias gradient = column sums of P (fused: one extra N=16 MMA per K step) */
+  int dbias_accumulate;
   void* workspace;      /* split-K partials */
   size_t workspace_bytes;
 } fo_wgrad_t;

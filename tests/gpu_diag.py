@@ -222,9 +222,11 @@ def case_wgrad():
         gy = bf(rnd(n, cout, h, w, seed=4))
         F.conv2d(x, wt, None, padding=(k - 1) // 2).backward(gy)
         dw = torch.full_like(wt, 7.0).detach()
-        ops.wgrad(ops.FORM_S1, 2, k, (to_cl(gy), cout, 0), (to_cl(x), cin, 0), dw, m_axis=0)
+        db = torch.full((cout,), 3.0, device=dev)
+        ops.wgrad(ops.FORM_S1, 2, k, (to_cl(gy), cout, 0), (to_cl(x), cin, 0), dw, m_axis=0, dbias=db)
         torch.cuda.synchronize()
         ok &= report(f"wgrad s1 {cin}->{cout} k{k} n{n} {h}x{w}", dw, wt.grad)
+        ok &= report(f"   fused bias grad", db, gy.sum((0, 2, 3)), tol=1e-4)
     # conv3d
     n, d, h, w, c = 1, 4, 16, 16, 128
     x = bf(rnd(n, c, d, h, w, seed=1))
@@ -243,9 +245,12 @@ def case_wgrad():
         gy = bf(rnd(*y.shape, seed=4))
         y.backward(gy)
         dw = torch.zeros_like(wt).detach()
-        ops.wgrad(ops.FORM_DOWN, 2, 4, (to_cl(gy), cout, 0), (to_cl(x), cin, 0), dw, m_axis=0)
+        db = torch.ones(cout, device=dev)
+        ops.wgrad(ops.FORM_DOWN, 2, 4, (to_cl(gy), cout, 0), (to_cl(x), cin, 0), dw, m_axis=0, dbias=db,
+                  dbias_accumulate=True)
         torch.cuda.synchronize()
         ok &= report(f"wgrad down {cin}->{cout}", dw, wt.grad)
+        ok &= report(f"   fused bias grad (accumulate)", db, 1 + gy.sum((0, 2, 3)), tol=1e-4)
     # transposed conv: P = x (low res), Q = dy (hi res), weight [cin, cout, 4, 4]
     for (n, h, w, cin, cout) in [(2, 16, 16, 128, 64), (2, 32, 32, 64, 6)]:
         x = bf(rnd(n, cin, h, w, seed=1))
