@@ -34,6 +34,13 @@ class _StatSink:
         q.apply_ema(counts, embed_sum)
 
 
+class _LocalStatSink(_StatSink):
+    """No collective: EMA from this process's statistics only (single-process runs inside a multi-rank job)."""
+
+    def submit(self, q, counts, embed_sum):
+        q.apply_ema(counts, embed_sum)
+
+
 _default_sink = _StatSink()
 
 
