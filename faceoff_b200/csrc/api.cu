@@ -124,7 +124,7 @@ static int encode_map(CUtensorMap* m, const void* ptr, int rank, const uint64_t*
 static int pow2_floor(int v) { int p = 1; while (p * 2 <= v) p *= 2; return p; }
 static int pow2_ceil(int v) { int p = 1; while (p < v) p *= 2; return p; }
 // choose box extents (powers of two, product == positions) over the tile domain ext[0..3]
-static void choose_box(const int ext[4], int positions, int box[4]) {
+static void choose_box(const int ext[4], int positions, int box[4], int max_first = 128) {
   int rem = positions;
   int last_used = 0;
   for (int d = 0; d < 4; ++d) {
@@ -133,6 +133,7 @@ static void choose_box(const int ext[4], int positions, int box[4]) {
       const int pf = pow2_floor(ext[d]);
       b = (ext[d] % pf == 0) ? pf : pow2_ceil(ext[d]);
       if (b > rem) b = rem;
+      if (d == 0 && b > max_first) b = max_first;   // keep >= 2 image rows per 256-position tile (halo stages)
       last_used = d;
     }
     box[d] = b;
@@ -176,9 +177,11 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   const int rowb = kc * 2;
   // N tiling
   const int cout_pad = (c->cout + 15) / 16 * 16;
-  if (cout_pad <= 256) { p.NT = cout_pad; p.n_tiles = 1; }
-  else if (cout_pad % 256 == 0) { p.NT = 256; p.n_tiles = cout_pad / 256; }
+  // N tiles of 128 columns whenever cout is a multiple of 128: two M=128 sub-tiles x 128 columns fill TMEM (2 x 2 x 128)
+  // and allow the halo / 256-position tiling below; the A tile is re-read per N tile from L2.
+  if (cout_pad <= 128) { p.NT = cout_pad; p.n_tiles = 1; }
   else if (cout_pad % 128 == 0) { p.NT = 128; p.n_tiles = cout_pad / 128; }
+  else if (cout_pad <= 256) { p.NT = cout_pad; p.n_tiles = 1; }
   else return fail(FO_ERR_INVALID, "cout %d unsupported", c->cout);
   out->npad = p.NT * p.n_tiles;
 
@@ -202,7 +205,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   p.MT = 1;
   p.TPS = 1;
   bool halo = false;
-  if (p.n_tiles == 1 && p.NT <= 128) {
+  if (p.NT <= 128) {
     int b2[4];
     choose_box(ext, 256, b2);
     long long tiles256 = 1;
@@ -212,12 +215,13 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
       if (b2[d] > 1 && b2[d] > pow2_ceil(ext[d])) exact = false;
     }
     const int sms = g_num_sms > 0 ? g_num_sms : 148;
-    if (exact && tiles256 >= 2LL * sms) {
+    if (exact && tiles256 * p.n_tiles >= 2LL * sms) {
       p.MT = 2;
       for (int d = 0; d < 4; ++d) box[d] = b2[d];
       const int tap_off = box[0] * rowb;
+      const int halo_stage = box[0] * (box[1] + 2) * rowb + 3 * p.NT * rowb;
       if (s1 && c->ksize == 3 && box[2] == 1 && box[3] == 1 && box[0] * box[1] == 256 && tap_off % 1024 == 0 &&
-          box[1] + 2 <= 256) {
+          box[1] + 2 <= 256 && 2 * halo_stage <= kMaxDynSmem - 16384) {
         halo = true;
         p.TPS = 3;
       }
@@ -354,7 +358,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   const int n_e = (c->mask != nullptr ? 1 : 0) + (c->addend != nullptr ? 1 : 0);
   const int e_one = n_e * 128 * (p.NT * 2 + 16);
   p.e_bufs = 0;
-  if (n_e > 0 && !nchw && c->out_f32 == nullptr && p.NT % 32 == 0 && p.n_tiles == 1) {
+  if (n_e > 0 && !nchw && c->out_f32 == nullptr && p.NT % 32 == 0) {
     if ((avail - p.MT * e_one) / stage_bytes >= 2) p.e_bufs = p.MT;   // one buffer set per M sub-tile (warp group)
   }
   int stages = (avail - p.e_bufs * e_one) / stage_bytes;
