@@ -48,6 +48,26 @@ __global__ void pack_nchw_wide_kernel(const float* __restrict__ x, __nv_bfloat16
   }
 }
 
+// one thread per pixel: reads its cs channels as 16-byte vectors, writes c planes (coalesced across the warp)
+template <int CS>
+__global__ void unpack_nchw_small_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int c, int hw,
+                                         size_t total) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / hw, px = i % hw;
+    float v[CS];
+    const uint4* src = reinterpret_cast<const uint4*>(x + i * CS);
+#pragma unroll
+    for (int q = 0; q < CS / 8; ++q) {
+      const uint4 u = __ldg(src + q);
+      v[8 * q + 0] = bf16lo(u.x); v[8 * q + 1] = bf16hi(u.x); v[8 * q + 2] = bf16lo(u.y); v[8 * q + 3] = bf16hi(u.y);
+      v[8 * q + 4] = bf16lo(u.z); v[8 * q + 5] = bf16hi(u.z); v[8 * q + 6] = bf16lo(u.w); v[8 * q + 7] = bf16hi(u.w);
+    }
+#pragma unroll
+    for (int cc = 0; cc < CS; ++cc)
+      if (cc < c) out[(n * c + cc) * hw + px] = v[cc];
+  }
+}
+
 __global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int c, int hw,
                                    int cs) {
   // block: 32 pixels x up to 32 channels per pass through smem
@@ -198,30 +218,44 @@ __global__ void maxpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__
     y[i] = o;
   }
 }
-// dx[pos] = (x[pos] == y && first such position in (row-major) window order) ? dy : 0, then optional ReLU mask of x
-__global__ void maxpool2_bwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ y,
-                                    const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx, int n, int h,
-                                    int w, int cs) {
+// dx[pos] = (x[pos] == y && first such position in (row-major) window order && x[pos] > 0) ? dy : 0
+// 8 channels (one 16-byte vector) per thread.  x is a post-ReLU activation: x == 0 means the gate is closed.
+__device__ __forceinline__ uint32_t pool_bwd_pair(uint32_t x, uint32_t y, uint32_t g, uint32_t& taken) {
+  // per bf16 half: hit = !taken && x == y ; out = hit && x > 0 ? g : 0
+  uint32_t out = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t sh = 16 * h;
+    const uint32_t xv = (x >> sh) & 0xFFFFu, yv = (y >> sh) & 0xFFFFu;
+    const bool tk = (taken >> h) & 1u;
+    const bool hit = !tk && xv == yv;     // post-ReLU values: no -0 / NaN, bit equality == value equality
+    if (hit) taken |= (1u << h);
+    if (hit && xv != 0u && !(xv & 0x8000u)) out |= ((g >> sh) & 0xFFFFu) << sh;
+  }
+  return out;
+}
+__global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
+                                    uint4* __restrict__ dx, int n, int h, int w, int vecs) {
   const int ho = h / 2, wo = w / 2;
-  const size_t total = (size_t)n * ho * wo * cs;
+  const size_t total = (size_t)n * ho * wo * vecs;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int c = (int)(i % cs);
-    size_t r = i / cs;
+    const int v = (int)(i % vecs);
+    size_t r = i / vecs;
     const int ox = (int)(r % wo); r /= wo;
     const int oy = (int)(r % ho);
     const size_t nn = r / ho;
-    const float yo = __bfloat162float(y[i]);
-    const __nv_bfloat16 g = dy[i];
-    const __nv_bfloat16 zero = __float2bfloat16(0.f);
-    bool taken = false;
+    const uint4 yo = __ldg(y + i), g = __ldg(dy + i);
+    uint32_t tk[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const size_t idx = ((nn * h + 2 * oy + (k >> 1)) * w + 2 * ox + (k & 1)) * cs + c;
-      const float xv = __bfloat162float(x[idx]);
-      const bool hit = !taken && (xv == yo);
-      // x is a post-ReLU activation: x == 0 means the ReLU gate is closed, so no gradient flows
-      dx[idx] = (hit && xv > 0.f) ? g : zero;
-      taken = taken || hit;
+      const size_t idx = ((nn * h + 2 * oy + (k >> 1)) * w + 2 * ox + (k & 1)) * vecs + v;
+      const uint4 xv = __ldg(x + idx);
+      uint4 o;
+      o.x = pool_bwd_pair(xv.x, yo.x, g.x, tk[0]);
+      o.y = pool_bwd_pair(xv.y, yo.y, g.y, tk[1]);
+      o.z = pool_bwd_pair(xv.z, yo.z, g.z, tk[2]);
+      o.w = pool_bwd_pair(xv.w, yo.w, g.w, tk[3]);
+      dx[idx] = o;
     }
   }
 }
@@ -341,6 +375,11 @@ cudaError_t launch_pack_nchw(const float* x, void* out, int n, int c, int hw, in
   return cudaGetLastError();
 }
 cudaError_t launch_unpack_nchw(const void* x, float* out, int n, int c, int hw, int cs, cudaStream_t st) {
+  if (cs == 16) {
+    const size_t total = (size_t)n * hw;
+    unpack_nchw_small_kernel<16><<<grid_for(total, 256, 148, 16), 256, 0, st>>>((const __nv_bfloat16*)x, out, c, hw, total);
+    return cudaGetLastError();
+  }
   dim3 grid((hw + 31) / 32, n);
   unpack_nchw_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, c, hw, cs);
   return cudaGetLastError();
@@ -387,9 +426,10 @@ cudaError_t launch_maxpool2(const void* x, void* y, int n, int h, int w, int cs,
 }
 cudaError_t launch_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int cs,
                                 int num_sms, cudaStream_t st) {
-  const size_t total = (size_t)n * (h / 2) * (w / 2) * cs;
-  maxpool2_bwd_kernel<<<grid_for(total, 256, num_sms), 256, 0, st>>>(
-      (const __nv_bfloat16*)x, (const __nv_bfloat16*)y, (const __nv_bfloat16*)dy, (__nv_bfloat16*)dx, n, h, w, cs);
+  const int vecs = cs / 8;
+  const size_t total = (size_t)n * (h / 2) * (w / 2) * vecs;
+  maxpool2_bwd_kernel<<<grid_for(total, 256, num_sms, 16), 256, 0, st>>>((const uint4*)x, (const uint4*)y,
+                                                                        (const uint4*)dy, (uint4*)dx, n, h, w, vecs);
   return cudaGetLastError();
 }
 
