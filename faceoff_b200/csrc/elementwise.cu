@@ -165,7 +165,24 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, size_
   const int r_in = threadIdx.x / vecs;
   float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (r_in < rpi) {
-    for (size_t r = (size_t)blockIdx.x * rpi + r_in; r < rows; r += (size_t)gridDim.x * rpi) {
+    const size_t stride = (size_t)gridDim.x * rpi;
+    size_t r = (size_t)blockIdx.x * rpi + r_in;
+    // four independent 16-byte loads in flight per thread
+    for (; r + 3 * stride < rows; r += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = __ldg(reinterpret_cast<const uint4*>(x + (r + u * stride) * cs) + lane_v);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          acc[2 * e] += bf16lo(w[e]);
+          acc[2 * e + 1] += bf16hi(w[e]);
+        }
+      }
+    }
+    for (; r < rows; r += stride) {
       const uint4 v = __ldg(reinterpret_cast<const uint4*>(x + r * cs) + lane_v);
       const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -267,20 +284,21 @@ __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __
 // tcgen05 kernel.  k = (ky*4+kx)*8 + c, value = x[c][2*oy+ky-1][2*ox+kx-1] (zero outside / for c >= C).
 __global__ void im2col4x4s2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int ca, int c, int h,
                                    int w) {
-  __shared__ float sm[8][4][68];  // [channel][input row][input col], cols 2*ox0-1 .. 2*ox0+64
-  const int wo = w / 2, ho = h / 2;
-  const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 32;
+  // block: 64 output pixels of one output row; input window 4 rows x 130 columns x c channels
+  __shared__ float sm[8][4][132];
+  const int wo = w / 2;
+  const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 64;
   const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy - 1;
-  for (int i = threadIdx.x; i < 8 * 4 * 66; i += blockDim.x) {
-    const int col = i % 66, r = (i / 66) % 4, cc = i / (66 * 4);
+  for (int i = threadIdx.x; i < 8 * 4 * 130; i += blockDim.x) {
+    const int col = i % 130, r = (i / 130) & 3, cc = i / (130 * 4);
     const int iy = iy0 + r, ix = ix0 + col;
     float v = 0.f;
     if (cc < c && iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + (((size_t)n * ca + cc) * h + iy) * w + ix);
     sm[cc][r][col] = v;
   }
   __syncthreads();
-  (void)ho;
-  for (int i = threadIdx.x; i < 32 * 16; i += blockDim.x) {
+#pragma unroll 2
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
     const int px = i >> 4, tap = i & 15;
     const int ox = ox0 + px;
     if (ox >= wo) continue;
@@ -336,10 +354,12 @@ __global__ void chansum_nchw_kernel(const float* __restrict__ x, int n, int ca, 
   __shared__ float red[32];
   const int cc = blockIdx.y;
   float acc = 0.f;
-  const size_t total = (size_t)n * hw;
+  const int hw4 = hw / 4;   // hw is a multiple of 4 (checked by the launcher)
+  const size_t total = (size_t)n * hw4;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t nn = i / hw, p = i % hw;
-    acc += x[(nn * ca + cc) * hw + p];
+    const size_t nn = i / hw4, p4 = i % hw4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(x + (nn * ca + cc) * hw) + p4);
+    acc += (v.x + v.y) + (v.z + v.w);
   }
   acc = warp_sum(acc);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
@@ -404,7 +424,7 @@ cudaError_t launch_bias_finalize(const float* part, int splits, int mc, int c, f
   bias_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(part, splits, mc, c, out, accumulate);
   return cudaGetLastError();
 }
-int colsum_blocks(int num_sms) { return num_sms * 4; }
+int colsum_blocks(int num_sms) { return num_sms * 8; }
 cudaError_t launch_colsum(const void* x, size_t rows, int cs, int c_off, int c, float* out, int accumulate,
                           float* workspace, int num_sms, cudaStream_t st) {
   const int threads = 256;
@@ -434,7 +454,7 @@ cudaError_t launch_maxpool2_bwd(const void* x, const void* y, const void* dy, vo
 }
 
 cudaError_t launch_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w, cudaStream_t st) {
-  dim3 grid((w / 2 + 31) / 32, h / 2, n);
+  dim3 grid((w / 2 + 63) / 64, h / 2, n);
   im2col4x4s2_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, ca, c, h, w);
   return cudaGetLastError();
 }
@@ -451,8 +471,9 @@ cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, fl
     cudaError_t e = cudaMemsetAsync(out, 0, sizeof(float) * c, st);
     if (e != cudaSuccess) return e;
   }
+  if (hw % 4 != 0) return cudaErrorInvalidValue;
   dim3 grid(num_sms * 2, c);
-  chansum_nchw_kernel<<<grid, 256, 0, st>>>(x, n, ca, c, hw, out);
+  chansum_nchw_kernel<<<grid, 512, 0, st>>>(x, n, ca, c, hw, out);
   return cudaGetLastError();
 }
 

@@ -206,29 +206,41 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
       mbar_wait(&a_empty[ab], ((it / p.a_bufs) & 1) ^ 1);
       uint8_t* a_base = sA + (size_t)ab * a_buf_bytes;
       const size_t row0 = (size_t)rt * 128;
-      for (int i = 0; i < q4; ++i) {
-        const int idx = i * 128 + t;
-        const int r = idx / q4, q = idx % q4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (row0 + r < p.rows) v = __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * p.dim) + q);
-        // |x|^2 of the row: reduce over the q4 lanes that share it
-        float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-        for (int o = q4 >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 32);
-        if (q == 0) sX2[(it & 3) * 128 + r] = s;
-        const __nv_bfloat16 h0 = __float2bfloat16(v.x), h1 = __float2bfloat16(v.y), h2 = __float2bfloat16(v.z),
-                            h3 = __float2bfloat16(v.w);
-        const float l0 = v.x - __bfloat162float(h0), l1 = v.y - __bfloat162float(h1),
-                    l2 = v.z - __bfloat162float(h2), l3 = v.w - __bfloat162float(h3);
-        const int k = q * 4;
-        const int kc = k >> 6, kin = k & 63;
-        const uint32_t off = (uint32_t)r * 128 + ((((uint32_t)kin >> 3) ^ ((uint32_t)r & 7)) << 4) + (kin & 7) * 2;
-        uint2 hv, lv;
-        hv.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        hv.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-        lv.x = pack_bf16x2(l0, l1);
-        lv.y = pack_bf16x2(l2, l3);
-        *reinterpret_cast<uint2*>(a_base + kc * a_sub + off) = hv;
-        *reinterpret_cast<uint2*>(a_base + (p.kchunks + kc) * a_sub + off) = lv;
+      // all global loads of the tile are issued before the first use (16 x 16 B in flight per thread): the loop would
+      // otherwise expose one DRAM latency per iteration
+      for (int i0 = 0; i0 < q4; i0 += 16) {
+        float4 vv[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int idx = (i0 + u) * 128 + t;
+          const int r = idx / q4, q = idx % q4;
+          vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + r < p.rows) vv[u] = __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * p.dim) + q);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+          const int idx = (i0 + u) * 128 + t;
+          const int r = idx / q4, q = idx % q4;
+          const float4 v = vv[u];
+          // |x|^2 of the row: reduce over the q4 lanes that share it
+          float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+          for (int o = q4 >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 32);
+          if (q == 0) sX2[(it & 3) * 128 + r] = s;
+          const __nv_bfloat16 h0 = __float2bfloat16(v.x), h1 = __float2bfloat16(v.y), h2 = __float2bfloat16(v.z),
+                              h3 = __float2bfloat16(v.w);
+          const float l0 = v.x - __bfloat162float(h0), l1 = v.y - __bfloat162float(h1),
+                      l2 = v.z - __bfloat162float(h2), l3 = v.w - __bfloat162float(h3);
+          const int k = q * 4;
+          const int kc = k >> 6, kin = k & 63;
+          const uint32_t off = (uint32_t)r * 128 + ((((uint32_t)kin >> 3) ^ ((uint32_t)r & 7)) << 4) + (kin & 7) * 2;
+          uint2 hv, lv;
+          hv.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          hv.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
+          lv.x = pack_bf16x2(l0, l1);
+          lv.y = pack_bf16x2(l2, l3);
+          *reinterpret_cast<uint2*>(a_base + kc * a_sub + off) = hv;
+          *reinterpret_cast<uint2*>(a_base + (p.kchunks + kc) * a_sub + off) = lv;
+        }
       }
       (void)rows_per_iter;
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
