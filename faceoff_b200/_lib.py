@@ -42,7 +42,7 @@ class WgradDesc(C.Structure):
         ("form", C.c_int), ("ndim", C.c_int), ("ksize", C.c_int),
         ("n", C.c_int), ("d", C.c_int), ("h", C.c_int), ("w", C.c_int),
         ("p", Src), ("q", Src), ("dweight", C.c_void_p), ("dimA", C.c_int), ("dimB", C.c_int),
-        ("m_axis", C.c_int), ("q_w_off", C.c_int), ("accumulate", C.c_int),
+        ("m_axis", C.c_int), ("q_w_off", C.c_int), ("q_shift_sign", C.c_int), ("accumulate", C.c_int),
         ("dbias", C.c_void_p), ("dbias_accumulate", C.c_int),
         ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
     ]

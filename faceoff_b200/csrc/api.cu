@@ -201,32 +201,45 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   // CTA tile: 128 positions, or 256 (two M=128 sub-tiles sharing every B tile) when the problem is large enough;
   // 3x3(x3) stride-1 filters additionally read their three vertical taps from one halo'd A box (see conv_igemm.cu).
   int box[4];
-  choose_box(ext, 128, box);
   p.MT = 1;
   p.TPS = 1;
   bool halo = false;
-  if (p.NT <= 128) {
-    int b2[4];
-    choose_box(ext, 256, b2);
-    long long tiles256 = 1;
+  const int smem_avail = kMaxDynSmem - 2048 - 1024 - 8 * 32 * 80;
+  const int n_e_plan = (c->mask != nullptr ? 1 : 0) + (c->addend != nullptr ? 1 : 0);
+  const bool want_prefetch = n_e_plan > 0 && !nchw && c->out_f32 == nullptr && p.NT % 32 == 0;
+  const int e_one_plan = n_e_plan * 128 * (p.NT * 2 + 16);
+  // candidate modes, best first: 256-position tiles (MT = 2) when the problem is large, else 128; each with halo
+  // stages when the filter is 3x3(x3) and a tile covers whole image rows of one frame.  A mode is skipped when the
+  // epilogue's operand prefetch (mask / addend present) would not fit next to two pipeline stages.
+  struct Mode { bool ok, halo; int box[4]; } modes[3] = {};
+  for (int mt = 1; mt <= (p.NT <= 128 ? 2 : 1); ++mt) {
+    Mode& md = modes[mt];
+    choose_box(ext, 128 * mt, md.box);
+    long long tiles = 1;
     bool exact = true;
     for (int d = 0; d < 4; ++d) {
-      tiles256 *= (ext[d] + b2[d] - 1) / b2[d];
-      if (b2[d] > 1 && b2[d] > pow2_ceil(ext[d])) exact = false;
+      tiles *= (ext[d] + md.box[d] - 1) / md.box[d];
+      if (md.box[d] > 1 && md.box[d] > pow2_ceil(ext[d])) exact = false;
     }
     const int sms = g_num_sms > 0 ? g_num_sms : 148;
-    if (exact && tiles256 * p.n_tiles >= 2LL * sms) {
-      p.MT = 2;
-      for (int d = 0; d < 4; ++d) box[d] = b2[d];
-      const int tap_off = box[0] * rowb;
-      const int halo_stage = box[0] * (box[1] + 2) * rowb + 3 * p.NT * rowb;
-      if (s1 && c->ksize == 3 && box[2] == 1 && box[3] == 1 && box[0] * box[1] == 256 && tap_off % 1024 == 0 &&
-          box[1] + 2 <= 256 && 2 * halo_stage <= kMaxDynSmem - 16384) {
-        halo = true;
-        p.TPS = 3;
-      }
-    }
+    md.ok = mt == 1 || (exact && tiles * p.n_tiles >= 2LL * sms);
+    const int tap_off = md.box[0] * rowb;
+    md.halo = s1 && c->ksize == 3 && md.box[2] == 1 && md.box[3] == 1 && md.box[0] * md.box[1] == 128 * mt &&
+              tap_off % 1024 == 0 && md.box[0] <= ext[0] && md.box[1] <= ext[1];
+    const int stage_b = ((md.halo ? md.box[0] * (md.box[1] + 2) : 128 * mt) * rowb + (md.halo ? 3 : 1) * p.NT * rowb + 1023) & ~1023;
+    if (md.halo && 2 * stage_b > smem_avail) md.halo = false;   // halo box too large: plain stages
   }
+  int pick = modes[2].ok ? 2 : 1;
+  {
+    const char* e = getenv("FO_FORCE_MT");   // experiments only
+    if (e && atoi(e) == 2 && modes[2].ok) pick = 2;
+    if (e && atoi(e) == 1) pick = 1;
+  }
+  p.MT = pick;
+  halo = modes[pick].halo;
+  p.TPS = halo ? 3 : 1;
+  for (int d = 0; d < 4; ++d) box[d] = modes[pick].box[d];
+  (void)n_e_plan; (void)want_prefetch; (void)e_one_plan;
   for (int d = 0; d < 4; ++d) {
     p.box[d] = box[d];
     p.tile_step[d] = box[d];
@@ -353,15 +366,17 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   p.num_ksteps = nk;
   out->ktot = n_pack * kc;
   const int stage_bytes = (p.a_bytes + p.TPS * p.NT * rowb + 1023) & ~1023;
-  // shared memory: pipeline stages + (optionally) the epilogue's prefetched mask / addend rows
+  // shared memory: pipeline stages + (as far as it fits next to two stages) the epilogue's prefetched addend / mask rows
   const int avail = kMaxDynSmem - 2048 - 1024 - 8 * 32 * 80;
-  const int n_e = (c->mask != nullptr ? 1 : 0) + (c->addend != nullptr ? 1 : 0);
-  const int e_one = n_e * 128 * (p.NT * 2 + 16);
-  p.e_bufs = 0;
-  if (n_e > 0 && !nchw && c->out_f32 == nullptr && p.NT % 32 == 0) {
-    if ((avail - p.MT * e_one) / stage_bytes >= 2) p.e_bufs = p.MT;   // one buffer set per M sub-tile (warp group)
+  const int e_tensor = p.MT * 128 * (p.NT * 2 + 16);   // one operand, all sub-tiles
+  p.e_bufs = 0; p.e_mask = 0; p.e_add = 0;
+  if (!nchw && c->out_f32 == nullptr && p.NT % 32 == 0) {
+    int room = avail - 2 * stage_bytes;
+    if (c->addend != nullptr && room >= e_tensor) { p.e_add = 1; room -= e_tensor; }
+    if (c->mask != nullptr && room >= e_tensor) { p.e_mask = 1; room -= e_tensor; }
+    if (p.e_add || p.e_mask) p.e_bufs = p.MT;
   }
-  int stages = (avail - p.e_bufs * e_one) / stage_bytes;
+  int stages = (avail - (p.e_add + p.e_mask) * e_tensor) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(FO_ERR_INVALID, "tile does not fit in shared memory");
   p.stages = stages;
@@ -508,14 +523,17 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
     const int k = g->ksize, pad = (k - 1) / 2;
     if (k != 1 && k != 3) return fail(FO_ERR_INVALID, "wgrad ksize unsupported");
     const int kd_n = g->ndim == 3 ? k : 1;
+    const int sg = g->q_shift_sign < 0 ? -1 : 1;
     if (p.halo) {
-      // pass = (kd, kw); the three slots of a pass are kh = 0, 1, 2 read from one box starting one row above
+      // pass = (kd, kw); the three slots of a pass are the vertical offsets -1, 0, +1 read from one box that starts one
+      // row above the tile; slot j serves filter row kh with sg * (kh - pad) == j - 1
       for (int kd = 0; kd < kd_n; ++kd)
         for (int kw = 0; kw < k; ++kw)
-          for (int kh = 0; kh < k; ++kh) {
+          for (int j = 0; j < k; ++j) {
+            const int kh = pad + sg * (j - 1);
             WgTap& t = p.taps[nt];
-            t.c0 = (int16_t)g->q.c_off; t.d1 = (int8_t)(kw - pad); t.d2 = (int8_t)(-1);
-            t.d3 = (int8_t)(g->ndim == 3 ? kd - pad : 0); t.map = 0; t.pad = 0;
+            t.c0 = (int16_t)g->q.c_off; t.d1 = (int8_t)(sg * (kw - pad)); t.d2 = (int8_t)(-1);
+            t.d3 = (int8_t)(g->ndim == 3 ? sg * (kd - pad) : 0); t.map = 0; t.pad = 0;
             f.tap_index[nt] = (int8_t)((kd * k + kh) * k + kw);
             ++nt;
           }
@@ -524,8 +542,8 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
         for (int kh = 0; kh < k; ++kh)
           for (int kw = 0; kw < k; ++kw) {
             WgTap& t = p.taps[nt];
-            t.c0 = (int16_t)g->q.c_off; t.d1 = (int8_t)(kw - pad); t.d2 = (int8_t)(kh - pad);
-            t.d3 = (int8_t)(g->ndim == 3 ? kd - pad : 0); t.map = 0; t.pad = 0;
+            t.c0 = (int16_t)g->q.c_off; t.d1 = (int8_t)(sg * (kw - pad)); t.d2 = (int8_t)(sg * (kh - pad));
+            t.d3 = (int8_t)(g->ndim == 3 ? sg * (kd - pad) : 0); t.map = 0; t.pad = 0;
             f.tap_index[nt] = (int8_t)nt;
             ++nt;
           }

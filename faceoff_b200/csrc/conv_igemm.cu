@@ -371,7 +371,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     // NT*2+16 B: conflict-free).
     const int e_pitch = p.NT * 2 + 16;
     const int e_warp_bytes = 32 * e_pitch;
-    const int n_e = (p.mask != nullptr ? 1 : 0) + (p.addend != nullptr ? 1 : 0);
+    const int n_e = p.e_mask + p.e_add;
     const bool prefetch = coalesced && p.e_bufs > 0 && n_e > 0;
     // layout: [e_buf][tensor][warp quarter][32 rows][pitch]
     auto e_ptr = [&](int ebuf, int tensor) -> uint8_t* {
@@ -385,11 +385,11 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
         const long long o = __shfl_sync(0xffffffffu, my_off, r);
         const bool ok = __shfl_sync(0xffffffffu, (int)my_valid, r) != 0;
         int t = 0;
-        if (p.mask != nullptr) {
+        if (p.e_mask) {
           if (ok) cp_async16(e_ptr(ebuf, t) + r * e_pitch + pc * 16, p.mask + o + ncol0 + pc * 8);
           ++t;
         }
-        if (p.addend != nullptr) {
+        if (p.e_add) {
           if (ok) cp_async16(e_ptr(ebuf, t) + r * e_pitch + pc * 16, p.addend + o + ncol0 + pc * 8);
         }
       }
@@ -428,8 +428,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
         const uint8_t* e_add = nullptr;
         if (prefetch) {
           int t = 0;
-          if (p.mask != nullptr) e_mask = e_ptr(ebuf, t++) + lane * e_pitch;
-          if (p.addend != nullptr) e_add = e_ptr(ebuf, t) + lane * e_pitch;
+          if (p.e_mask) e_mask = e_ptr(ebuf, t++) + lane * e_pitch;
+          if (p.e_add) e_add = e_ptr(ebuf, t) + lane * e_pitch;
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * p.MT + m) * p.NT;
         // rows handled by this lane in the transposed (coalesced) accesses
@@ -474,7 +474,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
 size_t conv_smem_bytes(const ConvParams& p) {
   const int rowb = p.KC * 2;
   const int stage_bytes = (p.a_bytes + p.TPS * p.NT * rowb + 1023) & ~1023;
-  const int n_e = (p.mask != nullptr ? 1 : 0) + (p.addend != nullptr ? 1 : 0);
+  const int n_e = p.e_mask + p.e_add;
   return (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024 + 8 * 32 * 80 +
          (size_t)p.e_bufs * n_e * 128 * (p.NT * 2 + 16) + 1024;
 }

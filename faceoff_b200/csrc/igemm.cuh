@@ -33,7 +33,8 @@ struct ConvParams {
   int a_ops;          // the A box is fetched by a_ops TMA operations of a_op_rows image rows each (more ops in flight)
   int a_op_rows;
   int dbg_skip_mma;   // debug: do not issue MMAs (measures the pure TMA streaming rate)
-  int e_bufs;         // epilogue operand prefetch: 0 = off, else buffers per tensor (1, or MT = one per sub-tile)
+  int e_bufs;         // epilogue operand prefetch: 0 = off, else MT (one buffer set per M sub-tile / warp group)
+  int e_mask, e_add;  // which of the two epilogue operands are prefetched (shared memory permitting)
   int n_tiles;        // N tiles of width NT
   int NT;             // columns per N tile (multiple of 16, <= 256)
   int KC;             // channels per K step: 16 / 32 / 64  (row bytes 32 / 64 / 128 = swizzle mode)

@@ -154,7 +154,13 @@ def conv_op(tape: Tape, form: int, ksize: int, srcs: Sequence[View], wname: str,
         for v, s in zip(srcs, src_list):
             if not param_grad:
                 break
-            if form == FORM_S1:
+            if form == FORM_S1 and len(srcs) == 1 and pad16(cout) < pad16(v.node.c):
+                # narrow output (ResBlock 3x3 C->32): make the wide tensor x the M side of the MMA and read dy at
+                # pix - tap; the (tiny) bias gradient then comes from the column-sum kernel
+                if gb is not None:
+                    ops.colsum(gt, cout, gb, c_off=g_off, accumulate=bacc)
+                ops.wgrad(FORM_S1, ndim, ksize, s, dy, gw, m_axis=1, q_w_off=0, accumulate=acc, q_shift_sign=-1)
+            elif form == FORM_S1:
                 ops.wgrad(FORM_S1, ndim, ksize, dy, s, gw, m_axis=0, q_w_off=w_off, accumulate=acc, dbias=gb,
                           dbias_accumulate=bacc)
             elif form == FORM_DOWN:

@@ -194,7 +194,8 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
 
 
 def wgrad(form: int, ndim: int, ksize: int, p: SrcT, q: SrcT, dweight: torch.Tensor, m_axis: int, q_w_off: int = 0,
-          accumulate: bool = False, dbias: Optional[torch.Tensor] = None, dbias_accumulate: bool = False):
+          accumulate: bool = False, dbias: Optional[torch.Tensor] = None, dbias_accumulate: bool = False,
+          q_shift_sign: int = 1):
     """dweight (fp32, PyTorch layout) (+)= sum_pix P (x) Q.  form: FORM_S1 or FORM_DOWN (Q = hi-res side)."""
     lib = L.load()
     g = WgradDesc()
@@ -209,6 +210,7 @@ def wgrad(form: int, ndim: int, ksize: int, p: SrcT, q: SrcT, dweight: torch.Ten
     assert dweight.dtype == torch.float32 and dweight.is_contiguous()
     g.dweight, g.dimA, g.dimB = dweight.data_ptr(), dweight.shape[0], dweight.shape[1]
     g.m_axis, g.q_w_off, g.accumulate = m_axis, q_w_off, int(accumulate)
+    g.q_shift_sign = q_shift_sign
     g.dbias, g.dbias_accumulate = _p(dbias), int(dbias_accumulate)
     need = lib.fo_wgrad_workspace_bytes(C.byref(g))
     if need == 0:

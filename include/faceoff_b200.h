@@ -105,6 +105,8 @@ typedef struct {
   int dimA, dimB;       /* sizes of the first two axes of dweight */
   int m_axis;           /* which weight axis the P channels index (0 or 1) */
   int q_w_off;          /* channel offset of Q's channels on the other weight axis (torch.cat second source) */
+  int q_shift_sign;     /* +1: Q is read at pix + tap (P = dy, Q = x); -1: at pix - tap (P = x, Q = dy; lets the wider
+                           tensor be the M side of the MMA).  0 is treated as +1. */
   int accumulate;
   float* dbias;         /* optional: fp32 [p.c] bias gradient = column sums of P (fused: one extra N=16 MMA per K step) */
   int dbias_accumulate;

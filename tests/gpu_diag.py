@@ -227,6 +227,16 @@ def case_wgrad():
         torch.cuda.synchronize()
         ok &= report(f"wgrad s1 {cin}->{cout} k{k} n{n} {h}x{w}", dw, wt.grad)
         ok &= report(f"   fused bias grad", db, gy.sum((0, 2, 3)), tol=1e-4)
+    # swapped roles (P = x, Q = dy read at pix - tap): narrow-output layers
+    for (n, h, w, cin, cout, k) in [(4, 16, 16, 128, 32, 3), (2, 32, 32, 128, 32, 3), (2, 8, 8, 128, 32, 3)]:
+        x = bf(rnd(n, cin, h, w, seed=1))
+        wt = bf(rnd(cout, cin, k, k, seed=2)).requires_grad_(True)
+        gy = bf(rnd(n, cout, h, w, seed=4))
+        F.conv2d(x, wt, None, padding=1).backward(gy)
+        dw = torch.zeros_like(wt).detach()
+        ops.wgrad(ops.FORM_S1, 2, k, (to_cl(x), cin, 0), (to_cl(gy), cout, 0), dw, m_axis=1, q_shift_sign=-1)
+        torch.cuda.synchronize()
+        ok &= report(f"wgrad s1 swapped {cin}->{cout} n{n} {h}x{w}", dw, wt.grad)
     # conv3d
     n, d, h, w, c = 1, 4, 16, 16, 128
     x = bf(rnd(n, c, d, h, w, seed=1))

@@ -66,6 +66,23 @@ def main():
         wu = torch.randn(128, 64, 4, 4, device=dev) * 0.03
         ms = timeit(lambda: ops.conv(ops.FORM_UP, 2, 4, [(x, 128, 0)], wu, 1, 64, bias=b, want_raw=False, want_relu=True))
         print(f"convT4x4s2 128->64 (UP)  : {ms:.3f} ms  {fld / ms / 1e9:.1f} TFLOP/s")
+    if which in ("resblock", "all"):
+        F_ = clips * T
+        x = torch.randn(F_, 64, 64, 128, device=dev).to(torch.bfloat16)
+        dh = torch.randn(F_, 64, 64, 32, device=dev).to(torch.bfloat16)
+        w32 = torch.randn(32, 128, 3, 3, device=dev) * 0.03
+        ms = timeit(lambda: ops.conv(ops.FORM_S1_DGRAD, 2, 3, [(dh, 32, 0)], w32, 1, 128, mask=x, addend=x))
+        gb = (dh.numel() + 3 * x.numel()) * 2 / 1e9
+        print(f"resblock dgrad3x3 32->128 (+mask+addend): {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        w1 = torch.randn(128, 32, 1, 1, device=dev) * 0.1
+        ms = timeit(lambda: ops.conv(ops.FORM_S1_DGRAD, 2, 1, [(x, 128, 0)], w1, 1, 32, mask=dh))
+        gb = (x.numel() + 2 * dh.numel()) * 2 / 1e9
+        print(f"resblock dgrad1x1 128->32 (+mask): {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        dw = torch.empty(32, 128, 3, 3, device=dev)
+        ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 2, 3, (x, 128, 0), (dh, 32, 0), dw, m_axis=1, q_shift_sign=-1))
+        print(f"resblock wgrad3x3 (swapped): {ms:.3f} ms")
+        ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 2, 3, (dh, 32, 0), (x, 128, 0), dw, m_axis=0))
+        print(f"resblock wgrad3x3 (P=dy): {ms:.3f} ms")
     if which in ("wgrad3d", "all"):
         x = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)
         dy = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)
