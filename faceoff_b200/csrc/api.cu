@@ -211,7 +211,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   // candidate modes, best first: 256-position tiles (MT = 2) when the problem is large, else 128; each with halo
   // stages when the filter is 3x3(x3) and a tile covers whole image rows of one frame.  A mode is skipped when the
   // epilogue's operand prefetch (mask / addend present) would not fit next to two pipeline stages.
-  struct Mode { bool ok, halo; int box[4]; } modes[3] = {};
+  struct Mode { bool ok; int halo; int box[4]; } modes[3] = {};   // halo = extra image rows in the A box (0, 1, 2)
   for (int mt = 1; mt <= (p.NT <= 128 ? 2 : 1); ++mt) {
     Mode& md = modes[mt];
     choose_box(ext, 128 * mt, md.box);
@@ -224,10 +224,13 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     const int sms = g_num_sms > 0 ? g_num_sms : 148;
     md.ok = mt == 1 || (exact && tiles * p.n_tiles >= 2LL * sms);
     const int tap_off = md.box[0] * rowb;
-    md.halo = s1 && c->ksize == 3 && md.box[2] == 1 && md.box[3] == 1 && md.box[0] * md.box[1] == 128 * mt &&
-              tap_off % 1024 == 0 && md.box[0] <= ext[0] && md.box[1] <= ext[1];
-    const int stage_b = ((md.halo ? md.box[0] * (md.box[1] + 2) : 128 * mt) * rowb + (md.halo ? 3 : 1) * p.NT * rowb + 1023) & ~1023;
-    if (md.halo && 2 * stage_b > smem_avail) md.halo = false;   // halo box too large: plain stages
+    const bool rows_ok = md.box[2] == 1 && md.box[3] == 1 && md.box[0] * md.box[1] == 128 * mt && tap_off % 1024 == 0 &&
+                         md.box[0] <= ext[0] && md.box[1] <= ext[1];
+    // 3x3(x3): the three vertical taps share one box of R+2 rows; 4x4 stride-2 transposed: the two vertical taps of a
+    // sub-pixel group share one box of R+1 rows
+    md.halo = !rows_ok ? 0 : (s1 && c->ksize == 3) ? 2 : (c->form == FO_FORM_UP && c->ndim == 2) ? 1 : 0;
+    const int stage_b = (md.box[0] * (md.box[1] + md.halo) * rowb + (md.halo + 1) * p.NT * rowb + 1023) & ~1023;
+    if (md.halo && 2 * stage_b > smem_avail) md.halo = 0;   // halo box too large: plain stages
   }
   int pick = modes[2].ok ? 2 : 1;
   {
@@ -236,8 +239,9 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     if (e && atoi(e) == 1) pick = 1;
   }
   p.MT = pick;
-  halo = modes[pick].halo;
-  p.TPS = halo ? 3 : 1;
+  const int halo_extra = modes[pick].halo;
+  halo = halo_extra > 0;
+  p.TPS = halo_extra + 1;
   for (int d = 0; d < 4; ++d) box[d] = modes[pick].box[d];
   (void)n_e_plan; (void)want_prefetch; (void)e_one_plan;
   for (int d = 0; d < 4; ++d) {
@@ -248,9 +252,9 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   }
   p.sub_off = 128 * rowb;
   p.tap_off = halo ? box[0] * rowb : 0;
-  p.a_bytes = (halo ? box[0] * (box[1] + 2) : 128 * p.MT) * rowb;
+  p.a_bytes = (halo ? box[0] * (box[1] + halo_extra) : 128 * p.MT) * rowb;
   // split the A box over dim 2 (image rows) into several TMA operations
-  const int a_rows = box[1] + (halo ? 2 : 0);
+  const int a_rows = box[1] + halo_extra;
   p.a_ops = 1;
   {
     const char* e = getenv("FO_A_OPS");
@@ -353,12 +357,24 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     static const int dd[2][2] = {{0, -1}, {1, 0}};
     for (int g = 0; g < 4; ++g) {
       const int py = g >> 1, px = g & 1;
-      for (int a = 0; a < 2; ++a)
-        for (int b = 0; b < 2; ++b)
-          for (int s = 0; s < c->n_src; ++s) {
-            const int tap = kk[py][a] * 4 + kk[px][b];
-            chunks(s, 0, dd[px][b], dd[py][a], 0, &tap);
-          }
+      if (halo) {
+        // vertical pair of the group in one box: rows start at min(dd[py]); slot 0 = upper input row
+        const int start = py == 0 ? -1 : 0;
+        int taps[2];
+        for (int b = 0; b < 2; ++b) {
+          // slot j reads input row offset start + j: py=0 -> (-1: ky=3, 0: ky=1); py=1 -> (0: ky=2, +1: ky=0)
+          taps[0] = (py == 0 ? 3 : 2) * 4 + kk[px][b];
+          taps[1] = (py == 0 ? 1 : 0) * 4 + kk[px][b];
+          for (int s = 0; s < c->n_src; ++s) chunks(s, 0, dd[px][b], start, 0, taps);
+        }
+      } else {
+        for (int a = 0; a < 2; ++a)
+          for (int b = 0; b < 2; ++b)
+            for (int s = 0; s < c->n_src; ++s) {
+              const int tap = kk[py][a] * 4 + kk[px][b];
+              chunks(s, 0, dd[px][b], dd[py][a], 0, &tap);
+            }
+      }
       if (g == 0) nk = n_stage;
     }
   }
