@@ -214,7 +214,9 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   struct Mode { bool ok; int halo; int box[4]; } modes[3] = {};   // halo = extra image rows in the A box (0, 1, 2)
   for (int mt = 1; mt <= (p.NT <= 128 ? 2 : 1); ++mt) {
     Mode& md = modes[mt];
-    choose_box(ext, 128 * mt, md.box);
+    // halo-eligible filters prefer 4 image rows per tile (box of 6 rows: 1.5x read amplification instead of 2x)
+    const bool halo_form = (s1 && c->ksize == 3) || (c->form == FO_FORM_UP && c->ndim == 2);
+    choose_box(ext, 128 * mt, md.box, halo_form ? 32 * mt : 128);
     long long tiles = 1;
     bool exact = true;
     for (int d = 0; d < 4; ++d) {
@@ -720,6 +722,13 @@ extern "C" int fo_im2col4x4s2(const float* x, void* out, int n, int ca, int c, i
   REQUIRE_INIT();
   if (c > 8 || c > ca || ((h | w) & 1)) return fail(FO_ERR_INVALID, "im2col4x4s2: need c <= 8, even h and w");
   CUDA_TRY(launch_im2col4x4s2(x, out, n, ca, c, h, w, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_im2col3x3(const float* x, void* out, int n, int c, int h, int w, const float* shift, const float* scale,
+                            fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (c > 3) return fail(FO_ERR_INVALID, "im2col3x3: need c <= 3");
+  CUDA_TRY(launch_im2col3x3(x, out, n, c, h, w, shift, scale, (cudaStream_t)stream));
   return FO_OK;
 }
 extern "C" int fo_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi,

@@ -313,6 +313,41 @@ __global__ void im2col4x4s2_kernel(const float* __restrict__ x, __nv_bfloat16* _
   }
 }
 
+// 3x3 pad-1 im2col for c <= 3 input channels (first VGG16 conv of LPIPS, reference models/lpips.py:119-127) with the
+// ScalingLayer folded in: out[n][y][x][(ky*3+kx)*3 + ch] = (x[ch][y+ky-1][x+kx-1] - shift[ch]) / scale[ch], zero outside
+// the image and for k >= 27 (K padded to 32 -> 64-byte rows, one K=32 GEMM step instead of nine 32-byte-row TMA boxes).
+__global__ void im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, int h, int w,
+                                 const float* __restrict__ shift, const float* __restrict__ scale) {
+  __shared__ float sm[3][3][68];
+  const int n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 64;
+  for (int i = threadIdx.x; i < 3 * 3 * 66; i += blockDim.x) {
+    const int col = i % 66, r = (i / 66) % 3, cc = i / (66 * 3);
+    const int iy = y - 1 + r, ix = x0 - 1 + col;
+    float v = 0.f;
+    if (cc < c && iy >= 0 && iy < h && ix >= 0 && ix < w) {
+      v = __ldg(x + (((size_t)n * c + cc) * h + iy) * w + ix);
+      if (shift != nullptr) v = (v - shift[cc]) / scale[cc];
+    }
+    sm[cc][r][col] = v;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
+    const int px = i >> 2, piece = i & 3;
+    if (x0 + px >= w) continue;
+    float v[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = piece * 8 + e;
+      const int tap = k / 3, cc = k % 3;
+      v[e] = k < 27 ? sm[cc][tap / 3][px + tap % 3] : 0.f;
+    }
+    uint4 o;
+    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+    reinterpret_cast<uint4*>(out + (((size_t)n * h + y) * w + x0 + px) * 32)[piece] = o;
+  }
+}
+
 // out[n][co][oy][ox] = bias[co] + sum of the (up to) 4 col entries that map to this output pixel
 __global__ void col2im4x4s2_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias,
                                    float* __restrict__ out, int c, int hi, int wi, size_t total) {
@@ -456,6 +491,12 @@ cudaError_t launch_maxpool2_bwd(const void* x, const void* y, const void* dy, vo
 cudaError_t launch_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w, cudaStream_t st) {
   dim3 grid((w / 2 + 63) / 64, h / 2, n);
   im2col4x4s2_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, ca, c, h, w);
+  return cudaGetLastError();
+}
+cudaError_t launch_im2col3x3(const float* x, void* out, int n, int c, int h, int w, const float* shift,
+                             const float* scale, cudaStream_t st) {
+  dim3 grid((w + 63) / 64, h, n);
+  im2col3x3_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, c, h, w, shift, scale);
   return cudaGetLastError();
 }
 cudaError_t launch_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, int num_sms,

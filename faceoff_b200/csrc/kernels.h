@@ -54,6 +54,8 @@ cudaError_t launch_maxpool2_bwd(const void* x, const void* y, const void* dy, vo
                                 int num_sms, cudaStream_t st);
 
 cudaError_t launch_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w, cudaStream_t st);
+cudaError_t launch_im2col3x3(const float* x, void* out, int n, int c, int h, int w, const float* shift,
+                             const float* scale, cudaStream_t st);
 cudaError_t launch_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, int num_sms,
                                cudaStream_t st);
 cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, float* out, int accumulate, int num_sms,

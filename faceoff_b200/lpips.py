@@ -13,7 +13,7 @@ import torch
 from torch import nn
 
 from . import ops
-from .graph import FORM_S1, Node, Tape, View, conv_op
+from .graph import FORM_S1, FORM_S1_DGRAD, Node, Tape, View, conv_op
 from .vqvae import _GraphFn, _params_of
 
 _VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
@@ -116,11 +116,32 @@ class LPIPS(nn.Module):
         backward).  Returns (input node, tap nodes)."""
         shift = self.scaling_layer.shift.reshape(-1).contiguous()
         scale = self.scaling_layer.scale.reshape(-1).contiguous()
-        xin = Node(3, raw=ops.pack_nchw(x.to(torch.float32), shift=shift, scale=scale))
+        x = x.to(torch.float32).contiguous()
+        xin = Node(3)
         cur, cur_relu = xin, False
         taps = []
+        first = True
         for kind, key, ch in self.net.layout:
-            if kind == "conv":
+            if kind == "conv" and first:
+                # first conv (3 -> 64): explicit im2col (K = 27 -> 32) + 1x1 GEMM; 3-channel 32-byte TMA rows are slow
+                first = False
+                w = tape.params["net." + key + ".weight"]
+                b = tape.params["net." + key + ".bias"]
+                col = ops.im2col3x3(x, shift, scale)
+                w2 = torch.zeros(ch, 32, dtype=torch.float32, device=w.device)
+                w2[:, :27] = w.detach().permute(0, 2, 3, 1).reshape(ch, 27)
+                _, act, _ = ops.conv(FORM_S1, 2, 1, [(col, 32, 0)], w2.view(ch, 32, 1, 1), 0, ch, bias=b,
+                                     want_raw=False, want_relu=True, wkey=(w, "im2col3x3"))
+                del col
+                cur = Node(ch, act=act)
+
+                def first_bwd(node=cur, w=w):
+                    dx, _, _ = ops.conv(FORM_S1_DGRAD, 2, 3, [(node.g[0], node.c, node.g[1])], w, 1, 3, out_cs=16)
+                    xin.g = (dx, 0)
+
+                tape.record(first_bwd)
+                cur_relu = True
+            elif kind == "conv":
                 cur = conv_op(tape, FORM_S1, 3, [View(cur, cur_relu)], "net." + key, ch, want_raw=False, want_relu=True,
                               param_grad=False)
                 cur_relu = True

@@ -274,6 +274,17 @@ def im2col4x4s2(x: torch.Tensor, c: int) -> torch.Tensor:
     return out
 
 
+def im2col3x3(x: torch.Tensor, shift: Optional[torch.Tensor] = None, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """NCHW fp32 [N, c<=3, H, W] -> bf16 [N, H, W, 32], k = (ky*3+kx)*3 + ch (27 valid), optional (x - shift) / scale."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, 32), dtype=torch.bfloat16, device=x.device)
+    L.check(lib.fo_im2col3x3(x.data_ptr(), out.data_ptr(), n, c, h, w, _p(shift), _p(scale), _stream()), "fo_im2col3x3")
+    _count(1)
+    return out
+
+
 def col2im4x4s2(col: torch.Tensor, bias: Optional[torch.Tensor], c: int) -> torch.Tensor:
     """bf16 [N, Hi, Wi, 128] (k = tap*8 + co) -> NCHW fp32 [N, c, 2Hi, 2Wi] (+ bias)."""
     lib = L.load()

@@ -136,6 +136,10 @@ size_t fo_colsum_workspace_bytes(int cs);
  * models/vqvae_conv3d_latent.py:109) and the gradient of the last ConvTranspose2d(64->6,4,2,1) (:154-156) into plain
  * K=128 GEMMs on the tcgen05 kernel. */
 int fo_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w, fo_stream_t stream);
+/* 3x3 pad-1 im2col for the first VGG16 conv of LPIPS (c <= 3): x NCHW fp32 -> bf16 [n, h, w, 32], k = (ky*3+kx)*3 + ch,
+ * with the ScalingLayer (x - shift) / scale folded in (reference models/lpips.py:96-103,119). */
+int fo_im2col3x3(const float* x, void* out, int n, int c, int h, int w, const float* shift, const float* scale,
+                 fo_stream_t stream);
 /* Inverse scatter for the last ConvTranspose2d: col bf16 [n, hi, wi, 128] (k = tap*8 + co) + bias -> NCHW fp32
  * [n, c, 2hi, 2wi]. */
 int fo_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, fo_stream_t stream);
