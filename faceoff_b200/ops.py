@@ -187,8 +187,13 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
     n_pos = 1
     for v_ in (lead if form != FORM_UP else t0.shape[:-1]):
         n_pos *= int(v_)
-    with _Timed("conv_igemm", 2.0 * n_pos * cin * cout * taps):
+    flops = 2.0 * n_pos * cin * cout * taps
+    with _Timed("conv_igemm", flops):
         L.check(lib.fo_conv_run(C.byref(d), _stream()), "fo_conv_run")
+    if PROFILE is not None:   # same events, second key: per layer class (for the roofline break-down)
+        kind = ("conv3d" if ndim == 3 else f"conv{ksize}x{ksize}" if form in (FORM_S1, FORM_S1_DGRAD) else
+                "conv4x4s2" if form == FORM_DOWN else "convT4x4s2") + f"_{cin}to{cout}"
+        PROFILE.setdefault("conv_igemm/" + kind, []).append(PROFILE["conv_igemm"][-1])
     _count(1)
     return raw, relu, of32
 

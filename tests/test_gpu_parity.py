@@ -338,3 +338,34 @@ def test_vqvae_odd_shapes(T, res, cin):
     assert abs(diff.item() - ref["diff"].item()) <= 2e-2 * abs(ref["diff"].item()) + 1e-2
     dec.square().mean().backward()
     assert all(q.grad is not None and torch.isfinite(q.grad).all() for q in m.parameters())
+
+
+def test_full_size_clip_train_step_vs_oracle():
+    """BASELINE configs[0] size: one 30-frame 256x256 clip, fwd+bwd, against the CPU oracle run live (a few seconds of
+    host time).  Losses within the bf16 tolerance, indices almost everywhere equal, every gradient norm within 10 %."""
+    from oracle import faceoff_oracle as O
+
+    p = O.init_vqvae_params(seed=0)
+    img, gt = O.synthetic_clip(1, 30, 256, 256, seed=1234)
+    model = _load_vqvae(p)
+    dec, diff, id_t, id_b = model.forward_with_ids(img.cuda(), clips=1)
+    recon = torch.nn.functional.mse_loss(dec[:, :3], gt.cuda())
+    (recon + diff.mean()).backward()
+    torch.cuda.synchronize()
+    torch.set_num_threads(os.cpu_count() or 1)
+    o = O.train_step(p, img, gt, n_clips=1)
+    assert abs(recon.item() - o["recon_loss"].item()) <= BF16_RTOL * abs(o["recon_loss"].item()) + BF16_ATOL
+    assert abs(diff.mean().item() - o["latent_loss"].item()) <= BF16_RTOL * abs(o["latent_loss"].item()) + BF16_ATOL
+    assert (id_t.cpu() == o["id_t"]).float().mean().item() > 0.98
+    assert (id_b.cpu() == o["id_b"]).float().mean().item() > 0.98
+    assert maxnorm_err(dec.cpu(), o["dec"]) < 3e-2
+    worst = 0.0
+    for k, v in model.named_parameters():
+        nref = o["grads"][k].norm().item()
+        rel = abs(v.grad.norm().item() - nref) / (nref + 1e-12)
+        worst = max(worst, rel)
+    print(f"full-size clip: worst grad-norm rel err {worst:.3e}")
+    assert worst < 0.1
+    for q in ("quantize_t", "quantize_b"):
+        for i, name in enumerate(("embed", "cluster_size", "embed_avg")):
+            assert maxnorm_err(getattr(getattr(model, q), name).cpu(), o["new_buffers"][q][i]) < 2e-2, (q, name)
