@@ -172,6 +172,10 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     if (src.c_off + cpad > src.cs) return fail(FO_ERR_INVALID, "source slice [%d,+%d) exceeds storage %d", src.c_off, cpad, src.cs);
     while (cpad % kc != 0) kc /= 2;
   }
+  {
+    const char* e = getenv("FO_FORCE_KC");   // experiments only
+    if (e && (atoi(e) == 32 || atoi(e) == 16) && atoi(e) < kc) kc = atoi(e);
+  }
   if (kc < 16) return fail(FO_ERR_INVALID, "channel counts must be multiples of 16 after padding");
   p.KC = kc;
   const int rowb = kc * 2;
