@@ -757,7 +757,7 @@ extern "C" int fo_vq_prep(const float* embed, int dim, int n_embed, void* e_spli
   return FO_OK;
 }
 extern "C" size_t fo_vq_assign_workspace_bytes(size_t rows, int dim) { return vq_assign_workspace_bytes(rows, dim); }
-extern "C" int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* embed, const void* e_split,
+extern "C" int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* e_t, const void* e_split,
                             const float* e_norm2, int64_t* embed_ind, int* n_flagged, void* workspace,
                             size_t workspace_bytes, fo_stream_t stream) {
   REQUIRE_INIT();
@@ -771,7 +771,7 @@ extern "C" int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, c
   uint32_t bx[2] = {64, 256};
   int rc = encode_map(&map_e, e_split, 2, dims, str, bx, 128);
   if (rc != FO_OK) return rc;
-  CUDA_TRY(launch_vq_assign(x, rows, dim, n_embed, embed, e_split, e_norm2, embed_ind, n_flagged, workspace, &map_e,
+  CUDA_TRY(launch_vq_assign(x, rows, dim, n_embed, e_t, e_split, e_norm2, embed_ind, n_flagged, workspace, &map_e,
                             g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }

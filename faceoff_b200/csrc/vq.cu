@@ -56,7 +56,8 @@ cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_spl
 }
 
 // =============================================================================== assign (tcgen05)
-constexpr int kVqThreads = 32 * 10;  // warp0 TMA(B), warp1 MMA, warps 2-5 loader/convert, warps 6-9 epilogue
+constexpr int kVqThreads = 32 * 14;  // warp0 TMA(B), warp1 MMA, warps 2-5 loader/convert, warps 6-13 epilogue (two
+                                     // column halves x four TMEM lane quarters)
 constexpr int kVqNT = 256;           // codes per accumulator
 constexpr int kVqBStages = 4;        // ring of [256 x 64] bf16 B tiles (32 KB each)
 constexpr float kVqBand = 1.5e-4f;   // |error of dist_k| <= kVqBand * |x| * |e_k|  (2.5x the split-bf16 bound 2*3*2^-17)
@@ -87,7 +88,8 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
   float* sE2 = reinterpret_cast<float*>(sB + (size_t)kVqBStages * b_tile);  // [n_tiles*256]
   float* sEN = sE2 + p.n_tiles * kVqNT;                                      // [n_tiles*256]  |e_k|
   float* sX2 = sEN + p.n_tiles * kVqNT;                                      // [4][128] (epilogue may lag the loader by 3 tiles)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sX2 + 4 * 128);
+  float* sMerge = sX2 + 4 * 128;                                             // [2][128][4] column-half hand-over
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sMerge + 2 * 128 * 4);
   uint64_t* b_full = bars;                    // [kVqBStages]
   uint64_t* b_empty = b_full + kVqBStages;    // [kVqBStages]
   uint64_t* a_full = b_empty + kVqBStages;    // [2]
@@ -113,7 +115,7 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
       mbar_init(&a_full[b], 128);
       mbar_init(&a_empty[b], 1);
       mbar_init(&t_full[b], 1);
-      mbar_init(&t_empty[b], 4);
+      mbar_init(&t_empty[b], 8);
     }
     fence_mbar_init();
   }
@@ -249,6 +251,7 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
   } else {
     // ---------------------------------------------------------------- epilogue: running top-2 argmin per row
     const int quarter = warp & 3;
+    const int half = (warp - 6) >> 2;        // which 128 columns of every 256-column accumulator this warp scans
     const int row = quarter * 32 + lane;
     const float INF = __int_as_float(0x7f800000);
     int it = 0, acc_it = 0;
@@ -256,8 +259,12 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
       // best = smallest distance so far; other_lb = smallest LOWER bound among all other codes, where code k's
       // distance is only known to +- kVqBand * |x| * |e_k| (split-bf16 product error, scaled per code so that dead
       // codes with huge norms -- the EMA renormalisation blows unused codes up, reference :70-75 -- do not widen it)
-      float best = INF, best_err = 0.f, other_lb = INF;
-      int besti = 0;
+      // Four independent running minima (columns j, j+4, ...): one chain would serialise 512 dependent compare/select
+      // steps per row; they are merged after the last code tile.
+      float best[4], berr[4], other[4];
+      int bidx[4];
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) { best[ch] = INF; berr[ch] = 0.f; other[ch] = INF; bidx[ch] = 0; }
       float x2 = 0.f, cx = 0.f;
       for (int nt = 0; nt < p.n_tiles; ++nt, ++acc_it) {
         const int tb = acc_it & 1;
@@ -271,33 +278,61 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
         const float* e2 = sE2 + nt * kVqNT;
         const float* en = sEN + nt * kVqNT;
 #pragma unroll 1
-        for (int c = 0; c < kVqNT; c += 32) {
+        for (int c = half * (kVqNT / 2); c < (half + 1) * (kVqNT / 2); c += 32) {
           uint32_t v[32];
           tmem_ld32(taddr + c, v);
           tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
+            const int ch = j & 3;
             // same association as the reference: (|x|^2 - 2 x.e) + |e|^2   (:49-53)
             const float d = (x2 - 2.f * __uint_as_float(v[j])) + e2[c + j];
             const float err = cx * en[c + j];
-            if (d < best) {
-              other_lb = fminf(other_lb, best - best_err);
-              best = d;
-              best_err = err;
-              besti = nt * kVqNT + c + j;
-            } else {
-              other_lb = fminf(other_lb, d - err);
-            }
+            const bool lt = d < best[ch];   // strict: the lower index wins ties inside a chain
+            // the loser of the comparison only contributes its lower bound
+            other[ch] = fminf(other[ch], lt ? best[ch] - berr[ch] : d - err);
+            best[ch] = lt ? d : best[ch];
+            berr[ch] = lt ? err : berr[ch];
+            bidx[ch] = lt ? nt * kVqNT + c + j : bidx[ch];
           }
         }
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[tb]);
       }
+      // merge the chains (ties -> lowest index, the reference's first-max rule :54)
+      float bestv = best[0], best_err = berr[0], other_lb = other[0];
+      int besti = bidx[0];
+#pragma unroll
+      for (int ch = 1; ch < 4; ++ch) {
+        const bool lt = best[ch] < bestv || (best[ch] == bestv && bidx[ch] < besti);
+        other_lb = fminf(other_lb, lt ? bestv - best_err : best[ch] - berr[ch]);
+        other_lb = fminf(other_lb, other[ch]);
+        bestv = lt ? best[ch] : bestv;
+        best_err = lt ? berr[ch] : best_err;
+        besti = lt ? bidx[ch] : besti;
+      }
+      // hand the upper column half over to the lower one (named barrier 1: the 256 epilogue threads)
+      float* mg = sMerge + ((it & 1) * 128 + row) * 4;
+      if (half == 1) {
+        mg[0] = bestv; mg[1] = best_err; mg[2] = other_lb; mg[3] = __int_as_float(besti);
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      if (half == 1) continue;
+      {
+        const float b1 = mg[0], e1 = mg[1], o1 = mg[2];
+        const int i1 = __float_as_int(mg[3]);
+        const bool lt = b1 < bestv || (b1 == bestv && i1 < besti);   // ties -> lowest index
+        other_lb = fminf(other_lb, lt ? bestv - best_err : b1 - e1);
+        other_lb = fminf(other_lb, o1);
+        bestv = lt ? b1 : bestv;
+        best_err = lt ? e1 : best_err;
+        besti = lt ? i1 : besti;
+      }
       const size_t grow = (size_t)rt * 128 + row;
       if (grow < p.rows) {
         p.embed_ind[grow] = besti;
-        if (!(other_lb > best + best_err)) {   // ambiguous within the error bound (also catches NaN)
+        if (!(other_lb > bestv + best_err)) {   // ambiguous within the error bound (also catches NaN)
           const int slot = atomicAdd(p.flag_count, 1);
           p.flag_rows[slot] = (int)grow;   // capacity = rows
         }
@@ -313,8 +348,10 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
   }
 }
 
-// exact re-evaluation of flagged rows: fp64 accumulation, first minimum wins (reference tie rule :54)
-__global__ void vq_refine_kernel(const float* __restrict__ x, const float* __restrict__ embed, int dim, int n_embed,
+// exact re-evaluation of flagged rows: fp64 accumulation, first minimum wins (reference tie rule :54).
+// One warp per row; each lane scans codes lane, lane+32, ... of the transposed codebook e_t [n_embed][dim] with 16-byte
+// loads and four independent fp64 accumulators.
+__global__ void vq_refine_kernel(const float* __restrict__ x, const float* __restrict__ e_t, int dim, int n_embed,
                                  const int* __restrict__ flag_count, const int* __restrict__ flag_rows,
                                  long long* __restrict__ embed_ind) {
   extern __shared__ float sx[];  // [warps][dim]
@@ -330,13 +367,18 @@ __global__ void vq_refine_kernel(const float* __restrict__ x, const float* __res
     double best = 1e300;
     int besti = 0x7fffffff;
     for (int k = lane; k < n_embed; k += 32) {
-      double dot = 0.0, e2 = 0.0;
-      for (int d = 0; d < dim; ++d) {
-        const double e = (double)embed[(size_t)d * n_embed + k];
-        dot += (double)myx[d] * e;
-        e2 += e * e;
+      const float4* er = reinterpret_cast<const float4*>(e_t + (size_t)k * dim);
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      for (int q = 0; q < dim / 4; ++q) {
+        const float4 e = __ldg(er + q);
+        const float4 xv = *reinterpret_cast<const float4*>(myx + 4 * q);
+        // e^2 - 2 x e, term by term (|x|^2 is common to all codes)
+        a0 += (double)e.x * ((double)e.x - 2.0 * (double)xv.x);
+        a1 += (double)e.y * ((double)e.y - 2.0 * (double)xv.y);
+        a2 += (double)e.z * ((double)e.z - 2.0 * (double)xv.z);
+        a3 += (double)e.w * ((double)e.w - 2.0 * (double)xv.w);
       }
-      const double dist = e2 - 2.0 * dot;  // |x|^2 is common to all codes
+      const double dist = (a0 + a1) + (a2 + a3);
       if (dist < best) { best = dist; besti = k; }
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -353,11 +395,11 @@ size_t vq_assign_smem_bytes(int dim, int n_embed) {
   const int a_bufs = dim <= 64 ? 2 : 1;
   const int n_tiles = (n_embed + kVqNT - 1) / kVqNT;
   return (size_t)a_bufs * 2 * kchunks * 128 * 128 + (size_t)kVqBStages * kVqNT * 128 + (size_t)n_tiles * kVqNT * 8 +
-         4 * 128 * 4 + (2 * kVqBStages + 8) * 8 + 16 + 1024;
+         4 * 128 * 4 + 2 * 128 * 4 * 4 + (2 * kVqBStages + 8) * 8 + 16 + 1024;
 }
 size_t vq_assign_workspace_bytes(size_t rows, int dim) { return 256 + rows * sizeof(int); }
 
-cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* embed,
+cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* e_t,
                              const void* e_split, const float* e_norm2, int64_t* embed_ind, int* n_flagged,
                              void* workspace, const CUtensorMap* map_e, int num_sms, cudaStream_t st) {
   (void)e_split;
@@ -379,7 +421,7 @@ cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, 
   if (e != cudaSuccess) return e;
   const int warps = 8;
   vq_refine_kernel<<<num_sms * 2, warps * 32, warps * dim * sizeof(float), st>>>(
-      x, embed, dim, n_embed, p.flag_count, p.flag_rows, reinterpret_cast<long long*>(embed_ind));
+      x, e_t, dim, n_embed, p.flag_count, p.flag_rows, reinterpret_cast<long long*>(embed_ind));
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (n_flagged != nullptr) e = cudaMemcpyAsync(n_flagged, p.flag_count, sizeof(int), cudaMemcpyDeviceToDevice, st);

@@ -355,17 +355,17 @@ def vq_prep(embed: torch.Tensor):
     return e_split, e_t, e_norm2
 
 
-def vq_assign(x: torch.Tensor, embed: torch.Tensor, e_split: torch.Tensor, e_norm2: torch.Tensor,
+def vq_assign(x: torch.Tensor, e_t: torch.Tensor, e_split: torch.Tensor, e_norm2: torch.Tensor,
               n_flagged: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """x fp32 [rows, dim] -> embed_ind int64 [rows]."""
+    """x fp32 [rows, dim] -> embed_ind int64 [rows]; e_t / e_split / e_norm2 from vq_prep."""
     lib = L.load()
     rows, dim = x.shape
-    n_embed = embed.shape[1]
-    assert x.dtype == torch.float32 and x.is_contiguous()
+    n_embed = e_t.shape[0]
+    assert x.dtype == torch.float32 and x.is_contiguous() and e_t.shape[1] == dim
     ind = torch.empty(rows, dtype=torch.int64, device=x.device)
     need = lib.fo_vq_assign_workspace_bytes(rows, dim)
     ws = workspace(need, x.device, "vq")
-    L.check(lib.fo_vq_assign(x.data_ptr(), rows, dim, n_embed, embed.data_ptr(), e_split.data_ptr(),
+    L.check(lib.fo_vq_assign(x.data_ptr(), rows, dim, n_embed, e_t.data_ptr(), e_split.data_ptr(),
                              e_norm2.data_ptr(), ind.data_ptr(), _p(n_flagged), ws.data_ptr(), ws.numel(), _stream()),
             "fo_vq_assign")
     _count(2)

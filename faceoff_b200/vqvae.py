@@ -48,7 +48,7 @@ def _quantize_forward(q: "Quantize", x32: torch.Tensor, want_bf16: bool):
     """x32: fp32 [rows, dim] contiguous.  Returns (q_f32, q_bf16|None, diff_sum[1], ind[rows], e_t)."""
     rows, dim = x32.shape
     e_split, e_t, e_n2 = ops.vq_prep(q.embed)
-    ind = ops.vq_assign(x32, q.embed, e_split, e_n2, q.n_flagged)
+    ind = ops.vq_assign(x32, e_t, e_split, e_n2, q.n_flagged)
     diff_sum = torch.zeros(1, dtype=torch.float32, device=x32.device)
     counts = embed_sum = None
     if q.training:

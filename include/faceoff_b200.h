@@ -160,9 +160,9 @@ int fo_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int 
 int fo_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
                fo_stream_t stream);
 /* Nearest-code assignment (:48-54).  x fp32 [rows, dim].  embed_ind int64 [rows].
- * Tensor-core distances (bf16 split, error-bounded) + exact fp32 re-evaluation of rows whose top-2 gap is
- * inside the error band; n_flagged (device int32, optional) counts those rows. */
-int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* embed, const void* e_split,
+ * e_t / e_split / e_norm2 come from fo_vq_prep.  Tensor-core distances (bf16 split, error-bounded per code) + exact
+ * (fp64-accumulated) re-evaluation of the rows that are ambiguous within the bound; n_flagged (device int32, optional) counts those rows. */
+int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* e_t, const void* e_split,
                  const float* e_norm2, int64_t* embed_ind, int* n_flagged, void* workspace, size_t workspace_bytes,
                  fo_stream_t stream);
 size_t fo_vq_assign_workspace_bytes(size_t rows, int dim);

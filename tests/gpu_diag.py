@@ -319,7 +319,7 @@ def case_vq():
         e = rnd(dim, K, seed=2)
         e_split, e_t, e_n2 = ops.vq_prep(e)
         nf = torch.zeros(1, dtype=torch.int32, device=dev)
-        ind = ops.vq_assign(x, e, e_split, e_n2, nf)
+        ind = ops.vq_assign(x, e_t, e_split, e_n2, nf)
         torch.cuda.synchronize()
         ref_ind, dist = O.quantize_assign(x.double().cpu(), e.double().cpu())
         mism = (ind.cpu() != ref_ind).sum().item()

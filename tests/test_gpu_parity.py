@@ -88,7 +88,7 @@ def test_vq_assign_bit_exact_vs_fp64(rows, dim, K):
     e = torch.randn(dim, K, generator=gen)
     xs, es = x.cuda(), e.cuda()
     e_split, e_t, e_n2 = ops.vq_prep(es)
-    ind = ops.vq_assign(xs, es, e_split, e_n2).cpu()
+    ind = ops.vq_assign(xs, e_t, e_split, e_n2).cpu()
     d = x.double().pow(2).sum(1, keepdim=True) - 2 * x.double() @ e.double() + e.double().pow(2).sum(0, keepdim=True)
     ref = d.argmin(1)
     assert torch.equal(ind, ref), f"{(ind != ref).sum().item()} mismatches"
@@ -314,7 +314,7 @@ def test_quantize_with_dead_codes_of_huge_norm():
     xs, es = x.cuda(), e.cuda()
     e_split, e_t, e_n2 = ops.vq_prep(es)
     nf = torch.zeros(1, dtype=torch.int32, device="cuda")
-    ind = ops.vq_assign(xs, es, e_split, e_n2, nf).cpu()
+    ind = ops.vq_assign(xs, e_t, e_split, e_n2, nf).cpu()
     d = x.double().pow(2).sum(1, keepdim=True) - 2 * x.double() @ e.double() + e.double().pow(2).sum(0, keepdim=True)
     assert torch.equal(ind, d.argmin(1))
     assert nf.item() < 0.05 * x.shape[0], f"{nf.item()} rows re-checked"
