@@ -269,6 +269,8 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
       p.a_ops = want;
     const char* sk = getenv("FO_SKIP_MMA");
     p.dbg_skip_mma = sk ? atoi(sk) : 0;
+    const char* bo = getenv("FO_BACKOFF");
+    p.backoff_ns = bo ? atoi(bo) : 0;
   }
   p.a_op_rows = a_rows / p.a_ops;
   if (s1) {
@@ -598,6 +600,8 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
   {
     const char* sk = getenv("FO_SKIP_MMA");
     p.dbg_skip_mma = sk ? atoi(sk) : 0;
+    const char* bo = getenv("FO_BACKOFF");
+    p.backoff_ns = bo ? atoi(bo) : 0;
     const char* st = getenv("FO_WG_STAGES");
     if (st && atoi(st) >= 2 && atoi(st) <= p.stages) p.stages = atoi(st);
   }

@@ -66,6 +66,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+// Same, for waits that are expected to be long (a producer whose ring is full, an issuer waiting for the epilogue): the
+// polling loop sleeps between probes so that it does not take issue slots from the warps doing the work.
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, unsigned ns) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  do {
+    __nanosleep(ns);
+    if (++spins > FO_SPIN_LIMIT) {
+      printf("[faceoff_b200] mbarrier timeout block %d thread %d bar@%u parity %u\n", blockIdx.x, threadIdx.x,
+             smem_u32(bar), parity);
+      __trap();
+    }
+  } while (!mbar_try_wait(bar, parity));
+}
+
+__device__ __forceinline__ void mbar_wait_ns(uint64_t* bar, uint32_t parity, int ns) {
+  if (ns > 0) mbar_wait_backoff(bar, parity, (unsigned)ns);
+  else mbar_wait(bar, parity);
+}
 
 // ------------------------------------------------------------------ cp.async (LDGSTS)
 __device__ __forceinline__ void cp_async16(void* dst_smem, const void* src) {

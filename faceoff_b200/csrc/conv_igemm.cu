@@ -292,7 +292,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
         const KStep* ks = p.ksteps + g * p.num_ksteps;
         const int kcol0 = g * p.num_ksteps * p.TPS * p.KC;
         for (int k = 0; k < p.num_ksteps; ++k) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
+          mbar_wait_ns(&empty_bar[stage], phase ^ 1, p.backoff_ns);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           mbar_expect_tx(&full_bar[stage], a_bytes + p.TPS * b_bytes);
@@ -319,7 +319,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     int it = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      mbar_wait(&tempty_bar[buf], ((it >> 1) & 1) ^ 1);
+      mbar_wait_ns(&tempty_bar[buf], ((it >> 1) & 1) ^ 1, p.backoff_ns);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + buf * p.MT * p.NT;
       for (int k = 0; k < p.num_ksteps; ++k) {
@@ -416,7 +416,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       row_geometry(base, g, my_m, off, valid);
       const int ebuf = my_m;
       if (prefetch) issue_prefetch(ebuf, off, valid, ncol0);   // buffer was last read by this warp in the previous tile
-      mbar_wait(&tfull_bar[buf], (it >> 1) & 1);
+      mbar_wait_ns(&tfull_bar[buf], (it >> 1) & 1, p.backoff_ns);
       tc_fence_after();
       {
         const int m = my_m;

@@ -33,6 +33,7 @@ struct ConvParams {
   int a_ops;          // the A box is fetched by a_ops TMA operations of a_op_rows image rows each (more ops in flight)
   int a_op_rows;
   int dbg_skip_mma;   // debug: do not issue MMAs (measures the pure TMA streaming rate)
+  int backoff_ns;     // sleep between mbarrier probes of the long waits (0 = plain polling)
   int e_bufs;         // epilogue operand prefetch: 0 = off, else MT (one buffer set per M sub-tile / warp group)
   int e_mask, e_add;  // which of the two epilogue operands are prefetched (shared memory permitting)
   int n_tiles;        // N tiles of width NT
@@ -91,6 +92,7 @@ struct WgradParams {
   int stages;
   int p_c0;              // channel offset of the P side inside its map
   int dbg_skip_mma;      // debug: do not issue MMAs (pure TMA streaming rate)
+  int backoff_ns;        // sleep between mbarrier probes of the long waits (0 = plain polling)
   float* partial;        // [splits][passes*taps_per_pass][MC][NC] fp32
   float* bias_partial;   // [passes][splits][MC] partial column sums of P (= bias gradient) or null
   WgTap taps[64];        // passes * taps_per_pass entries (padded entries have map = 255)

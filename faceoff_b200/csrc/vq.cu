@@ -61,28 +61,100 @@ constexpr int kVqThreads = 32 * 14;  // warp0 TMA(B), warp1 MMA, warps 2-5 loade
 constexpr int kVqNT = 256;           // codes per accumulator
 constexpr int kVqBStages = 4;        // ring of [256 x 64] bf16 B tiles (32 KB each)
 constexpr float kVqBand = 1.5e-4f;   // |error of dist_k| <= kVqBand * |x| * |e_k|  (2.5x the split-bf16 bound 2*3*2^-17)
+constexpr float kVqBig = 1e38f;      // score of padded codes / "no candidate yet" (finite: the index tag must not make a NaN)
 
 struct VqAssignParams {
   const float* x;
   size_t rows;
   int dim, n_embed;
   int n_tiles;      // ceil(n_embed / 256)
-  int kchunks;      // dim / 64
   int a_bufs;       // 1 or 2
   int row_tiles;    // ceil(rows / 128)
   const float* e_norm2;  // [n_embed + 1]
   long long* embed_ind;
   int* flag_count;
   int* flag_rows;
+  float* flag_u;    // per flagged row: certain upper bound of the winner's |e|^2 - 2 x.e
 };
 
-__global__ void __launch_bounds__(kVqThreads, 1)
+// tcgen05.wait::ld that also names the destination registers, so that no consumer can be scheduled above it
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&v)[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                 "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]),
+                 "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]),
+                 "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
+}
+
+// One halving step of a transposed butterfly reduction: N values per lane, lanes `off` apart exchange the half they do
+// not keep.  After the steps off = 8N/16 ... the lane whose index bits select value u holds its full sum in s[0].
+template <int N>
+__device__ __forceinline__ void vq_halve(float (&s)[16], int lane, int off) {
+  const bool upper = (lane & off) != 0;
+#pragma unroll
+  for (int j = 0; j < N / 2; ++j) {
+    const float keep = upper ? s[j + N / 2] : s[j];
+    const float send = upper ? s[j] : s[j + N / 2];
+    s[j] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+  }
+}
+
+// Scan 32 accumulator columns: lower bound lo_k = (|e_k|^2 - 2 x.e_k) - band_k of every code's distance (|x|^2 is
+// common to the row and dropped), tagged with the column number in the 5 low mantissa bits, folded into the running
+// two smallest (m1 <= m2).  About 4.5 issue slots per code: 2 x 1/2 FFMA2, 1 LOP3, ~2.5 FMNMX/FMNMX3, 1/2 LDS.
+__device__ __forceinline__ void vq_scan32(const uint32_t (&v)[32], const float* __restrict__ e2,
+                                          const float* __restrict__ en, float ncx, uint32_t tag_mask, float& r1,
+                                          float& r2, int& ridx, int code0) {
+  float a1 = kVqBig, a2 = kVqBig, b1 = kVqBig, b2 = kVqBig;
+  const float2 neg2 = make_float2(-2.f, -2.f), nc = make_float2(ncx, ncx);
+#pragma unroll
+  for (int j4 = 0; j4 < 32; j4 += 4) {
+    const float4 q2 = *reinterpret_cast<const float4*>(e2 + j4);
+    const float4 qn = *reinterpret_cast<const float4*>(en + j4);
+    const float2 d01 = __ffma2_rn(make_float2(__uint_as_float(v[j4]), __uint_as_float(v[j4 + 1])), neg2,
+                                  make_float2(q2.x, q2.y));
+    const float2 d23 = __ffma2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), neg2,
+                                  make_float2(q2.z, q2.w));
+    const float2 l01 = __ffma2_rn(make_float2(qn.x, qn.y), nc, d01);
+    const float2 l23 = __ffma2_rn(make_float2(qn.z, qn.w), nc, d23);
+    const float lo[4] = {l01.x, l01.y, l23.x, l23.y};
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj) {
+      // tag_mask lives in a register so that (lo & mask) | j is ONE LOP3 (a single immediate per instruction)
+      const float t = __uint_as_float((__float_as_uint(lo[jj]) & tag_mask) | (uint32_t)(j4 + jj));
+      if (jj & 1) {
+        const float mx = fmaxf(b1, t);
+        b1 = fminf(b1, t);
+        b2 = fminf(b2, mx);
+      } else {
+        const float mx = fmaxf(a1, t);
+        a1 = fminf(a1, t);
+        a2 = fminf(a2, mx);
+      }
+    }
+  }
+  const float m1 = fminf(a1, b1);
+  const float m2 = fminf(fmaxf(a1, b1), fminf(a2, b2));
+  const bool lt = m1 < r1;
+  r2 = fminf(fminf(r2, m2), fmaxf(r1, m1));
+  ridx = lt ? code0 + (int)(__float_as_uint(m1) & 31u) : ridx;
+  r1 = fminf(r1, m1);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kVqThreads, 1)   // 128 registers: 4 warps of a 16 K-register SM sub-partition
 vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant__ CUtensorMap map_e) {
+  constexpr int KCH = DIM / 64;                         // 64-wide K chunks
+  constexpr int Q4 = DIM / 4;                           // float4 (= loader lanes) per row: 16 or 32
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int a_sub = 128 * 128;                          // one [128 x 64] bf16 swizzled sub-tile
-  const int a_buf_bytes = 2 * p.kchunks * a_sub;        // hi chunks then lo chunks
-  const int b_tile = kVqNT * 128;                       // [256 x 64] bf16
+  // (offset arithmetic instead of a pointer round-trip keeps the shared address space known: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  constexpr int a_sub = 128 * 128;                      // one [128 x 64] bf16 swizzled sub-tile
+  constexpr int a_buf_bytes = 2 * KCH * a_sub;          // hi chunks then lo chunks
+  constexpr int b_tile = kVqNT * 128;                   // [256 x 64] bf16
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_bufs * a_buf_bytes;
   float* sE2 = reinterpret_cast<float*>(sB + (size_t)kVqBStages * b_tile);  // [n_tiles*256]
@@ -119,9 +191,9 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     }
     fence_mbar_init();
   }
-  // |e|^2 to smem (padded codes get +inf so they never win)
+  // |e|^2 and |e| to smem (padded codes get a huge score so they never win)
   for (int k = threadIdx.x; k < p.n_tiles * kVqNT; k += blockDim.x) {
-    sE2[k] = k < p.n_embed ? p.e_norm2[k] : __int_as_float(0x7f800000);
+    sE2[k] = k < p.n_embed ? p.e_norm2[k] : kVqBig;
     sEN[k] = k < p.n_embed ? sqrtf(p.e_norm2[k]) : 0.f;
   }
   tc_fence_before();
@@ -137,11 +209,11 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
       uint32_t phase = 0;
       for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
         for (int nt = 0; nt < p.n_tiles; ++nt)
-          for (int kc = 0; kc < p.kchunks; ++kc)
+          for (int kc = 0; kc < KCH; ++kc)
             for (int part = 0; part < 2; ++part) {  // 0: hi, 1: lo
-              mbar_wait(&b_empty[stage], phase ^ 1);
+              mbar_wait_backoff(&b_empty[stage], phase ^ 1, 64);
               mbar_expect_tx(&b_full[stage], b_tile);
-              tma_load_2d(sB + (size_t)stage * b_tile, &map_e, &b_full[stage], part * p.dim + kc * 64, nt * kVqNT);
+              tma_load_2d(sB + (size_t)stage * b_tile, &map_e, &b_full[stage], part * DIM + kc * 64, nt * kVqNT);
               if (++stage == kVqBStages) { stage = 0; phase ^= 1; }
             }
       }
@@ -155,19 +227,20 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     int it = 0, acc_it = 0;
     for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, ++it) {
       const int ab = it % p.a_bufs;
-      mbar_wait(&a_full[ab], (it / p.a_bufs) & 1);
+      mbar_wait_backoff(&a_full[ab], (it / p.a_bufs) & 1, 32);
       tc_fence_after();
       const uint32_t a_base = smem_u32(sA + (size_t)ab * a_buf_bytes);
       for (int nt = 0; nt < p.n_tiles; ++nt, ++acc_it) {
         const int tb = acc_it & 1;
-        mbar_wait(&t_empty[tb], ((acc_it >> 1) & 1) ^ 1);
+        mbar_wait_backoff(&t_empty[tb], ((acc_it >> 1) & 1) ^ 1, 32);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + tb * kVqNT;
-        for (int kc = 0; kc < p.kchunks; ++kc) {
+#pragma unroll
+        for (int kc = 0; kc < KCH; ++kc) {
           const uint64_t a_hi = desc_base + (((a_base + kc * a_sub) & 0x3FFFF) >> 4);
-          const uint64_t a_lo = desc_base + (((a_base + (p.kchunks + kc) * a_sub) & 0x3FFFF) >> 4);
+          const uint64_t a_lo = desc_base + (((a_base + (KCH + kc) * a_sub) & 0x3FFFF) >> 4);
           // B hi tile: hi*hi and lo*hi
-          mbar_wait(&b_full[stage], phase);
+          mbar_wait_backoff(&b_full[stage], phase, 20);
           tc_fence_after();
           if (lane == 0) {
             const uint64_t sb = desc_base + ((smem_u32(sB + (size_t)stage * b_tile) & 0x3FFFF) >> 4);
@@ -180,7 +253,7 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
           __syncwarp();
           if (++stage == kVqBStages) { stage = 0; phase ^= 1; }
           // B lo tile: hi*lo
-          mbar_wait(&b_full[stage], phase);
+          mbar_wait_backoff(&b_full[stage], phase, 20);
           tc_fence_after();
           if (lane == 0) {
             const uint64_t sb = desc_base + ((smem_u32(sB + (size_t)stage * b_tile) & 0x3FFFF) >> 4);
@@ -199,142 +272,130 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     }
   } else if (warp < 6) {
     // ---------------------------------------------------------------- loader: fp32 rows -> bf16 hi/lo swizzled tiles
+    // Q4 consecutive lanes read one row (coalesced 16-byte loads); a thread's 16 loads of a batch belong to 16 rows.
     const int t = threadIdx.x - 64;         // 0..127
-    const int q4 = p.dim / 4;               // float4 per row
-    const int rows_per_iter = 128 / q4;     // 8 (dim 64) or 4 (dim 128)
+    const int q = t & (Q4 - 1);             // float4 column of this lane
+    const int rsub = t / Q4;                // row within the 128/Q4 rows one load instruction covers
+    constexpr int RPI = 128 / Q4;           // rows per load instruction: 8 or 4
+    const int kc = (q * 4) >> 6, kin = (q * 4) & 63;
     int it = 0;
     for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, ++it) {
       const int ab = it % p.a_bufs;
-      mbar_wait(&a_empty[ab], ((it / p.a_bufs) & 1) ^ 1);
-      uint8_t* a_base = sA + (size_t)ab * a_buf_bytes;
       const size_t row0 = (size_t)rt * 128;
-      // all global loads of the tile are issued before the first use (16 x 16 B in flight per thread): the loop would
-      // otherwise expose one DRAM latency per iteration
-      for (int i0 = 0; i0 < q4; i0 += 16) {
+      uint8_t* a_base = sA + (size_t)ab * a_buf_bytes;
+      bool waited = false;
+#pragma unroll 1
+      for (int i0 = 0; i0 < Q4; i0 += 16) {
+        // all 16 loads are in flight before the first use; they do not depend on the smem buffer being free
         float4 vv[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const int idx = (i0 + u) * 128 + t;
-          const int r = idx / q4, q = idx % q4;
+          const int r = (i0 + u) * RPI + rsub;
           vv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row0 + r < p.rows) vv[u] = __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * p.dim) + q);
+          if (row0 + r < p.rows) vv[u] = __ldg(reinterpret_cast<const float4*>(p.x + (row0 + r) * DIM) + q);
         }
+        if (!waited) {
+          mbar_wait_backoff(&a_empty[ab], ((it / p.a_bufs) & 1) ^ 1, 64);
+          waited = true;
+        }
+        float s[16];
 #pragma unroll
         for (int u = 0; u < 16; ++u) {
-          const int idx = (i0 + u) * 128 + t;
-          const int r = idx / q4, q = idx % q4;
+          const int r = (i0 + u) * RPI + rsub;
           const float4 v = vv[u];
-          // |x|^2 of the row: reduce over the q4 lanes that share it
-          float s = v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-          for (int o = q4 >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o, 32);
-          if (q == 0) sX2[(it & 3) * 128 + r] = s;
-          const __nv_bfloat16 h0 = __float2bfloat16(v.x), h1 = __float2bfloat16(v.y), h2 = __float2bfloat16(v.z),
-                              h3 = __float2bfloat16(v.w);
-          const float l0 = v.x - __bfloat162float(h0), l1 = v.y - __bfloat162float(h1),
-                      l2 = v.z - __bfloat162float(h2), l3 = v.w - __bfloat162float(h3);
-          const int k = q * 4;
-          const int kc = k >> 6, kin = k & 63;
-          const uint32_t off = (uint32_t)r * 128 + ((((uint32_t)kin >> 3) ^ ((uint32_t)r & 7)) << 4) + (kin & 7) * 2;
+          s[u] = (v.x * v.x + v.y * v.y) + (v.z * v.z + v.w * v.w);
+          // hi = bf16(v) (packed pair conversion), lo = bf16(v - hi)
           uint2 hv, lv;
-          hv.x = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          hv.y = (uint32_t)__bfloat16_as_ushort(h2) | ((uint32_t)__bfloat16_as_ushort(h3) << 16);
-          lv.x = pack_bf16x2(l0, l1);
-          lv.y = pack_bf16x2(l2, l3);
+          hv.x = pack_bf16x2(v.x, v.y);
+          hv.y = pack_bf16x2(v.z, v.w);
+          lv.x = pack_bf16x2(v.x - __uint_as_float(hv.x << 16), v.y - __uint_as_float(hv.x & 0xFFFF0000u));
+          lv.y = pack_bf16x2(v.z - __uint_as_float(hv.y << 16), v.w - __uint_as_float(hv.y & 0xFFFF0000u));
+          const uint32_t off = (uint32_t)r * 128 + ((((uint32_t)kin >> 3) ^ ((uint32_t)r & 7)) << 4) + (kin & 7) * 2;
           *reinterpret_cast<uint2*>(a_base + kc * a_sub + off) = hv;
-          *reinterpret_cast<uint2*>(a_base + (p.kchunks + kc) * a_sub + off) = lv;
+          *reinterpret_cast<uint2*>(a_base + (KCH + kc) * a_sub + off) = lv;
+        }
+        // |x|^2 of the 16 rows: transposed butterfly over the Q4 lanes of a row (15 or 16 shuffles instead of 64+)
+        if (Q4 == 32) {
+          vq_halve<16>(s, lane, 16); vq_halve<8>(s, lane, 8); vq_halve<4>(s, lane, 4); vq_halve<2>(s, lane, 2);
+          s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
+          if ((q & 1) == 0) sX2[(it & 3) * 128 + (i0 + (q >> 1)) * RPI + rsub] = s[0];
+        } else {
+          vq_halve<16>(s, lane, 8); vq_halve<8>(s, lane, 4); vq_halve<4>(s, lane, 2); vq_halve<2>(s, lane, 1);
+          sX2[(it & 3) * 128 + (i0 + q) * RPI + rsub] = s[0];
         }
       }
-      (void)rows_per_iter;
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(&a_full[ab]);
     }
   } else {
-    // ---------------------------------------------------------------- epilogue: running top-2 argmin per row
+    // ---------------------------------------------------------------- epilogue: two smallest lower bounds per row
+    // Code k's distance is only known to +- band_k = kVqBand * |x| * |e_k| (split-bf16 product error, scaled per code
+    // so that dead codes with huge norms -- the EMA renormalisation blows unused codes up, reference :70-75 -- do not
+    // widen it).  With lo_k = d_k - band_k: the code k1 with the smallest lo is the certain winner iff its upper bound
+    // lo_k1 + 2 band_k1 stays below the second smallest lo; every other row goes to the exact re-check.
     const int quarter = warp & 3;
     const int half = (warp - 6) >> 2;        // which 128 columns of every 256-column accumulator this warp scans
     const int row = quarter * 32 + lane;
-    const float INF = __int_as_float(0x7f800000);
+    // 0xffffffe0, derived from a launch parameter so that it is not constant-folded (see vq_scan32)
+    const uint32_t tag_mask = 0xffffffe0u | ((uint32_t)p.n_tiles >> 30);
     int it = 0, acc_it = 0;
     for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, ++it) {
-      // best = smallest distance so far; other_lb = smallest LOWER bound among all other codes, where code k's
-      // distance is only known to +- kVqBand * |x| * |e_k| (split-bf16 product error, scaled per code so that dead
-      // codes with huge norms -- the EMA renormalisation blows unused codes up, reference :70-75 -- do not widen it)
-      // Four independent running minima (columns j, j+4, ...): one chain would serialise 512 dependent compare/select
-      // steps per row; they are merged after the last code tile.
-      float best[4], berr[4], other[4];
-      int bidx[4];
-#pragma unroll
-      for (int ch = 0; ch < 4; ++ch) { best[ch] = INF; berr[ch] = 0.f; other[ch] = INF; bidx[ch] = 0; }
-      float x2 = 0.f, cx = 0.f;
+      float r1 = kVqBig, r2 = kVqBig;
+      int ridx = 0;
+      float cx = 0.f;
       for (int nt = 0; nt < p.n_tiles; ++nt, ++acc_it) {
         const int tb = acc_it & 1;
         mbar_wait(&t_full[tb], (acc_it >> 1) & 1);
         tc_fence_after();
-        if (nt == 0) {
-          x2 = sX2[(it & 3) * 128 + row];   // written before a_full, which precedes t_full
-          cx = kVqBand * sqrtf(x2);
-        }
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tb * kVqNT;
-        const float* e2 = sE2 + nt * kVqNT;
-        const float* en = sEN + nt * kVqNT;
-#pragma unroll 1
-        for (int c = half * (kVqNT / 2); c < (half + 1) * (kVqNT / 2); c += 32) {
-          uint32_t v[32];
-          tmem_ld32(taddr + c, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int ch = j & 3;
-            // same association as the reference: (|x|^2 - 2 x.e) + |e|^2   (:49-53)
-            const float d = (x2 - 2.f * __uint_as_float(v[j])) + e2[c + j];
-            const float err = cx * en[c + j];
-            const bool lt = d < best[ch];   // strict: the lower index wins ties inside a chain
-            // the loser of the comparison only contributes its lower bound
-            other[ch] = fminf(other[ch], lt ? best[ch] - berr[ch] : d - err);
-            best[ch] = lt ? d : best[ch];
-            berr[ch] = lt ? err : berr[ch];
-            bidx[ch] = lt ? nt * kVqNT + c + j : bidx[ch];
-          }
-        }
+        if (nt == 0) cx = kVqBand * sqrtf(sX2[(it & 3) * 128 + row]);   // written before a_full, which precedes t_full
+        const int c0 = half * (kVqNT / 2);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tb * kVqNT + c0;
+        const float* e2 = sE2 + nt * kVqNT + c0;
+        const float* en = sEN + nt * kVqNT + c0;
+        const int code0 = nt * kVqNT + c0;
+        // software pipeline over the four 32-column chunks: the next TMEM read is in flight while one is scanned
+        uint32_t va[32], vb[32];
+        tmem_ld32(taddr, va);
+        tmem_ld_wait32(va);
+        tmem_ld32(taddr + 32, vb);
+        vq_scan32(va, e2, en, -cx, tag_mask, r1, r2, ridx, code0);
+        tmem_ld_wait32(vb);
+        tmem_ld32(taddr + 64, va);
+        vq_scan32(vb, e2 + 32, en + 32, -cx, tag_mask, r1, r2, ridx, code0 + 32);
+        tmem_ld_wait32(va);
+        tmem_ld32(taddr + 96, vb);
+        vq_scan32(va, e2 + 64, en + 64, -cx, tag_mask, r1, r2, ridx, code0 + 64);
+        tmem_ld_wait32(vb);
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&t_empty[tb]);
-      }
-      // merge the chains (ties -> lowest index, the reference's first-max rule :54)
-      float bestv = best[0], best_err = berr[0], other_lb = other[0];
-      int besti = bidx[0];
-#pragma unroll
-      for (int ch = 1; ch < 4; ++ch) {
-        const bool lt = best[ch] < bestv || (best[ch] == bestv && bidx[ch] < besti);
-        other_lb = fminf(other_lb, lt ? bestv - best_err : best[ch] - berr[ch]);
-        other_lb = fminf(other_lb, other[ch]);
-        bestv = lt ? best[ch] : bestv;
-        best_err = lt ? berr[ch] : best_err;
-        besti = lt ? bidx[ch] : besti;
+        if (lane == 0) mbar_arrive(&t_empty[tb]);   // the accumulator is in registers: release it before the last scan
+        vq_scan32(vb, e2 + 96, en + 96, -cx, tag_mask, r1, r2, ridx, code0 + 96);
       }
       // hand the upper column half over to the lower one (named barrier 1: the 256 epilogue threads)
       float* mg = sMerge + ((it & 1) * 128 + row) * 4;
       if (half == 1) {
-        mg[0] = bestv; mg[1] = best_err; mg[2] = other_lb; mg[3] = __int_as_float(besti);
+        mg[0] = r1; mg[1] = r2; mg[2] = __int_as_float(ridx);
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
       if (half == 1) continue;
       {
-        const float b1 = mg[0], e1 = mg[1], o1 = mg[2];
-        const int i1 = __float_as_int(mg[3]);
-        const bool lt = b1 < bestv || (b1 == bestv && i1 < besti);   // ties -> lowest index
-        other_lb = fminf(other_lb, lt ? bestv - best_err : b1 - e1);
-        other_lb = fminf(other_lb, o1);
-        bestv = lt ? b1 : bestv;
-        best_err = lt ? e1 : best_err;
-        besti = lt ? i1 : besti;
+        const float o1 = mg[0], o2 = mg[1];
+        const int oi = __float_as_int(mg[2]);
+        const bool lt = o1 < r1;
+        r2 = fminf(fminf(r2, o2), fmaxf(r1, o1));
+        ridx = lt ? oi : ridx;
+        r1 = fminf(r1, o1);
       }
       const size_t grow = (size_t)rt * 128 + row;
       if (grow < p.rows) {
-        p.embed_ind[grow] = besti;
-        if (!(other_lb > bestv + best_err)) {   // ambiguous within the error bound (also catches NaN)
+        p.embed_ind[grow] = ridx;
+        // the index tag moved each value by < 2^-18 of its magnitude
+        const float slack = 7.7e-6f * (fabsf(r1) + fabsf(r2));
+        const float up = r1 + 2.f * cx * sEN[ridx] + slack;
+        if (!(up < r2)) {   // ambiguous within the error bound (also catches NaN rows)
           const int slot = atomicAdd(p.flag_count, 1);
           p.flag_rows[slot] = (int)grow;   // capacity = rows
+          p.flag_u[slot] = up;
         }
       }
     }
@@ -349,44 +410,123 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
 }
 
 // exact re-evaluation of flagged rows: fp64 accumulation, first minimum wins (reference tie rule :54).
-// One warp per row; each lane scans codes lane, lane+32, ... of the transposed codebook e_t [n_embed][dim] with 16-byte
-// loads and four independent fp64 accumulators.
-__global__ void vq_refine_kernel(const float* __restrict__ x, const float* __restrict__ e_t, int dim, int n_embed,
-                                 const int* __restrict__ flag_count, const int* __restrict__ flag_rows,
-                                 long long* __restrict__ embed_ind) {
-  extern __shared__ float sx[];  // [warps][dim]
+// A 128-thread CTA takes kVqRefineRows flagged rows at a time and streams the transposed codebook e_t [n_embed][dim]
+// once for all of them (thread t scans codes t, t+128, ...).  Each code is first scored in fp32; only codes whose fp32
+// score can still reach the row's upper bound U (left by the assign kernel: the certain upper bound of the winner's
+// distance) are evaluated in fp64 -- typically two or three per row.
+constexpr int kVqRefineThreads = 128;
+constexpr int kVqRefineRows = 8;
+
+template <int DIM>
+__device__ __forceinline__ double vq_exact_score(const float* __restrict__ er, const float* xs) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+#pragma unroll 4
+  for (int q = 0; q < DIM / 4; ++q) {
+    const float4 e = __ldg(reinterpret_cast<const float4*>(er) + q);
+    const float4 xv = *reinterpret_cast<const float4*>(xs + 4 * q);
+    // e^2 - 2 x e, term by term (|x|^2 is common to all codes)
+    a0 += (double)e.x * ((double)e.x - 2.0 * (double)xv.x);
+    a1 += (double)e.y * ((double)e.y - 2.0 * (double)xv.y);
+    a2 += (double)e.z * ((double)e.z - 2.0 * (double)xv.z);
+    a3 += (double)e.w * ((double)e.w - 2.0 * (double)xv.w);
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+
+template <int DIM>
+__global__ void __launch_bounds__(kVqRefineThreads)
+vq_refine_kernel(const float* __restrict__ x, const float* __restrict__ e_t, const float* __restrict__ e_norm2,
+                 int n_embed, const int* __restrict__ flag_count, const int* __restrict__ flag_rows,
+                 const float* __restrict__ flag_u, long long* __restrict__ embed_ind) {
+  constexpr int R = kVqRefineRows;
+  __shared__ __align__(16) float sx[R][DIM];
+  __shared__ float s_u[R], s_xn[R];
+  __shared__ int s_row[R];
+  __shared__ double s_best[R][kVqRefineThreads / 32];
+  __shared__ int s_idx[R][kVqRefineThreads / 32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nwarps = blockDim.x >> 5;
   const int total = *flag_count;
-  float* myx = sx + warp * dim;
-  for (int f = blockIdx.x * nwarps + warp; f < total; f += gridDim.x * nwarps) {
-    const int row = flag_rows[f];
-    __syncwarp();
-    for (int d = lane; d < dim; d += 32) myx[d] = x[(size_t)row * dim + d];
-    __syncwarp();
-    double best = 1e300;
-    int besti = 0x7fffffff;
-    for (int k = lane; k < n_embed; k += 32) {
-      const float4* er = reinterpret_cast<const float4*>(e_t + (size_t)k * dim);
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      for (int q = 0; q < dim / 4; ++q) {
-        const float4 e = __ldg(er + q);
-        const float4 xv = *reinterpret_cast<const float4*>(myx + 4 * q);
-        // e^2 - 2 x e, term by term (|x|^2 is common to all codes)
-        a0 += (double)e.x * ((double)e.x - 2.0 * (double)xv.x);
-        a1 += (double)e.y * ((double)e.y - 2.0 * (double)xv.y);
-        a2 += (double)e.z * ((double)e.z - 2.0 * (double)xv.z);
-        a3 += (double)e.w * ((double)e.w - 2.0 * (double)xv.w);
+  // fp32 score error: (DIM + 4) roundings of relative size 2^-24 on terms bounded by |e|^2 + 2|x||e|  (x2 margin)
+  const float ctol = 2.f * (float)(DIM + 4) * 5.9604645e-8f;
+  for (int f0 = blockIdx.x * R; f0 < total; f0 += gridDim.x * R) {
+    __syncthreads();   // previous group fully consumed
+    for (int i = threadIdx.x; i < R * (DIM / 4); i += kVqRefineThreads) {
+      const int r = i / (DIM / 4), q = i % (DIM / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (f0 + r < total) v = __ldg(reinterpret_cast<const float4*>(x + (size_t)flag_rows[f0 + r] * DIM) + q);
+      reinterpret_cast<float4*>(&sx[r][0])[q] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < R) {
+      const int r = threadIdx.x;
+      float n2 = 0.f;
+      for (int d = 0; d < DIM; ++d) n2 = fmaf(sx[r][d], sx[r][d], n2);
+      s_xn[r] = sqrtf(n2) * 1.0001f;
+      const bool live = f0 + r < total;
+      s_row[r] = live ? flag_rows[f0 + r] : -1;
+      const float u = live ? flag_u[f0 + r] : -__int_as_float(0x7f800000);
+      s_u[r] = (u == u) ? u : __int_as_float(0x7f800000);   // a NaN bound (NaN row) checks every code
+    }
+    __syncthreads();
+    double best[R];
+    int besti[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { best[r] = 1e300; besti[r] = 0x7fffffff; }
+    for (int k = threadIdx.x; k < n_embed; k += kVqRefineThreads) {
+      const float4* er = reinterpret_cast<const float4*>(e_t + (size_t)k * DIM);
+      float acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.f;
+#pragma unroll 1
+      for (int q0 = 0; q0 < DIM / 4; q0 += 16) {
+        float4 ev[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) ev[u] = __ldg(er + q0 + u);
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+          for (int r = 0; r < R; ++r) {
+            const float4 xv = *reinterpret_cast<const float4*>(&sx[r][4 * (q0 + u)]);
+            acc[r] = fmaf(ev[u].x, xv.x, acc[r]);
+            acc[r] = fmaf(ev[u].y, xv.y, acc[r]);
+            acc[r] = fmaf(ev[u].z, xv.z, acc[r]);
+            acc[r] = fmaf(ev[u].w, xv.w, acc[r]);
+          }
+        }
       }
-      const double dist = (a0 + a1) + (a2 + a3);
-      if (dist < best) { best = dist; besti = k; }
+      const float e2 = __ldg(e_norm2 + k);
+      const float en = sqrtf(e2);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float d32 = fmaf(-2.f, acc[r], e2);
+        const float tol = ctol * fmaf(2.f * s_xn[r], en, e2);
+        if (d32 - tol <= s_u[r]) {
+          const double dist = vq_exact_score<DIM>(reinterpret_cast<const float*>(er), &sx[r][0]);
+          if (dist < best[r]) { best[r] = dist; besti[r] = k; }   // k ascends: the first minimum is kept
+        }
+      }
     }
-    for (int o = 16; o > 0; o >>= 1) {
-      const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
-      if (ob < best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double bv = best[r];
+      int bi = besti[r];
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob < bv || (ob == bv && oi < bi)) { bv = ob; bi = oi; }
+      }
+      if (lane == 0) { s_best[r][warp] = bv; s_idx[r][warp] = bi; }
     }
-    if (lane == 0) embed_ind[row] = besti;
+    __syncthreads();
+    if (threadIdx.x < R && s_row[threadIdx.x] >= 0) {
+      const int r = threadIdx.x;
+      double bv = s_best[r][0];
+      int bi = s_idx[r][0];
+#pragma unroll
+      for (int w = 1; w < kVqRefineThreads / 32; ++w)
+        if (s_best[r][w] < bv || (s_best[r][w] == bv && s_idx[r][w] < bi)) { bv = s_best[r][w]; bi = s_idx[r][w]; }
+      embed_ind[s_row[r]] = bi == 0x7fffffff ? 0 : bi;
+    }
   }
 }
 
@@ -397,7 +537,7 @@ size_t vq_assign_smem_bytes(int dim, int n_embed) {
   return (size_t)a_bufs * 2 * kchunks * 128 * 128 + (size_t)kVqBStages * kVqNT * 128 + (size_t)n_tiles * kVqNT * 8 +
          4 * 128 * 4 + 2 * 128 * 4 * 4 + (2 * kVqBStages + 8) * 8 + 16 + 1024;
 }
-size_t vq_assign_workspace_bytes(size_t rows, int dim) { return 256 + rows * sizeof(int); }
+size_t vq_assign_workspace_bytes(size_t rows, int dim) { return 256 + rows * (sizeof(int) + sizeof(float)); }
 
 cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* e_t,
                              const void* e_split, const float* e_norm2, int64_t* embed_ind, int* n_flagged,
@@ -406,29 +546,38 @@ cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, 
   VqAssignParams p;
   p.x = x; p.rows = rows; p.dim = dim; p.n_embed = n_embed;
   p.n_tiles = (n_embed + kVqNT - 1) / kVqNT;
-  p.kchunks = dim / 64;
   p.a_bufs = dim <= 64 ? 2 : 1;
   p.row_tiles = (int)((rows + 127) / 128);
   p.e_norm2 = e_norm2;
   p.embed_ind = reinterpret_cast<long long*>(embed_ind);
   p.flag_count = reinterpret_cast<int*>(workspace);
   p.flag_rows = reinterpret_cast<int*>(reinterpret_cast<uint8_t*>(workspace) + 256);
+  p.flag_u = reinterpret_cast<float*>(p.flag_rows + rows);
   cudaError_t e = cudaMemsetAsync(p.flag_count, 0, sizeof(int), st);
   if (e != cudaSuccess) return e;
   const int grid = p.row_tiles < num_sms ? p.row_tiles : num_sms;
-  vq_assign_kernel<<<grid, kVqThreads, vq_assign_smem_bytes(dim, n_embed), st>>>(p, *map_e);
+  if (dim == 64)
+    vq_assign_kernel<64><<<grid, kVqThreads, vq_assign_smem_bytes(dim, n_embed), st>>>(p, *map_e);
+  else
+    vq_assign_kernel<128><<<grid, kVqThreads, vq_assign_smem_bytes(dim, n_embed), st>>>(p, *map_e);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  const int warps = 8;
-  vq_refine_kernel<<<num_sms * 2, warps * 32, warps * dim * sizeof(float), st>>>(
-      x, e_t, dim, n_embed, p.flag_count, p.flag_rows, reinterpret_cast<long long*>(embed_ind));
+  long long* ind = reinterpret_cast<long long*>(embed_ind);
+  if (dim == 64)
+    vq_refine_kernel<64><<<num_sms * 4, kVqRefineThreads, 0, st>>>(x, e_t, e_norm2, n_embed, p.flag_count, p.flag_rows,
+                                                                   p.flag_u, ind);
+  else
+    vq_refine_kernel<128><<<num_sms * 4, kVqRefineThreads, 0, st>>>(x, e_t, e_norm2, n_embed, p.flag_count, p.flag_rows,
+                                                                    p.flag_u, ind);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   if (n_flagged != nullptr) e = cudaMemcpyAsync(n_flagged, p.flag_count, sizeof(int), cudaMemcpyDeviceToDevice, st);
   return e;
 }
 cudaError_t init_vq() {
-  return cudaFuncSetAttribute(vq_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  cudaError_t e = cudaFuncSetAttribute(vq_assign_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(vq_assign_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
 }
 
 // =============================================================================== gather + ST + loss + EMA stats

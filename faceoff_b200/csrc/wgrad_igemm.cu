@@ -101,7 +101,7 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
           base[d] = (r % c) * p.tile_step[d];
           r /= c;
         }
-        mbar_wait(&empty_bar[stage], phase ^ 1);
+        mbar_wait_ns(&empty_bar[stage], phase ^ 1, p.backoff_ns);
         uint8_t* sp = smem + (size_t)stage * stage_bytes;
         mbar_expect_tx(&full_bar[stage], p_bytes + q_loads * q_bytes);
         const int p_cw = p.p_rowb / 2;
@@ -167,7 +167,7 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
     const int quarter = warp & 3;
     const int row = quarter * 32 + lane;
     if (n_my > 0) {
-      mbar_wait(done_bar, 0);
+      mbar_wait_ns(done_bar, 0, p.backoff_ns);
       tc_fence_after();
     }
     for (int tp = 0; tp < p.taps_per_pass; ++tp) {

@@ -1,6 +1,6 @@
 """Quantiser sweep (BASELINE configs[3]): n_embed 512/1024/2048 x embed_dim 64/128 at N = 122,880 x clips rows.
 
-    python tests/gpu_profile_vq.py [clips]      -> one markdown table row per configuration
+    python tests/gpu_profile_vq.py [clips [dim n_embed]]   -> one markdown table row per configuration
 Reports the assign kernel (tcgen05 split-bf16 GEMM + argmin + exact re-check) in algorithmic TFLOP/s (2*D*K per row)
 and GB/s (4D + 8 bytes per row), and the fused gather/ST/loss/stats kernel in GB/s (8D + 8 (+2D bf16) bytes per row).
 """
@@ -33,8 +33,11 @@ def main():
     print(f"rows = {rows}")
     print("| dim | n_embed | assign ms | TFLOP/s (2DK/row) | GB/s (4D+8 B/row) | rows re-checked | gather+stats ms | GB/s |")
     print("|---:|---:|---:|---:|---:|---:|---:|---:|")
+    only = (int(sys.argv[2]), int(sys.argv[3])) if len(sys.argv) > 3 else None
     for dim in (64, 128):
         for K in (512, 1024, 2048):
+            if only is not None and (dim, K) != only:
+                continue
             torch.manual_seed(0)
             x = torch.randn(rows, dim, device="cuda")
             e = torch.randn(dim, K, device="cuda")
