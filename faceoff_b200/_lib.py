@@ -11,7 +11,8 @@ import subprocess
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_SO = os.path.join(_HERE, "libfaceoff_b200.so")
+# FACEOFF_B200_LIB selects another build of the same C ABI (A/B timing of kernel variants); default: the in-tree build
+_SO = os.environ.get("FACEOFF_B200_LIB") or os.path.join(_HERE, "libfaceoff_b200.so")
 _lock = threading.Lock()
 _lib = None
 

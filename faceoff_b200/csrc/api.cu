@@ -34,6 +34,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
+static int g_pair_ok = 1;   // clusters of two CTAs can be scheduled on every TPC
 static std::once_flag g_once;
 static int g_init_rc = FO_ERR_NO_DEVICE;
 static char g_init_err[512] = "fo_init not called";
@@ -389,7 +390,19 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   if (!ok) return fail(FO_ERR_INVALID, "too many K steps (> %d)", kMaxKSteps);
   p.num_ksteps = nk;
   out->ktot = n_pack * kc;
-  const int stage_bytes = (p.a_bytes + p.TPS * p.NT * rowb + 1023) & ~1023;
+  // CTA pairs (cta_group::2): two neighbouring position tiles share every B tile; needs an even tile count per
+  // (group, n-tile) so that both CTAs of a pair always have work with the same K-step list
+  p.pos_tiles = p.tile_cnt[0] * p.tile_cnt[1] * p.tile_cnt[2] * p.tile_cnt[3];
+  {
+    // worth it for the long-K layers (3x3 / 4x4 / 3x3x3 filters over >= 64 channels); the short 1x1 layers are bound by
+    // their epilogue and only pay for the pair's extra synchronisation.  FO_CTA_PAIR=0 disables, =2 forces (debug).
+    const char* e = getenv("FO_CTA_PAIR");
+    const int want = e ? atoi(e) : 1;
+    const bool heavy = p.num_ksteps * p.TPS * kc >= 576;
+    p.cta_pair = (want == 2 || (want == 1 && heavy)) && p.pos_tiles % 2 == 0 && p.NT % 32 == 0 &&
+                 g_num_sms % 2 == 0 && g_pair_ok && p.dbg_skip_mma == 0;
+  }
+  const int stage_bytes = (p.a_bytes + p.TPS * (p.NT / (p.cta_pair ? 2 : 1)) * rowb + 1023) & ~1023;
   // shared memory: pipeline stages + (as far as it fits next to two stages) the epilogue's prefetched addend / mask rows
   const int avail = kMaxDynSmem - 2048 - 1024 - 8 * 32 * 80;
   const int e_tensor = p.MT * 128 * (p.NT * 2 + 16);   // one operand, all sub-tiles
@@ -445,7 +458,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   {
     uint64_t dims[2] = {(uint64_t)out->ktot, (uint64_t)out->npad};
     uint64_t str[2] = {1, (uint64_t)out->ktot};
-    uint32_t bx[2] = {(uint32_t)kc, (uint32_t)p.NT};
+    uint32_t bx[2] = {(uint32_t)kc, (uint32_t)(p.NT / (p.cta_pair ? 2 : 1))};   // a pair's CTAs load half a B tile each
     int rc = encode_map(&out->maps.b, c->wpacked, 2, dims, str, bx, rowb);
     if (rc != FO_OK) return rc;
   }

@@ -31,9 +31,18 @@ namespace fo {
 constexpr int kConvThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue of sub-tile 0, warps 6-9 of sub-tile 1
 
 __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& g, int& nt, int (&base)[4]) {
-  // n-tile fastest so CTAs that share an A tile run concurrently and hit L2
-  nt = tile % p.n_tiles;
-  int t = tile / p.n_tiles;
+  int t;
+  if (p.cta_pair) {
+    // position tile fastest: tiles 2i and 2i+1 (the two CTAs of a pair) share the n-tile and the group
+    t = tile % p.pos_tiles;
+    const int rest = tile / p.pos_tiles;
+    nt = rest % p.n_tiles;
+    t += (rest / p.n_tiles) * p.pos_tiles;
+  } else {
+    // n-tile fastest so CTAs that share an A tile run concurrently and hit L2
+    nt = tile % p.n_tiles;
+    t = tile / p.n_tiles;
+  }
 #pragma unroll
   for (int d = 0; d < 4; ++d) {
     int c = p.tile_cnt[d];
@@ -229,6 +238,21 @@ __device__ __forceinline__ void epilogue_chunk32_coalesced(const ConvParams& p, 
   }
 }
 
+template <int CG>
+__device__ __forceinline__ void umma_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  if (CG == 2) umma_bf16_pair(tmem_d, adesc, bdesc, idesc, acc);
+  else umma_bf16(tmem_d, adesc, bdesc, idesc, acc);
+}
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint64_t* bar) {
+  if (CG == 2) umma_commit_pair(bar);
+  else umma_commit(bar);
+}
+
+// CG = 1: one CTA per tile.  CG = 2: the CTAs of a cluster of two work on tiles 2i / 2i+1 with cta_group::2 MMAs (M = 256):
+// each CTA loads its own A box and HALF of every B tile, so B costs half the L2->SM traffic and half the shared-memory
+// reads per SM.  Rank 0 issues the MMAs for both; see common.cuh "CTA pairs".
+template <int CG>
 __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ ConvMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -236,8 +260,10 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int rowb = p.KC * 2;
   const int a_bytes = p.a_bytes;
-  const int b_bytes = p.NT * rowb;
+  const int b_bytes = (p.NT / CG) * rowb;   // this CTA's share of a B tile
   const int stage_bytes = (a_bytes + p.TPS * b_bytes + 1023) & ~1023;
+  const uint32_t cta_rank = CG == 2 ? cluster_ctarank() : 0;
+  const int tile0 = CG == 2 ? (int)(blockIdx.x & ~1u) + (int)cta_rank : (int)blockIdx.x;   // first tile of this CTA
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full_bar = bars;                  // [stages]
   uint64_t* empty_bar = bars + p.stages;      // [stages]
@@ -259,8 +285,13 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       tma_prefetch_desc(&maps.b);
     }
     __syncwarp();
-    tmem_alloc(tmem_ptr, tmem_cols);
-    tmem_relinquish();
+    if (CG == 2) {
+      tmem_alloc_pair(tmem_ptr, tmem_cols);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_ptr, tmem_cols);
+      tmem_relinquish();
+    }
   } else if (warp == 1 && lane == 0) {
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -268,7 +299,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
-      mbar_init(&tempty_bar[b], 4 * p.MT);
+      mbar_init(&tempty_bar[b], 4 * p.MT * CG);   // CG == 2: the epilogue warps of both CTAs arrive at rank 0
     }
     fence_mbar_init();
   }
@@ -276,7 +307,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   if (bias_in_smem)
     for (int i = threadIdx.x; i < p.NT; i += blockDim.x) s_bias[i] = p.bias[i];
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // the peer's barriers must be initialised before anything is sent to them
+  else __syncthreads();
   tc_fence_after();
   // warp-uniform copy (the shuffle lets the compiler keep MMA operands in uniform registers)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
@@ -286,7 +318,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      for (int tile = tile0; tile < p.total_tiles; tile += gridDim.x) {
         int g, nt, base[4];
         decode_tile(p, tile, g, nt, base);
         const KStep* ks = p.ksteps + g * p.num_ksteps;
@@ -295,29 +327,47 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
           mbar_wait_ns(&empty_bar[stage], phase ^ 1, p.backoff_ns);
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full_bar[stage], a_bytes + p.TPS * b_bytes);
+          if (p.dbg_skip_mma == 2) {   // debug: MMAs over whatever is in shared memory, no loads
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           const KStep s = ks[k];
           const int a_op_bytes = a_bytes / p.a_ops;
-          for (int o = 0; o < p.a_ops; ++o)
-            tma_load_5d(sa + o * a_op_bytes, &maps.a[s.map], &full_bar[stage], s.c0, base[0] + s.d1,
-                        base[1] + s.d2 + o * p.a_op_rows, base[2] + s.d3, base[3]);
-          for (int j = 0; j < p.TPS; ++j)
-            tma_load_2d(sb + j * b_bytes, &maps.b, &full_bar[stage], kcol0 + (k * p.TPS + j) * p.KC, nt * p.NT);
+          if (CG == 2) {
+            // both CTAs' loads complete on rank 0's barrier, which rank 0 arms for the bytes of the pair
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (a_bytes + p.TPS * b_bytes));
+            const uint32_t fb = mapa_u32(&full_bar[stage], 0);
+            for (int o = 0; o < p.a_ops; ++o)
+              tma_load_5d_pair(sa + o * a_op_bytes, &maps.a[s.map], fb, s.c0, base[0] + s.d1,
+                               base[1] + s.d2 + o * p.a_op_rows, base[2] + s.d3, base[3]);
+            for (int j = 0; j < p.TPS; ++j)
+              tma_load_2d_pair(sb + j * b_bytes, &maps.b, fb, kcol0 + (k * p.TPS + j) * p.KC,
+                               nt * p.NT + (int)cta_rank * (p.NT / 2));
+          } else {
+            mbar_expect_tx(&full_bar[stage], a_bytes + p.TPS * b_bytes);
+            for (int o = 0; o < p.a_ops; ++o)
+              tma_load_5d(sa + o * a_op_bytes, &maps.a[s.map], &full_bar[stage], s.c0, base[0] + s.d1,
+                          base[1] + s.d2 + o * p.a_op_rows, base[2] + s.d3, base[3]);
+            for (int j = 0; j < p.TPS; ++j)
+              tma_load_2d(sb + j * b_bytes, &maps.b, &full_bar[stage], kcol0 + (k * p.TPS + j) * p.KC, nt * p.NT);
+          }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    const uint32_t idesc = make_idesc_bf16(128, p.NT, 0, 0);
+    // ------------------------------------------------------------------ MMA issuer (rank 0 of a pair)
+    if (cta_rank == 0) {
+    const uint32_t idesc = make_idesc_bf16(128 * CG, p.NT, 0, 0);
     const uint64_t desc_base = make_smem_desc(0, rowb, 16);   // start-address field left at 0
-    const int n_taps = p.dbg_skip_mma ? 0 : p.TPS;
+    const int n_taps = p.dbg_skip_mma == 1 ? 0 : p.TPS;
     const int kk_n = p.KC / 16;
     const int b_step16 = b_bytes >> 4, sub16 = p.sub_off >> 4, tap16 = p.tap_off >> 4;
     int stage = 0;
     uint32_t phase = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile0; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       mbar_wait_ns(&tempty_bar[buf], ((it >> 1) & 1) ^ 1, p.backoff_ns);
       tc_fence_after();
@@ -325,7 +375,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       for (int k = 0; k < p.num_ksteps; ++k) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
+        if (elect_one()) {
           // The single issuing thread must stay well under one MMA time (64 cycles at N=128) per instruction, so
           // descriptors are formed by adding a pre-shifted byte offset to a per-stage base instead of re-encoding.
           const uint32_t sa = smem_u32(smem + (size_t)stage * stage_bytes);
@@ -333,28 +383,40 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
           const uint64_t b_base = a_base + (a_bytes >> 4);
           for (int j = 0; j < n_taps; ++j) {
             const uint64_t bj = b_base + (uint32_t)(j * b_step16);
-            for (int m = 0; m < p.MT; ++m) {
-              const uint64_t am = a_base + (uint32_t)(m * sub16 + j * tap16);
-              const uint32_t dm = d_tmem + m * p.NT;
+            const uint64_t a0 = a_base + (uint32_t)(j * tap16);
+            const uint32_t acc = (k | j) != 0;
+            if (p.MT == 2) {
+              // alternate the two sub-tile accumulators: consecutive MMAs never wait for each other's accumulate
+              const uint64_t a1 = a0 + (uint32_t)sub16;
+              const uint32_t d0 = d_tmem, d1 = d_tmem + p.NT;
+              umma_cg<CG>(d0, a0, bj, idesc, acc);
+              umma_cg<CG>(d1, a1, bj, idesc, acc);
+              if (kk_n >= 2) {
+                umma_cg<CG>(d0, a0 + 2, bj + 2, idesc, 1);
+                umma_cg<CG>(d1, a1 + 2, bj + 2, idesc, 1);
+              }
               if (kk_n == 4) {
-                umma_bf16(dm, am, bj, idesc, (k | j) != 0);
-                umma_bf16(dm, am + 2, bj + 2, idesc, 1);
-                umma_bf16(dm, am + 4, bj + 4, idesc, 1);
-                umma_bf16(dm, am + 6, bj + 6, idesc, 1);
-              } else if (kk_n == 2) {
-                umma_bf16(dm, am, bj, idesc, (k | j) != 0);
-                umma_bf16(dm, am + 2, bj + 2, idesc, 1);
-              } else {
-                umma_bf16(dm, am, bj, idesc, (k | j) != 0);
+                umma_cg<CG>(d0, a0 + 4, bj + 4, idesc, 1);
+                umma_cg<CG>(d1, a1 + 4, bj + 4, idesc, 1);
+                umma_cg<CG>(d0, a0 + 6, bj + 6, idesc, 1);
+                umma_cg<CG>(d1, a1 + 6, bj + 6, idesc, 1);
+              }
+            } else {
+              umma_cg<CG>(d_tmem, a0, bj, idesc, acc);
+              if (kk_n >= 2) umma_cg<CG>(d_tmem, a0 + 2, bj + 2, idesc, 1);
+              if (kk_n == 4) {
+                umma_cg<CG>(d_tmem, a0 + 4, bj + 4, idesc, 1);
+                umma_cg<CG>(d_tmem, a0 + 6, bj + 6, idesc, 1);
               }
             }
           }
-          umma_commit(&empty_bar[stage]);
-          if (k == p.num_ksteps - 1) umma_commit(&tfull_bar[buf]);
+          umma_commit_cg<CG>(&empty_bar[stage]);
+          if (k == p.num_ksteps - 1) umma_commit_cg<CG>(&tfull_bar[buf]);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+    }
     }
   } else if (warp - 2 < 4 * p.MT) {
     // ------------------------------------------------------------------ epilogue (warps 2..5: sub-tile 0, 6..9: 1)
@@ -406,7 +468,9 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       off = p.out_off[g] + c1 * p.out_stride[0] + c2 * p.out_stride[1] + c3 * p.out_stride[2] + c4 * p.out_stride[3];
     };
     int it = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++it) {
+    const uint32_t tempty_remote[2] = {CG == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u,
+                                       CG == 2 ? mapa_u32(&tempty_bar[1], 0) : 0u};
+    for (int tile = tile0; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       int g, nt, base[4];
       decode_tile(p, tile, g, nt, base);
@@ -459,21 +523,26 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+      if (lane == 0) {
+        if (CG == 2) mbar_arrive_cluster(tempty_remote[buf]);
+        else mbar_arrive(&tempty_bar[buf]);
+      }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync_all();   // rank 0's MMAs read the peer's shared memory and write its TMEM until the end
+  else __syncthreads();
   if (warp == 0) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, tmem_cols);
+    if (CG == 2) tmem_dealloc_pair(tmem_base, tmem_cols);
+    else tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
 size_t conv_smem_bytes(const ConvParams& p) {
   const int rowb = p.KC * 2;
-  const int stage_bytes = (p.a_bytes + p.TPS * p.NT * rowb + 1023) & ~1023;
+  const int stage_bytes = (p.a_bytes + p.TPS * (p.NT / (p.cta_pair ? 2 : 1)) * rowb + 1023) & ~1023;
   const int n_e = p.e_mask + p.e_add;
   return (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024 + 8 * 32 * 80 +
          (size_t)p.e_bufs * n_e * 128 * (p.NT * 2 + 16) + 1024;
@@ -482,12 +551,30 @@ size_t conv_smem_bytes(const ConvParams& p) {
 cudaError_t launch_conv_igemm(const ConvParams& p, const ConvMaps& maps, int num_sms, cudaStream_t stream) {
   const size_t smem = conv_smem_bytes(p);
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
-  conv_igemm_kernel<<<grid, kConvThreads, smem, stream>>>(p, maps);
+  if (p.cta_pair) {
+    grid &= ~1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kConvThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<2>, p, maps);
+  }
+  conv_igemm_kernel<1><<<grid, kConvThreads, smem, stream>>>(p, maps);
   return cudaGetLastError();
 }
 
 cudaError_t init_conv_igemm() {
-  return cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(conv_igemm_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
 }
 
 }  // namespace fo

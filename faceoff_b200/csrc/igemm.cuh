@@ -34,6 +34,8 @@ struct ConvParams {
   int a_op_rows;
   int dbg_skip_mma;   // debug: do not issue MMAs (measures the pure TMA streaming rate)
   int backoff_ns;     // sleep between mbarrier probes of the long waits (0 = plain polling)
+  int cta_pair;       // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2): tiles 2i / 2i+1 share every B tile
+  int pos_tiles;      // position tiles per (group, n-tile) = product of tile_cnt
   int e_bufs;         // epilogue operand prefetch: 0 = off, else MT (one buffer set per M sub-tile / warp group)
   int e_mask, e_add;  // which of the two epilogue operands are prefetched (shared memory permitting)
   int n_tiles;        // N tiles of width NT

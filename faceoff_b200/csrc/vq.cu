@@ -242,7 +242,7 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
           // B hi tile: hi*hi and lo*hi
           mbar_wait_backoff(&b_full[stage], phase, 20);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint64_t sb = desc_base + ((smem_u32(sB + (size_t)stage * b_tile) & 0x3FFFF) >> 4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, a_hi + 2 * kk, sb + 2 * kk, idesc, (kc | kk) != 0);
@@ -255,7 +255,7 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
           // B lo tile: hi*lo
           mbar_wait_backoff(&b_full[stage], phase, 20);
           tc_fence_after();
-          if (lane == 0) {
+          if (elect_one()) {
             const uint64_t sb = desc_base + ((smem_u32(sB + (size_t)stage * b_tile) & 0x3FFFF) >> 4);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) umma_bf16(d_tmem, a_hi + 2 * kk, sb + 2 * kk, idesc, 1);

@@ -133,7 +133,7 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
     for (int i = 0; i < n_my; ++i) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
+      if (elect_one()) {
         const uint32_t sp = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint64_t a0 = a_desc_base + ((sp & 0x3FFFF) >> 4);
         const uint64_t b0 = b_desc_base + (((sp + p_bytes) & 0x3FFFF) >> 4);
