@@ -836,6 +836,16 @@ extern "C" int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, 
 }
 extern "C" int fo_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, fo_stream_t stream) {
   REQUIRE_INIT();
+  if (hw % 4 != 0 || c > ca) return fail(FO_ERR_INVALID, "mse: hw must be a multiple of 4 and c <= ca");
+  if ((size_t)n * c * hw == 0) return FO_OK;
   CUDA_TRY(launch_mse(a, b, n, ca, c, hw, sum_out, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_mse_grad(const float* a, const float* b, int n, int ca, int c, int hw, const float* gscale,
+                           float scale, float* grad, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (hw % 4 != 0 || c > ca) return fail(FO_ERR_INVALID, "mse_grad: hw must be a multiple of 4 and c <= ca");
+  if ((size_t)n * ca * hw == 0) return FO_OK;
+  CUDA_TRY(launch_mse_grad(a, b, n, ca, c, hw, gscale, scale, grad, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }

@@ -201,13 +201,33 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, size_
     part[(size_t)blockIdx.x * cs + c] = s;
   }
 }
-__global__ void colsum_final_kernel(const float* __restrict__ part, int nblocks, int cs, int c_off, int c,
-                                    float* __restrict__ out, int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  float s = 0.f;
-  for (int b = 0; b < nblocks; ++b) s += part[(size_t)b * cs + c_off + i];
-  if (accumulate) out[i] += s; else out[i] = s;
+// 32 channels per CTA, 8 slices of the partial rows per channel (coalesced over channels), fixed-order tree over slices
+__global__ void __launch_bounds__(256)
+colsum_final_kernel(const float* __restrict__ part, int nblocks, int cs, int c_off, int c, float* __restrict__ out,
+                    int accumulate) {
+  __shared__ float red[8][33];
+  const int ci = threadIdx.x & 31, sl = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ci;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  if (i < c) {
+    const float* col = part + c_off + i;
+    int b = sl;
+    for (; b + 24 < nblocks; b += 32) {
+      s0 += col[(size_t)b * cs];
+      s1 += col[(size_t)(b + 8) * cs];
+      s2 += col[(size_t)(b + 16) * cs];
+      s3 += col[(size_t)(b + 24) * cs];
+    }
+    for (; b < nblocks; b += 8) s0 += col[(size_t)b * cs];
+  }
+  red[sl][ci] = (s0 + s1) + (s2 + s3);
+  __syncthreads();
+  if (sl == 0 && i < c) {
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][ci];
+    if (accumulate) out[i] += s; else out[i] = s;
+  }
 }
 
 // ---------------------------------------------------------------- 2x2 max pool, channels-last bf16
@@ -470,7 +490,7 @@ cudaError_t launch_colsum(const void* x, size_t rows, int cs, int c_off, int c, 
   if ((size_t)nblocks > need) nblocks = (int)(need ? need : 1);
   colsum_partial_kernel<<<nblocks, threads, (size_t)rpi * cs * sizeof(float), st>>>((const __nv_bfloat16*)x, rows, cs,
                                                                                      workspace);
-  colsum_final_kernel<<<(c + 127) / 128, 128, 0, st>>>(workspace, nblocks, cs, c_off, c, out, accumulate);
+  colsum_final_kernel<<<(c + 31) / 32, 256, 0, st>>>(workspace, nblocks, cs, c_off, c, out, accumulate);
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool2(const void* x, void* y, int n, int h, int w, int cs, int num_sms, cudaStream_t st) {

@@ -85,5 +85,7 @@ cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w,
                                  void* d_f0, const void* addend, int num_sms, cudaStream_t st);
 cudaError_t launch_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, int num_sms,
                        cudaStream_t st);
+cudaError_t launch_mse_grad(const float* a, const float* b, int n, int ca, int c, int hw, const float* gscale,
+                            float scale, float* grad, int num_sms, cudaStream_t st);
 
 }  // namespace fo

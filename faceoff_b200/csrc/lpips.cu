@@ -190,32 +190,74 @@ cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w,
 }
 
 // sum((a[:, :c] - b)^2), NCHW fp32
-__global__ void mse_kernel(const float* __restrict__ a, const float* __restrict__ b, int ca, int c, int hw, size_t total,
-                           float* __restrict__ out) {
-  __shared__ float red[32];
+// sum((a[:, :c] - b)^2) and, with GRAD, grad[n, ca, hw] = g * (a[:, :c] - b) (channels >= c: 0), 16-byte accesses.
+// a: [n, ca, hw] fp32 NCHW, b: [n, c, hw]; hw % 4 == 0.
+template <bool GRAD>
+__global__ void __launch_bounds__(256)
+mse_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int ca, int c, int hw4, size_t total4,
+           float* __restrict__ out, const float* __restrict__ gscale, float scale, float4* __restrict__ grad) {
+  __shared__ float red[8];
   float acc = 0.f;
-  const size_t chw = (size_t)c * hw;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t n = i / chw, r = i % chw;
-    const float d = a[n * (size_t)ca * hw + r] - b[i];
-    acc += d * d;
+  const float g = GRAD ? __ldg(gscale) * scale : 0.f;
+  // GRAD walks a's index space (it must also zero the channels beyond c), the plain sum walks b's
+  const size_t per_n = (size_t)(GRAD ? ca : c) * hw4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i0 < total4; i0 += 4 * stride) {
+    float4 va[4], vb[4];
+    size_t ia[4];
+    bool live[4], in_c[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const size_t i = i0 + u * stride;
+      live[u] = i < total4;
+      const size_t n = live[u] ? i / per_n : 0, r = live[u] ? i % per_n : 0;
+      in_c[u] = live[u] && r < (size_t)c * hw4;
+      ia[u] = n * (size_t)ca * hw4 + r;
+      va[u] = vb[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (in_c[u]) {
+        va[u] = __ldg(a + ia[u]);
+        vb[u] = __ldg(b + n * (size_t)c * hw4 + r);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float4 d = make_float4(va[u].x - vb[u].x, va[u].y - vb[u].y, va[u].z - vb[u].z, va[u].w - vb[u].w);
+      if (GRAD) {
+        if (live[u]) grad[ia[u]] = make_float4(g * d.x, g * d.y, g * d.z, g * d.w);
+      } else {
+        acc += (d.x * d.x + d.y * d.y) + (d.z * d.z + d.w * d.w);
+      }
+    }
   }
-  acc = warp_sum(acc);
-  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
-    atomicAdd(out, s);
+  if (!GRAD) {
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+      atomicAdd(out, s);
+    }
   }
 }
 cudaError_t launch_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, int num_sms,
                        cudaStream_t st) {
-  const size_t total = (size_t)n * c * hw;
-  size_t blocks = (total + 255) / 256;
+  const size_t total4 = (size_t)n * c * (hw / 4);
+  size_t blocks = (total4 + 1023) / 1024;
   if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
   if (blocks < 1) blocks = 1;
-  mse_kernel<<<(int)blocks, 256, 0, st>>>(a, b, ca, c, hw, total, sum_out);
+  mse_kernel<false><<<(int)blocks, 256, 0, st>>>((const float4*)a, (const float4*)b, ca, c, hw / 4, total4, sum_out,
+                                                 nullptr, 0.f, nullptr);
+  return cudaGetLastError();
+}
+cudaError_t launch_mse_grad(const float* a, const float* b, int n, int ca, int c, int hw, const float* gscale,
+                            float scale, float* grad, int num_sms, cudaStream_t st) {
+  const size_t total4 = (size_t)n * ca * (hw / 4);
+  size_t blocks = (total4 + 1023) / 1024;
+  if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
+  if (blocks < 1) blocks = 1;
+  mse_kernel<true><<<(int)blocks, 256, 0, st>>>((const float4*)a, (const float4*)b, ca, c, hw / 4, total4, nullptr,
+                                                gscale, scale, (float4*)grad);
   return cudaGetLastError();
 }
 

@@ -229,9 +229,9 @@ def first_conv_op(tape: Tape, x_nchw: torch.Tensor, wname: str, cin: int, cout: 
     def backward():
         gt, g_off = out.g
         gb, acc = tape.grad_buffer(wname + ".bias")
-        ops.colsum(gt, cout, gb, c_off=g_off, accumulate=acc)
         dw2 = torch.empty(cout, 128, 1, 1, dtype=torch.float32, device=w.device)
-        ops.wgrad(FORM_S1, 2, 1, (gt, cout, g_off), (col, 128, 0), dw2, m_axis=0)
+        # bias gradient fused into the weight-gradient launch (all-ones MMA operand)
+        ops.wgrad(FORM_S1, 2, 1, (gt, cout, g_off), (col, 128, 0), dw2, m_axis=0, dbias=gb, dbias_accumulate=acc)
         gw, acc = tape.grad_buffer(wname + ".weight")
         dw = dw2.view(cout, 16, 8)[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, 4, 4)
         if acc:

@@ -228,6 +228,9 @@ def wgrad(form: int, ndim: int, ksize: int, p: SrcT, q: SrcT, dweight: torch.Ten
         n_pos *= int(v_)
     with _Timed("wgrad_igemm", 2.0 * n_pos * p[1] * q[1] * taps):
         L.check(lib.fo_wgrad_run(C.byref(g), _stream()), "fo_wgrad_run")
+    if PROFILE is not None:
+        kind = ("wgrad3d" if ndim == 3 else f"wgrad{ksize}x{ksize}" if form == FORM_S1 else "wgrad4x4s2") + f"_{p[1]}x{q[1]}"
+        PROFILE.setdefault("wgrad_igemm/" + kind, []).append(PROFILE["wgrad_igemm"][-1])
     _count(2 + (dbias is not None))
 
 
@@ -430,3 +433,29 @@ def lpips_tap_bwd(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.
                                  _p(addend), _stream()), "fo_lpips_tap_bwd")
     _count(1)
     return d
+
+
+# ------------------------------------------------------------------------------------------------
+# reconstruction loss
+# ------------------------------------------------------------------------------------------------
+def mse_sum(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """sum((a[:, :C] - b)^2) for fp32 NCHW a [N, Ca, H, W], b [N, C, H, W] -> fp32 scalar tensor [1]."""
+    lib = L.load()
+    n, ca, h, w = a.shape
+    c = b.shape[1]
+    out = torch.zeros(1, dtype=torch.float32, device=a.device)
+    L.check(lib.fo_mse(a.data_ptr(), b.data_ptr(), n, ca, c, h * w, out.data_ptr(), _stream()), "fo_mse")
+    _count(1)
+    return out
+
+
+def mse_grad(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor, scale: float) -> torch.Tensor:
+    """g * scale * (a[:, :C] - b) as an fp32 tensor shaped like a (channels >= C zero); g is a device scalar."""
+    lib = L.load()
+    n, ca, h, w = a.shape
+    c = b.shape[1]
+    grad = torch.empty_like(a)
+    L.check(lib.fo_mse_grad(a.data_ptr(), b.data_ptr(), n, ca, c, h * w, g.data_ptr(), float(scale), grad.data_ptr(),
+                            _stream()), "fo_mse_grad")
+    _count(1)
+    return grad

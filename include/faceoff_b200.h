@@ -191,9 +191,14 @@ int fo_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, 
 /* Gradient wrt f0: d_f0 (bf16, same layout), scaled by g[n] (fp32 per image), masked by f0 > 0 (ReLU tap). */
 int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c, void* d_f0,
                      const void* addend, fo_stream_t stream);
-/* sum((a[:, :c] - b)^2) over NCHW fp32 a [n, ca, hw] and b [n, c, hw]; grad (optional) = gscale * 2 (a - b) into
- * channels-last bf16 [n, hw, cs] (channels >= c zero). */
+/* Reconstruction loss (reference train_faceoff_perceptual.py:38-40: nn.MSELoss()(out[:, :3], gt)).
+ * fo_mse: *sum_out += sum((a[:, :c] - b)^2) over NCHW fp32 a [n, ca, hw] and b [n, c, hw] (hw % 4 == 0); the caller
+ * zeroes sum_out and divides by n*c*hw.
+ * fo_mse_grad: grad [n, ca, hw] = (*gscale) * scale * (a[:, :c] - b), channels >= c zero -- the gradient of the mean with
+ * scale = 2 / (n*c*hw) and *gscale the upstream gradient (a device scalar: no host synchronisation). */
 int fo_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, fo_stream_t stream);
+int fo_mse_grad(const float* a, const float* b, int n, int ca, int c, int hw, const float* gscale, float scale,
+                float* grad, fo_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,6 +1,6 @@
 """Stand-alone launches of the hot conv / wgrad kernels at production shapes, for ncu captures and A/B timing.
 
-    python tests/gpu_profile_conv.py [conv3d|conv3x3|wgrad3d|all] [clips]
+    python tests/gpu_profile_conv.py [conv3d|conv3x3|resblock|wgrad_down|wgrad3d|all] [clips]
 """
 import os
 import sys
@@ -83,6 +83,20 @@ def main():
         print(f"resblock wgrad3x3 (swapped): {ms:.3f} ms")
         ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 2, 3, (dh, 32, 0), (x, 128, 0), dw, m_axis=0))
         print(f"resblock wgrad3x3 (P=dy): {ms:.3f} ms")
+    if which in ("wgrad_down", "all"):
+        F_ = clips * T
+        dy = torch.randn(F_, 64, 64, 128, device=dev).to(torch.bfloat16)
+        xh = torch.randn(F_, 128, 128, 64, device=dev).to(torch.bfloat16)
+        dw = torch.empty(128, 64, 4, 4, device=dev)
+        db = torch.zeros(128, device=dev)
+        fl = 2.0 * F_ * 64 * 64 * 128 * 64 * 16
+        ms = timeit(lambda: ops.wgrad(ops.FORM_DOWN, 2, 4, (dy, 128, 0), (xh, 64, 0), dw, m_axis=0, dbias=db))
+        print(f"wgrad4x4s2 128x64 (enc conv 64->128 @128): {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        xl = torch.randn(F_, 64, 64, 128, device=dev).to(torch.bfloat16)
+        dyh = torch.randn(F_, 128, 128, 64, device=dev).to(torch.bfloat16)
+        dwt = torch.empty(128, 64, 4, 4, device=dev)
+        ms = timeit(lambda: ops.wgrad(ops.FORM_DOWN, 2, 4, (xl, 128, 0), (dyh, 64, 0), dwt, m_axis=0))
+        print(f"wgrad4x4s2 128x64 (dec convT 128->64 @64): {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
     if which in ("wgrad3d", "all"):
         x = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)
         dy = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)

@@ -417,6 +417,24 @@ def test_three_optimizer_steps_track_the_oracle():
         assert abs(a - b) <= 3e-2 * abs(b) + 1e-2
 
 
+@pytest.mark.parametrize("n,ca,c,h,w", [(5, 3, 3, 64, 64), (3, 6, 3, 32, 16), (1, 3, 3, 2, 2)])
+def test_fused_mse_loss_matches_torch(n, ca, c, h, w):
+    """mse_loss(out, gt) == nn.MSELoss()(out[:, :c], gt) (reference train_faceoff_perceptual.py:38-40), value and grad
+    (fp32: rtol 1e-5; the upstream gradient is a device scalar, here 0.37)."""
+    from faceoff_b200.losses import mse_loss
+
+    torch.manual_seed(0)
+    out = torch.randn(n, ca, h, w, device="cuda", requires_grad=True)
+    gt = torch.randn(n, c, h, w, device="cuda")
+    loss = mse_loss(out, gt)
+    (loss * 0.37).backward()
+    ref_in = out.detach().clone().requires_grad_(True)
+    ref = torch.nn.functional.mse_loss(ref_in[:, :c], gt)
+    (ref * 0.37).backward()
+    torch.testing.assert_close(loss, ref, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(out.grad, ref_in.grad, rtol=1e-5, atol=1e-9)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_rank_data_parallel_matches_single_process():
     import subprocess
