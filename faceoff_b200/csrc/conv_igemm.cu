@@ -257,7 +257,8 @@ __global__ void __launch_bounds__(kConvThreads, 1)
 conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ ConvMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [stages x (A tile | B tile)] | barriers | tmem ptr
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic, not a pointer round-trip: the compiler keeps the shared address space -> LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int rowb = p.KC * 2;
   const int a_bytes = p.a_bytes;
   const int b_bytes = (p.NT / CG) * rowb;   // this CTA's share of a B tile

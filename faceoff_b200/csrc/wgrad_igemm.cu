@@ -25,7 +25,8 @@ constexpr int kWgThreads = 192;
 __global__ void __launch_bounds__(kWgThreads, 1)
 wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant__ WgradMaps maps) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic, not a pointer round-trip: the compiler keeps the shared address space -> LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int p_chunk_bytes = p.kpix * p.p_rowb;
   const int q_chunk_bytes = p.q_box_bytes;
   const int p_bytes = p.p_chunks * p_chunk_bytes;

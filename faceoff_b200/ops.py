@@ -43,7 +43,14 @@ class _Timed:
             PROFILE.setdefault(self.name, []).append((self.a, self.b, self.work))
 
 
+_raw_stream = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+
+
 def _stream() -> C.c_void_p:
+    """cudaStream_t of PyTorch's current stream on the current device (raw handle: ~20x cheaper than building a
+    torch.cuda.Stream object per launch)."""
+    if _raw_stream is not None:
+        return C.c_void_p(_raw_stream(torch.cuda.current_device()))
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
