@@ -302,23 +302,41 @@ __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __
 // implicit GEMM (32-byte TMA rows, N=16 MMAs).  Their image-side operand is therefore laid out as an explicit
 // [pixels, 16 taps x 8 channels = 128] bf16 matrix so that the layer becomes a plain K=128 (or N=128) GEMM on the same
 // tcgen05 kernel.  k = (ky*4+kx)*8 + c, value = x[c][2*oy+ky-1][2*ox+kx-1] (zero outside / for c >= C).
-__global__ void im2col4x4s2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int ca, int c, int h,
-                                   int w) {
-  // block: 64 output pixels of one output row; input window 4 rows x 130 columns x c channels
+__global__ void __launch_bounds__(256)
+im2col4x4s2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int ca, int c, int h, int w) {
+  // block: 64 output pixels of one output row; input window 4 rows x 130 columns x c channels.
+  // Warp cc stages channel cc (lanes run along the row: coalesced, no per-element index arithmetic).
   __shared__ float sm[8][4][132];
   const int wo = w / 2;
   const int n = blockIdx.z, oy = blockIdx.y, ox0 = blockIdx.x * 64;
   const int ix0 = 2 * ox0 - 1, iy0 = 2 * oy - 1;
-  for (int i = threadIdx.x; i < 8 * 4 * 130; i += blockDim.x) {
-    const int col = i % 130, r = (i / 130) & 3, cc = i / (130 * 4);
-    const int iy = iy0 + r, ix = ix0 + col;
-    float v = 0.f;
-    if (cc < c && iy >= 0 && iy < h && ix >= 0 && ix < w) v = __ldg(x + (((size_t)n * ca + cc) * h + iy) * w + ix);
-    sm[cc][r][col] = v;
+  const int cc = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  {
+    float v[4][5];
+    const float* xc = x + ((size_t)n * ca + cc) * h * w;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int iy = iy0 + r;
+      const bool row_ok = cc < c && iy >= 0 && iy < h;
+      const float* xr = xc + (size_t)iy * w;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int col = lane + 32 * k, ix = ix0 + col;
+        v[r][k] = (row_ok && col < 130 && ix >= 0 && ix < w) ? __ldg(xr + ix) : 0.f;
+      }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+      for (int k = 0; k < 5; ++k) {
+        const int col = lane + 32 * k;
+        if (col < 130) sm[cc][r][col] = v[r][k];
+      }
   }
   __syncthreads();
-#pragma unroll 2
-  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) {
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int i = threadIdx.x + it * 256;
     const int px = i >> 4, tap = i & 15;
     const int ox = ox0 + px;
     if (ox >= wo) continue;
@@ -369,39 +387,39 @@ __global__ void im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __r
 }
 
 // out[n][co][oy][ox] = bias[co] + sum of the (up to) 4 col entries that map to this output pixel
-__global__ void col2im4x4s2_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias,
-                                   float* __restrict__ out, int c, int hi, int wi, size_t total) {
+// grid (ceil(wo / 256), ho, n): one thread per output pixel, no index divisions
+__global__ void __launch_bounds__(256)
+col2im4x4s2_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias, float* __restrict__ out, int c,
+                   int hi, int wi) {
   const int ho = 2 * hi, wo = 2 * wi;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % wo);
-    size_t r = i / wo;
-    const int oy = (int)(r % ho);
-    const size_t n = r / ho;
-    const int hy = oy >> 1, hx = ox >> 1;
-    // oy = 2*iy - 1 + ky : even oy -> (iy=hy, ky=1), (hy-1, 3) ; odd oy -> (hy+1, 0), (hy, 2)
-    const int iy_[2] = {(oy & 1) ? hy + 1 : hy, (oy & 1) ? hy : hy - 1};
-    const int ky_[2] = {(oy & 1) ? 0 : 1, (oy & 1) ? 2 : 3};
-    const int ix_[2] = {(ox & 1) ? hx + 1 : hx, (ox & 1) ? hx : hx - 1};
-    const int kx_[2] = {(ox & 1) ? 0 : 1, (ox & 1) ? 2 : 3};
-    float acc[8];
+  const int ox = blockIdx.x * 256 + threadIdx.x;
+  const int oy = blockIdx.y;
+  const size_t n = blockIdx.z;
+  if (ox >= wo) return;
+  const int hy = oy >> 1, hx = ox >> 1;
+  // oy = 2*iy - 1 + ky : even oy -> (iy=hy, ky=1), (hy-1, 3) ; odd oy -> (hy+1, 0), (hy, 2)
+  const int iy_[2] = {(oy & 1) ? hy + 1 : hy, (oy & 1) ? hy : hy - 1};
+  const int ky_[2] = {(oy & 1) ? 0 : 1, (oy & 1) ? 2 : 3};
+  const int ix_[2] = {(ox & 1) ? hx + 1 : hx, (ox & 1) ? hx : hx - 1};
+  const int kx_[2] = {(ox & 1) ? 0 : 1, (ox & 1) ? 2 : 3};
+  float acc[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
 #pragma unroll
-    for (int a = 0; a < 2; ++a) {
-      if (iy_[a] < 0 || iy_[a] >= hi) continue;
+  for (int a = 0; a < 2; ++a) {
+    if (iy_[a] < 0 || iy_[a] >= hi) continue;
 #pragma unroll
-      for (int b = 0; b < 2; ++b) {
-        if (ix_[b] < 0 || ix_[b] >= wi) continue;
-        const uint4 u = __ldg(reinterpret_cast<const uint4*>(col + ((n * hi + iy_[a]) * wi + ix_[b]) * 128) +
-                              (ky_[a] * 4 + kx_[b]));
-        acc[0] += bf16lo(u.x); acc[1] += bf16hi(u.x); acc[2] += bf16lo(u.y); acc[3] += bf16hi(u.y);
-        acc[4] += bf16lo(u.z); acc[5] += bf16hi(u.z); acc[6] += bf16lo(u.w); acc[7] += bf16hi(u.w);
-      }
+    for (int b = 0; b < 2; ++b) {
+      if (ix_[b] < 0 || ix_[b] >= wi) continue;
+      const uint4 u = __ldg(reinterpret_cast<const uint4*>(col + ((n * hi + iy_[a]) * wi + ix_[b]) * 128) +
+                            (ky_[a] * 4 + kx_[b]));
+      acc[0] += bf16lo(u.x); acc[1] += bf16hi(u.x); acc[2] += bf16lo(u.y); acc[3] += bf16hi(u.y);
+      acc[4] += bf16lo(u.z); acc[5] += bf16hi(u.z); acc[6] += bf16lo(u.w); acc[7] += bf16hi(u.w);
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e)
-      if (e < c) out[((n * c + e) * ho + oy) * wo + ox] = acc[e] + (bias != nullptr ? bias[e] : 0.f);
   }
+#pragma unroll
+  for (int e = 0; e < 8; ++e)
+    if (e < c) out[((n * c + e) * ho + oy) * wo + ox] = acc[e] + (bias != nullptr ? bias[e] : 0.f);
 }
 
 // out[c] (+)= sum over n, hw of x[n][c][hw]   (bias gradient of the last layer, NCHW fp32 gradient)
@@ -521,9 +539,9 @@ cudaError_t launch_im2col3x3(const float* x, void* out, int n, int c, int h, int
 }
 cudaError_t launch_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, int num_sms,
                                cudaStream_t st) {
-  const size_t total = (size_t)n * (2 * hi) * (2 * wi);
-  col2im4x4s2_kernel<<<grid_for(total, 256, num_sms, 16), 256, 0, st>>>((const __nv_bfloat16*)col, bias, out, c, hi, wi,
-                                                                       total);
+  (void)num_sms;
+  dim3 grid((2 * wi + 255) / 256, 2 * hi, n);
+  col2im4x4s2_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)col, bias, out, c, hi, wi);
   return cudaGetLastError();
 }
 cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, float* out, int accumulate, int num_sms,
