@@ -584,7 +584,8 @@ cudaError_t init_vq() {
 // LPR lanes share a row (float4 each).  Per-CTA statistics are privatised in shared memory
 // ([n_embed][dim] fp32 + counts) when they fit, then flushed with one global atomic per entry.
 template <bool SMEM_STATS>
-__global__ void vq_gather_stats_kernel(const float* __restrict__ x, const long long* __restrict__ ind, size_t rows,
+__global__ void __launch_bounds__(512)
+vq_gather_stats_kernel(const float* __restrict__ x, const long long* __restrict__ ind, size_t rows,
                                        int dim, int n_embed, const float* __restrict__ e_t, float* __restrict__ q_f32,
                                        __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ diff_sum,
                                        float* __restrict__ counts, float* __restrict__ embed_sum) {
@@ -597,40 +598,81 @@ __global__ void vq_gather_stats_kernel(const float* __restrict__ x, const long l
   }
   float* s_sum = sm;
   float* s_cnt = sm + (size_t)n_embed * dim;
-  const int q4 = dim / 4;
-  const size_t total = rows * q4;
+  const int q4 = dim / 4;                 // lanes per row (16 or 32; dim is 64 or 128 on this path, any multiple of 4 works)
   float dacc = 0.f;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-    const size_t r = i / q4;
-    const int q = (int)(i % q4);
-    const int k = (int)ind[r];
-    const float4 xv = __ldg(reinterpret_cast<const float4*>(x + r * dim) + q);
-    const float4 ev = __ldg(reinterpret_cast<const float4*>(e_t + (size_t)k * dim) + q);
-    // (:77) diff = (quantize - input)^2 ; (:78) quantize = input + (quantize - input)
-    const float t0 = ev.x - xv.x, t1 = ev.y - xv.y, t2 = ev.z - xv.z, t3 = ev.w - xv.w;
-    dacc += t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
-    const float4 qv = make_float4(xv.x + t0, xv.y + t1, xv.z + t2, xv.w + t3);
-    if (q_f32 != nullptr) reinterpret_cast<float4*>(q_f32 + r * dim)[q] = qv;
-    if (q_bf16 != nullptr) {
-      uint2 o;
-      o.x = pack_bf16x2(qv.x, qv.y);
-      o.y = pack_bf16x2(qv.z, qv.w);
-      reinterpret_cast<uint2*>(q_bf16 + r * dim)[q] = o;
+  // A group of q4 lanes walks kSeg CONSECUTIVE rows; statistics of a run of rows with the same code are summed in
+  // registers and flushed with one atomic per component when the code changes.  Neighbouring latent pixels mostly share
+  // their code (and an untrained / collapsed codebook uses a handful of codes), which is exactly when per-row atomics on
+  // the same few addresses would serialise.
+  constexpr int kSeg = 32;
+  const int groups_per_block = blockDim.x / q4;
+  const int q = threadIdx.x % q4;
+  const size_t group = (size_t)blockIdx.x * groups_per_block + threadIdx.x / q4;
+  const size_t n_groups = (size_t)gridDim.x * groups_per_block;
+  const size_t n_seg = (rows + kSeg - 1) / kSeg;
+  auto flush = [&](int k, const float4& a, float cnt) {
+    if (k < 0) return;
+    if (SMEM_STATS) {
+      float* d = s_sum + (size_t)k * dim + q * 4;
+      atomicAdd(d + 0, a.x); atomicAdd(d + 1, a.y); atomicAdd(d + 2, a.z); atomicAdd(d + 3, a.w);
+      if (q == 0) atomicAdd(s_cnt + k, cnt);
+    } else {
+      const int d0 = q * 4;
+      atomicAdd(embed_sum + (size_t)(d0 + 0) * n_embed + k, a.x);
+      atomicAdd(embed_sum + (size_t)(d0 + 1) * n_embed + k, a.y);
+      atomicAdd(embed_sum + (size_t)(d0 + 2) * n_embed + k, a.z);
+      atomicAdd(embed_sum + (size_t)(d0 + 3) * n_embed + k, a.w);
+      if (q == 0) atomicAdd(counts + k, cnt);
     }
-    if (stats) {
-      if (SMEM_STATS) {
-        float* d = s_sum + (size_t)k * dim + q * 4;
-        atomicAdd(d + 0, xv.x); atomicAdd(d + 1, xv.y); atomicAdd(d + 2, xv.z); atomicAdd(d + 3, xv.w);
-        if (q == 0) atomicAdd(s_cnt + k, 1.f);
-      } else {
-        const int d0 = q * 4;
-        atomicAdd(embed_sum + (size_t)(d0 + 0) * n_embed + k, xv.x);
-        atomicAdd(embed_sum + (size_t)(d0 + 1) * n_embed + k, xv.y);
-        atomicAdd(embed_sum + (size_t)(d0 + 2) * n_embed + k, xv.z);
-        atomicAdd(embed_sum + (size_t)(d0 + 3) * n_embed + k, xv.w);
-        if (q == 0) atomicAdd(counts + k, 1.f);
+  };
+  const bool lane_live = (int)threadIdx.x < groups_per_block * q4;   // blockDim need not be a multiple of q4
+  for (size_t seg = lane_live ? group : n_seg; seg < n_seg; seg += n_groups) {
+    const size_t r0 = seg * kSeg;
+    int cur_k = -1;
+    float4 run = make_float4(0.f, 0.f, 0.f, 0.f);
+    float run_n = 0.f;
+#pragma unroll 1
+    for (int j0 = 0; j0 < kSeg; j0 += 4) {
+      int kk[4];
+      float4 xv[4], ev[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {   // four rows in flight
+        const size_t r = r0 + j0 + u;
+        kk[u] = r < rows ? (int)ind[r] : -1;
+        xv[u] = ev[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (kk[u] >= 0) {
+          xv[u] = __ldg(reinterpret_cast<const float4*>(x + r * dim) + q);
+          ev[u] = __ldg(reinterpret_cast<const float4*>(e_t + (size_t)kk[u] * dim) + q);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (kk[u] < 0) continue;
+        const size_t r = r0 + j0 + u;
+        // (:77) diff = (quantize - input)^2 ; (:78) quantize = input + (quantize - input)
+        const float t0 = ev[u].x - xv[u].x, t1 = ev[u].y - xv[u].y, t2 = ev[u].z - xv[u].z, t3 = ev[u].w - xv[u].w;
+        dacc += t0 * t0 + t1 * t1 + t2 * t2 + t3 * t3;
+        const float4 qv = make_float4(xv[u].x + t0, xv[u].y + t1, xv[u].z + t2, xv[u].w + t3);
+        if (q_f32 != nullptr) reinterpret_cast<float4*>(q_f32 + r * dim)[q] = qv;
+        if (q_bf16 != nullptr) {
+          uint2 o;
+          o.x = pack_bf16x2(qv.x, qv.y);
+          o.y = pack_bf16x2(qv.z, qv.w);
+          reinterpret_cast<uint2*>(q_bf16 + r * dim)[q] = o;
+        }
+        if (stats) {
+          if (kk[u] != cur_k) {
+            flush(cur_k, run, run_n);
+            cur_k = kk[u];
+            run = make_float4(0.f, 0.f, 0.f, 0.f);
+            run_n = 0.f;
+          }
+          run.x += xv[u].x; run.y += xv[u].y; run.z += xv[u].z; run.w += xv[u].w;
+          run_n += 1.f;
+        }
       }
     }
+    if (stats) flush(cur_k, run, run_n);
   }
   // block reduce of the commitment-loss partial
   dacc = warp_sum(dacc);
@@ -671,7 +713,7 @@ cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t ro
       configured = true;
     }
     if (blocks > (size_t)num_sms) blocks = num_sms;  // one CTA per SM (smem-limited)
-    vq_gather_stats_kernel<true><<<(int)blocks, 1024, smem, st>>>(x, (const long long*)ind, rows, dim, n_embed, e_t,
+    vq_gather_stats_kernel<true><<<(int)blocks, 512, smem, st>>>(x, (const long long*)ind, rows, dim, n_embed, e_t,
                                                                    q_f32, (__nv_bfloat16*)q_bf16, diff_sum, counts,
                                                                    embed_sum);
   } else {
