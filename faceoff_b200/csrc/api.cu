@@ -400,7 +400,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     const int want = e ? atoi(e) : 1;
     const bool heavy = p.num_ksteps * p.TPS * kc >= 576;
     p.cta_pair = (want == 2 || (want == 1 && heavy)) && p.pos_tiles % 2 == 0 && p.NT % 32 == 0 &&
-                 g_num_sms % 2 == 0 && g_pair_ok && p.dbg_skip_mma == 0;
+                 g_num_sms % 2 == 0 && g_pair_ok && (p.dbg_skip_mma == 0 || p.dbg_skip_mma >= 3);
   }
   const int stage_bytes = (p.a_bytes + p.TPS * (p.NT / (p.cta_pair ? 2 : 1)) * rowb + 1023) & ~1023;
   // shared memory: pipeline stages + (as far as it fits next to two stages) the epilogue's prefetched addend / mask rows
@@ -412,8 +412,14 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     if (c->addend != nullptr && room >= e_tensor) { p.e_add = 1; room -= e_tensor; }
     if (c->mask != nullptr && room >= e_tensor) { p.e_mask = 1; room -= e_tensor; }
     if (p.e_add || p.e_mask) p.e_bufs = p.MT;
+    // short-K layers (1x1, 32-channel inputs): the tile's MMAs are too short to hide the fetch, so fetch one tile ahead
+    // when a second copy fits next to two pipeline stages
+    const char* ed = getenv("FO_E_DEPTH");
+    const int want_depth = ed ? atoi(ed) : 2;
+    if (p.e_bufs && want_depth == 2 && p.NT >= 64 && room >= (p.e_add + p.e_mask) * e_tensor) p.e_depth = 2;   // two stages stay
   }
-  int stages = (avail - (p.e_add + p.e_mask) * e_tensor) / stage_bytes;
+  if (p.e_depth < 1) p.e_depth = 1;
+  int stages = (avail - (p.e_add + p.e_mask) * e_tensor * p.e_depth) / stage_bytes;
   if (stages > 8) stages = 8;
   if (stages < 2) return fail(FO_ERR_INVALID, "tile does not fit in shared memory");
   p.stages = stages;

@@ -37,6 +37,7 @@ struct ConvParams {
   int cta_pair;       // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2): tiles 2i / 2i+1 share every B tile
   int pos_tiles;      // position tiles per (group, n-tile) = product of tile_cnt
   int e_bufs;         // epilogue operand prefetch: 0 = off, else MT (one buffer set per M sub-tile / warp group)
+  int e_depth;        // 1: rows of a tile are fetched while its MMAs run; 2: one tile ahead (double-buffered)
   int e_mask, e_add;  // which of the two epilogue operands are prefetched (shared memory permitting)
   int n_tiles;        // N tiles of width NT
   int NT;             // columns per N tile (multiple of 16, <= 256)
