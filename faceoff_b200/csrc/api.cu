@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -718,6 +719,19 @@ extern "C" int fo_relu(const void* x, void* y, size_t numel, fo_stream_t stream)
   REQUIRE_INIT();
   if (numel % 8 != 0) return fail(FO_ERR_INVALID, "relu: numel must be a multiple of 8");
   CUDA_TRY(launch_relu(x, y, numel, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_adam_chunk_elems(void) { return 16384; }
+extern "C" int fo_adam_step(const fo_adam_tensor_t* table_dev, const int* chunks_dev, int n_chunks, float lr, float beta1,
+                            float beta2, float eps, float weight_decay, int step, float grad_scale, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (step < 1) return fail(FO_ERR_INVALID, "adam: step counts from 1");
+  if (n_chunks <= 0) return FO_OK;
+  // bias corrections in double like torch (1 - beta ** step), then rounded once
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float sbc2 = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  CUDA_TRY(launch_adam(table_dev, chunks_dev, n_chunks, lr, beta1, beta2, eps, weight_decay, bc1, sbc2, grad_scale,
+                       g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
 extern "C" size_t fo_colsum_workspace_bytes(int cs) {

@@ -477,6 +477,54 @@ cudaError_t launch_unpack_nchw(const void* x, float* out, int n, int c, int hw, 
   unpack_nchw_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, c, hw, cs);
   return cudaGetLastError();
 }
+// ---------------------------------------------------------------- fused multi-tensor Adam
+// Reference: optim.Adam(model.parameters(), lr=3e-4) train_faceoff_perceptual.py:190 (torch defaults: betas (0.9, 0.999),
+// eps 1e-8, weight_decay 0, no amsgrad).  One launch updates every parameter tensor: `table` (device) lists the tensors,
+// `chunks` (device) maps each 16,384-element chunk to (tensor, first element).  Same arithmetic, in the same order,
+// as torch's single-tensor path: m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; p -= (lr / bc1) * m / (sqrt(v) / sqrt(bc2) + eps).
+struct AdamTensor {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long numel;
+};
+constexpr int kAdamChunk = 16384;
+__global__ void __launch_bounds__(256)
+adam_kernel(const AdamTensor* __restrict__ table, const int2* __restrict__ chunks, int n_chunks, float lr, float beta1,
+            float beta2, float eps, float weight_decay, float bias_c1, float sqrt_bias_c2, float grad_scale) {
+  for (int c = blockIdx.x; c < n_chunks; c += gridDim.x) {
+    const int2 ch = chunks[c];
+    const AdamTensor t = table[ch.x];
+    const long long start = (long long)ch.y * kAdamChunk;
+    const long long n = t.numel - start < kAdamChunk ? t.numel - start : kAdamChunk;
+    const float step_size = lr / bias_c1;
+    for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+      const long long j = start + i;
+      float g = t.grad[j] * grad_scale;
+      const float p = t.param[j];
+      if (weight_decay != 0.f) g = fmaf(weight_decay, p, g);
+      // torch: exp_avg.lerp_(grad, 1 - beta1) ; exp_avg_sq.mul_(beta2).addcmul_(grad, grad, value=1 - beta2)
+      const float m0 = t.exp_avg[j];
+      const float m = m0 + (g - m0) * (1.f - beta1);
+      const float v = t.exp_avg_sq[j] * beta2 + (1.f - beta2) * g * g;
+      t.exp_avg[j] = m;
+      t.exp_avg_sq[j] = v;
+      const float denom = sqrtf(v) / sqrt_bias_c2 + eps;
+      t.param[j] = p - step_size * (m / denom);
+    }
+  }
+}
+cudaError_t launch_adam(const void* table, const void* chunks, int n_chunks, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, float bias_c1, float sqrt_bias_c2, float grad_scale, int num_sms,
+                        cudaStream_t st) {
+  int blocks = n_chunks < num_sms * 8 ? n_chunks : num_sms * 8;
+  if (blocks < 1) return cudaSuccess;
+  adam_kernel<<<blocks, 256, 0, st>>>((const AdamTensor*)table, (const int2*)chunks, n_chunks, lr, beta1, beta2, eps,
+                                      weight_decay, bias_c1, sqrt_bias_c2, grad_scale);
+  return cudaGetLastError();
+}
+
 cudaError_t launch_relu(const void* x, void* y, size_t numel, int num_sms, cudaStream_t st) {
   const size_t nvec = numel / 8;
   relu_kernel<<<grid_for(nvec, 256, num_sms), 256, 0, st>>>((const uint4*)x, (uint4*)y, nvec);

@@ -42,6 +42,9 @@ cudaError_t launch_pack_nchw(const float* x, void* out, int n, int c, int hw, in
                              const float* scale, int num_sms, cudaStream_t st);
 cudaError_t launch_unpack_nchw(const void* x, float* out, int n, int c, int hw, int cs, cudaStream_t st);
 cudaError_t launch_relu(const void* x, void* y, size_t numel, int num_sms, cudaStream_t st);
+cudaError_t launch_adam(const void* table, const void* chunks, int n_chunks, float lr, float beta1, float beta2,
+                        float eps, float weight_decay, float bias_c1, float sqrt_bias_c2, float grad_scale, int num_sms,
+                        cudaStream_t st);
 cudaError_t launch_pack_weights(const float* w, void* out, const PackParams& pp, int num_sms, cudaStream_t st);
 cudaError_t launch_wgrad_finalize(const FinalizeParams& fp, int num_sms, cudaStream_t st);
 cudaError_t launch_bias_finalize(const float* part, int splits, int mc, int c, float* out, int accumulate,

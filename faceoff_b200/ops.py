@@ -466,3 +466,20 @@ def mse_grad(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor, scale: float) ->
                             _stream()), "fo_mse_grad")
     _count(1)
     return grad
+
+
+# ------------------------------------------------------------------------------------------------
+# optimizer
+# ------------------------------------------------------------------------------------------------
+def adam_chunk_elems() -> int:
+    return int(L.load().fo_adam_chunk_elems())
+
+
+def adam_step(table: torch.Tensor, chunks: torch.Tensor, n_chunks: int, lr: float, beta1: float, beta2: float,
+              eps: float, weight_decay: float, step: int, grad_scale: float = 1.0):
+    """One fused Adam update over every tensor listed in ``table`` (device int64 [n, 5]: param, grad, exp_avg,
+    exp_avg_sq pointers and numel) using the chunk map ``chunks`` (device int32 [n_chunks, 2])."""
+    lib = L.load()
+    L.check(lib.fo_adam_step(table.data_ptr(), chunks.data_ptr(), n_chunks, lr, beta1, beta2, eps, weight_decay, step,
+                             grad_scale, _stream()), "fo_adam_step")
+    _count(1)

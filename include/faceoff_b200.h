@@ -200,6 +200,22 @@ int fo_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* 
 int fo_mse_grad(const float* a, const float* b, int n, int ca, int c, int hw, const float* gscale, float scale,
                 float* grad, fo_stream_t stream);
 
+/* Optimizer step (reference optim.Adam(model.parameters(), lr=3e-4), train_faceoff_perceptual.py:190,
+ * torch.optim.Adam semantics without amsgrad): one launch over all parameter tensors.
+ * table_dev : DEVICE array of n tensors; chunks_dev : DEVICE array of n_chunks (tensor index, chunk index) int pairs, a
+ * chunk being fo_adam_chunk_elems() consecutive elements of that tensor.  step counts from 1.  grad_scale multiplies the
+ * gradients first (e.g. 1/world after a SUM all-reduce). */
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long numel;
+} fo_adam_tensor_t;
+int fo_adam_chunk_elems(void);
+int fo_adam_step(const fo_adam_tensor_t* table_dev, const int* chunks_dev, int n_chunks, float lr, float beta1, float beta2,
+                 float eps, float weight_decay, int step, float grad_scale, fo_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif
