@@ -27,14 +27,33 @@ def _count(n: int):
     LAUNCHES += n
 
 
+_event_pool: list = []   # timing events are recycled: creating two CUDA events per launch costs more host time than the launch
+
+
+def _take_event():
+    return _event_pool.pop() if _event_pool else torch.cuda.Event(enable_timing=True)
+
+
+def recycle_events(profile: dict):
+    """Give the events of a finished PROFILE dict back to the pool (after their times were read)."""
+    seen = set()
+    for recs in profile.values():
+        for a, b, _ in recs:
+            if id(a) not in seen:
+                seen.add(id(a))
+                _event_pool.extend((a, b))
+
+
 class _Timed:
+    __slots__ = ("name", "work", "a", "b")
+
     def __init__(self, name: str, work: float):
         self.name, self.work = name, work
 
     def __enter__(self):
         if PROFILE is not None:
-            self.a = torch.cuda.Event(enable_timing=True)
-            self.b = torch.cuda.Event(enable_timing=True)
+            self.a = _take_event()
+            self.b = _take_event()
             self.a.record()
 
     def __exit__(self, *exc):

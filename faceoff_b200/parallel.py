@@ -15,6 +15,8 @@ DDP's buffer broadcast is dropped.
 """
 from __future__ import annotations
 
+import os
+
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -86,7 +88,7 @@ class FusedDataParallel(nn.Module):
         super().__init__()
         self.module = module
         self.world = dist_fn.get_world_size()
-        self.n_chunks = max(1, n_chunks)
+        self.n_chunks = max(1, int(os.environ.get("FO_DP_CHUNKS", n_chunks)))   # env: experiments only
         self._pending_ema: List = []
         self._bucket: Optional[torch.Tensor] = None
         self._grad_views: Dict[str, torch.Tensor] = {}
