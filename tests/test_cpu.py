@@ -144,6 +144,23 @@ def test_no_cpu_fallback_fails_loudly():
         q(torch.randn(4, 64))
 
 
+def test_loss_and_optimizer_have_no_cpu_path():
+    """faceoff_b200.losses.mse_loss / optim.FusedAdam refuse CPU tensors instead of silently computing in PyTorch."""
+    from faceoff_b200 import _lib
+    from faceoff_b200.losses import mse_loss
+    from faceoff_b200.optim import FusedAdam
+
+    with pytest.raises(_lib.FaceoffB200Error):
+        mse_loss(torch.randn(2, 3, 8, 8, requires_grad=True), torch.randn(2, 3, 8, 8))
+    p = torch.nn.Parameter(torch.randn(10))
+    p.grad = torch.randn(10)
+    opt = FusedAdam([p], lr=3e-4)
+    with pytest.raises(_lib.FaceoffB200Error):
+        opt.step()
+    with pytest.raises(ValueError):
+        FusedAdam([p], lr=-1.0)
+
+
 def test_product_never_imports_oracle():
     pkg = os.path.join(ROOT, "faceoff_b200")
     for dirpath, _, files in os.walk(pkg):
