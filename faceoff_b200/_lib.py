@@ -85,6 +85,7 @@ _SIGS = {
     "fo_maxpool2": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fo_maxpool2_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                   C.c_void_p]),
+    "fo_vq_split_elems": (C.c_size_t, [C.c_int, C.c_int]),
     "fo_vq_prep": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fo_vq_assign_workspace_bytes": (C.c_size_t, [C.c_size_t, C.c_int]),
     "fo_vq_assign": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -793,6 +793,7 @@ extern "C" int fo_vq_prep(const float* embed, int dim, int n_embed, void* e_spli
   CUDA_TRY(launch_vq_prep(embed, dim, n_embed, e_split, e_t, e_norm2, (cudaStream_t)stream));
   return FO_OK;
 }
+extern "C" size_t fo_vq_split_elems(int dim, int n_embed) { return vq_split_elems(dim, n_embed); }
 extern "C" size_t fo_vq_assign_workspace_bytes(size_t rows, int dim) { return vq_assign_workspace_bytes(rows, dim); }
 extern "C" int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* e_t, const void* e_split,
                             const float* e_norm2, int64_t* embed_ind, int* n_flagged, void* workspace,
@@ -808,8 +809,16 @@ extern "C" int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, c
   uint32_t bx[2] = {64, 256};
   int rc = encode_map(&map_e, e_split, 2, dims, str, bx, 128);
   if (rc != FO_OK) return rc;
+  // the augmented K slice [n_pad][16] bf16 behind the split codebook (see fo_vq_prep): 32-byte rows, 32B swizzle
+  CUtensorMap map_x;
+  const uint64_t n_pad = ((uint64_t)n_embed + 255) / 256 * 256;
+  uint64_t xdims[2] = {16, n_pad};
+  uint64_t xstr[2] = {1, 16};
+  uint32_t xbx[2] = {16, 256};
+  rc = encode_map(&map_x, (const uint8_t*)e_split + (size_t)n_embed * 2 * dim * 2, 2, xdims, xstr, xbx, 32);
+  if (rc != FO_OK) return rc;
   CUDA_TRY(launch_vq_assign(x, rows, dim, n_embed, e_t, e_split, e_norm2, embed_ind, n_flagged, workspace, &map_e,
-                            g_num_sms, (cudaStream_t)stream));
+                            &map_x, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
 extern "C" int fo_vq_gather_stats(const float* x, const int64_t* embed_ind, size_t rows, int dim, int n_embed,

@@ -68,9 +68,11 @@ cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, fl
 cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
                            cudaStream_t st);
 size_t vq_assign_workspace_bytes(size_t rows, int dim);
+size_t vq_split_elems(int dim, int n_embed);
 cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* e_t,
                              const void* e_split, const float* e_norm2, int64_t* embed_ind, int* n_flagged,
-                             void* workspace, const CUtensorMap* map_e, int num_sms, cudaStream_t st);
+                             void* workspace, const CUtensorMap* map_e, const CUtensorMap* map_x, int num_sms,
+                             cudaStream_t st);
 cudaError_t init_vq();
 cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t rows, int dim, int n_embed,
                                    const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,

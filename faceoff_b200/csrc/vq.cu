@@ -18,10 +18,26 @@
 namespace fo {
 
 // =============================================================================== prep
-__global__ void vq_prep_kernel(const float* __restrict__ embed, int dim, int n_embed, __nv_bfloat16* __restrict__ e_split,
-                               float* __restrict__ e_t, float* __restrict__ e_norm2) {
+constexpr int kVqNTc = 256;   // codes per accumulator tile (= kVqNT below)
+size_t vq_split_elems(int dim, int n_embed) {
+  const size_t n_pad = (size_t)(n_embed + kVqNTc - 1) / kVqNTc * kVqNTc;
+  return (size_t)n_embed * 2 * dim + n_pad * 16;
+}
+// e_split holds the split codebook [n_embed][2*dim] followed by the AUGMENTED K slice [n_pad][16] (n_pad = n_embed rounded
+// up to 256): per code {-h, -m, -l, en_up, 0 x 12} with |e_k|^2 / 2 = h + m + l (three bf16 terms: fp32-exact) and en_up =
+// |e_k| rounded up to bf16.  Against the row vector {1, 1, 1, cx/2, 0...} one extra K=16 MMA turns the accumulator into
+// x.e_k - |e_k|^2/2 + (cx/2)|e_k| = -(lower bound of the distance)/2, so the epilogue needs no per-code arithmetic.
+// Pad codes get -1e30: they can never win.
+__global__ void vq_prep_kernel(const float* __restrict__ embed, int dim, int n_embed, int n_pad,
+                               __nv_bfloat16* __restrict__ e_split, float* __restrict__ e_t, float* __restrict__ e_norm2) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= n_embed) return;
+  if (k >= n_pad) return;
+  __nv_bfloat16* aug = e_split + (size_t)n_embed * 2 * dim + (size_t)k * 16;
+  if (k >= n_embed) {
+    aug[0] = __float2bfloat16(-1e30f);
+    for (int j = 1; j < 16; ++j) aug[j] = __float2bfloat16(0.f);
+    return;
+  }
   float s = 0.f;
   for (int d = 0; d < dim; ++d) {
     const float v = embed[(size_t)d * n_embed + k];
@@ -33,6 +49,14 @@ __global__ void vq_prep_kernel(const float* __restrict__ embed, int dim, int n_e
     e_t[(size_t)k * dim + d] = v;
   }
   e_norm2[k] = s;
+  const float hv = -0.5f * s;
+  const __nv_bfloat16 h = __float2bfloat16(hv);
+  const float r1 = hv - __bfloat162float(h);
+  const __nv_bfloat16 m = __float2bfloat16(r1);
+  const __nv_bfloat16 l = __float2bfloat16(r1 - __bfloat162float(m));
+  aug[0] = h; aug[1] = m; aug[2] = l;
+  aug[3] = __float2bfloat16_ru(sqrtf(s));
+  for (int j = 4; j < 16; ++j) aug[j] = __float2bfloat16(0.f);
 }
 __global__ void vq_e2max_kernel(float* e_norm2, int n_embed) {
   // e_norm2[n_embed] = max_k |e_k|^2 (error-band scale for vq_assign)
@@ -50,7 +74,8 @@ __global__ void vq_e2max_kernel(float* e_norm2, int n_embed) {
 
 cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
                            cudaStream_t st) {
-  vq_prep_kernel<<<(n_embed + 127) / 128, 128, 0, st>>>(embed, dim, n_embed, (__nv_bfloat16*)e_split, e_t, e_norm2);
+  const int n_pad = (n_embed + kVqNTc - 1) / kVqNTc * kVqNTc;
+  vq_prep_kernel<<<(n_pad + 127) / 128, 128, 0, st>>>(embed, dim, n_embed, n_pad, (__nv_bfloat16*)e_split, e_t, e_norm2);
   vq_e2max_kernel<<<1, 256, 0, st>>>(e_norm2, n_embed);
   return cudaGetLastError();
 }
@@ -59,9 +84,9 @@ cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_spl
 constexpr int kVqThreads = 32 * 14;  // warp0 TMA(B), warp1 MMA, warps 2-5 loader/convert, warps 6-13 epilogue (two
                                      // column halves x four TMEM lane quarters)
 constexpr int kVqNT = 256;           // codes per accumulator
-constexpr int kVqBStages = 4;        // ring of [256 x 64] bf16 B tiles (32 KB each)
+constexpr int kVqBStages = 3;        // ring of [256 x 64] bf16 B tiles (32 KB each)
 constexpr float kVqBand = 1.5e-4f;   // |error of dist_k| <= kVqBand * |x| * |e_k|  (2.5x the split-bf16 bound 2*3*2^-17)
-constexpr float kVqBig = 1e38f;      // score of padded codes / "no candidate yet" (finite: the index tag must not make a NaN)
+constexpr float kVqBig = 1e38f;      // -kVqBig = "no candidate yet" (finite: the index tag must not make a NaN)
 
 struct VqAssignParams {
   const float* x;
@@ -102,51 +127,40 @@ __device__ __forceinline__ void vq_halve(float (&s)[16], int lane, int off) {
   }
 }
 
-// Scan 32 accumulator columns: lower bound lo_k = (|e_k|^2 - 2 x.e_k) - band_k of every code's distance (|x|^2 is
-// common to the row and dropped), tagged with the column number in the 5 low mantissa bits, folded into the running
-// two smallest (m1 <= m2).  About 4.5 issue slots per code: 2 x 1/2 FFMA2, 1 LOP3, ~2.5 FMNMX/FMNMX3, 1/2 LDS.
-__device__ __forceinline__ void vq_scan32(const uint32_t (&v)[32], const float* __restrict__ e2,
-                                          const float* __restrict__ en, float ncx, uint32_t tag_mask, float& r1,
-                                          float& r2, int& ridx, int code0) {
-  float a1 = kVqBig, a2 = kVqBig, b1 = kVqBig, b2 = kVqBig;
-  const float2 neg2 = make_float2(-2.f, -2.f), nc = make_float2(ncx, ncx);
+// bf16-rounded-up half band of a row: cx/2 with cx = kVqBand * |x| (the row's entry of the augmented K slice)
+__device__ __forceinline__ __nv_bfloat16 vq_half_band(float x2) { return __float2bfloat16_ru(0.5f * kVqBand * sqrtf(x2)); }
+
+// Scan 32 accumulator columns.  Thanks to the augmented K slice the accumulator IS v_k = -(lower bound of code k's
+// distance)/2, so a code costs one LOP3 (column tag in the 5 low mantissa bits) and ~2.5 FMNMX for the running two largest.
+__device__ __forceinline__ void vq_scan32(const uint32_t (&v)[32], uint32_t tag_mask, float& r1, float& r2, int& ridx,
+                                          int code0) {
+  float a1 = -kVqBig, a2 = -kVqBig, b1 = -kVqBig, b2 = -kVqBig;
 #pragma unroll
-  for (int j4 = 0; j4 < 32; j4 += 4) {
-    const float4 q2 = *reinterpret_cast<const float4*>(e2 + j4);
-    const float4 qn = *reinterpret_cast<const float4*>(en + j4);
-    const float2 d01 = __ffma2_rn(make_float2(__uint_as_float(v[j4]), __uint_as_float(v[j4 + 1])), neg2,
-                                  make_float2(q2.x, q2.y));
-    const float2 d23 = __ffma2_rn(make_float2(__uint_as_float(v[j4 + 2]), __uint_as_float(v[j4 + 3])), neg2,
-                                  make_float2(q2.z, q2.w));
-    const float2 l01 = __ffma2_rn(make_float2(qn.x, qn.y), nc, d01);
-    const float2 l23 = __ffma2_rn(make_float2(qn.z, qn.w), nc, d23);
-    const float lo[4] = {l01.x, l01.y, l23.x, l23.y};
-#pragma unroll
-    for (int jj = 0; jj < 4; ++jj) {
-      // tag_mask lives in a register so that (lo & mask) | j is ONE LOP3 (a single immediate per instruction)
-      const float t = __uint_as_float((__float_as_uint(lo[jj]) & tag_mask) | (uint32_t)(j4 + jj));
-      if (jj & 1) {
-        const float mx = fmaxf(b1, t);
-        b1 = fminf(b1, t);
-        b2 = fminf(b2, mx);
-      } else {
-        const float mx = fmaxf(a1, t);
-        a1 = fminf(a1, t);
-        a2 = fminf(a2, mx);
-      }
+  for (int j = 0; j < 32; ++j) {
+    // tag_mask lives in a register so that (v & mask) | j is ONE LOP3 (a single immediate per instruction)
+    const float t = __uint_as_float((v[j] & tag_mask) | (uint32_t)j);
+    if (j & 1) {
+      const float mn = fminf(b1, t);
+      b1 = fmaxf(b1, t);
+      b2 = fmaxf(b2, mn);
+    } else {
+      const float mn = fminf(a1, t);
+      a1 = fmaxf(a1, t);
+      a2 = fmaxf(a2, mn);
     }
   }
-  const float m1 = fminf(a1, b1);
-  const float m2 = fminf(fmaxf(a1, b1), fminf(a2, b2));
-  const bool lt = m1 < r1;
-  r2 = fminf(fminf(r2, m2), fmaxf(r1, m1));
-  ridx = lt ? code0 + (int)(__float_as_uint(m1) & 31u) : ridx;
-  r1 = fminf(r1, m1);
+  const float m1 = fmaxf(a1, b1);
+  const float m2 = fmaxf(fminf(a1, b1), fmaxf(a2, b2));
+  const bool gt = m1 > r1;
+  r2 = fmaxf(fmaxf(r2, m2), fminf(r1, m1));
+  ridx = gt ? code0 + (int)(__float_as_uint(m1) & 31u) : ridx;
+  r1 = fmaxf(r1, m1);
 }
 
 template <int DIM>
 __global__ void __launch_bounds__(kVqThreads, 1)   // 128 registers: 4 warps of a 16 K-register SM sub-partition
-vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant__ CUtensorMap map_e) {
+vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant__ CUtensorMap map_e,
+                 const __grid_constant__ CUtensorMap map_x) {
   constexpr int KCH = DIM / 64;                         // 64-wide K chunks
   constexpr int Q4 = DIM / 4;                           // float4 (= loader lanes) per row: 16 or 32
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -157,14 +171,19 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
   constexpr int b_tile = kVqNT * 128;                   // [256 x 64] bf16
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)p.a_bufs * a_buf_bytes;
-  float* sE2 = reinterpret_cast<float*>(sB + (size_t)kVqBStages * b_tile);  // [n_tiles*256]
-  float* sEN = sE2 + p.n_tiles * kVqNT;                                      // [n_tiles*256]  |e_k|
+  constexpr int ax_tile = 128 * 32;                     // augmented slice of the rows: [128 x 16] bf16, 32B swizzle
+  constexpr int bx_tile = kVqNT * 32;                   // augmented slice of a code tile: [256 x 16] bf16
+  uint8_t* sAx = sB + (size_t)kVqBStages * b_tile;      // [a_bufs]
+  uint8_t* sBx = sAx + (size_t)p.a_bufs * ax_tile;      // [2]
+  float* sEN = reinterpret_cast<float*>(sBx + 2 * bx_tile);                  // [n_tiles*256]  |e_k| rounded up to bf16
   float* sX2 = sEN + p.n_tiles * kVqNT;                                      // [4][128] (epilogue may lag the loader by 3 tiles)
   float* sMerge = sX2 + 4 * 128;                                             // [2][128][4] column-half hand-over
   uint64_t* bars = reinterpret_cast<uint64_t*>(sMerge + 2 * 128 * 4);
   uint64_t* b_full = bars;                    // [kVqBStages]
   uint64_t* b_empty = b_full + kVqBStages;    // [kVqBStages]
-  uint64_t* a_full = b_empty + kVqBStages;    // [2]
+  uint64_t* bx_full = b_empty + kVqBStages;   // [2]
+  uint64_t* bx_empty = bx_full + 2;           // [2]
+  uint64_t* a_full = bx_empty + 2;            // [2]
   uint64_t* a_empty = a_full + 2;             // [2]
   uint64_t* t_full = a_empty + 2;             // [2]
   uint64_t* t_empty = t_full + 2;             // [2]
@@ -174,7 +193,10 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
   const int lane = threadIdx.x & 31;
 
   if (warp == 0) {
-    if (lane == 0) tma_prefetch_desc(&map_e);
+    if (lane == 0) {
+      tma_prefetch_desc(&map_e);
+      tma_prefetch_desc(&map_x);
+    }
     __syncwarp();
     tmem_alloc(tmem_ptr, 512);
     tmem_relinquish();
@@ -184,6 +206,8 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
       mbar_init(&b_empty[s], 1);
     }
     for (int b = 0; b < 2; ++b) {
+      mbar_init(&bx_full[b], 1);
+      mbar_init(&bx_empty[b], 1);
       mbar_init(&a_full[b], 128);
       mbar_init(&a_empty[b], 1);
       mbar_init(&t_full[b], 1);
@@ -191,11 +215,9 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     }
     fence_mbar_init();
   }
-  // |e|^2 and |e| to smem (padded codes get a huge score so they never win)
-  for (int k = threadIdx.x; k < p.n_tiles * kVqNT; k += blockDim.x) {
-    sE2[k] = k < p.n_embed ? p.e_norm2[k] : kVqBig;
-    sEN[k] = k < p.n_embed ? sqrtf(p.e_norm2[k]) : 0.f;
-  }
+  // |e_k| exactly as the augmented slice holds it (rounded up to bf16): the winner's band is recomputed from it
+  for (int k = threadIdx.x; k < p.n_tiles * kVqNT; k += blockDim.x)
+    sEN[k] = k < p.n_embed ? __bfloat162float(__float2bfloat16_ru(sqrtf(p.e_norm2[k]))) : 0.f;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -207,8 +229,15 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
+      int xit = 0;
       for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x) {
-        for (int nt = 0; nt < p.n_tiles; ++nt)
+        for (int nt = 0; nt < p.n_tiles; ++nt, ++xit) {
+          {   // augmented slice of this code tile
+            const int xs = xit & 1;
+            mbar_wait_backoff(&bx_empty[xs], ((xit >> 1) & 1) ^ 1, 64);
+            mbar_expect_tx(&bx_full[xs], bx_tile);
+            tma_load_2d(sBx + xs * bx_tile, &map_x, &bx_full[xs], 0, nt * kVqNT);
+          }
           for (int kc = 0; kc < KCH; ++kc)
             for (int part = 0; part < 2; ++part) {  // 0: hi, 1: lo
               mbar_wait_backoff(&b_empty[stage], phase ^ 1, 64);
@@ -216,12 +245,14 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
               tma_load_2d(sB + (size_t)stage * b_tile, &map_e, &b_full[stage], part * DIM + kc * 64, nt * kVqNT);
               if (++stage == kVqBStages) { stage = 0; phase ^= 1; }
             }
+        }
       }
     }
   } else if (warp == 1) {
     // ---------------------------------------------------------------- MMA issuer
     const uint32_t idesc = make_idesc_bf16(128, kVqNT, 0, 0);
     const uint64_t desc_base = make_smem_desc(0, 128, 16);
+    const uint64_t desc32_base = make_smem_desc(0, 32, 16);   // the K=16 augmented slice: 32-byte rows, 32B swizzle
     int stage = 0;
     uint32_t phase = 0;
     int it = 0, acc_it = 0;
@@ -263,6 +294,18 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
           }
           __syncwarp();
           if (++stage == kVqBStages) { stage = 0; phase ^= 1; }
+        }
+        {   // augmented K slice: + (-|e|^2/2 + (cx/2)|e|)
+          const int xs = acc_it & 1;
+          mbar_wait_backoff(&bx_full[xs], (acc_it >> 1) & 1, 20);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint64_t ax = desc32_base + ((smem_u32(sAx + (size_t)ab * ax_tile) & 0x3FFFF) >> 4);
+            const uint64_t bxd = desc32_base + ((smem_u32(sBx + xs * bx_tile) & 0x3FFFF) >> 4);
+            umma_bf16(d_tmem, ax, bxd, idesc, 1);
+            umma_commit(&bx_empty[xs]);
+          }
+          __syncwarp();
         }
         if (lane == 0) umma_commit(&t_full[tb]);
         __syncwarp();
@@ -315,24 +358,36 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
           *reinterpret_cast<uint2*>(a_base + (KCH + kc) * a_sub + off) = lv;
         }
         // |x|^2 of the 16 rows: transposed butterfly over the Q4 lanes of a row (15 or 16 shuffles instead of 64+)
+        int xr = -1;   // row whose |x|^2 this lane ends up holding
         if (Q4 == 32) {
           vq_halve<16>(s, lane, 16); vq_halve<8>(s, lane, 8); vq_halve<4>(s, lane, 4); vq_halve<2>(s, lane, 2);
           s[0] += __shfl_xor_sync(0xffffffffu, s[0], 1);
-          if ((q & 1) == 0) sX2[(it & 3) * 128 + (i0 + (q >> 1)) * RPI + rsub] = s[0];
+          if ((q & 1) == 0) xr = (i0 + (q >> 1)) * RPI + rsub;
         } else {
           vq_halve<16>(s, lane, 8); vq_halve<8>(s, lane, 4); vq_halve<4>(s, lane, 2); vq_halve<2>(s, lane, 1);
-          sX2[(it & 3) * 128 + (i0 + q) * RPI + rsub] = s[0];
+          xr = (i0 + q) * RPI + rsub;
+        }
+        if (xr >= 0) {
+          sX2[(it & 3) * 128 + xr] = s[0];
+          // augmented slice of the row: {1, 1, 1, cx/2, 0 x 12} as a 32-byte row, 16-byte chunks swizzled by row bit 2
+          const uint32_t hb = (uint32_t)__bfloat16_as_ushort(vq_half_band(s[0]));
+          uint8_t* rowp = sAx + (size_t)ab * ax_tile + xr * 32;
+          const int c0 = (xr >> 2) & 1;
+          *reinterpret_cast<uint4*>(rowp + c0 * 16) = make_uint4(0x3F803F80u, 0x3F80u | (hb << 16), 0u, 0u);
+          *reinterpret_cast<uint4*>(rowp + (c0 ^ 1) * 16) = make_uint4(0u, 0u, 0u, 0u);
         }
       }
       fence_proxy_async();   // generic-proxy smem writes -> visible to the tensor core (async proxy)
       mbar_arrive(&a_full[ab]);
     }
   } else {
-    // ---------------------------------------------------------------- epilogue: two smallest lower bounds per row
-    // Code k's distance is only known to +- band_k = kVqBand * |x| * |e_k| (split-bf16 product error, scaled per code
-    // so that dead codes with huge norms -- the EMA renormalisation blows unused codes up, reference :70-75 -- do not
-    // widen it).  With lo_k = d_k - band_k: the code k1 with the smallest lo is the certain winner iff its upper bound
-    // lo_k1 + 2 band_k1 stays below the second smallest lo; every other row goes to the exact re-check.
+    // ---------------------------------------------------------------- epilogue: two largest scores per row
+    // The accumulator holds v_k = x.e_k - |e_k|^2/2 + band_k/2 with band_k = cx' * en'_k >= kVqBand * |x| * |e_k| (both
+    // factors rounded up to bf16; the split-bf16 product error of 2 x.e_k stays below it; it is scaled per code so that
+    // dead codes with huge norms -- the EMA renormalisation blows unused codes up, reference :70-75 -- do not widen it).
+    // -2 v_k is a LOWER bound of the distance (|x|^2 dropped) and -2 v_k + 2 band_k an upper bound, so the code k1 with
+    // the largest v is the certain winner iff v_k1 - v_k2 > band_k1 for the runner-up k2; every other row goes to the
+    // exact re-check together with U = -2 v_k1 + 2 band_k1.
     const int quarter = warp & 3;
     const int half = (warp - 6) >> 2;        // which 128 columns of every 256-column accumulator this warp scans
     const int row = quarter * 32 + lane;
@@ -340,36 +395,32 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     const uint32_t tag_mask = 0xffffffe0u | ((uint32_t)p.n_tiles >> 30);
     int it = 0, acc_it = 0;
     for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, ++it) {
-      float r1 = kVqBig, r2 = kVqBig;
+      float r1 = -kVqBig, r2 = -kVqBig;
       int ridx = 0;
-      float cx = 0.f;
       for (int nt = 0; nt < p.n_tiles; ++nt, ++acc_it) {
         const int tb = acc_it & 1;
         mbar_wait(&t_full[tb], (acc_it >> 1) & 1);
         tc_fence_after();
-        if (nt == 0) cx = kVqBand * sqrtf(sX2[(it & 3) * 128 + row]);   // written before a_full, which precedes t_full
         const int c0 = half * (kVqNT / 2);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tb * kVqNT + c0;
-        const float* e2 = sE2 + nt * kVqNT + c0;
-        const float* en = sEN + nt * kVqNT + c0;
         const int code0 = nt * kVqNT + c0;
         // software pipeline over the four 32-column chunks: the next TMEM read is in flight while one is scanned
         uint32_t va[32], vb[32];
         tmem_ld32(taddr, va);
         tmem_ld_wait32(va);
         tmem_ld32(taddr + 32, vb);
-        vq_scan32(va, e2, en, -cx, tag_mask, r1, r2, ridx, code0);
+        vq_scan32(va, tag_mask, r1, r2, ridx, code0);
         tmem_ld_wait32(vb);
         tmem_ld32(taddr + 64, va);
-        vq_scan32(vb, e2 + 32, en + 32, -cx, tag_mask, r1, r2, ridx, code0 + 32);
+        vq_scan32(vb, tag_mask, r1, r2, ridx, code0 + 32);
         tmem_ld_wait32(va);
         tmem_ld32(taddr + 96, vb);
-        vq_scan32(va, e2 + 64, en + 64, -cx, tag_mask, r1, r2, ridx, code0 + 64);
+        vq_scan32(va, tag_mask, r1, r2, ridx, code0 + 64);
         tmem_ld_wait32(vb);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[tb]);   // the accumulator is in registers: release it before the last scan
-        vq_scan32(vb, e2 + 96, en + 96, -cx, tag_mask, r1, r2, ridx, code0 + 96);
+        vq_scan32(vb, tag_mask, r1, r2, ridx, code0 + 96);
       }
       // hand the upper column half over to the lower one (named barrier 1: the 256 epilogue threads)
       float* mg = sMerge + ((it & 1) * 128 + row) * 4;
@@ -381,21 +432,23 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
       {
         const float o1 = mg[0], o2 = mg[1];
         const int oi = __float_as_int(mg[2]);
-        const bool lt = o1 < r1;
-        r2 = fminf(fminf(r2, o2), fmaxf(r1, o1));
-        ridx = lt ? oi : ridx;
-        r1 = fminf(r1, o1);
+        const bool gt = o1 > r1;
+        r2 = fmaxf(fmaxf(r2, o2), fminf(r1, o1));
+        ridx = gt ? oi : ridx;
+        r1 = fmaxf(r1, o1);
       }
       const size_t grow = (size_t)rt * 128 + row;
       if (grow < p.rows) {
         p.embed_ind[grow] = ridx;
+        // written before a_full, which precedes t_full; same rounding as the loader's augmented row
+        const float cxp = 2.f * __bfloat162float(vq_half_band(sX2[(it & 3) * 128 + row]));
+        const float band1 = cxp * sEN[ridx];
         // the index tag moved each value by < 2^-18 of its magnitude
         const float slack = 7.7e-6f * (fabsf(r1) + fabsf(r2));
-        const float up = r1 + 2.f * cx * sEN[ridx] + slack;
-        if (!(up < r2)) {   // ambiguous within the error bound (also catches NaN rows)
+        if (!(r1 - r2 > band1 + slack)) {   // ambiguous within the error bound (also catches NaN rows)
           const int slot = atomicAdd(p.flag_count, 1);
           p.flag_rows[slot] = (int)grow;   // capacity = rows
-          p.flag_u[slot] = up;
+          p.flag_u[slot] = -2.f * r1 + 2.f * band1 + 2.f * slack;
         }
       }
     }
@@ -534,14 +587,16 @@ size_t vq_assign_smem_bytes(int dim, int n_embed) {
   const int kchunks = dim / 64;
   const int a_bufs = dim <= 64 ? 2 : 1;
   const int n_tiles = (n_embed + kVqNT - 1) / kVqNT;
-  return (size_t)a_bufs * 2 * kchunks * 128 * 128 + (size_t)kVqBStages * kVqNT * 128 + (size_t)n_tiles * kVqNT * 8 +
-         4 * 128 * 4 + 2 * 128 * 4 * 4 + (2 * kVqBStages + 8) * 8 + 16 + 1024;
+  return (size_t)a_bufs * 2 * kchunks * 128 * 128 + (size_t)kVqBStages * kVqNT * 128 + (size_t)a_bufs * 128 * 32 +
+         2 * (size_t)kVqNT * 32 + (size_t)n_tiles * kVqNT * 4 + 4 * 128 * 4 + 2 * 128 * 4 * 4 +
+         (2 * kVqBStages + 12) * 8 + 16 + 1024;
 }
 size_t vq_assign_workspace_bytes(size_t rows, int dim) { return 256 + rows * (sizeof(int) + sizeof(float)); }
 
 cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* e_t,
                              const void* e_split, const float* e_norm2, int64_t* embed_ind, int* n_flagged,
-                             void* workspace, const CUtensorMap* map_e, int num_sms, cudaStream_t st) {
+                             void* workspace, const CUtensorMap* map_e, const CUtensorMap* map_x, int num_sms,
+                             cudaStream_t st) {
   (void)e_split;
   VqAssignParams p;
   p.x = x; p.rows = rows; p.dim = dim; p.n_embed = n_embed;
@@ -557,9 +612,9 @@ cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, 
   if (e != cudaSuccess) return e;
   const int grid = p.row_tiles < num_sms ? p.row_tiles : num_sms;
   if (dim == 64)
-    vq_assign_kernel<64><<<grid, kVqThreads, vq_assign_smem_bytes(dim, n_embed), st>>>(p, *map_e);
+    vq_assign_kernel<64><<<grid, kVqThreads, vq_assign_smem_bytes(dim, n_embed), st>>>(p, *map_e, *map_x);
   else
-    vq_assign_kernel<128><<<grid, kVqThreads, vq_assign_smem_bytes(dim, n_embed), st>>>(p, *map_e);
+    vq_assign_kernel<128><<<grid, kVqThreads, vq_assign_smem_bytes(dim, n_embed), st>>>(p, *map_e, *map_x);
   e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   long long* ind = reinterpret_cast<long long*>(embed_ind);

@@ -371,11 +371,12 @@ def maxpool2_bwd(x: torch.Tensor, y: torch.Tensor, dy: torch.Tensor) -> torch.Te
 # vector quantiser
 # ------------------------------------------------------------------------------------------------
 def vq_prep(embed: torch.Tensor):
-    """embed fp32 [dim, n_embed] -> (e_split bf16 [n_embed, 2*dim], e_t fp32 [n_embed, dim], e_norm2 fp32 [n_embed+1])."""
+    """embed fp32 [dim, n_embed] -> (e_split bf16 (split codebook [n_embed, 2*dim] + augmented K slice, flat), e_t fp32
+    [n_embed, dim], e_norm2 fp32 [n_embed+1])."""
     lib = L.load()
     dim, n_embed = embed.shape
     dev = embed.device
-    e_split = torch.empty((n_embed, 2 * dim), dtype=torch.bfloat16, device=dev)
+    e_split = torch.empty(lib.fo_vq_split_elems(dim, n_embed), dtype=torch.bfloat16, device=dev)
     e_t = torch.empty((n_embed, dim), dtype=torch.float32, device=dev)
     e_norm2 = torch.empty(n_embed + 1, dtype=torch.float32, device=dev)
     L.check(lib.fo_vq_prep(embed.data_ptr(), dim, n_embed, e_split.data_ptr(), e_t.data_ptr(), e_norm2.data_ptr(),

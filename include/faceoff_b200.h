@@ -154,9 +154,12 @@ int fo_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int 
 /* ---------------------------------------------------------------------------------------------
  * Vector quantiser (reference models/vqvae_conv3d_latent.py:33-83)
  * ------------------------------------------------------------------------------------------- */
-/* Codebook prep: embed fp32 [dim, n_embed] -> e_split bf16 [n_embed, 2*dim] (hi | lo halves, the GEMM B operand),
- * e_t fp32 [n_embed, dim] (transposed copy: the gather operand; keep it for fo_vq_backward because the EMA
- * update overwrites embed inside forward), e_norm2 fp32 [n_embed + 1] (|e_k|^2, then max_k |e_k|^2). */
+/* Codebook prep: embed fp32 [dim, n_embed] -> e_split bf16, fo_vq_split_elems(dim, n_embed) elements: the split codebook
+ * [n_embed, 2*dim] (hi | lo halves, the GEMM B operand) followed by the augmented K slice [n_pad, 16] (n_pad = n_embed
+ * rounded up to 256; per code -|e|^2/2 as three bf16 terms and |e| rounded up: one extra K=16 MMA folds |e|^2 and the error
+ * band into the accumulator); e_t fp32 [n_embed, dim] (transposed copy: the gather operand; keep it for fo_vq_backward
+ * because the EMA update overwrites embed inside forward), e_norm2 fp32 [n_embed + 1] (|e_k|^2, then max_k |e_k|^2). */
+size_t fo_vq_split_elems(int dim, int n_embed);
 int fo_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
                fo_stream_t stream);
 /* Nearest-code assignment (:48-54).  x fp32 [rows, dim].  embed_ind int64 [rows].
