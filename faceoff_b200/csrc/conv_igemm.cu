@@ -12,17 +12,19 @@
 //
 // Warp roles (320 threads, 1 CTA / SM, persistent over tiles):
 //   warp 0      TMA producer      (one A box + TPS B boxes [NT x KC] per stage, 128B/64B/32B swizzle)
-//   warp 1      MMA issuer        (lane 0 issues tcgen05.mma kind::f16 BF16xBF16->FP32, M=128, N=NT)
+//   warp 1      MMA issuer        (one elected lane issues tcgen05.mma kind::f16 BF16xBF16->FP32, M=128 per CTA, N=NT)
 //   warps 2..9  epilogue          (tcgen05.ld -> +bias -> *mask -> +addend -> relu -> bf16/fp32 stores); warps 2-5 own
 //                                 M sub-tile 0, warps 6-9 sub-tile 1 (two warps per scheduler hide each other's latency)
 // TMEM holds two sets of accumulators (2 x MT x NT columns) so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
-// The kernel is L2->SM bandwidth bound (about 32 B/clk/SM are available, a 128x128x64 MMA step wants 128 B/clk when A
-// and B are both streamed), so operand reuse is what matters:
+// What bounds the tensor-bound layers is the SM's shared-memory port, shared by TMA writes and UMMA operand reads (an
+// SS-mode 128x128x16 MMA reads 4 KB of A + 4 KB of B in its 64 math cycles; measured: Conv3d with TMA only 1.21 ms, MMAs
+// only 1.97 ms, both 2.44 ms), so operand reuse is what matters:
 //   MT = 2   the CTA tile is 256 output positions = two M=128 MMAs per B tile (B traffic / 2);
 //   TPS = 3  "halo" stages for 3x3(x3) filters: the A box holds R+2 image rows; the three vertical taps are the SAME
 //            shared-memory box read through descriptors offset by one image row (S*rowb bytes, a multiple of the
-//            1024-byte swizzle atom), so A traffic drops by 3R/(R+2).
+//            1024-byte swizzle atom), so A traffic drops by 3R/(R+2);
+//   CG = 2   CTA pairs (cta_group::2, M = 256 over two SMs): each CTA loads half of every B tile (long-K layers).
 #include "common.cuh"
 #include "igemm.cuh"
 

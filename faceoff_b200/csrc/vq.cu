@@ -1,15 +1,17 @@
 // Vector quantiser kernels (reference models/vqvae_conv3d_latent.py:33-83).
 //
-//  vq_prep        codebook fp32 [dim, n_embed] -> bf16 hi/lo split [n_embed, 2*dim] (K-major GEMM B operand),
-//                 transposed fp32 copy [n_embed, dim] (gather operand) and |e|^2.
+//  vq_prep        codebook fp32 [dim, n_embed] -> bf16 hi/lo split [n_embed, 2*dim] (K-major GEMM B operand) followed by
+//                 the augmented K slice [n_pad, 16] (-|e|^2/2 as three bf16 terms, |e| rounded up), transposed fp32 copy
+//                 [n_embed, dim] (gather operand) and |e|^2.
 //  vq_assign      nearest code per row (:48-54).  The distance matrix is a dense contraction, so it runs on
 //                 tcgen05: A = x split into bf16 hi + lo on the fly (fp32 rows are loaded coalesced, split in
 //                 registers, written into 128B-swizzled smem tiles), B = codebook hi/lo tiles streamed by TMA,
-//                 three MMAs per K block (hi*hi + lo*hi + hi*lo ~ 2^-17 relative error), accumulators
-//                 double-buffered in TMEM.  The epilogue keeps (best, second best, argbest) per row in registers
-//                 -- the [rows, n_embed] distance matrix never exists in HBM.  Rows whose top-2 gap is inside
-//                 the error band are re-evaluated exactly (fp64 accumulation of the fp32 data) by vq_refine,
-//                 which makes embed_ind bit-exact w.r.t. the reference outside true near-ties.
+//                 three MMAs per K block (hi*hi + lo*hi + hi*lo ~ 2^-17 relative error) plus one K=16 MMA per code
+//                 tile that adds -|e|^2/2 and half the error band, accumulators double-buffered in TMEM.  The epilogue
+//                 keeps the two largest scores and the arg-best per row in registers -- the [rows, n_embed] distance
+//                 matrix never exists in HBM.  Rows whose top-2 gap is inside the error band are re-evaluated exactly
+//                 (fp32 filter, then fp64 accumulation of the fp32 data) by vq_refine, which makes embed_ind bit-exact
+//                 w.r.t. the reference outside true near-ties.
 //  vq_gather_stats gather + straight-through + commitment loss + EMA statistics in one pass (:55-61,77-78).
 //  vq_ema         EMA + renormalisation (:66-75).     vq_backward   grad of :77-78.
 #include "common.cuh"
