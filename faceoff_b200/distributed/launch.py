@@ -16,7 +16,9 @@ def find_free_port():
         return s.getsockname()[1]
 
 
-def launch(fn, n_gpu_per_machine, n_machine=1, machine_rank=0, dist_url=None, args=()):
+def launch(fn, n_gpu_per_machine, n_machine=1, machine_rank=0, dist_url=None, args=(), backend="nccl"):
+    """Same positional signature as the reference; ``backend`` (extra, keyword) exists so the spawn / rendezvous /
+    local-group logic can be exercised with gloo on a machine without GPUs."""
     world_size = n_machine * n_gpu_per_machine
     if world_size <= 1:
         fn(*args)
@@ -29,7 +31,7 @@ def launch(fn, n_gpu_per_machine, n_machine=1, machine_rank=0, dist_url=None, ar
     if n_machine > 1 and dist_url.startswith("file://"):
         raise ValueError("file:// is not a reliable init method in multi-machine jobs. Prefer tcp://")
     mp.spawn(distributed_worker, nprocs=n_gpu_per_machine,
-             args=(fn, world_size, n_gpu_per_machine, machine_rank, dist_url, args), daemon=False)
+             args=(fn, world_size, n_gpu_per_machine, machine_rank, dist_url, args, backend), daemon=False)
 
 
 def distributed_worker(local_rank, fn, world_size, n_gpu_per_machine, machine_rank, dist_url, args,

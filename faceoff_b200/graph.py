@@ -139,6 +139,8 @@ def conv_op(tape: Tape, form: int, ksize: int, srcs: Sequence[View], wname: str,
     out = Node(cout, raw=flat(raw), act=flat(relu), f32=of32 if f32 == "nchw" else flat(of32))
 
     def backward():
+        if out.g is None and not param_grad:
+            return      # frozen layer (LPIPS trunk) that no gradient reached: nothing to do
         assert out.g is not None, f"no gradient reached {wname}"
         gt, g_off = out.g
         dy = (shaped(gt), cout, g_off)

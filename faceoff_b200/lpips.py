@@ -8,16 +8,39 @@ from __future__ import annotations
 
 import os
 import warnings
+from collections import namedtuple
 
 import torch
 from torch import nn
 
 from . import ops
 from .graph import FORM_S1, FORM_S1_DGRAD, Node, Tape, View, conv_op
+from ._lib import FaceoffB200Error
 from .vqvae import _GraphFn, _params_of
 
 _VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 _SLICE_ENDS = [4, 9, 16, 23, 30]  # reference models/lpips.py:127-136
+
+
+CKPT_MAP = {"vgg_lpips": "vgg.pth"}
+MD5_MAP = {"vgg_lpips": "d507d7349b931f0638a25a48a722f98a"}   # reference models/lpips.py:20-22
+
+
+def get_ckpt_path(name, root, check=False):
+    """Path of the LPIPS checkpoint if it is already on disk (reference models/lpips.py:40-48 would download it; this
+    environment has no network), else None.  ``check`` verifies the reference's md5."""
+    assert name in CKPT_MAP
+    path = os.path.join(root, CKPT_MAP[name])
+    if not os.path.exists(path):
+        return None
+    if check:
+        import hashlib
+
+        with open(path, "rb") as f:
+            md5 = hashlib.md5(f.read()).hexdigest()
+        if md5 != MD5_MAP[name]:
+            raise FaceoffB200Error(f"{path}: md5 {md5} != {MD5_MAP[name]}")
+    return path
 
 
 class ScalingLayer(nn.Module):
@@ -47,6 +70,7 @@ class vgg16(nn.Module):
     def __init__(self, requires_grad=False, pretrained=True):
         super().__init__()
         self.N_slices = 5
+        self.trunk_loaded = False   # True once real (non-random) trunk weights were loaded
         slices = [nn.Sequential() for _ in range(5)]
         idx, cin, which = 0, 3, 0
         self.layout = []  # (kind, key, cout)
@@ -68,9 +92,138 @@ class vgg16(nn.Module):
             if idx in _SLICE_ENDS:
                 self.layout.append(("tap", None, cin))
         self.slice1, self.slice2, self.slice3, self.slice4, self.slice5 = slices
+        if pretrained:
+            self._load_torchvision_features()
         if not requires_grad:
             for p in self.parameters():
                 p.requires_grad = False
+
+    def _load_torchvision_features(self):
+        """The reference builds the trunk from ``torchvision.models.vgg16(pretrained=True).features``
+        (models/lpips.py:118).  There is no network here, so only an already cached torchvision checkpoint
+        (``<torch hub>/checkpoints/vgg16-*.pth``) can be used; otherwise the trunk stays RANDOM and every consumer is
+        told so loudly (``trunk_loaded`` stays False, LPIPS warns)."""
+        ckpt_dir = os.path.join(torch.hub.get_dir(), "checkpoints")
+        cands = sorted(f for f in (os.listdir(ckpt_dir) if os.path.isdir(ckpt_dir) else []) if f.startswith("vgg16-"))
+        if not cands:
+            return
+        self.load_torchvision_state_dict(torch.load(os.path.join(ckpt_dir, cands[0]), map_location="cpu"))
+
+    def load_torchvision_state_dict(self, sd):
+        """Load a torchvision ``vgg16`` (or ``vgg16().features``) state_dict: key ``features.{idx}.weight`` ->
+        ``slice{k}.{idx}.weight`` with k the LPIPS slice holding module ``idx`` (reference models/lpips.py:127-136)."""
+        own = dict(self.named_parameters())
+        hit = 0
+        for k, v in sd.items():
+            k = k[len("features."):] if k.startswith("features.") else k
+            parts = k.split(".")
+            if len(parts) != 2 or not parts[0].isdigit():
+                continue
+            idx = int(parts[0])
+            if idx >= _SLICE_ENDS[-1]:
+                continue
+            which = next(i for i, e in enumerate(_SLICE_ENDS) if idx < e) + 1
+            name = f"slice{which}.{idx}.{parts[1]}"
+            if name in own:
+                with torch.no_grad():
+                    own[name].copy_(v)
+                hit += 1
+        if hit != len(own):
+            raise FaceoffB200Error(f"vgg16: state_dict covered {hit} of {len(own)} trunk tensors")
+        self.trunk_loaded = True
+
+    def forward(self, X):
+        """[N,3,H,W] (already scaled) -> VggOutputs(relu1_2, relu2_2, relu3_3, relu4_3, relu5_3), NCHW fp32
+        (reference models/lpips.py:139-152); gradients flow back to X."""
+        net = self
+
+        def runner(tape: Tape, x: torch.Tensor):
+            holders = []
+
+            def tap_hook(k, node):
+                h = {}
+                holders.append(h)
+
+                def tap_bwd():
+                    g = h.get("g")
+                    if g is None:
+                        return
+                    g = ops.pack_nchw(g, cs=node.act.shape[-1])
+                    node.g = (g if node.g is None else node.g[0] + g, 0)
+
+                tape.record(tap_bwd)
+
+            xin, taps = _vgg_trunk(tape, net.layout, "", x, None, None, tap_hook)
+            outs = tuple(ops.unpack_nchw(t.act, t.c) for t in taps)
+
+            def seed(tape_, gouts):
+                for h, g in zip(holders, gouts):
+                    if g is not None:
+                        h["g"] = g.to(torch.float32).contiguous()
+
+            def input_grad():
+                return ops.unpack_nchw(xin.g[0], 3) if xin.g is not None else None
+
+            return outs, {"seed": seed, "input_grad": input_grad}
+
+        ps = _params_of(self)
+        outs = _GraphFn.apply(runner, X, tuple(ps.keys()), *ps.values())
+        vgg_outputs = namedtuple("VggOutputs", ["relu1_2", "relu2_2", "relu3_3", "relu4_3", "relu5_3"])
+        return vgg_outputs(*outs)
+
+
+def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, tap_hook=None):
+    """(Optional scaling layer +) VGG16 trunk on channels-last bf16.  ``tap_hook(k, node)`` is called at each of the
+    five taps, at the tape position of the tap (so whatever it records is replayed after the following pool's
+    backward).  Returns (input node, tap nodes)."""
+    x = x.to(torch.float32).contiguous()
+    xin = Node(3)
+    cur, cur_relu = xin, False
+    taps = []
+    first = True
+    for kind, key, ch in layout:
+        if kind == "conv" and first:
+            # first conv (3 -> 64): explicit im2col (K = 27 -> 32) + 1x1 GEMM; 3-channel 32-byte TMA rows are slow
+            first = False
+            w = tape.params[prefix + key + ".weight"]
+            b = tape.params[prefix + key + ".bias"]
+            col = ops.im2col3x3(x, shift, scale)
+            w2 = torch.zeros(ch, 32, dtype=torch.float32, device=w.device)
+            w2[:, :27] = w.detach().permute(0, 2, 3, 1).reshape(ch, 27)
+            _, act, _ = ops.conv(FORM_S1, 2, 1, [(col, 32, 0)], w2.view(ch, 32, 1, 1), 0, ch, bias=b,
+                                 want_raw=False, want_relu=True, wkey=(w, "im2col3x3"))
+            del col
+            cur = Node(ch, act=act)
+
+            def first_bwd(node=cur, w=w):
+                if node.g is None:
+                    return
+                dx, _, _ = ops.conv(FORM_S1_DGRAD, 2, 3, [(node.g[0], node.c, node.g[1])], w, 1, 3, out_cs=16)
+                xin.g = (dx, 0)
+
+            tape.record(first_bwd)
+            cur_relu = True
+        elif kind == "conv":
+            cur = conv_op(tape, FORM_S1, 3, [View(cur, cur_relu)], prefix + key, ch, want_raw=False, want_relu=True,
+                          param_grad=False)
+            cur_relu = True
+        elif kind == "tap":
+            if tap_hook is not None:
+                tap_hook(len(taps), cur)
+            taps.append(cur)
+        else:  # 2x2 max pool
+            src = cur
+            pooled = Node(ch, raw=ops.maxpool2(src.act))
+
+            def pool_bwd(src=src, pooled=pooled):
+                if pooled.g is None:
+                    return
+                assert src.g is None
+                src.g = (ops.maxpool2_bwd(src.act, pooled.raw, pooled.g[0]), 0)
+
+            tape.record(pool_bwd)
+            cur, cur_relu = pooled, False
+    return xin, taps
 
 
 def normalize_tensor(x, eps=1e-10):
@@ -100,66 +253,47 @@ class LPIPS(nn.Module):
             param.requires_grad = False
 
     def load_from_pretrained(self, name="vgg_lpips"):
-        """The reference downloads vgg.pth (models/lpips.py:66-69).  There is no network here: load the file if it
-        is already at the reference's relative path, otherwise keep the (random) initialisation."""
-        ckpt = os.path.join("taming/modules/autoencoder/lpips", "vgg.pth")
-        if os.path.exists(ckpt):
-            self.load_state_dict(torch.load(ckpt, map_location=torch.device("cpu")), strict=False)
-        else:
-            warnings.warn(f"LPIPS: {ckpt} not found and downloads are disabled; weights stay randomly initialised "
-                          "(load a state_dict explicitly)")
+        """The reference downloads vgg.pth (models/lpips.py:66-69) -- to my reading a file holding the five ``lin*``
+        layers only; its trunk comes from torchvision's ImageNet checkpoint (:118).  There is no network here: the file
+        is loaded if it already sits at the reference's relative path, and the module says loudly which parts are
+        still random."""
+        ckpt = get_ckpt_path(name, "taming/modules/autoencoder/lpips")
+        if ckpt is None:
+            warnings.warn(f"LPIPS: {CKPT_MAP[name]} not found under taming/modules/autoencoder/lpips and downloads are "
+                          "disabled; the lin layers" + ("" if self.net.trunk_loaded else " AND the VGG16 trunk") +
+                          " stay randomly initialised (load_state_dict / net.load_torchvision_state_dict explicitly)")
+            return
+        self._load_checkpoint(ckpt)
 
-    # ------------------------------------------------------------------------------------------
+    def _load_checkpoint(self, ckpt):
+        sd = torch.load(ckpt, map_location=torch.device("cpu"))
+        res = self.load_state_dict(sd, strict=False)
+        if any(k.startswith("net.") for k in sd) and not any(k.startswith("net.") for k in res.missing_keys):
+            self.net.trunk_loaded = True
+        missing_lin = [k for k in res.missing_keys if k.startswith("lin")]
+        if missing_lin:
+            raise FaceoffB200Error(f"LPIPS: {ckpt} does not hold {missing_lin}")
+        if not self.net.trunk_loaded:
+            warnings.warn(f"LPIPS: {ckpt} carries no VGG16 trunk (net.*) and no cached torchvision vgg16 checkpoint was "
+                          "found: the trunk is RANDOM and the perceptual loss meaningless until "
+                          "net.load_torchvision_state_dict(torchvision vgg16 state_dict) is called")
+
+    @classmethod
+    def from_pretrained(cls, name="vgg_lpips"):
+        """reference models/lpips.py:71-78"""
+        if name != "vgg_lpips":
+            raise NotImplementedError
+        model = cls()
+        ckpt = get_ckpt_path(name, "taming/modules/autoencoder/lpips")
+        if ckpt is not None:
+            model._load_checkpoint(ckpt)
+        return model
+
     def _trunk(self, tape: Tape, x: torch.Tensor, tap_hook=None):
-        """Scaling layer + VGG16 trunk on channels-last bf16.  ``tap_hook(k, node)`` is called at each of the five
-        taps, at the tape position of the tap (so whatever it records is replayed after the following pool's
-        backward).  Returns (input node, tap nodes)."""
+        """Scaling layer + VGG16 trunk on channels-last bf16 (see ``_vgg_trunk``)."""
         shift = self.scaling_layer.shift.reshape(-1).contiguous()
         scale = self.scaling_layer.scale.reshape(-1).contiguous()
-        x = x.to(torch.float32).contiguous()
-        xin = Node(3)
-        cur, cur_relu = xin, False
-        taps = []
-        first = True
-        for kind, key, ch in self.net.layout:
-            if kind == "conv" and first:
-                # first conv (3 -> 64): explicit im2col (K = 27 -> 32) + 1x1 GEMM; 3-channel 32-byte TMA rows are slow
-                first = False
-                w = tape.params["net." + key + ".weight"]
-                b = tape.params["net." + key + ".bias"]
-                col = ops.im2col3x3(x, shift, scale)
-                w2 = torch.zeros(ch, 32, dtype=torch.float32, device=w.device)
-                w2[:, :27] = w.detach().permute(0, 2, 3, 1).reshape(ch, 27)
-                _, act, _ = ops.conv(FORM_S1, 2, 1, [(col, 32, 0)], w2.view(ch, 32, 1, 1), 0, ch, bias=b,
-                                     want_raw=False, want_relu=True, wkey=(w, "im2col3x3"))
-                del col
-                cur = Node(ch, act=act)
-
-                def first_bwd(node=cur, w=w):
-                    dx, _, _ = ops.conv(FORM_S1_DGRAD, 2, 3, [(node.g[0], node.c, node.g[1])], w, 1, 3, out_cs=16)
-                    xin.g = (dx, 0)
-
-                tape.record(first_bwd)
-                cur_relu = True
-            elif kind == "conv":
-                cur = conv_op(tape, FORM_S1, 3, [View(cur, cur_relu)], "net." + key, ch, want_raw=False, want_relu=True,
-                              param_grad=False)
-                cur_relu = True
-            elif kind == "tap":
-                if tap_hook is not None:
-                    tap_hook(len(taps), cur)
-                taps.append(cur)
-            else:  # 2x2 max pool
-                src = cur
-                pooled = Node(ch, raw=ops.maxpool2(src.act))
-
-                def pool_bwd(src=src, pooled=pooled):
-                    assert src.g is None
-                    src.g = (ops.maxpool2_bwd(src.act, pooled.raw, pooled.g[0]), 0)
-
-                tape.record(pool_bwd)
-                cur, cur_relu = pooled, False
-        return xin, taps
+        return _vgg_trunk(tape, self.net.layout, "net.", x, shift, scale, tap_hook)
 
     def forward(self, input, target):
         """LPIPS distance [N,1,1,1].  The value is symmetric in (input, target); gradients flow to whichever side

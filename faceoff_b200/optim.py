@@ -73,6 +73,9 @@ class FusedAdam(torch.optim.Optimizer):
             b1, b2 = group["betas"]
             ops.adam_step(table, cmap, n_chunks, group["lr"], b1, b2, group["eps"], group["weight_decay"], step,
                           grad_scale)
+            # the kernel writes through raw pointers: tell autograd (and the packed-weight cache in ops.packed_weights,
+            # which is keyed on the tensor version) that every parameter changed in place
+            torch._C._increment_version(plist)
             for s in states:
                 s["step"] = torch.tensor(float(step))
         return loss

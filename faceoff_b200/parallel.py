@@ -12,9 +12,20 @@ side stream while the remaining backward still runs.  Afterwards gradients are s
 EMA update (:66-75) is applied with the summed statistics -- legal because ``quantize`` uses the pre-update codebook
 (:57 precedes :75) and nothing reads ``embed`` again within the step.  Codebooks stay bit-identical across ranks, so
 DDP's buffer broadcast is dropped.
+
+The deferral is per forward: only a train-mode forward of the fused graph that records a backward routes its statistics
+into the bucket (``begin_forward``).  Everything else -- ``torch.no_grad()``, the eager sub-method path
+(``encode_quantized``), a stand-alone ``Quantize`` -- keeps the reference behaviour (all_reduce x2 + EMA inside forward).
+A deferred forward whose backward never ran is flushed (statistics all-reduced, EMA applied) before the next one starts,
+so no EMA update is ever lost or applied twice.
+
+Micro-batches (SURVEY 8(e)): inside ``with ddp.no_sync():`` backward neither communicates nor updates the codebooks;
+gradients AND statistics keep accumulating in the bucket, and the first backward outside the context all-reduces the
+accumulated bucket once and applies ONE EMA update for the whole step.
 """
 from __future__ import annotations
 
+import contextlib
 import os
 
 from typing import Dict, List, Optional, Sequence
@@ -24,59 +35,6 @@ from torch import distributed as dist
 from torch import nn
 
 from . import distributed as dist_fn
-
-
-class FlatBucket:
-    """Flat fp32 buffer holding gradient tensors (averaged over ranks) and statistic tensors (summed)."""
-
-    def __init__(self, grads: Sequence[torch.Tensor], stats: Sequence[torch.Tensor], device=None):
-        self.ext_grads, self.ext_stats = list(grads), list(stats)
-        device = device if device is not None else self.ext_grads[0].device
-        n_stats = sum(t.numel() for t in self.ext_stats)
-        n_grads = sum(t.numel() for t in self.ext_grads)
-        self.flat = torch.zeros(n_stats + n_grads, dtype=torch.float32, device=device)
-        self.n_stats = n_stats
-        self.stat_views, self.grad_views = [], []
-        off = 0
-        for t in self.ext_stats:
-            self.stat_views.append(self.flat[off:off + t.numel()].view(t.shape))
-            off += t.numel()
-        for t in self.ext_grads:
-            self.grad_views.append(self.flat[off:off + t.numel()].view(t.shape))
-            off += t.numel()
-
-    def pack(self):
-        for v, t in zip(self.stat_views + self.grad_views, self.ext_stats + self.ext_grads):
-            v.copy_(t)
-
-    def all_reduce(self, lo: int = 0, hi: Optional[int] = None, async_op: bool = False):
-        hi = self.flat.numel() if hi is None else hi
-        if dist_fn.get_world_size() == 1 or hi <= lo:
-            return None
-        return dist.all_reduce(self.flat[lo:hi], op=dist.ReduceOp.SUM, async_op=async_op)
-
-    def scale_grads(self):
-        ws = dist_fn.get_world_size()
-        if ws > 1:
-            self.flat[self.n_stats:].mul_(1.0 / ws)
-
-    def unpack(self):
-        self.scale_grads()
-        for v, t in zip(self.stat_views + self.grad_views, self.ext_stats + self.ext_grads):
-            t.copy_(v)
-
-
-class _DeferredStatSink:
-    """Quantize.stat_sink replacement: statistics live in the bucket, EMA is applied after the collective."""
-
-    def __init__(self, owner: "FusedDataParallel"):
-        self.owner = owner
-
-    def buffers(self, q):
-        return self.owner._stat_buffers(q)
-
-    def submit(self, q, counts, embed_sum):
-        self.owner._pending_ema.append((q, counts, embed_sum))
 
 
 class FusedDataParallel(nn.Module):
@@ -89,7 +47,9 @@ class FusedDataParallel(nn.Module):
         self.module = module
         self.world = dist_fn.get_world_size()
         self.n_chunks = max(1, int(os.environ.get("FO_DP_CHUNKS", n_chunks)))   # env: experiments only
-        self._pending_ema: List = []
+        self._pending_ema: List = []       # quantisers whose statistics sit in the bucket, EMA not applied yet
+        self._accumulating = False         # statistics of earlier micro-batches (no_sync) are in the bucket
+        self._sync = True                  # False inside no_sync()
         self._bucket: Optional[torch.Tensor] = None
         self._grad_views: Dict[str, torch.Tensor] = {}
         self._stat_views: Dict[int, tuple] = {}
@@ -101,11 +61,17 @@ class FusedDataParallel(nn.Module):
         from .vqvae import Quantize
 
         self._quantizers = [m for m in module.modules() if isinstance(m, Quantize)]
-        if self.world > 1:
-            sink = _DeferredStatSink(self)
-            for q in self._quantizers:
-                q.stat_sink = sink
         module._dp = self
+
+    @contextlib.contextmanager
+    def no_sync(self):
+        """Like DistributedDataParallel.no_sync(): backward passes inside accumulate locally (gradients and the
+        quantisers' EMA statistics); the first backward after the context does the one collective + one EMA update."""
+        old, self._sync = self._sync, False
+        try:
+            yield
+        finally:
+            self._sync = old
 
     # ---- bucket layout ------------------------------------------------------------------------
     def _build(self, backward_order: Sequence[str], params: Dict[str, torch.Tensor]):
@@ -113,6 +79,7 @@ class FusedDataParallel(nn.Module):
         n_stats = sum(q.n_embed + q.dim * q.n_embed for q in self._quantizers)
         n_grads = sum(params[n].numel() for n in backward_order)
         self._bucket = torch.zeros(n_stats + n_grads, dtype=torch.float32, device=device)
+        self._grad_views, self._stat_views = {}, {}
         off = 0
         for q in self._quantizers:
             c = self._bucket[off:off + q.n_embed]
@@ -128,24 +95,44 @@ class FusedDataParallel(nn.Module):
             self._offsets[n] = (off, off + k)
             off += k
         self._order = list(backward_order)
+        self._start_of = {self._offsets[n][0]: n for n in self._order}
         total = self._bucket.numel()
         self._chunk_bounds = [total * (i + 1) // self.n_chunks for i in range(self.n_chunks)]
-        if device.type == "cuda":
-            self._comm_stream = torch.cuda.Stream(device=device)
+        self._comm_stream = torch.cuda.Stream(device=device) if device.type == "cuda" else None
 
-    def _stat_buffers(self, q):
-        c, s = self._stat_views[id(q)]
-        c.zero_()
-        s.zero_()
-        return c, s
-
-    # ---- tape hooks (called from vqvae._GraphFn) ---------------------------------------------
+    # ---- forward-side hooks (called from vqvae.VQVAE._runner) -----------------------------------
     def begin_forward(self, params: Dict[str, torch.Tensor], forward_order: Sequence[str]):
-        """Called at the start of the module's forward: lay the bucket out (once) so the quantisers can write
-        their statistics into it."""
+        """Start of a deferred (train-mode, backward-recording) forward: lay the bucket out (once), settle a previous
+        forward whose backward never ran, and zero the statistics unless micro-batches are being accumulated."""
         if self._bucket is None or self._bucket.device != next(iter(params.values())).device:
             self._build(list(reversed(list(forward_order))), params)
+        if self._pending_ema and not self._accumulating:
+            self._flush_pending()
+        if not self._accumulating:
+            self._bucket[:self._n_stats].zero_()
 
+    def stat_buffers(self, q):
+        """(counts, embed_sum) views of the bucket for quantiser ``q``; the gather kernel ADDS into them."""
+        return self._stat_views[id(q)]
+
+    def submit_stats(self, q):
+        if all(e is not q for e in self._pending_ema):
+            self._pending_ema.append(q)
+
+    def _apply_pending(self):
+        for q in self._pending_ema:
+            counts, embed_sum = self._stat_views[id(q)]
+            q.apply_ema(counts, embed_sum)
+        self._pending_ema.clear()
+        self._accumulating = False
+
+    def _flush_pending(self):
+        """A deferred forward was never followed by backward: do what the reference does inside forward (:63-75)."""
+        if self.world > 1:
+            dist.all_reduce(self._bucket[:self._n_stats], op=dist.ReduceOp.SUM)
+        self._apply_pending()
+
+    # ---- tape hooks (called from vqvae._GraphFn.backward) ---------------------------------------
     def begin_step(self, tape):
         """Called when backward starts: hand the gradient views to the tape."""
         self._done = set()
@@ -164,24 +151,22 @@ class FusedDataParallel(nn.Module):
         self._done.add(name)
         # advance the contiguous ready frontier
         while True:
-            nxt = next((n for n in self._order if self._offsets[n][0] == self._ready_upto), None)
+            nxt = self._start_of.get(self._ready_upto)
             if nxt is None or nxt not in self._done:
                 break
             self._ready_upto = self._offsets[nxt][1]
-        self._launch_ready_chunks()
+        if self._sync:
+            self._launch_ready_chunks()
 
-    def _launch_ready_chunks(self, force: bool = False):
+    def _launch_ready_chunks(self):
         if self.world == 1:
             return
         for b in self._chunk_bounds:
             if b <= self._launched_upto:
                 continue
-            if b <= self._ready_upto or force:
-                hi = b if not force else self._bucket.numel()
-                self._launch(self._launched_upto, hi)
-                self._launched_upto = hi
-                if force:
-                    break
+            if b <= self._ready_upto:
+                self._launch(self._launched_upto, b)
+                self._launched_upto = b
 
     def _launch(self, lo: int, hi: int):
         seg = self._bucket[lo:hi]
@@ -194,6 +179,9 @@ class FusedDataParallel(nn.Module):
 
     def end_step(self):
         """Called when backward finished: flush, wait (stream-ordered), average grads, apply EMA."""
+        if not self._sync:
+            self._accumulating = True      # keep gradients and statistics in the bucket for the next micro-batch
+            return
         if self.world > 1:
             if self._launched_upto < self._bucket.numel():
                 self._launch(self._launched_upto, self._bucket.numel())
@@ -203,9 +191,7 @@ class FusedDataParallel(nn.Module):
             if self._comm_stream is not None:
                 torch.cuda.current_stream().wait_stream(self._comm_stream)
             self._bucket[self._n_stats:].mul_(1.0 / self.world)
-        for q, counts, embed_sum in self._pending_ema:
-            q.apply_ema(counts, embed_sum)
-        self._pending_ema.clear()
+        self._apply_pending()
 
     def grads_for_autograd(self, tape, names: Sequence[str]):
         """Gradients live in the bucket: bind them to ``.grad`` directly (no copy) and return None to autograd."""
@@ -223,6 +209,13 @@ class FusedDataParallel(nn.Module):
             else:
                 out.append(v)  # foreign .grad tensor: let autograd accumulate into it
         return tuple(out)
+
+    def bucket_checksums(self):
+        """(statistics+gradient bucket, codebook buffers) as two fp64 sums -- identical on every rank after a
+        synchronised step (used by bench.py's dp_check and the 2-rank tests)."""
+        bsum = self._bucket.double().sum() if self._bucket is not None else torch.zeros((), dtype=torch.float64)
+        csum = sum(b.double().sum() for q in self._quantizers for b in (q.embed, q.cluster_size, q.embed_avg))
+        return bsum, csum
 
     def forward(self, *args, **kwargs):
         return self.module(*args, **kwargs)

@@ -16,6 +16,7 @@ from torch import nn
 
 from . import distributed as dist_fn
 from . import ops
+from ._lib import FaceoffB200Error
 from .graph import (FORM_DOWN, FORM_S1, FORM_UP, Node, Tape, View, conv_op, first_conv_op, last_convT_op,
                     resblock_op)
 
@@ -25,8 +26,8 @@ from .graph import (FORM_DOWN, FORM_S1, FORM_UP, Node, Tape, View, conv_op, firs
 # ------------------------------------------------------------------------------------------------
 class _StatSink:
     """Where a quantiser's EMA statistics go.  Default: the reference behaviour -- all_reduce(SUM) both
-    tensors right away (:63-64) then EMA (:66-75).  The fused data-parallel reducer (parallel.py) installs
-    a deferred sink that folds them into the single per-step bucket."""
+    tensors right away (:63-64) then EMA (:66-75).  (The fused data-parallel reducer, parallel.py, bypasses the sink
+    for the forwards it owns and folds the statistics into its single per-step bucket.)"""
 
     def submit(self, q: "Quantize", counts: torch.Tensor, embed_sum: torch.Tensor):
         dist_fn.all_reduce(counts)
@@ -44,22 +45,27 @@ class _LocalStatSink(_StatSink):
 _default_sink = _StatSink()
 
 
-def _quantize_forward(q: "Quantize", x32: torch.Tensor, want_bf16: bool):
-    """x32: fp32 [rows, dim] contiguous.  Returns (q_f32, q_bf16|None, diff_sum[1], ind[rows], e_t)."""
+def _quantize_forward(q: "Quantize", x32: torch.Tensor, want_bf16: bool, dp=None):
+    """x32: fp32 [rows, dim] contiguous.  Returns (q_f32, q_bf16|None, diff_sum[1], ind[rows], e_t).
+    ``dp``: the FusedDataParallel whose ``begin_forward`` ran for this forward (statistics go into its bucket and the
+    EMA update is deferred to the end of backward), or None: reference behaviour, all_reduce x2 + EMA right here."""
     rows, dim = x32.shape
     e_split, e_t, e_n2 = ops.vq_prep(q.embed)
     ind = ops.vq_assign(x32, e_t, e_split, e_n2, q.n_flagged)
     diff_sum = torch.zeros(1, dtype=torch.float32, device=x32.device)
     counts = embed_sum = None
     if q.training:
-        if hasattr(q.stat_sink, "buffers"):  # fused data-parallel: statistics live in the flat bucket
-            counts, embed_sum = q.stat_sink.buffers(q)
+        if dp is not None:
+            counts, embed_sum = dp.stat_buffers(q)
         else:
             counts = torch.zeros(q.n_embed, dtype=torch.float32, device=x32.device)
             embed_sum = torch.zeros(dim, q.n_embed, dtype=torch.float32, device=x32.device)
     q32, q16 = ops.vq_gather_stats(x32, ind, e_t, diff_sum, counts, embed_sum, want_f32=True, want_bf16=want_bf16)
     if q.training:
-        q.stat_sink.submit(q, counts, embed_sum)
+        if dp is not None:
+            dp.submit_stats(q)
+        else:
+            q.stat_sink.submit(q, counts, embed_sum)
     return q32, q16, diff_sum, ind, e_t
 
 
@@ -136,6 +142,10 @@ class _GraphFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, *gouts):
         tape, state = ctx.tape, ctx.state
+        if tape is None:
+            raise FaceoffB200Error("backward through a faceoff_b200 graph a second time: the fused tape frees its saved "
+                                   "activations during the first backward (retain_graph=True is not supported); sum the "
+                                   "losses and call backward once, or run forward again")
         dp = state.get("dp")
         if dp is not None:
             dp.begin_step(tape)
@@ -208,19 +218,20 @@ class ResBlock(nn.Module):
 def _encoder_graph(tape: Tape, x, prefix: str, channel: int, n_res_block: int, n_res_channel: int, stride: int,
                    input_needs_grad: bool) -> Node:
     """Encoder (reference :103-131).  Returns a node whose ``act`` is the encoder output (post final ReLU).
-    ``x``: a Node, or (stride 4 only) the raw fp32 NCHW image with <= 8 channels (im2col first layer, no input grad)."""
+    ``x``: a View (which of raw / relu the encoder reads is the CALLER's statement, never guessed), or (stride 4 only)
+    the raw fp32 NCHW image with <= 8 channels (im2col first layer, no input grad)."""
     if stride == 4:
         if isinstance(x, torch.Tensor):
             a = first_conv_op(tape, x, prefix + "blocks.0", x.shape[1], channel // 2)
         else:
-            a = conv_op(tape, FORM_DOWN, 4, [View(x, x.raw is None)], prefix + "blocks.0", channel // 2,
+            a = conv_op(tape, FORM_DOWN, 4, [x], prefix + "blocks.0", channel // 2,
                         want_raw=False, want_relu=True, input_needs_grad=input_needs_grad)
         a = conv_op(tape, FORM_DOWN, 4, [View(a, True)], prefix + "blocks.2", channel, want_raw=False, want_relu=True)
         a = conv_op(tape, FORM_S1, 3, [View(a, True)], prefix + "blocks.4", channel, want_raw=True,
                     want_relu=True)
         start = 5
     else:
-        a = conv_op(tape, FORM_DOWN, 4, [View(x, x.raw is None)], prefix + "blocks.0", channel // 2, want_raw=False,
+        a = conv_op(tape, FORM_DOWN, 4, [x], prefix + "blocks.0", channel // 2, want_raw=False,
                     want_relu=True, input_needs_grad=input_needs_grad)
         a = conv_op(tape, FORM_S1, 3, [View(a, True)], prefix + "blocks.2", channel, want_raw=True, want_relu=True)
         start = 3
@@ -287,7 +298,7 @@ class Encoder(nn.Module):
         in_channel, channel, n_res_block, n_res_channel, stride = self.cfg
 
         def build(tape, x):
-            return _encoder_graph(tape, x, "", channel, n_res_block, n_res_channel, stride,
+            return _encoder_graph(tape, View(x, False), "", channel, n_res_block, n_res_channel, stride,
                                   input_needs_grad=input.requires_grad), True
 
         return _run_graph(self, _io_wrap(build, in_channel, None), input)[0]
@@ -407,9 +418,9 @@ class VQVAE(nn.Module):
             else:
                 dp = None
             x = x.to(torch.float32).contiguous()
-            xin = x if cin <= 8 else Node(cin, raw=ops.pack_nchw(x))
+            xin = x if cin <= 8 else View(Node(cin, raw=ops.pack_nchw(x)), False)
             enc_b = _encoder_graph(tape, xin, "enc_b.", ch, nrb, nrc, 4, input_needs_grad=False)
-            enc_t = _encoder_graph(tape, enc_b, "enc_t.", ch, nrb, nrc, 2, input_needs_grad=True)
+            enc_t = _encoder_graph(tape, View(enc_b, True), "enc_t.", ch, nrb, nrc, 2, input_needs_grad=True)
             eb_c = _conv3d_graph(tape, View(enc_b, True), "conv3d_encoded_b.", 128, clips)
             et_c = _conv3d_graph(tape, View(enc_t, True), "conv3d_encoded_t.", 128, clips)
 
@@ -417,7 +428,7 @@ class VQVAE(nn.Module):
 
             def quantize(qmod: Quantize, pre: Node):
                 x32 = pre.f32.view(-1, ed)
-                q32, q16, diff_sum, ind, e_t = _quantize_forward(qmod, x32, want_bf16=True)
+                q32, q16, diff_sum, ind, e_t = _quantize_forward(qmod, x32, want_bf16=True, dp=dp)
                 node = Node(ed, raw=q16.view(*pre.f32.shape))
                 rec = dict(x32=x32, ind=ind, diff_sum=diff_sum)
 

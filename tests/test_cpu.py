@@ -222,27 +222,93 @@ _GLOO_WORKER = r"""
 import os, sys, torch
 sys.path.insert(0, %(root)r)
 import torch.distributed as td
+from torch import nn
 from faceoff_b200 import distributed as dist
-from faceoff_b200.parallel import FlatBucket
+from faceoff_b200.parallel import FusedDataParallel
+from faceoff_b200.graph import Tape
+from faceoff_b200.vqvae import Quantize
+from oracle import faceoff_oracle as O
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 td.init_process_group("gloo", init_method="tcp://127.0.0.1:%(port)d", rank=rank, world_size=world)
 assert dist.get_world_size() == 2 and dist.get_rank() == rank
 t = torch.full((4,), float(rank + 1)); dist.all_reduce(t); assert torch.equal(t, torch.full((4,), 3.0))
 objs = dist.all_gather({"mse_sum": rank * 1.5, "mse_n": 30})
 assert [o["mse_sum"] for o in objs] == [0.0, 1.5]
-# fused bucket: grads are averaged (DDP semantics), EMA statistics are summed (reference distributed.py:64)
-g1, g2 = torch.full((5,), float(rank)), torch.full((2, 3), 2.0 * rank)
-cnt, es = torch.full((8,), float(rank + 1)), torch.full((4, 8), 10.0 * (rank + 1))
-b = FlatBucket([g1, g2], [cnt, es], device="cpu")
-b.pack(); b.all_reduce(); b.unpack()
-assert torch.allclose(g1, torch.full((5,), 0.5)) and torch.allclose(g2, torch.full((2, 3), 1.0))
-assert torch.allclose(cnt, torch.full((8,), 3.0)) and torch.allclose(es, torch.full((4, 8), 30.0))
+red = dist.reduce_dict({"a": torch.tensor(float(rank)), "b": torch.tensor(2.0)})
+if rank == 0:
+    assert abs(red["a"].item() - 0.5) < 1e-6 and abs(red["b"].item() - 2.0) < 1e-6
+
+# ---- the PRODUCT reducer (FusedDataParallel) driven through its tape hooks on CPU tensors.  The only CUDA call it
+# ---- makes is Quantize.apply_ema (fo_vq_ema); here that one method is replaced by the oracle's EMA formula.
+class Net(nn.Module):
+    def __init__(self):
+        super().__init__()
+        self.a = nn.Linear(5, 3); self.b = nn.Linear(3, 2)
+        self.quantize_t = Quantize(4, 8)
+    def param_forward_order(self):
+        return ["a.weight", "a.bias", "b.weight", "b.bias"]
+torch.manual_seed(0)
+net = Net()
+ema_calls = []
+def cpu_ema(self, counts, embed_sum):
+    ema_calls.append((counts.clone(), embed_sum.clone()))
+    e, c, a = O.quantize_ema(self.embed, self.cluster_size, self.embed_avg, counts, embed_sum, self.decay, self.eps)
+    self.embed.copy_(e); self.cluster_size.copy_(c); self.embed_avg.copy_(a)
+Quantize.apply_ema = cpu_ema
+ddp = FusedDataParallel(net, n_chunks=3)
+params = dict(net.named_parameters())
+q = net.quantize_t
+
+def one_pass(scale, sync_ctx=None):
+    tape = Tape(params, need_grad=True)
+    ddp.begin_forward(params, net.param_forward_order())
+    counts, esum = ddp.stat_buffers(q)
+    counts += float(rank + 1) * scale; esum += 10.0 * (rank + 1) * scale     # what the gather kernel does: ADD
+    ddp.submit_stats(q)
+    ddp.begin_step(tape)
+    for name in reversed(net.param_forward_order()):                          # backward order
+        g, acc = tape.grad_buffer(name)
+        val = torch.full_like(g, float(rank + 1) * scale)
+        g.add_(val) if acc else g.copy_(val)
+        tape.grad_ready(name)
+    ddp.end_step()
+    ddp.grads_for_autograd(tape, tuple(params))
+
+one_pass(1.0)
+assert len(ddp._works) >= 2, "bucket must be reduced in several chunks"
+for n, p_ in params.items():
+    assert p_.grad is not None and torch.allclose(p_.grad, torch.full_like(p_, 1.5)), (n, p_.grad)   # mean of 1, 2
+assert len(ema_calls) == 1
+assert torch.allclose(ema_calls[0][0], torch.full((8,), 3.0)) and torch.allclose(ema_calls[0][1], torch.full((4, 8), 30.0))
+# codebooks identical on both ranks
+gathered = dist.all_gather(q.embed.clone())
+assert torch.equal(gathered[0], gathered[1])
+# micro-batches: two passes inside no_sync + one outside = ONE collective, ONE EMA with the summed statistics
+net.zero_grad(set_to_none=True)
+ema_calls.clear()
+with ddp.no_sync():
+    one_pass(1.0); one_pass(2.0)
+assert not ema_calls and ddp._accumulating
+one_pass(4.0)
+assert len(ema_calls) == 1 and torch.allclose(ema_calls[0][0], torch.full((8,), 3.0 * 7.0))
+for n, p_ in params.items():
+    assert torch.allclose(p_.grad, torch.full_like(p_, 1.5 * 7.0)), (n, p_.grad)
+# a deferred forward whose backward never runs is settled (all-reduce + EMA) before the next forward starts
+ema_calls.clear()
+ddp.begin_forward(params, net.param_forward_order())
+c, e = ddp.stat_buffers(q); c += 1.0; ddp.submit_stats(q)
+ddp.begin_forward(params, net.param_forward_order())
+assert len(ema_calls) == 1 and torch.allclose(ema_calls[0][0], torch.full((8,), 2.0))
+assert float(ddp.stat_buffers(q)[0].sum()) == 0.0
+b0, c0 = ddp.bucket_checksums()
+both = dist.all_gather((float(b0), float(c0)))
+assert both[0] == both[1]
 td.destroy_process_group()
 print("ok", rank)
 """
 
 
-def test_gloo_world2_collectives_and_fused_bucket(tmp_path):
+def test_gloo_world2_collectives_and_fused_data_parallel(tmp_path):
     import socket
 
     with socket.socket() as s:
@@ -258,3 +324,26 @@ def test_gloo_world2_collectives_and_fused_bucket(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_launch_spawns_world2(tmp_path):
+    """distributed.launch (reference distributed/launch.py:22-92) with n_gpu_per_machine=2: spawn, tcp rendezvous on
+    127.0.0.1, per-machine LOCAL_PROCESS_GROUP, helpers -- exercised with the gloo backend (no GPU here)."""
+    code = (f"import sys; sys.path.insert(0, {ROOT!r}); sys.path.insert(0, {HERE!r})\n"
+            "from faceoff_b200 import distributed as dist\n"
+            "import _launch_worker\n"
+            f"if __name__ == '__main__':\n"
+            f"    dist.launch(_launch_worker.worker, 2, dist_url='auto', args=({str(tmp_path)!r}, 'x'), backend='gloo')\n")
+    script = tmp_path / "l.py"
+    script.write_text(code)
+    r = subprocess.run([sys.executable, str(script)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=240)
+    assert r.returncode == 0, r.stdout[-2000:]
+    got = sorted(open(tmp_path / f"rank{i}.txt").read() for i in range(2))
+    assert got == ["x 0 2 3.0 1 1", "x 1 2 3.0 1 0"], got
+    from faceoff_b200 import distributed as dist
+
+    with pytest.raises(ValueError):
+        dist.launch(lambda: None, 2, n_machine=2, dist_url="auto")
+    with pytest.raises(ValueError):
+        dist.launch(lambda: None, 2, n_machine=2, dist_url="file:///tmp/x")
