@@ -31,10 +31,10 @@ class ConvDesc(C.Structure):
     _fields_ = [
         ("form", C.c_int), ("ndim", C.c_int), ("ksize", C.c_int),
         ("n", C.c_int), ("d", C.c_int), ("h", C.c_int), ("w", C.c_int),
-        ("n_src", C.c_int), ("src", Src * 2), ("cout", C.c_int),
+        ("n_src", C.c_int), ("src", Src * 6), ("cout", C.c_int),
         ("wpacked", C.c_void_p), ("bias", C.c_void_p), ("mask", C.c_void_p), ("addend", C.c_void_p),
         ("out_bf16", C.c_void_p), ("out_relu", C.c_void_p), ("out_f32", C.c_void_p),
-        ("out_cs", C.c_int), ("out_f32_nchw", C.c_int), ("relu_f32", C.c_int),
+        ("out_cs", C.c_int), ("out_f32_nchw", C.c_int), ("relu_f32", C.c_int), ("split_out", C.c_int),
     ]
 
 
@@ -99,6 +99,17 @@ _SIGS = {
     "fo_lpips_tap": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fo_lpips_tap_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_lpips_tap_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p,
+                                     C.c_void_p]),
+    "fo_lpips_tap_bwd_split": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                                         C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_split_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_longlong, C.c_longlong,
+                               C.c_void_p, C.c_int, C.c_void_p]),
+    "fo_merge_f32": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_longlong, C.c_longlong,
+                               C.c_longlong, C.c_void_p]),
+    "fo_maxpool2_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fo_maxpool2_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.c_void_p]),
     "fo_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fo_adam_chunk_elems": (C.c_int, []),
     "fo_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,
@@ -110,9 +121,14 @@ _SIGS = {
 EXPORTED_SYMBOLS = tuple(_SIGS)
 
 
+_ready = False   # fo_init succeeded in this process: load() is then a plain global read (it runs once per op)
+
+
 def load(init: bool = True):
     """Load the shared library (and, with ``init``, require an sm_100 device)."""
-    global _lib
+    global _lib, _ready
+    if _ready:
+        return _lib
     with _lock:
         if _lib is None:
             if not os.path.exists(_SO):
@@ -129,6 +145,7 @@ def load(init: bool = True):
         rc = _lib.fo_init()
         if rc != 0:
             raise FaceoffB200Error(f"fo_init failed ({rc}): {_lib.fo_last_error().decode()}")
+        _ready = True
     return _lib
 
 

@@ -159,7 +159,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   ConvParams& p = out->p;
   memset(&p, 0, sizeof(p));
   memset(&out->pack, 0, sizeof(out->pack));
-  if (c->n_src < 1 || c->n_src > 2) return fail(FO_ERR_INVALID, "n_src must be 1 or 2");
+  if (c->n_src < 1 || c->n_src > kMaxAMaps) return fail(FO_ERR_INVALID, "n_src must be 1..%d", kMaxAMaps);
   const bool s1 = c->form == FO_FORM_S1 || c->form == FO_FORM_S1_DGRAD;
   if (!s1 && c->form != FO_FORM_DOWN && c->form != FO_FORM_UP) return fail(FO_ERR_INVALID, "bad form %d", c->form);
   if (c->ndim != 2 && !(c->ndim == 3 && s1)) return fail(FO_ERR_INVALID, "ndim %d unsupported for form %d", c->ndim, c->form);
@@ -408,7 +408,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   const int avail = kMaxDynSmem - 2048 - 1024 - 8 * 32 * 80;
   const int e_tensor = p.MT * 128 * (p.NT * 2 + 16);   // one operand, all sub-tiles
   p.e_bufs = 0; p.e_mask = 0; p.e_add = 0;
-  if (!nchw && c->out_f32 == nullptr && p.NT % 32 == 0) {
+  if (!nchw && c->out_f32 == nullptr && p.NT % 32 == 0 && !c->split_out) {
     int room = avail - 2 * stage_bytes;
     if (c->addend != nullptr && room >= e_tensor) { p.e_add = 1; room -= e_tensor; }
     if (c->mask != nullptr && room >= e_tensor) { p.e_mask = 1; room -= e_tensor; }
@@ -439,6 +439,12 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   p.out_relu = (__nv_bfloat16*)c->out_relu;
   p.out_f32 = c->out_f32;
   p.relu_f32 = c->relu_f32;
+  p.split_off = 0;
+  if (c->split_out) {
+    if (nchw || (c->out_cs & 31) != 0 || c->out_cs / 2 < out->npad)
+      return fail(FO_ERR_INVALID, "split_out needs channels-last outputs with out_cs = 2 * padded cout");
+    p.split_off = c->out_cs / 2;
+  }
 
   if (!need_maps) return FO_OK;
   // tensor maps
@@ -863,6 +869,51 @@ extern "C" int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, 
   CUDA_TRY(launch_lpips_tap_bwd(f0, f1, w, g, n, hw, c, d_f0, addend, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
+extern "C" int fo_lpips_tap_split(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out,
+                                  fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (c % 64 != 0 || c > 512) return fail(FO_ERR_INVALID, "lpips_tap: c must be 64..512, multiple of 64");
+  CUDA_TRY(launch_lpips_tap(f0, f1, w, n, hw, c, out, g_num_sms, (cudaStream_t)stream, 1));
+  return FO_OK;
+}
+extern "C" int fo_lpips_tap_bwd_split(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
+                                      void* d_f0, const void* addend, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (c % 64 != 0 || c > 512) return fail(FO_ERR_INVALID, "lpips_tap_bwd: c must be 64..512, multiple of 64");
+  CUDA_TRY(launch_lpips_tap_bwd(f0, f1, w, g, n, hw, c, d_f0, addend, g_num_sms, (cudaStream_t)stream, 1));
+  return FO_OK;
+}
+// ------------------------------------------------------------------------------------------ verification mode helpers
+extern "C" int fo_split_f32(const float* x, int n, int c, int hw, long long sn, long long sc, long long sp, void* out,
+                            int cp, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (cp % 16 != 0 || c > cp) return fail(FO_ERR_INVALID, "split_f32: cp must be a multiple of 16 and >= c");
+  if ((size_t)n * hw == 0) return FO_OK;
+  CUDA_TRY(launch_split_f32(x, n, c, hw, sn, sc, sp, out, cp, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_merge_f32(const void* in, int n, int c, int hw, int cp, float* out, long long sn, long long sc,
+                            long long sp, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (cp % 16 != 0 || c > cp) return fail(FO_ERR_INVALID, "merge_f32: cp must be a multiple of 16 and >= c");
+  if ((size_t)n * hw == 0) return FO_OK;
+  CUDA_TRY(launch_merge_f32(in, n, c, hw, cp, out, sn, sc, sp, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_maxpool2_f32(const float* x, float* y, int n, int h, int w, int c, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if ((h | w) & 1) return fail(FO_ERR_INVALID, "maxpool2_f32: even h, w required");
+  CUDA_TRY(launch_maxpool2_f32(x, y, n, h, w, c, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_maxpool2_bwd_f32(const float* x, const float* y, const float* dy, float* dx, int n, int h, int w, int c,
+                                   fo_stream_t stream) {
+  REQUIRE_INIT();
+  if ((h | w) & 1) return fail(FO_ERR_INVALID, "maxpool2_bwd_f32: even h, w required");
+  CUDA_TRY(launch_maxpool2_bwd_f32(x, y, dy, dx, n, h, w, c, (cudaStream_t)stream));
+  return FO_OK;
+}
+
 extern "C" int fo_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, fo_stream_t stream) {
   REQUIRE_INIT();
   if (hw % 4 != 0 || c > ca) return fail(FO_ERR_INVALID, "mse: hw must be a multiple of 4 and c <= ca");

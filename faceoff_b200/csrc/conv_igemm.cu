@@ -82,15 +82,18 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
     }
   }
   if (p.addend != nullptr && full) {
-    const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + col0);
+    // split mode: the addend is a hi|lo pair, both halves are added
+    for (int part = 0; part < (p.split_off > 0 ? 2 : 1); ++part) {
+      const uint4* ap = reinterpret_cast<const uint4*>(p.addend + off + part * p.split_off + col0);
 #pragma unroll
-    for (int q = 0; q < NCH / 8; ++q) {
-      uint4 m = __ldg(ap + q);
-      uint32_t w[4] = {m.x, m.y, m.z, m.w};
+      for (int q = 0; q < NCH / 8; ++q) {
+        uint4 m = __ldg(ap + q);
+        uint32_t w[4] = {m.x, m.y, m.z, m.w};
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        f[q * 8 + 2 * e] += bf16lo(w[e]);
-        f[q * 8 + 2 * e + 1] += bf16hi(w[e]);
+        for (int e = 0; e < 4; ++e) {
+          f[q * 8 + 2 * e] += bf16lo(w[e]);
+          f[q * 8 + 2 * e + 1] += bf16hi(w[e]);
+        }
       }
     }
   }
@@ -116,28 +119,32 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
     }
   }
   if (full) {
-    if (p.out_bf16 != nullptr) {
-      uint4* op = reinterpret_cast<uint4*>(p.out_bf16 + off + col0);
+    // bf16 outputs: value (and, in split mode, the bf16 rounding residual lo = bf16(v - hi) split_off channels further)
+    for (int which = 0; which < 2; ++which) {
+      __nv_bfloat16* dst = which == 0 ? p.out_bf16 : p.out_relu;
+      if (dst == nullptr) continue;
+      float v[NCH];
 #pragma unroll
-      for (int q = 0; q < NCH / 8; ++q) {
-        uint4 o;
-        o.x = pack_bf16x2(f[8 * q + 0], f[8 * q + 1]);
-        o.y = pack_bf16x2(f[8 * q + 2], f[8 * q + 3]);
-        o.z = pack_bf16x2(f[8 * q + 4], f[8 * q + 5]);
-        o.w = pack_bf16x2(f[8 * q + 6], f[8 * q + 7]);
-        op[q] = o;
-      }
-    }
-    if (p.out_relu != nullptr) {
-      uint4* op = reinterpret_cast<uint4*>(p.out_relu + off + col0);
+      for (int j = 0; j < NCH; ++j) v[j] = which == 0 ? f[j] : fmaxf(f[j], 0.f);
+      for (int part = 0; part < (p.split_off > 0 ? 2 : 1); ++part) {
+        uint4* op = reinterpret_cast<uint4*>(dst + off + part * p.split_off + col0);
 #pragma unroll
-      for (int q = 0; q < NCH / 8; ++q) {
-        uint4 o;
-        o.x = pack_bf16x2(fmaxf(f[8 * q + 0], 0.f), fmaxf(f[8 * q + 1], 0.f));
-        o.y = pack_bf16x2(fmaxf(f[8 * q + 2], 0.f), fmaxf(f[8 * q + 3], 0.f));
-        o.z = pack_bf16x2(fmaxf(f[8 * q + 4], 0.f), fmaxf(f[8 * q + 5], 0.f));
-        o.w = pack_bf16x2(fmaxf(f[8 * q + 6], 0.f), fmaxf(f[8 * q + 7], 0.f));
-        op[q] = o;
+        for (int q = 0; q < NCH / 8; ++q) {
+          uint4 o;
+          o.x = pack_bf16x2(v[8 * q + 0], v[8 * q + 1]);
+          o.y = pack_bf16x2(v[8 * q + 2], v[8 * q + 3]);
+          o.z = pack_bf16x2(v[8 * q + 4], v[8 * q + 5]);
+          o.w = pack_bf16x2(v[8 * q + 6], v[8 * q + 7]);
+          op[q] = o;
+          if (p.split_off > 0) {
+            const uint32_t w[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[8 * q + 2 * e] -= bf16lo(w[e]);
+              v[8 * q + 2 * e + 1] -= bf16hi(w[e]);
+            }
+          }
+        }
       }
     }
   }
@@ -430,7 +437,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     const int row = quarter * 32 + lane;    // pixel row inside the 128-row sub-tile
     uint8_t* stg = stg_all + (warp - 2) * (32 * kStgPitch);
     // bf16 channels-last tensors only (fp32 outputs keep the per-lane path)
-    const bool coalesced = p.out_f32 == nullptr && p.out_cstride == 1;
+    const bool coalesced = p.out_f32 == nullptr && p.out_cstride == 1 && p.split_off == 0;
     // Epilogue operand prefetch.  The mask / addend tiles are the only *loads* of the epilogue; with 4 warps of
     // dependent load->use chains they would be latency bound (~8 KB in flight per SM).  Each warp therefore copies its 32
     // rows of every such tile into shared memory with cp.async BEFORE waiting for the accumulator, i.e. overlapped with

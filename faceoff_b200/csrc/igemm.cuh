@@ -5,8 +5,8 @@
 
 namespace fo {
 
-constexpr int kMaxKSteps = 160;   // 27 taps x 4 channel chunks, VGG 9 x 8, ...
-constexpr int kMaxAMaps = 3;
+constexpr int kMaxKSteps = 256;   // 27 taps x 4 channel chunks, VGG 9 x 8, x3 in the split (hi|lo) verification mode
+constexpr int kMaxAMaps = 6;       // sources of one conv: torch.cat of 2, x3 in the split (hi|lo) verification mode
 constexpr int kMaxDynSmem = 232448;  // 227 KB opt-in limit per CTA on sm_100
 constexpr int kMaxGroups = 4;     // sub-pixel (parity) classes of a stride-2 transposed conv
 
@@ -58,6 +58,7 @@ struct ConvParams {
   __nv_bfloat16* out_relu;       // relu(result) or null
   float* out_f32;                // raw result in fp32 (channel stride out_cstride) or null
   int relu_f32;                  // apply relu to out_f32 too
+  int split_off;                 // > 0: bf16 tensors of the epilogue are hi|lo pairs, lo part split_off channels after hi
   KStep ksteps[kMaxKSteps];
 };
 

@@ -85,9 +85,18 @@ cudaError_t launch_vq_backward(const void* g_q, int g_q_is_bf16, int g_cs, int g
 
 // lpips.cu
 cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out,
-                             int num_sms, cudaStream_t st);
+                             int num_sms, cudaStream_t st, int split = 0);
 cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
-                                 void* d_f0, const void* addend, int num_sms, cudaStream_t st);
+                                 void* d_f0, const void* addend, int num_sms, cudaStream_t st, int split = 0);
+
+// precise.cu (verification mode)
+cudaError_t launch_split_f32(const float* x, int n, int c, int hw, long long sn, long long sc, long long sp, void* out,
+                             int cp, cudaStream_t st);
+cudaError_t launch_merge_f32(const void* in, int n, int c, int hw, int cp, float* out, long long sn, long long sc,
+                             long long sp, cudaStream_t st);
+cudaError_t launch_maxpool2_f32(const float* x, float* y, int n, int h, int w, int c, cudaStream_t st);
+cudaError_t launch_maxpool2_bwd_f32(const float* x, const float* y, const float* dy, float* dx, int n, int h, int w, int c,
+                                    cudaStream_t st);
 cudaError_t launch_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* sum_out, int num_sms,
                        cudaStream_t st);
 cudaError_t launch_mse_grad(const float* a, const float* b, int n, int ca, int c, int hw, const float* gscale,

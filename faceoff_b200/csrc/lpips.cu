@@ -10,8 +10,9 @@ namespace fo {
 constexpr float kLpipsEps = 1e-10f;  // models/lpips.py:155 -- added to the norm, outside the sqrt
 
 // LPP lanes cooperate on one pixel; each lane holds VPL 16-byte vectors (8 channels) of f0 and f1.
-template <int VPL>
-__device__ __forceinline__ void load_pix(const __nv_bfloat16* p, int lpp, int sub, float (&v)[VPL * 8]) {
+// SPLIT (verification mode, fo_conv_t.split_out): a pixel holds c hi values followed by c lo values; the feature is hi + lo.
+template <int VPL, bool SPLIT>
+__device__ __forceinline__ void load_pix(const __nv_bfloat16* p, int lpp, int sub, int c, float (&v)[VPL * 8]) {
   const uint4* q = reinterpret_cast<const uint4*>(p);
 #pragma unroll
   for (int i = 0; i < VPL; ++i) {
@@ -22,6 +23,15 @@ __device__ __forceinline__ void load_pix(const __nv_bfloat16* p, int lpp, int su
       v[i * 8 + 2 * e] = bf16lo(w[e]);
       v[i * 8 + 2 * e + 1] = bf16hi(w[e]);
     }
+    if (SPLIT) {
+      const uint4 ul = __ldg(q + c / 8 + i * lpp + sub);
+      const uint32_t wl[4] = {ul.x, ul.y, ul.z, ul.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        v[i * 8 + 2 * e] += bf16lo(wl[e]);
+        v[i * 8 + 2 * e + 1] += bf16hi(wl[e]);
+      }
+    }
   }
 }
 __device__ __forceinline__ float group_sum(float s, int lpp) {
@@ -29,7 +39,7 @@ __device__ __forceinline__ float group_sum(float s, int lpp) {
   return s;
 }
 
-template <int VPL>
+template <int VPL, bool SPLIT>
 __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
                                  const float* __restrict__ w, int hw, int c, int lpp, float* __restrict__ out) {
   __shared__ float red[32];
@@ -48,9 +58,9 @@ __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __n
     const int pix = p0 + warp * ppw + pw;
     const bool ok = pix < hw;
     float a[VPL * 8], b[VPL * 8];
-    const size_t off = ((size_t)n * hw + (ok ? pix : 0)) * c;
-    load_pix<VPL>(f0 + off, lpp, sub, a);
-    load_pix<VPL>(f1 + off, lpp, sub, b);
+    const size_t off = ((size_t)n * hw + (ok ? pix : 0)) * c * (SPLIT ? 2 : 1);
+    load_pix<VPL, SPLIT>(f0 + off, lpp, sub, c, a);
+    load_pix<VPL, SPLIT>(f1 + off, lpp, sub, c, b);
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL * 8; ++j) { s0 += a[j] * a[j]; s1 += b[j] * b[j]; }
@@ -78,7 +88,7 @@ __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __n
 // d/df0 of the tap value, times g[n], gated by the ReLU that produced f0, plus optional addend (pool gradient).
 //   a = f0/n0, n0 = |f0| + eps ;  u_c = (2/hw) w_c (a_c - b_c)
 //   dL/df0_j = u_j / n0 - (sum_c u_c f0_c) f0_j / (n0^2 |f0|)
-template <int VPL>
+template <int VPL, bool SPLIT>
 __global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
                                      const float* __restrict__ w, const float* __restrict__ g, int hw, int c, int lpp,
                                      __nv_bfloat16* __restrict__ d_f0, const __nv_bfloat16* __restrict__ addend) {
@@ -97,9 +107,9 @@ __global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const
     const int pix = p0 + warp * ppw + pw;
     const bool ok = pix < hw;
     float a[VPL * 8], b[VPL * 8];
-    const size_t off = ((size_t)n * hw + (ok ? pix : 0)) * c;
-    load_pix<VPL>(f0 + off, lpp, sub, a);
-    load_pix<VPL>(f1 + off, lpp, sub, b);
+    const size_t off = ((size_t)n * hw + (ok ? pix : 0)) * c * (SPLIT ? 2 : 1);
+    load_pix<VPL, SPLIT>(f0 + off, lpp, sub, c, a);
+    load_pix<VPL, SPLIT>(f1 + off, lpp, sub, c, b);
     float s0 = 0.f, s1 = 0.f;
 #pragma unroll
     for (int j = 0; j < VPL * 8; ++j) { s0 += a[j] * a[j]; s1 += b[j] * b[j]; }
@@ -119,7 +129,7 @@ __global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const
     const float k2 = r0 > 0.f ? dot * i0 * i0 / r0 : 0.f;
     float ad[VPL * 8];
     if (addend != nullptr) {
-      load_pix<VPL>(addend + off, lpp, sub, ad);
+      load_pix<VPL, SPLIT>(addend + off, lpp, sub, c, ad);
     } else {
 #pragma unroll
       for (int j = 0; j < VPL * 8; ++j) ad[j] = 0.f;
@@ -139,6 +149,15 @@ __global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const
         ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
         ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
         dst[i * lpp + sub] = ov;
+        if (SPLIT) {   // lo = bf16(value - hi)
+          const uint32_t wv2[4] = {ov.x, ov.y, ov.z, ov.w};
+          uint4 ol;
+          ol.x = pack_bf16x2(o[0] - bf16lo(wv2[0]), o[1] - bf16hi(wv2[0]));
+          ol.y = pack_bf16x2(o[2] - bf16lo(wv2[1]), o[3] - bf16hi(wv2[1]));
+          ol.z = pack_bf16x2(o[4] - bf16lo(wv2[2]), o[5] - bf16hi(wv2[2]));
+          ol.w = pack_bf16x2(o[6] - bf16lo(wv2[3]), o[7] - bf16hi(wv2[3]));
+          dst[c / 8 + i * lpp + sub] = ol;
+        }
       }
     }
   }
@@ -151,7 +170,7 @@ static void lpips_geometry(int c, int& lpp, int& vpl) {
 }
 
 cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out,
-                             int num_sms, cudaStream_t st) {
+                             int num_sms, cudaStream_t st, int split) {
   int lpp, vpl;
   lpips_geometry(c, lpp, vpl);
   const int threads = 256;
@@ -162,13 +181,15 @@ cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int
   if (bx < 1) bx = 1;
   dim3 grid(bx, n);
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
-  if (vpl == 1) lpips_tap_kernel<1><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
-  else if (vpl == 2) lpips_tap_kernel<2><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  if (vpl == 1 && !split) lpips_tap_kernel<1, false><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  else if (vpl == 2 && !split) lpips_tap_kernel<2, false><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  else if (vpl == 1) lpips_tap_kernel<1, true><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  else if (vpl == 2) lpips_tap_kernel<2, true><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
-                                 void* d_f0, const void* addend, int num_sms, cudaStream_t st) {
+                                 void* d_f0, const void* addend, int num_sms, cudaStream_t st, int split) {
   int lpp, vpl;
   lpips_geometry(c, lpp, vpl);
   const int threads = 256;
@@ -179,12 +200,12 @@ cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w,
   if (bx < 1) bx = 1;
   dim3 grid(bx, n);
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
-  if (vpl == 1)
-    lpips_tap_bwd_kernel<1><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, (__nv_bfloat16*)d_f0,
-                                                      (const __nv_bfloat16*)addend);
-  else if (vpl == 2)
-    lpips_tap_bwd_kernel<2><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, (__nv_bfloat16*)d_f0,
-                                                      (const __nv_bfloat16*)addend);
+  __nv_bfloat16* d = (__nv_bfloat16*)d_f0;
+  const __nv_bfloat16* ad = (const __nv_bfloat16*)addend;
+  if (vpl == 1 && !split) lpips_tap_bwd_kernel<1, false><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 2 && !split) lpips_tap_bwd_kernel<2, false><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 1) lpips_tap_bwd_kernel<1, true><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 2) lpips_tap_bwd_kernel<2, true><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }

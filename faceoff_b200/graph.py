@@ -60,6 +60,7 @@ class Tape:
         self.need_grad = need_grad
         self.grads: Dict[str, torch.Tensor] = {}
         self._bwd: List[Callable[[], None]] = []
+        self.precise = ops.PRECISE     # verification mode (ops.PRECISE) is a property of the tape: backward re-enters it
         self.dp = None                 # optional FusedDataParallel: grads are born in its flat bucket
         self._fresh: set = set()       # pre-allocated gradient buffers not written yet
 
@@ -68,8 +69,12 @@ class Tape:
             self._bwd.append(fn)
 
     def backward(self):
-        for fn in reversed(self._bwd):
-            fn()
+        old, ops.PRECISE = ops.PRECISE, self.precise
+        try:
+            for fn in reversed(self._bwd):
+                fn()
+        finally:
+            ops.PRECISE = old
         self._bwd.clear()
 
     def grad_buffer(self, name: str) -> Tuple[torch.Tensor, bool]:
@@ -183,7 +188,7 @@ def conv_op(tape: Tape, form: int, ksize: int, srcs: Sequence[View], wname: str,
             if residual.g is None:
                 residual.g = (gt, 0)
             else:
-                residual.g = (residual.g[0] + gt, 0)
+                residual.g = (ops.add_grads(residual.g[0], gt), 0)
         # data gradient
         if not input_needs_grad:
             return

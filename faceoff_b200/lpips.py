@@ -149,7 +149,7 @@ class vgg16(nn.Module):
                     if g is None:
                         return
                     g = ops.pack_nchw(g, cs=node.act.shape[-1])
-                    node.g = (g if node.g is None else node.g[0] + g, 0)
+                    node.g = (g if node.g is None else ops.add_grads(node.g[0], g), 0)
 
                 tape.record(tap_bwd)
 
@@ -182,7 +182,14 @@ def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, t
     taps = []
     first = True
     for kind, key, ch in layout:
-        if kind == "conv" and first:
+        if kind == "conv" and first and tape.precise:
+            # verification mode: the plain implicit-GEMM path on the 3-channel (hi|lo pair) input
+            first = False
+            xin.raw = ops.pack_nchw(x, shift=shift, scale=scale)
+            cur = conv_op(tape, FORM_S1, 3, [View(xin, False)], prefix + key, ch, want_raw=False, want_relu=True,
+                          param_grad=False)
+            cur_relu = True
+        elif kind == "conv" and first:
             # first conv (3 -> 64): explicit im2col (K = 27 -> 32) + 1x1 GEMM; 3-channel 32-byte TMA rows are slow
             first = False
             w = tape.params[prefix + key + ".weight"]

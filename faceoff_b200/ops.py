@@ -82,6 +82,67 @@ def pad16(c: int) -> int:
 
 
 # ------------------------------------------------------------------------------------------------
+# Verification mode (tests only): fp32-accurate activations as hi|lo bf16 pairs through the SAME tensor-core kernels
+# ------------------------------------------------------------------------------------------------
+# With PRECISE set, every activation / activation-gradient tensor produced by this module holds an fp32 value per
+# logical channel as two bf16 numbers: [.., 2*Cp] with hi = bf16(v) in channels [0, Cp) and lo = bf16(v - hi) in
+# [Cp, 2*Cp) (Cp = pad16(C)).  A convolution lists each source three times (hi, lo, hi) against weights packed as
+# (w_hi, w_hi, w_lo), i.e. hi*w_hi + lo*w_hi + hi*w_lo with fp32 accumulation (the term lo*w_lo ~ 2^-18 is dropped);
+# weight gradients are three accumulating launches (P_hi Q_hi + P_lo Q_hi + P_hi Q_lo).  The planner, K-step tables,
+# packed-weight order, halo / pair / parity addressing and the epilogue fusions are exactly the product's, so a wrong
+# tap, a missed residual or a mis-scaled bias gradient shows up at the 1e-4 level against an fp64 CPU restatement instead of
+# hiding inside the bf16 tolerance.  ~3-4x slower than the product path; never enabled outside tests.
+PRECISE = False
+
+
+class precise_mode:
+    """``with ops.precise_mode(): loss = step(...); loss.backward()`` -- see PRECISE above."""
+
+    def __enter__(self):
+        global PRECISE
+        self._old, PRECISE = PRECISE, True
+        return self
+
+    def __exit__(self, *exc):
+        global PRECISE
+        PRECISE = self._old
+
+
+def split_cl(x: torch.Tensor, c: Optional[int] = None, cp: Optional[int] = None) -> torch.Tensor:
+    """fp32 channels-last [.., Cs] (first c channels) -> hi|lo pairs bf16 [.., 2*cp]."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    cs = x.shape[-1]
+    c = cs if c is None else c
+    cp = pad16(c) if cp is None else cp
+    rows = x.numel() // cs
+    out = torch.empty((*x.shape[:-1], 2 * cp), dtype=torch.bfloat16, device=x.device)
+    L.check(lib.fo_split_f32(x.data_ptr(), 1, c, rows, 0, 1, cs, out.data_ptr(), cp, _stream()), "fo_split_f32")
+    _count(1)
+    return out
+
+
+def merge_cl(t: torch.Tensor, c: int, c_off: int = 0) -> torch.Tensor:
+    """hi|lo pairs bf16 [.., 2*cp] -> fp32 channels-last [.., c] (logical channels c_off .. c_off + c)."""
+    lib = L.load()
+    assert t.dtype == torch.bfloat16 and t.is_contiguous()
+    cp = t.shape[-1] // 2
+    rows = t.numel() // t.shape[-1]
+    out = torch.empty((*t.shape[:-1], c), dtype=torch.float32, device=t.device)
+    L.check(lib.fo_merge_f32(t.data_ptr() + 2 * c_off, 1, c, rows, cp, out.data_ptr(), 0, 1, c, _stream()), "fo_merge_f32")
+    _count(1)
+    return out
+
+
+def add_grads(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Sum of two activation gradients of the same layout (rare path: a node with several raw consumers)."""
+    if PRECISE:
+        c = a.shape[-1] // 2
+        return split_cl(merge_cl(a, c) + merge_cl(b, c), c, c)
+    return a + b
+
+
+# ------------------------------------------------------------------------------------------------
 # workspaces (per device, grown on demand; all users are ordered on the current stream)
 # ------------------------------------------------------------------------------------------------
 _ws: Dict[Tuple[int, str], torch.Tensor] = {}
@@ -171,6 +232,22 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
     f32: None | 'cl' (channels-last fp32 [.., out_cs]) | 'nchw' (fp32 [N, cout, H, W]).
     """
     lib = L.load()
+    precise = PRECISE
+    if precise:
+        # (hi, lo, hi) sources against (w_hi, w_hi, w_lo) weights; the K axis of the weight is the one that is not N
+        k_axis = 1 - n_axis
+        w_hi = weight.detach().bfloat16().float()
+        w_lo = weight.detach() - w_hi
+        srcs3, parts, o = [], [], 0
+        for (t, c, off) in srcs:
+            half = t.shape[-1] // 2
+            srcs3 += [(t, c, off), (t, c, off + half), (t, c, off)]
+            parts += [w_hi.narrow(k_axis, o, c), w_hi.narrow(k_axis, o, c), w_lo.narrow(k_axis, o, c)]
+            o += c
+        wkey = (weight, "precise") if wkey is None else (wkey[0], ("precise", wkey[1]))
+        weight = torch.cat(parts, k_axis).contiguous()
+        logical_srcs, srcs = srcs, srcs3
+        assert n_scale is None
     d = _conv_desc(form, ndim, ksize, srcs, cout)
     # the packed column order depends on the planner's tiling mode, which depends on the geometry
     key_extra = tuple((s[1], s[0].shape[-1], s[2]) for s in srcs) + (cout, d.n, d.d, d.h, d.w)
@@ -178,7 +255,7 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
     d.wpacked = wp.data_ptr()
     t0 = srcs[0][0]
     lead = out_spatial(form, t0.shape[:-1])
-    ocs = out_cs if out_cs is not None else pad16(cout)
+    ocs = out_cs if out_cs is not None else pad16(cout) * (2 if precise and f32 is None else 1)
     dev = t0.device
     raw = relu = of32 = None
     if f32 == "nchw":
@@ -191,7 +268,10 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
             relu = torch.empty((*lead, ocs), dtype=torch.bfloat16, device=dev)
         if f32 == "cl":
             of32 = torch.empty((*lead, ocs), dtype=torch.float32, device=dev)
-    if ocs > pad16(cout):
+    if precise and (raw is not None or relu is not None or mask is not None or addend is not None):
+        assert ocs == 2 * pad16(cout) and f32 is None, "verification mode: bf16 epilogue tensors are hi|lo pairs"
+        d.split_out = 1
+    elif ocs > pad16(cout):
         # channels beyond the computed ones are never written by the kernel
         for t in (raw, relu):
             if t is not None and t is not out_raw:
@@ -208,7 +288,7 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
         if t is not None:
             assert t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape) == (*lead, ocs), (t.shape, lead, ocs)
     # algorithmic FLOPs: 2 * positions * cin * cout * taps (positions: outputs, or inputs for the scatter form)
-    cin = sum(s_[1] for s_ in srcs)
+    cin = sum(s_[1] for s_ in (logical_srcs if precise else srcs))
     taps = 16 if form in (FORM_DOWN, FORM_UP) else ksize ** ndim
     n_pos = 1
     for v_ in (lead if form != FORM_UP else t0.shape[:-1]):
@@ -226,8 +306,16 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
 
 def wgrad(form: int, ndim: int, ksize: int, p: SrcT, q: SrcT, dweight: torch.Tensor, m_axis: int, q_w_off: int = 0,
           accumulate: bool = False, dbias: Optional[torch.Tensor] = None, dbias_accumulate: bool = False,
-          q_shift_sign: int = 1):
+          q_shift_sign: int = 1, _raw: bool = False):
     """dweight (fp32, PyTorch layout) (+)= sum_pix P (x) Q.  form: FORM_S1 or FORM_DOWN (Q = hi-res side)."""
+    if PRECISE and not _raw:
+        # P_hi Q_hi + P_lo Q_hi + P_hi Q_lo; the bias gradient (column sums of P) takes hi from the first launch, lo from the second
+        hp, hq = p[0].shape[-1] // 2, q[0].shape[-1] // 2
+        p_lo, q_lo = (p[0], p[1], p[2] + hp), (q[0], q[1], q[2] + hq)
+        wgrad(form, ndim, ksize, p, q, dweight, m_axis, q_w_off, accumulate, dbias, dbias_accumulate, q_shift_sign, True)
+        wgrad(form, ndim, ksize, p_lo, q, dweight, m_axis, q_w_off, True, dbias, True, q_shift_sign, True)
+        wgrad(form, ndim, ksize, p, q_lo, dweight, m_axis, q_w_off, True, None, False, q_shift_sign, True)
+        return
     lib = L.load()
     g = WgradDesc()
     pt = p[0]
@@ -260,15 +348,20 @@ def wgrad(form: int, ndim: int, ksize: int, p: SrcT, q: SrcT, dweight: torch.Ten
     _count(2 + (dbias is not None))
 
 
-def colsum(x: torch.Tensor, c: int, out: torch.Tensor, c_off: int = 0, accumulate: bool = False):
+def colsum(x: torch.Tensor, c: int, out: torch.Tensor, c_off: int = 0, accumulate: bool = False, _raw: bool = False):
     """out[:c] (+)= x.reshape(-1, Cs)[:, c_off:c_off+c].sum(0)   (bias gradient)."""
+    if PRECISE and not _raw:
+        colsum(x, c, out, c_off, accumulate, True)
+        colsum(x, c, out, c_off + x.shape[-1] // 2, True, True)
+        return
     lib = L.load()
     cs = x.shape[-1]
     rows = x.numel() // cs
     need = lib.fo_colsum_workspace_bytes(cs)
     ws = workspace(need, x.device, "colsum")
-    L.check(lib.fo_colsum(x.data_ptr(), rows, cs, c_off, c, out.data_ptr(), int(accumulate), ws.data_ptr(), ws.numel(),
-                          _stream()), "fo_colsum")
+    with _Timed("hbm/colsum", 2.0 * rows * cs):
+        L.check(lib.fo_colsum(x.data_ptr(), rows, cs, c_off, c, out.data_ptr(), int(accumulate), ws.data_ptr(),
+                              ws.numel(), _stream()), "fo_colsum")
     _count(2)
 
 
@@ -279,10 +372,20 @@ def pack_nchw(x: torch.Tensor, cs: Optional[int] = None, shift: Optional[torch.T
     assert x.dtype == torch.float32 and x.dim() == 4
     x = x.contiguous()
     n, c, h, w = x.shape
+    if PRECISE:
+        if shift is not None:
+            x = ((x - shift.view(1, -1, 1, 1)[:, :c]) / scale.view(1, -1, 1, 1)[:, :c]).contiguous()
+        cp = pad16(c) if cs is None else cs // 2
+        out = torch.empty((n, h, w, 2 * cp), dtype=torch.bfloat16, device=x.device)
+        L.check(lib.fo_split_f32(x.data_ptr(), n, c, h * w, c * h * w, h * w, 1, out.data_ptr(), cp, _stream()),
+                "fo_split_f32")
+        _count(1)
+        return out
     cs = cs or pad16(c)
     out = torch.empty((n, h, w, cs), dtype=torch.bfloat16, device=x.device)
-    L.check(lib.fo_pack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _p(shift), _p(scale), _stream()),
-            "fo_pack_nchw")
+    with _Timed("hbm/pack_nchw", n * h * w * (4.0 * c + 2.0 * cs)):
+        L.check(lib.fo_pack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _p(shift), _p(scale), _stream()),
+                "fo_pack_nchw")
     _count(1)
     return out
 
@@ -292,7 +395,13 @@ def unpack_nchw(x: torch.Tensor, c: int) -> torch.Tensor:
     lib = L.load()
     n, h, w, cs = x.shape
     out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
-    L.check(lib.fo_unpack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _stream()), "fo_unpack_nchw")
+    if PRECISE:
+        L.check(lib.fo_merge_f32(x.data_ptr(), n, c, h * w, cs // 2, out.data_ptr(), c * h * w, h * w, 1, _stream()),
+                "fo_merge_f32")
+        _count(1)
+        return out
+    with _Timed("hbm/unpack_nchw", n * h * w * (4.0 * c + 2.0 * cs)):
+        L.check(lib.fo_unpack_nchw(x.data_ptr(), out.data_ptr(), n, c, h * w, cs, _stream()), "fo_unpack_nchw")
     _count(1)
     return out
 
@@ -303,7 +412,8 @@ def im2col4x4s2(x: torch.Tensor, c: int) -> torch.Tensor:
     assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
     n, ca, h, w = x.shape
     out = torch.empty((n, h // 2, w // 2, 128), dtype=torch.bfloat16, device=x.device)
-    L.check(lib.fo_im2col4x4s2(x.data_ptr(), out.data_ptr(), n, ca, c, h, w, _stream()), "fo_im2col4x4s2")
+    with _Timed("hbm/im2col4x4s2", n * h * w * 4.0 * c + out.numel() * 2.0):
+        L.check(lib.fo_im2col4x4s2(x.data_ptr(), out.data_ptr(), n, ca, c, h, w, _stream()), "fo_im2col4x4s2")
     _count(1)
     return out
 
@@ -314,7 +424,9 @@ def im2col3x3(x: torch.Tensor, shift: Optional[torch.Tensor] = None, scale: Opti
     assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
     n, c, h, w = x.shape
     out = torch.empty((n, h, w, 32), dtype=torch.bfloat16, device=x.device)
-    L.check(lib.fo_im2col3x3(x.data_ptr(), out.data_ptr(), n, c, h, w, _p(shift), _p(scale), _stream()), "fo_im2col3x3")
+    with _Timed("hbm/im2col3x3", n * h * w * 4.0 * c + out.numel() * 2.0):
+        L.check(lib.fo_im2col3x3(x.data_ptr(), out.data_ptr(), n, c, h, w, _p(shift), _p(scale), _stream()),
+                "fo_im2col3x3")
     _count(1)
     return out
 
@@ -325,7 +437,9 @@ def col2im4x4s2(col: torch.Tensor, bias: Optional[torch.Tensor], c: int) -> torc
     n, hi, wi, k = col.shape
     assert k == 128 and col.dtype == torch.bfloat16 and col.is_contiguous()
     out = torch.empty((n, c, 2 * hi, 2 * wi), dtype=torch.float32, device=col.device)
-    L.check(lib.fo_col2im4x4s2(col.data_ptr(), _p(bias), out.data_ptr(), n, c, hi, wi, _stream()), "fo_col2im4x4s2")
+    with _Timed("hbm/col2im4x4s2", col.numel() * 2.0 + out.numel() * 4.0):
+        L.check(lib.fo_col2im4x4s2(col.data_ptr(), _p(bias), out.data_ptr(), n, c, hi, wi, _stream()),
+                "fo_col2im4x4s2")
     _count(1)
     return out
 
@@ -335,12 +449,16 @@ def chansum_nchw(x: torch.Tensor, c: int, out: torch.Tensor, accumulate: bool = 
     lib = L.load()
     assert x.dtype == torch.float32 and x.is_contiguous()
     n, ca, h, w = x.shape
-    L.check(lib.fo_chansum_nchw(x.data_ptr(), n, ca, c, h * w, out.data_ptr(), int(accumulate), _stream()),
-            "fo_chansum_nchw")
+    with _Timed("hbm/chansum_nchw", 4.0 * n * c * h * w):
+        L.check(lib.fo_chansum_nchw(x.data_ptr(), n, ca, c, h * w, out.data_ptr(), int(accumulate), _stream()),
+                "fo_chansum_nchw")
     _count(1)
 
 
 def relu(x: torch.Tensor) -> torch.Tensor:
+    if PRECISE:
+        c = x.shape[-1] // 2
+        return split_cl(merge_cl(x, c).clamp_min_(0), c, c)
     lib = L.load()
     y = torch.empty_like(x)
     L.check(lib.fo_relu(x.data_ptr(), y.data_ptr(), x.numel(), _stream()), "fo_relu")
@@ -351,8 +469,16 @@ def relu(x: torch.Tensor) -> torch.Tensor:
 def maxpool2(x: torch.Tensor) -> torch.Tensor:
     lib = L.load()
     n, h, w, cs = x.shape
+    if PRECISE:
+        c = cs // 2
+        x32 = merge_cl(x, c)
+        y32 = torch.empty((n, h // 2, w // 2, c), dtype=torch.float32, device=x.device)
+        L.check(lib.fo_maxpool2_f32(x32.data_ptr(), y32.data_ptr(), n, h, w, c, _stream()), "fo_maxpool2_f32")
+        _count(1)
+        return split_cl(y32, c, c)
     y = torch.empty((n, h // 2, w // 2, cs), dtype=torch.bfloat16, device=x.device)
-    L.check(lib.fo_maxpool2(x.data_ptr(), y.data_ptr(), n, h, w, cs, _stream()), "fo_maxpool2")
+    with _Timed("hbm/maxpool2", 2.5 * x.numel()):
+        L.check(lib.fo_maxpool2(x.data_ptr(), y.data_ptr(), n, h, w, cs, _stream()), "fo_maxpool2")
     _count(1)
     return y
 
@@ -360,9 +486,18 @@ def maxpool2(x: torch.Tensor) -> torch.Tensor:
 def maxpool2_bwd(x: torch.Tensor, y: torch.Tensor, dy: torch.Tensor) -> torch.Tensor:
     lib = L.load()
     n, h, w, cs = x.shape
+    if PRECISE:
+        c = cs // 2
+        x32, y32, dy32 = merge_cl(x, c), merge_cl(y, c), merge_cl(dy, c)
+        dx32 = torch.empty_like(x32)
+        L.check(lib.fo_maxpool2_bwd_f32(x32.data_ptr(), y32.data_ptr(), dy32.data_ptr(), dx32.data_ptr(), n, h, w, c,
+                                        _stream()), "fo_maxpool2_bwd_f32")
+        _count(1)
+        return split_cl(dx32, c, c)
     dx = torch.empty_like(x)
-    L.check(lib.fo_maxpool2_bwd(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, cs, _stream()),
-            "fo_maxpool2_bwd")
+    with _Timed("hbm/maxpool2_bwd", 5.0 * x.numel()):
+        L.check(lib.fo_maxpool2_bwd(x.data_ptr(), y.data_ptr(), dy.data_ptr(), dx.data_ptr(), n, h, w, cs, _stream()),
+                "fo_maxpool2_bwd")
     _count(1)
     return dx
 
@@ -395,9 +530,10 @@ def vq_assign(x: torch.Tensor, e_t: torch.Tensor, e_split: torch.Tensor, e_norm2
     ind = torch.empty(rows, dtype=torch.int64, device=x.device)
     need = lib.fo_vq_assign_workspace_bytes(rows, dim)
     ws = workspace(need, x.device, "vq")
-    L.check(lib.fo_vq_assign(x.data_ptr(), rows, dim, n_embed, e_t.data_ptr(), e_split.data_ptr(),
-                             e_norm2.data_ptr(), ind.data_ptr(), _p(n_flagged), ws.data_ptr(), ws.numel(), _stream()),
-            "fo_vq_assign")
+    with _Timed("vq_assign", 2.0 * rows * dim * n_embed):
+        L.check(lib.fo_vq_assign(x.data_ptr(), rows, dim, n_embed, e_t.data_ptr(), e_split.data_ptr(),
+                                 e_norm2.data_ptr(), ind.data_ptr(), _p(n_flagged), ws.data_ptr(), ws.numel(),
+                                 _stream()), "fo_vq_assign")
     _count(2)
     return ind
 
@@ -408,11 +544,19 @@ def vq_gather_stats(x: torch.Tensor, ind: torch.Tensor, e_t: torch.Tensor, diff_
     lib = L.load()
     rows, dim = x.shape
     n_embed = e_t.shape[0]
+    precise_pairs = PRECISE and want_bf16
+    if precise_pairs:           # the bf16 copy for the decoder becomes a hi|lo pair tensor made from the fp32 result
+        want_f32, want_bf16 = True, False
     q32 = torch.empty_like(x) if want_f32 else None
     q16 = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
-    L.check(lib.fo_vq_gather_stats(x.data_ptr(), ind.data_ptr(), rows, dim, n_embed, e_t.data_ptr(), _p(q32), _p(q16),
-                                   diff_sum.data_ptr(), _p(counts), _p(embed_sum), _stream()), "fo_vq_gather_stats")
+    # algorithmic bytes per row: read x 4D + index 8, write q 4D (+ 2D for the bf16 copy)
+    with _Timed("hbm/vq_gather_stats", rows * (4.0 * dim + 8 + (4.0 * dim if want_f32 else 0) + (2.0 * dim if want_bf16 else 0))):
+        L.check(lib.fo_vq_gather_stats(x.data_ptr(), ind.data_ptr(), rows, dim, n_embed, e_t.data_ptr(), _p(q32),
+                                       _p(q16), diff_sum.data_ptr(), _p(counts), _p(embed_sum), _stream()),
+                "fo_vq_gather_stats")
     _count(1)
+    if precise_pairs:
+        q16 = split_cl(q32, dim)
     return q32, q16
 
 
@@ -429,12 +573,20 @@ def vq_backward(g_q: Optional[torch.Tensor], g_c_off: int, g_diff: Optional[torc
     lib = L.load()
     rows, dim = x.shape
     n_embed = e_t.shape[0]
+    if PRECISE and (want_bf16 or (g_q is not None and g_q.dtype == torch.bfloat16)):
+        # pair tensors in and out: merge -> the fp32 kernel -> split
+        gq32 = None if g_q is None else (merge_cl(g_q, dim, g_c_off) if g_q.dtype == torch.bfloat16 else g_q)
+        g32, _ = vq_backward(gq32, 0 if g_q is None or g_q.dtype == torch.bfloat16 else g_c_off, g_diff, x, ind, e_t,
+                             want_f32=True, want_bf16=False)
+        return (g32 if want_f32 else None), (split_cl(g32, dim) if want_bf16 else None)
     g32 = torch.empty_like(x) if want_f32 else None
     g16 = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     is_bf16 = int(g_q is not None and g_q.dtype == torch.bfloat16)
     g_cs = g_q.shape[-1] if g_q is not None else dim
-    L.check(lib.fo_vq_backward(_p(g_q), is_bf16, g_cs, g_c_off, _p(g_diff), x.data_ptr(), ind.data_ptr(),
-                               e_t.data_ptr(), rows, dim, n_embed, _p(g32), _p(g16), _stream()), "fo_vq_backward")
+    gbytes = 0.0 if g_q is None else (2.0 if is_bf16 else 4.0) * dim
+    with _Timed("hbm/vq_backward", rows * (gbytes + 4.0 * dim + 8 + (4.0 * dim if want_f32 else 0) + (2.0 * dim if want_bf16 else 0))):
+        L.check(lib.fo_vq_backward(_p(g_q), is_bf16, g_cs, g_c_off, _p(g_diff), x.data_ptr(), ind.data_ptr(),
+                                   e_t.data_ptr(), rows, dim, n_embed, _p(g32), _p(g16), _stream()), "fo_vq_backward")
     _count(1)
     return g32, g16
 
@@ -446,8 +598,14 @@ def lpips_tap(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, out: torch.Te
     """out[n] += mean_hw sum_c w_c (norm(f0) - norm(f1))^2 ; f0, f1 bf16 [N,H,W,C]."""
     lib = L.load()
     n, h, wd, c = f0.shape
-    L.check(lib.fo_lpips_tap(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), n, h * wd, c, out.data_ptr(), _stream()),
-            "fo_lpips_tap")
+    if PRECISE:
+        L.check(lib.fo_lpips_tap_split(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), n, h * wd, c // 2, out.data_ptr(),
+                                       _stream()), "fo_lpips_tap_split")
+        _count(1)
+        return
+    with _Timed("hbm/lpips_tap", 4.0 * f0.numel()):
+        L.check(lib.fo_lpips_tap(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), n, h * wd, c, out.data_ptr(), _stream()),
+                "fo_lpips_tap")
     _count(1)
 
 
@@ -456,8 +614,14 @@ def lpips_tap_bwd(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.
     lib = L.load()
     n, h, wd, c = f0.shape
     d = torch.empty_like(f0)
-    L.check(lib.fo_lpips_tap_bwd(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), g.data_ptr(), n, h * wd, c, d.data_ptr(),
-                                 _p(addend), _stream()), "fo_lpips_tap_bwd")
+    if PRECISE:
+        L.check(lib.fo_lpips_tap_bwd_split(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), g.data_ptr(), n, h * wd, c // 2,
+                                           d.data_ptr(), _p(addend), _stream()), "fo_lpips_tap_bwd_split")
+        _count(1)
+        return d
+    with _Timed("hbm/lpips_tap_bwd", (6.0 + (2.0 if addend is not None else 0.0)) * f0.numel()):
+        L.check(lib.fo_lpips_tap_bwd(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), g.data_ptr(), n, h * wd, c,
+                                     d.data_ptr(), _p(addend), _stream()), "fo_lpips_tap_bwd")
     _count(1)
     return d
 
@@ -471,7 +635,8 @@ def mse_sum(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     n, ca, h, w = a.shape
     c = b.shape[1]
     out = torch.zeros(1, dtype=torch.float32, device=a.device)
-    L.check(lib.fo_mse(a.data_ptr(), b.data_ptr(), n, ca, c, h * w, out.data_ptr(), _stream()), "fo_mse")
+    with _Timed("hbm/mse", 8.0 * b.numel()):
+        L.check(lib.fo_mse(a.data_ptr(), b.data_ptr(), n, ca, c, h * w, out.data_ptr(), _stream()), "fo_mse")
     _count(1)
     return out
 
@@ -482,8 +647,9 @@ def mse_grad(a: torch.Tensor, b: torch.Tensor, g: torch.Tensor, scale: float) ->
     n, ca, h, w = a.shape
     c = b.shape[1]
     grad = torch.empty_like(a)
-    L.check(lib.fo_mse_grad(a.data_ptr(), b.data_ptr(), n, ca, c, h * w, g.data_ptr(), float(scale), grad.data_ptr(),
-                            _stream()), "fo_mse_grad")
+    with _Timed("hbm/mse_grad", 8.0 * b.numel() + 4.0 * a.numel()):
+        L.check(lib.fo_mse_grad(a.data_ptr(), b.data_ptr(), n, ca, c, h * w, g.data_ptr(), float(scale),
+                                grad.data_ptr(), _stream()), "fo_mse_grad")
     _count(1)
     return grad
 

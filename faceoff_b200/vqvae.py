@@ -137,6 +137,9 @@ class _GraphFn(torch.autograd.Function):
         ctx.tape, ctx.state, ctx.names = tape, state, names
         ctx.inp_needs_grad = inp.requires_grad
         ctx.n_out = len(outs)
+        nd = [outs[i] for i in state.get("non_diff", ())]
+        if nd:
+            ctx.mark_non_differentiable(*nd)
         return tuple(outs)
 
     @staticmethod
@@ -149,9 +152,13 @@ class _GraphFn(torch.autograd.Function):
         dp = state.get("dp")
         if dp is not None:
             dp.begin_step(tape)
-        state["seed"](tape, gouts)
-        tape.backward()
-        gi = state["input_grad"]() if ctx.inp_needs_grad else None
+        old, ops.PRECISE = ops.PRECISE, tape.precise
+        try:
+            state["seed"](tape, gouts)
+            tape.backward()
+            gi = state["input_grad"]() if ctx.inp_needs_grad else None
+        finally:
+            ops.PRECISE = old
         if dp is not None:
             dp.end_step()
             grads = dp.grads_for_autograd(tape, ctx.names)
@@ -182,7 +189,11 @@ def _io_wrap(build, c_in: int, c_out_fn):
             g = ops.pack_nchw(gouts[0].to(torch.float32), cs=t.shape[-1])
             if out_relu:
                 # gradient arrives w.r.t. relu(raw): gate it (rare stand-alone path; index plumbing in torch)
-                g = g * (t > 0)
+                if tape_.precise:
+                    m = t[..., :t.shape[-1] // 2] > 0
+                    g = g * torch.cat([m, m], -1)
+                else:
+                    g = g * (t > 0)
             out_node.g = (g, 0)
             return g
 
@@ -252,7 +263,7 @@ def _decoder_graph(tape: Tape, srcs, prefix: str, out_channel: int, channel: int
     if stride == 4:
         a = conv_op(tape, FORM_UP, 4, [View(a, True)], f"{prefix}blocks.{k}", channel // 2, transposed=True,
                     want_raw=False, want_relu=True)
-        if final_f32 == "nchw" and out_channel <= 8:
+        if final_f32 == "nchw" and out_channel <= 8 and not tape.precise:
             return last_convT_op(tape, View(a, True), f"{prefix}blocks.{k + 2}", out_channel)
         return conv_op(tape, FORM_UP, 4, [View(a, True)], f"{prefix}blocks.{k + 2}", out_channel, transposed=True,
                        want_raw=final_f32 is None, f32=final_f32)
@@ -403,7 +414,7 @@ class VQVAE(nn.Module):
             raise ValueError("the reference hard-wires the Conv3d stacks to 128 channels; channel must be 128")
 
     # -- the fused training graph ----------------------------------------------------------------
-    def _runner(self, clips: int, want_ids: bool):
+    def _runner(self, clips: int, want_ids: bool, want_pre: bool = False):
         cfg = self.cfg
         ch, nrb, nrc, ed = cfg["channel"], cfg["n_res_block"], cfg["n_res_channel"], cfg["embed_dim"]
         cin = cfg["in_channel"]
@@ -418,7 +429,8 @@ class VQVAE(nn.Module):
             else:
                 dp = None
             x = x.to(torch.float32).contiguous()
-            xin = x if cin <= 8 else View(Node(cin, raw=ops.pack_nchw(x)), False)
+            small = cin <= 8 and not tape.precise   # im2col / col2im fast path for the 6-channel image-side layers
+            xin = x if small else View(Node(cin, raw=ops.pack_nchw(x)), False)
             enc_b = _encoder_graph(tape, xin, "enc_b.", ch, nrb, nrc, 4, input_needs_grad=False)
             enc_t = _encoder_graph(tape, View(enc_b, True), "enc_t.", ch, nrb, nrc, 2, input_needs_grad=True)
             eb_c = _conv3d_graph(tape, View(enc_b, True), "conv3d_encoded_b.", 128, clips)
@@ -429,14 +441,14 @@ class VQVAE(nn.Module):
             def quantize(qmod: Quantize, pre: Node):
                 x32 = pre.f32.view(-1, ed)
                 q32, q16, diff_sum, ind, e_t = _quantize_forward(qmod, x32, want_bf16=True, dp=dp)
-                node = Node(ed, raw=q16.view(*pre.f32.shape))
+                node = Node(ed, raw=q16.view(*pre.f32.shape[:-1], -1))
                 rec = dict(x32=x32, ind=ind, diff_sum=diff_sum)
 
                 def vq_bwd():  # recorded right after the producing conv => replayed right before its backward
                     gq, g_off = node.g if node.g is not None else (None, 0)
                     _, g16 = ops.vq_backward(None if gq is None else gq.view(-1, gq.shape[-1]), g_off,
                                              gdiff_holder.get("g"), x32, ind, e_t, want_f32=False, want_bf16=True)
-                    pre.g = (g16.view(*pre.f32.shape), 0)
+                    pre.g = (g16.view(*pre.f32.shape[:-1], -1), 0)
 
                 tape.record(vq_bwd)
                 return node, rec
@@ -458,7 +470,7 @@ class VQVAE(nn.Module):
                 if g_dec is None:
                     g_dec = torch.zeros_like(dec)
                 g_dec = g_dec.to(torch.float32).contiguous()
-                if cin <= 8:
+                if small:
                     out.gdec = g_dec
                 else:
                     out.g = (ops.pack_nchw(g_dec), 0)
@@ -468,7 +480,10 @@ class VQVAE(nn.Module):
             outs = [dec, diff]
             if want_ids:
                 outs += [rec_t["ind"].view(*pre_t.f32.shape[:-1]), rec_b["ind"].view(*pre_b.f32.shape[:-1])]
-            return tuple(outs), {"seed": seed, "input_grad": lambda: None, "dp": dp}
+            if want_pre:    # the fp32 rows the quantisers saw ([F, h, w, embed_dim]); parity tests re-run the argmin on them
+                outs += [pre_t.f32, pre_b.f32]
+            return tuple(outs), {"seed": seed, "input_grad": lambda: None, "dp": dp,
+                                 "non_diff": tuple(range(2, len(outs)))}
 
         return runner
 
@@ -480,8 +495,8 @@ class VQVAE(nn.Module):
             order += [f"{sub}.{k}" for k, _ in getattr(self, sub).named_parameters()]
         return order
 
-    def _forward_clips(self, x4: torch.Tensor, clips: int, want_ids: bool = False):
-        return _run_vqvae(self, self._runner(clips, want_ids), x4)
+    def _forward_clips(self, x4: torch.Tensor, clips: int, want_ids: bool = False, want_pre: bool = False):
+        return _run_vqvae(self, self._runner(clips, want_ids, want_pre), x4)
 
     def forward(self, input):
         """input [T, Cin, H, W] (one clip, reference semantics) or [B, T, Cin, H, W] (B clips, extension).
@@ -493,9 +508,10 @@ class VQVAE(nn.Module):
         outs = self._forward_clips(input, 1)
         return outs[0], outs[1]
 
-    def forward_with_ids(self, input, clips: int = 1):
-        """(dec, diff, id_t, id_b) -- used by parity tests and by the data-parallel trainer."""
-        return self._forward_clips(input, clips, want_ids=True)
+    def forward_with_ids(self, input, clips: int = 1, return_pre: bool = False):
+        """(dec, diff, id_t, id_b[, pre_t, pre_b]) -- used by parity tests and by the data-parallel trainer.
+        ``return_pre`` appends the fp32 pre-quantiser activations (the exact rows the argmin ran on)."""
+        return self._forward_clips(input, clips, want_ids=True, want_pre=return_pre)
 
     # -- reference sub-methods (eager composition of the drop-in modules; used for inference / tests) ----
     def only_encode(self, input):

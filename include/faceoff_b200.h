@@ -66,8 +66,9 @@ typedef struct {
   int ksize; /* 1 or 3 for S1 forms; ignored (4) for DOWN / UP */
   /* input-side extents (the tensor the A operand is read from).  2-D: n = frames, d = 1. */
   int n, d, h, w;
-  int n_src; /* 1 or 2: torch.cat([src0, src1], dim=1) folded into the K loop */
-  fo_src_t src[2];
+  int n_src; /* 1..6: torch.cat([src0, src1, ...], dim=1) folded into the K loop (the hi|lo verification mode lists
+                each tensor three times: hi, lo, hi -- see split_out) */
+  fo_src_t src[6];
   int cout; /* logical output channels (N of the GEMM) */
   /* packed weights produced by fo_conv_pack_weights for the SAME descriptor */
   const void* wpacked;
@@ -81,6 +82,12 @@ typedef struct {
   int out_cs;             /* storage channels of the channels-last outputs */
   int out_f32_nchw;
   int relu_f32;
+  /* Verification mode (tests only): every bf16 tensor of the epilogue (mask, addend, out_bf16, out_relu) holds an fp32
+   * value as a pair of bf16 numbers, hi = bf16(v) in channels [0, out_cs/2) and lo = bf16(v - hi) in [out_cs/2, out_cs).
+   * Together with sources listed as (hi, lo, hi) against weights packed as (w_hi, w_hi, w_lo) the SAME kernels compute
+   * the convolution to ~2^-16 relative accuracy, which lets parity tests compare gradients with an fp64 CPU restatement at 1e-4
+   * instead of the bf16 tolerance.  0 = off (the product path). */
+  int split_out;
 } fo_conv_t;
 
 /* Bytes of packed-weight workspace needed for this descriptor. */
@@ -194,6 +201,24 @@ int fo_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, 
 /* Gradient wrt f0: d_f0 (bf16, same layout), scaled by g[n] (fp32 per image), masked by f0 > 0 (ReLU tap). */
 int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c, void* d_f0,
                      const void* addend, fo_stream_t stream);
+/* Verification mode (tests only; see fo_conv_t.split_out): the same two kernels on hi|lo pair tensors [n, hw, 2c]
+ * (feature = hi + lo; d_f0 and addend are pairs too). */
+int fo_lpips_tap_split(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out,
+                       fo_stream_t stream);
+int fo_lpips_tap_bwd_split(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
+                           void* d_f0, const void* addend, fo_stream_t stream);
+/* Verification mode helpers: fp32 <-> hi|lo bf16 pairs (out / in: bf16 channels-last [n*hw, 2*cp], hi in [0, cp), lo in
+ * [cp, 2cp)).  Element (n, ch, p) of the fp32 tensor is x[n*sn + ch*sc + p*sp] (NCHW: sn = C*hw, sc = hw, sp = 1;
+ * channels-last: sn = hw*Cs, sc = 1, sp = Cs).  fp32 channels-last 2x2/2 max pool + gradient (first maximum wins, ReLU
+ * gate x > 0 fused like fo_maxpool2_bwd) for the LPIPS trunk in that mode. */
+int fo_split_f32(const float* x, int n, int c, int hw, long long sn, long long sc, long long sp, void* out, int cp,
+                 fo_stream_t stream);
+int fo_merge_f32(const void* in, int n, int c, int hw, int cp, float* out, long long sn, long long sc, long long sp,
+                 fo_stream_t stream);
+int fo_maxpool2_f32(const float* x, float* y, int n, int h, int w, int c, fo_stream_t stream);
+int fo_maxpool2_bwd_f32(const float* x, const float* y, const float* dy, float* dx, int n, int h, int w, int c,
+                        fo_stream_t stream);
+
 /* Reconstruction loss (reference train_faceoff_perceptual.py:38-40: nn.MSELoss()(out[:, :3], gt)).
  * fo_mse: *sum_out += sum((a[:, :c] - b)^2) over NCHW fp32 a [n, ca, hw] and b [n, c, hw] (hw % 4 == 0); the caller
  * zeroes sum_out and divides by n*c*hw.

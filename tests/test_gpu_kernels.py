@@ -1,0 +1,225 @@
+"""Isolated GPU tests of the non-GEMM kernels against a torch fp64 restatement on IDENTICAL (bf16-representable) inputs,
+so that the bf16 storage of the surrounding conv stack cannot hide an error (run on the B200 box: ``pytest -m gpu``).
+
+fp32-accumulating reductions: rtol 1e-5.  bf16 outputs: at most one bf16 rounding (2^-8 relative) away from the fp64 value.
+Index / routing work (max-pool, gather): bit-exact.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+SWEEP = [(64, 512), (64, 1024), (64, 2048), (128, 512), (128, 1024), (128, 2048)]   # BASELINE configs[3]
+
+
+def _bf16(*shape, gen, scale=1.0, relu=False):
+    x = torch.randn(*shape, generator=gen) * scale
+    if relu:
+        x = x.relu()
+    return x.bfloat16()
+
+
+def _one_ulp_close(got_bf16, ref64, extra=0.0):
+    """|got - ref| <= one bf16 rounding of ref (2^-8 relative) + extra absolute slack."""
+    got = got_bf16.double().cpu()
+    tol = ref64.abs() * 2.0 ** -8 + extra
+    bad = (got - ref64).abs() > tol
+    assert not bad.any(), f"{bad.sum().item()} elements off by more than one bf16 rounding; worst " \
+                          f"{((got - ref64).abs() / (ref64.abs() + 1e-30)).max().item():.3e}"
+
+
+# ------------------------------------------------------------------------------------------------ LPIPS head
+def _lpips_tap_ref(f0, f1, w):
+    """models/lpips.py:80-93,155-161 for one tap: normalise (eps outside the sqrt), squared diff, 1x1 lin, spatial mean."""
+    def nrm(x):
+        return x / (x.pow(2).sum(-1, keepdim=True).sqrt() + 1e-10)
+    d = (nrm(f0) - nrm(f1)).pow(2)
+    return (d * w).sum(-1).mean((1, 2))
+
+
+@pytest.mark.parametrize("n,h,w,c", [(3, 16, 16, 64), (2, 8, 8, 128), (2, 8, 4, 256), (1, 4, 4, 512), (5, 2, 2, 512)])
+def test_lpips_tap_forward_and_backward(n, h, w, c):
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(c + n)
+    f0 = _bf16(n, h, w, c, gen=gen, relu=True)
+    f1 = _bf16(n, h, w, c, gen=gen, relu=True)
+    f0[0, 0, 0] = 0          # an all-zero feature vector: the eps-outside-the-sqrt path
+    lw = torch.rand(c, generator=gen) * 0.1
+    g = torch.randn(n, generator=gen)
+    add = _bf16(n, h, w, c, gen=gen, scale=0.01)
+    out = torch.zeros(n, device="cuda")
+    out += 0.25                                  # the kernel accumulates into out (five taps share it)
+    ops.lpips_tap(f0.cuda(), f1.cuda(), lw.cuda(), out)
+    a = f0.double().requires_grad_(True)
+    ref = _lpips_tap_ref(a, f1.double(), lw.double())
+    torch.testing.assert_close(out.cpu().double() - 0.25, ref.detach(), rtol=1e-5, atol=1e-7)
+    (ref * g.double()).sum().backward()
+    # The kernel returns the gradient w.r.t. the PRE-ReLU activation of the tap (gate f0 > 0; the pool gradient passed as
+    # ``addend`` goes through the same gate).  At an all-zero feature vector torch's autograd of sqrt gives NaN (0/0); the
+    # kernel defines that gradient as 0.
+    zero_pix = (f0.double().pow(2).sum(-1, keepdim=True) == 0)
+    assert zero_pix.any() and torch.isnan(a.grad[zero_pix.expand_as(a.grad)]).all()
+    gate = (f0.double() > 0)
+    for addend in (None, add):
+        d = ops.lpips_tap_bwd(f0.cuda(), f1.cuda(), lw.cuda(), g.cuda(), None if addend is None else addend.cuda())
+        want = torch.where(gate, torch.nan_to_num(a.grad) + (0 if addend is None else addend.double()),
+                           torch.zeros((), dtype=torch.float64))
+        assert torch.isfinite(d.float()).all()
+        _one_ulp_close(d, want, extra=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ pooling / layout
+@pytest.mark.parametrize("n,h,w,cs", [(2, 8, 8, 64), (1, 4, 6, 128), (3, 2, 2, 16)])
+def test_maxpool2_and_backward_bit_exact(n, h, w, cs):
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(h * w)
+    x = _bf16(n, h, w, cs, gen=gen, relu=True)      # post-ReLU input: plenty of exact ties at 0
+    dy = _bf16(n, h // 2, w // 2, cs, gen=gen)
+    y = ops.maxpool2(x.cuda())
+    xr = x.float().permute(0, 3, 1, 2).requires_grad_(True)
+    yr = F.max_pool2d(xr, 2, 2)
+    assert torch.equal(y.float().cpu(), yr.detach().permute(0, 2, 3, 1))
+    yr.backward(dy.float().permute(0, 3, 1, 2))
+    # the kernel fuses the ReLU gate of the (post-ReLU) pool input: dx is the gradient w.r.t. the PRE-ReLU value, i.e.
+    # torch's routing (first maximum of the window wins) times (x > 0)
+    want = xr.grad.permute(0, 2, 3, 1) * (x.float() > 0)
+    dx = ops.maxpool2_bwd(x.cuda(), y, dy.cuda())
+    assert torch.equal(dx.float().cpu(), want), "max-pool gradient routing (first maximum wins) + ReLU gate"
+
+
+@pytest.mark.parametrize("n,c,hi,wi", [(2, 6, 8, 8), (1, 3, 4, 16), (1, 8, 2, 2)])
+def test_col2im4x4s2_matches_conv_transpose_scatter(n, c, hi, wi):
+    """col[n,iy,ix,(ky*4+kx)*8+co] scattered to out[n,co,2iy-1+ky,2ix-1+kx] (+bias) == F.fold of the same columns."""
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(wi)
+    col = _bf16(n, hi, wi, 128, gen=gen)
+    bias = torch.randn(c, generator=gen)
+    out = ops.col2im4x4s2(col.cuda(), bias.cuda(), c)
+    cols = col.double().view(n, hi * wi, 16, 8)[..., :c]                     # [n, L, taps, co]
+    cols = cols.permute(0, 3, 2, 1).reshape(n, c * 16, hi * wi)               # fold wants [n, co*taps, L]
+    ref = F.fold(cols, (2 * hi, 2 * wi), kernel_size=4, stride=2, padding=1) + bias.double().view(1, c, 1, 1)
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,c,h,w", [(2, 6, 16, 16), (1, 3, 8, 32)])
+def test_im2col4x4s2_matches_unfold(n, c, h, w):
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(h)
+    x = torch.randn(n, c, h, w, generator=gen)
+    col = ops.im2col4x4s2(x.cuda(), c).float().cpu()                          # [n, h/2, w/2, 16 taps x 8]
+    ref = F.unfold(x.bfloat16().float(), kernel_size=4, stride=2, padding=1)  # [n, c*16, L]
+    ref = ref.view(n, c, 16, (h // 2) * (w // 2)).permute(0, 3, 2, 1)         # [n, L, taps, c]
+    got = col.view(n, (h // 2) * (w // 2), 16, 8)
+    assert torch.equal(got[..., :c], ref) and got[..., c:].abs().max().item() == 0.0
+
+
+def test_im2col3x3_with_scaling_layer():
+    """First VGG conv operand: (x - shift) / scale folded into the column matrix (models/lpips.py:96-103)."""
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(2)
+    x = torch.rand(2, 3, 8, 12, generator=gen) * 2 - 1
+    shift = torch.tensor([-.030, -.088, -.188])
+    scale = torch.tensor([.458, .448, .450])
+    col = ops.im2col3x3(x.cuda(), shift.cuda(), scale.cuda()).float().cpu()   # [n, h, w, 32]; k = (ky*3+kx)*3 + ch
+    xs = (x - shift.view(1, 3, 1, 1)) / scale.view(1, 3, 1, 1)
+    ref = F.unfold(xs, kernel_size=3, padding=1).view(2, 3, 9, 8 * 12).permute(0, 3, 2, 1).reshape(2, 8, 12, 27)
+    torch.testing.assert_close(col[..., :27], ref.bfloat16().float(), rtol=2.0 ** -7, atol=1e-6)
+    assert col[..., 27:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("rows,cs,c_off,c", [(4096, 128, 0, 128), (1000, 192, 64, 64), (7, 32, 0, 6), (70000, 64, 0, 64)])
+def test_colsum_bias_gradient(rows, cs, c_off, c):
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(rows)
+    x = _bf16(rows, cs, gen=gen)
+    out = torch.full((c,), 3.0, device="cuda")
+    ops.colsum(x.cuda().view(rows, 1, 1, cs), c, out, c_off=c_off, accumulate=True)
+    ref = x.double()[:, c_off:c_off + c].sum(0) + 3.0
+    torch.testing.assert_close(out.cpu().double(), ref, rtol=1e-5, atol=1e-4)
+    ops.colsum(x.cuda().view(rows, 1, 1, cs), c, out, c_off=c_off, accumulate=False)
+    torch.testing.assert_close(out.cpu().double(), ref - 3.0, rtol=1e-5, atol=1e-4)
+
+
+def test_pack_unpack_nchw_roundtrip():
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(0)
+    x = torch.randn(3, 6, 8, 8, generator=gen)
+    p = ops.pack_nchw(x.cuda())
+    assert p.shape == (3, 8, 8, 16) and p[..., 6:].abs().max().item() == 0
+    assert torch.equal(p[..., :6].float().cpu(), x.bfloat16().float().permute(0, 2, 3, 1))
+    assert torch.equal(ops.unpack_nchw(p, 6).cpu(), x.bfloat16().float())
+
+
+# ------------------------------------------------------------------------------------------------ quantiser sweep
+@pytest.mark.parametrize("dim,n_embed", SWEEP)
+def test_vq_assign_bit_exact_on_the_codebook_sweep(dim, n_embed):
+    """BASELINE configs[3]: every (embed_dim, n_embed) of the sweep, indices == fp64 argmin (first minimum)."""
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(dim + n_embed)
+    rows = 40000
+    x = torch.randn(rows, dim, generator=gen)
+    e = torch.randn(dim, n_embed, generator=gen)
+    e_split, e_t, e_n2 = ops.vq_prep(e.cuda())
+    ind = ops.vq_assign(x.cuda(), e_t, e_split, e_n2).cpu()
+    d = x.double().pow(2).sum(1, keepdim=True) - 2 * x.double() @ e.double() + e.double().pow(2).sum(0, keepdim=True)
+    assert torch.equal(ind, d.argmin(1))
+
+
+@pytest.mark.parametrize("dim,n_embed", SWEEP)
+@pytest.mark.parametrize("skew", [False, True])
+def test_vq_gather_stats_ema_backward_on_the_codebook_sweep(dim, n_embed, skew):
+    """gather + straight-through + diff + EMA statistics + EMA update + backward vs the oracle (fp32 path: rtol 1e-5),
+    on every sweep shape (shared-memory and global-atomic variants), uniform and collapsed (3 hot codes) assignments."""
+    from faceoff_b200 import ops
+    from oracle import faceoff_oracle as O
+
+    gen = torch.Generator().manual_seed(dim * 3 + n_embed)
+    rows = 20000
+    x = torch.randn(rows, dim, generator=gen)
+    e = torch.randn(dim, n_embed, generator=gen)
+    ind = torch.randint(0, 3 if skew else n_embed, (rows,), generator=gen)
+    cs0 = torch.rand(n_embed, generator=gen) * 5
+    ea0 = e * cs0 + 0.1 * torch.randn(dim, n_embed, generator=gen)
+    xs, inds = x.cuda(), ind.cuda()
+    e_t = e.t().contiguous().cuda()
+    diff_sum = torch.zeros(1, device="cuda")
+    counts = torch.zeros(n_embed, device="cuda")
+    esum = torch.zeros(dim, n_embed, device="cuda")
+    q32, q16 = ops.vq_gather_stats(xs, inds, e_t, diff_sum, counts, esum, want_f32=True, want_bf16=True)
+    qref = e.t()[ind]
+    st = x + (qref - x)                                             # :78, evaluated in fp32 like the reference
+    assert torch.equal(q32.cpu(), st)
+    assert torch.equal(q16.float().cpu(), st.bfloat16().float())
+    torch.testing.assert_close(diff_sum.cpu().double() / x.numel(), (qref.double() - x.double()).pow(2).mean().reshape(1),
+                               rtol=1e-5, atol=1e-9)
+    c_ref, s_ref = O.quantize_stats(x.double(), ind, n_embed)
+    assert torch.equal(counts.cpu().double(), c_ref), "counts are exact integers"
+    # fp32 accumulation (any order) of n terms: |err| <= ~eps * sum|x_i|; the reference's fp32 matmul (:61) has the same bound
+    abs_sum = (F.one_hot(ind, n_embed).double().t() @ x.double().abs()).t()
+    err = (esum.cpu().double() - s_ref).abs()
+    assert (err <= 1e-5 * s_ref.abs() + 3e-7 * abs_sum + 1e-6).all(), f"embed_sum worst err {err.max().item():.3e}"
+    # EMA with the (exact) fp64 statistics rounded to fp32
+    emb, cs, ea = e.clone().cuda(), cs0.clone().cuda(), ea0.clone().cuda()
+    ops.vq_ema(emb, cs, ea, c_ref.float().cuda(), s_ref.float().cuda(), 0.99, 1e-5)
+    e1, c1, a1 = O.quantize_ema(e.double(), cs0.double(), ea0.double(), c_ref, s_ref, 0.99, 1e-5)
+    torch.testing.assert_close(cs.cpu().double(), c1, rtol=1e-5, atol=1e-7)
+    # a1 = 0.99 ea0 + 0.01 s may cancel: the fp32 rounding is relative to the two terms, not to their sum
+    mag = 0.99 * ea0.double().abs() + 0.01 * s_ref.abs()
+    assert ((ea.cpu().double() - a1).abs() <= 1e-5 * a1.abs() + 2e-7 * mag + 1e-9).all()
+    csn = (c1 + 1e-5) / (c1.sum() + n_embed * 1e-5) * c1.sum()
+    assert ((emb.cpu().double() - e1).abs() <= 2e-5 * e1.abs() + 4e-7 * mag / csn + 1e-9).all()
+    # backward: gx = g_q + g_diff * 2 (x - q) / numel   (autograd of :77-78)
+    gq = torch.randn(rows, dim, generator=gen)
+    gd = torch.tensor([0.7])
+    g32, _ = ops.vq_backward(gq.cuda(), 0, gd.cuda(), xs, inds, e_t)
+    gref = gq.double() + 0.7 * 2 * (x.double() - qref.double()) / x.numel()
+    torch.testing.assert_close(g32.cpu().double(), gref, rtol=1e-5, atol=1e-9)
