@@ -838,9 +838,10 @@ extern "C" int fo_vq_gather_stats(const float* x, const int64_t* embed_ind, size
   return FO_OK;
 }
 extern "C" int fo_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts,
-                         const float* embed_sum, int dim, int n_embed, float decay, float eps, fo_stream_t stream) {
+                         const float* embed_sum, int dim, int n_embed, float decay, float one_minus_decay, float eps,
+                         fo_stream_t stream) {
   REQUIRE_INIT();
-  CUDA_TRY(launch_vq_ema(embed, cluster_size, embed_avg, counts, embed_sum, dim, n_embed, decay, eps,
+  CUDA_TRY(launch_vq_ema(embed, cluster_size, embed_avg, counts, embed_sum, dim, n_embed, decay, one_minus_decay, eps,
                          (cudaStream_t)stream));
   return FO_OK;
 }

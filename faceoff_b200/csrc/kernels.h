@@ -78,7 +78,8 @@ cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t ro
                                    const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
                                    float* embed_sum, int num_sms, cudaStream_t st);
 cudaError_t launch_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts,
-                          const float* embed_sum, int dim, int n_embed, float decay, float eps, cudaStream_t st);
+                          const float* embed_sum, int dim, int n_embed, float decay, float one_minus_decay, float eps,
+                          cudaStream_t st);
 cudaError_t launch_vq_backward(const void* g_q, int g_q_is_bf16, int g_cs, int g_c_off, const float* g_diff,
                                const float* x, const int64_t* ind, const float* e_t, size_t rows, int dim,
                                int n_embed, float* gx_f32, void* gx_bf16, int num_sms, cudaStream_t st);

@@ -784,12 +784,12 @@ cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t ro
 // =============================================================================== EMA (:66-75)
 __global__ void vq_ema_kernel(float* __restrict__ embed, float* __restrict__ cluster_size, float* __restrict__ embed_avg,
                               const float* __restrict__ counts, const float* __restrict__ embed_sum, int dim,
-                              int n_embed, float decay, float eps) {
+                              int n_embed, float decay, float omd, float eps) {
   __shared__ float red[32];
   __shared__ float n_total;
   float part = 0.f;
   for (int k = threadIdx.x; k < n_embed; k += blockDim.x) {
-    const float cs = cluster_size[k] * decay + counts[k] * (1.f - decay);
+    const float cs = cluster_size[k] * decay + counts[k] * omd;
     cluster_size[k] = cs;
     part += cs;
   }
@@ -806,15 +806,17 @@ __global__ void vq_ema_kernel(float* __restrict__ embed, float* __restrict__ clu
   const float denom = n + n_embed * eps;
   for (int i = threadIdx.x; i < dim * n_embed; i += blockDim.x) {
     const int k = i % n_embed;
-    const float ea = embed_avg[i] * decay + embed_sum[i] * (1.f - decay);
+    const float ea = embed_avg[i] * decay + embed_sum[i] * omd;
     embed_avg[i] = ea;
     const float cs = (cluster_size[k] + eps) / denom * n;
     embed[i] = ea / cs;
   }
 }
 cudaError_t launch_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts,
-                          const float* embed_sum, int dim, int n_embed, float decay, float eps, cudaStream_t st) {
-  vq_ema_kernel<<<1, 1024, 0, st>>>(embed, cluster_size, embed_avg, counts, embed_sum, dim, n_embed, decay, eps);
+                          const float* embed_sum, int dim, int n_embed, float decay, float one_minus_decay, float eps,
+                          cudaStream_t st) {
+  vq_ema_kernel<<<1, 1024, 0, st>>>(embed, cluster_size, embed_avg, counts, embed_sum, dim, n_embed, decay,
+                                    one_minus_decay, eps);
   return cudaGetLastError();
 }
 

@@ -16,7 +16,7 @@ from torch import nn
 from . import ops
 from .graph import FORM_S1, FORM_S1_DGRAD, Node, Tape, View, conv_op
 from ._lib import FaceoffB200Error
-from .vqvae import _GraphFn, _params_of
+from .vqvae import _params_of, apply_graph
 
 _VGG_CFG = [64, 64, "M", 128, 128, "M", 256, 256, 256, "M", 512, 512, 512, "M", 512, 512, 512]
 _SLICE_ENDS = [4, 9, 16, 23, 30]  # reference models/lpips.py:127-136
@@ -167,7 +167,7 @@ class vgg16(nn.Module):
             return outs, {"seed": seed, "input_grad": input_grad}
 
         ps = _params_of(self)
-        outs = _GraphFn.apply(runner, X, tuple(ps.keys()), *ps.values())
+        outs = apply_graph(runner, X, tuple(ps.keys()), ps.values())
         vgg_outputs = namedtuple("VggOutputs", ["relu1_2", "relu2_2", "relu3_3", "relu4_3", "relu5_3"])
         return vgg_outputs(*outs)
 
@@ -355,7 +355,7 @@ class LPIPS(nn.Module):
             return (val.view(n, 1, 1, 1),), {"seed": seed, "input_grad": input_grad}
 
         ps = _params_of(self)
-        return _GraphFn.apply(runner, diff_side, tuple(ps.keys()), *ps.values())[0]
+        return apply_graph(runner, diff_side, tuple(ps.keys()), ps.values())[0]
 
 
 class VQLPIPS(nn.Module):

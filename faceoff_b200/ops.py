@@ -564,7 +564,7 @@ def vq_ema(embed, cluster_size, embed_avg, counts, embed_sum, decay: float, eps:
     lib = L.load()
     dim, n_embed = embed.shape
     L.check(lib.fo_vq_ema(embed.data_ptr(), cluster_size.data_ptr(), embed_avg.data_ptr(), counts.data_ptr(),
-                          embed_sum.data_ptr(), dim, n_embed, decay, eps, _stream()), "fo_vq_ema")
+                          embed_sum.data_ptr(), dim, n_embed, decay, 1 - decay, eps, _stream()), "fo_vq_ema")
     _count(1)
 
 

@@ -130,8 +130,9 @@ class _GraphFn(torch.autograd.Function):
     """One autograd node for a whole sub-graph executed through the tape."""
 
     @staticmethod
-    def forward(ctx, runner, inp, names, *params):
-        need_grad = any(ctx.needs_input_grad)
+    def forward(ctx, runner, inp, names, grad_mode, *params):
+        # needs_input_grad ignores torch.no_grad(), and grad mode is always off inside forward: the caller passes it in
+        need_grad = grad_mode and any(ctx.needs_input_grad)
         tape = Tape(dict(zip(names, params)), need_grad)
         outs, state = runner(tape, inp.detach())
         ctx.tape, ctx.state, ctx.names = tape, state, names
@@ -165,13 +166,18 @@ class _GraphFn(torch.autograd.Function):
         else:
             grads = tuple(tape.grads.get(n) for n in ctx.names)
         ctx.tape = ctx.state = None
-        return (None, gi, None) + grads
+        return (None, gi, None, None) + grads
+
+
+def apply_graph(runner, inp: torch.Tensor, names, params):
+    """Run ``runner`` as ONE autograd node; the tape records a backward only when autograd is enabled right now."""
+    return _GraphFn.apply(runner, inp, names, torch.is_grad_enabled(), *params)
 
 
 def _run_graph(module: nn.Module, runner, inp: torch.Tensor):
     ps = _params_of(module)
     names = tuple(ps.keys())
-    return _GraphFn.apply(runner, inp, names, *ps.values())
+    return apply_graph(runner, inp, names, ps.values())
 
 
 def _io_wrap(build, c_in: int, c_out_fn):
@@ -545,7 +551,7 @@ class VQVAE(nn.Module):
 
 def _run_vqvae(model: VQVAE, runner, x4: torch.Tensor):
     ps = _params_of(model)
-    return _GraphFn.apply(runner, x4, tuple(ps.keys()), *ps.values())
+    return apply_graph(runner, x4, tuple(ps.keys()), ps.values())
 
 
 def _conv1x1_module(m: nn.Conv2d, x: torch.Tensor) -> torch.Tensor:
@@ -570,4 +576,4 @@ def _convT_module(m: nn.ConvTranspose2d, x: torch.Tensor) -> torch.Tensor:
 def _run_graph_named(m: nn.Module, build, cin: int, x: torch.Tensor):
     ps = {"." + k: v for k, v in m.named_parameters()}
     names = tuple(ps.keys())
-    return _GraphFn.apply(_io_wrap(build, cin, None), x, names, *ps.values())[0]
+    return apply_graph(_io_wrap(build, cin, None), x, names, ps.values())[0]

@@ -184,9 +184,10 @@ int fo_vq_gather_stats(const float* x, const int64_t* embed_ind, size_t rows, in
                        const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
                        float* embed_sum, fo_stream_t stream);
 /* EMA update + renormalisation (:66-75), in place on the three buffers; counts / embed_sum are the
- * (all-reduced) statistics. */
+ * (all-reduced) statistics.  one_minus_decay is passed separately because the reference forms ``alpha = 1 - decay`` in
+ * double precision before rounding it to fp32 (1.f - 0.99f differs from (float)0.01 by 1e-6 relative). */
 int fo_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts, const float* embed_sum,
-              int dim, int n_embed, float decay, float eps, fo_stream_t stream);
+              int dim, int n_embed, float decay, float one_minus_decay, float eps, fo_stream_t stream);
 /* Backward of :77-78: gx = g_q + g_diff * 2 (x - q) / (rows*dim).  g_q fp32 or bf16 (g_q_is_bf16). */
 int fo_vq_backward(const void* g_q, int g_q_is_bf16, int g_cs, int g_c_off, const float* g_diff, const float* x,
                    const int64_t* embed_ind, const float* e_t, size_t rows, int dim, int n_embed, float* gx_f32,

@@ -187,6 +187,42 @@ def quantize_forward(inp: Tensor, embed: Tensor, cluster_size: Tensor, embed_avg
 # ----------------------------------------------------------------------------------------------
 
 
+# Optional probe (tests only): when RELU_PROBE is a list, every ReLU appends (min |x|, max |x|, numel) of its input.  A test
+# that compares GRADIENTS tightly uses it to know how close the nearest pre-activation is to the (discontinuous) gate.
+RELU_PROBE = None
+# Optional hooks (tests only): callables ``hook(x) -> tensor | None`` that may replace relu(x) / max_pool2d(x, 2, 2) by
+# the SAME piecewise-linear branch another run took (gates / pooling winners given), see tests/gate_consistent.py.  ReLU and
+# max-pool are discontinuous in their gradients: a pre-activation within the forward rounding error of zero (or a pooling
+# window whose two largest values are that close) legitimately sends the gradient elsewhere, which no finite-precision
+# implementation -- the reference's own fp32 included -- can reproduce bit for bit.
+RELU_HOOK = None
+MAXPOOL_HOOK = None
+
+
+def _relu(x):
+    if RELU_PROBE is not None:
+        a = x.detach().abs()
+        RELU_PROBE.append((a.min().item(), a.max().item(), a.numel()))
+    if RELU_HOOK is not None:
+        y = RELU_HOOK(x)
+        if y is not None:
+            return y
+    return F.relu(x)
+
+
+def _maxpool2(x):
+    if MAXPOOL_HOOK is not None:
+        y = MAXPOOL_HOOK(x)
+        if y is not None:
+            return y
+    return F.max_pool2d(x, 2, 2)
+
+
+def relu_margin(probe):
+    """Smallest |pre-activation| / max |pre-activation| over the probed ReLU inputs."""
+    return min(mn / mx for mn, mx, _ in probe) if probe else float("inf")
+
+
 def _c2(p, name, x, stride=1, padding=0):
     return F.conv2d(x, p[name + ".weight"], p[name + ".bias"], stride=stride, padding=padding)
 
@@ -197,9 +233,9 @@ def _ct2(p, name, x):
 
 def resblock(p, prefix, x):
     """ResBlock :86-101 -- ReLU, conv3x3 C->r, ReLU, conv1x1 r->C, += input."""
-    h = F.relu(x)
+    h = _relu(x)
     h = _c2(p, prefix + ".conv.1", h, padding=1)
-    h = F.relu(h)
+    h = _relu(h)
     h = _c2(p, prefix + ".conv.3", h)
     return h + x
 
@@ -207,17 +243,17 @@ def resblock(p, prefix, x):
 def encoder(p, prefix, x, stride, n_res_block=2):
     """Encoder :103-131."""
     if stride == 4:
-        x = F.relu(_c2(p, prefix + ".blocks.0", x, 2, 1))
-        x = F.relu(_c2(p, prefix + ".blocks.2", x, 2, 1))
+        x = _relu(_c2(p, prefix + ".blocks.0", x, 2, 1))
+        x = _relu(_c2(p, prefix + ".blocks.2", x, 2, 1))
         x = _c2(p, prefix + ".blocks.4", x, 1, 1)
         start = 5
     else:
-        x = F.relu(_c2(p, prefix + ".blocks.0", x, 2, 1))
+        x = _relu(_c2(p, prefix + ".blocks.0", x, 2, 1))
         x = _c2(p, prefix + ".blocks.2", x, 1, 1)
         start = 3
     for i in range(n_res_block):
         x = resblock(p, f"{prefix}.blocks.{start + i}", x)
-    return F.relu(x)
+    return _relu(x)
 
 
 def decoder(p, prefix, x, stride, n_res_block=2):
@@ -225,10 +261,10 @@ def decoder(p, prefix, x, stride, n_res_block=2):
     x = _c2(p, prefix + ".blocks.0", x, 1, 1)
     for i in range(n_res_block):
         x = resblock(p, f"{prefix}.blocks.{1 + i}", x)
-    x = F.relu(x)
+    x = _relu(x)
     x = _ct2(p, f"{prefix}.blocks.{2 + n_res_block}", x)
     if stride == 4:
-        x = _ct2(p, f"{prefix}.blocks.{4 + n_res_block}", F.relu(x))
+        x = _ct2(p, f"{prefix}.blocks.{4 + n_res_block}", _relu(x))
     return x
 
 
@@ -237,7 +273,7 @@ def conv3d_postnet(p, prefix, x):
     for i in range(3):
         x = F.conv3d(x, p[f"{prefix}.conv3d.{i}.0.weight"], p[f"{prefix}.conv3d.{i}.0.bias"], padding=1)
         if i < 2:
-            x = F.relu(x)
+            x = _relu(x)
     return x
 
 
@@ -297,11 +333,11 @@ def vgg_taps(p: Dict[str, Tensor], x: Tensor):
     idx = 0
     for v in VGG_CFG:
         if v == "M":
-            x = F.max_pool2d(x, 2, 2)
+            x = _maxpool2(x)
             idx += 1
         else:
             k = _vgg_key(VGG_CONV_IDX[ci])
-            x = F.relu(F.conv2d(x, p[k + ".weight"], p[k + ".bias"], padding=1))
+            x = _relu(F.conv2d(x, p[k + ".weight"], p[k + ".bias"], padding=1))
             ci += 1
             idx += 2
         if idx in VGG_SLICE_ENDS:

@@ -6,10 +6,13 @@ Tolerances (BASELINE.json north_star): fp32 path (Quantize) rtol 1e-5, indices b
 (relative gap < 1e-6); bf16 conv path rtol 2e-2 / atol 1e-2, checked as max-normalised error per tensor.
 """
 import os
+import sys
 import warnings
 
 import pytest
 import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 
 pytestmark = pytest.mark.gpu
 
@@ -661,14 +664,95 @@ def test_full_size_clip_with_lpips_vs_oracle():
     assert worst < 0.1
 
 
+def maxnorm_err64(a, b):
+    return ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-300)).item()
+
+
+def _precise_module_check(mod, ref_fn, x, tol=5e-5):
+    """Stand-alone drop-in module under the verification mode vs its fp64 restatement on the same piecewise-linear branch
+    (tests/gate_consistent.py): output, input gradient and every parameter gradient, max-normalised; plus the per-launch
+    verifier (tests/op_verifier.py) on every tensor-core launch."""
+    from faceoff_b200 import ops
+    from gate_consistent import GateRecorder
+    from op_verifier import OpVerifier
+
+    mod = mod.cuda()
+    xc = x.cuda().requires_grad_(True)
+    with ops.precise_mode(), OpVerifier() as ver, GateRecorder() as rec:
+        y = mod(xc)
+        go = torch.randn(y.shape, generator=torch.Generator().manual_seed(1)).cuda()
+        y.backward(go)
+    torch.cuda.synchronize()
+    w_err, w_desc = ver.worst()
+    print(f"     per-launch verifier: {len(ver.records)} launches, worst {w_err:.1e} ({w_desc})")
+    p64 = {"m." + k: v.detach().cpu().double().requires_grad_(v.requires_grad) for k, v in mod.state_dict(keep_vars=True).items()}
+    x64 = x.double().requires_grad_(True)
+    rec.install()
+    try:
+        r = ref_fn(p64, x64)
+        r.backward(go.cpu().double())
+    finally:
+        rec.uninstall()
+    print("     " + rec.summary())
+    errs = {"out": maxnorm_err64(y.detach().cpu(), r.detach()), "dx": maxnorm_err64(xc.grad.cpu(), x64.grad)}
+    for k, v in mod.named_parameters():
+        errs[k] = maxnorm_err64(v.grad.cpu(), p64["m." + k].grad)
+    for k, e in errs.items():
+        print(f"     {k:28s} {e:.1e}{'   <-- BAD' if e > tol else ''}")
+    bad = {k: e for k, e in errs.items() if e > tol}
+    if w_err > tol:
+        bad["per-launch"] = (w_err, w_desc)
+    return bad
+
+
+def test_precise_mode_conv_layers_vs_fp64():
+    """Every convolution form of the hot path through the tensor-core kernels in the verification mode against fp64:
+    4x4 stride-2 (+its transposed form), 3x3 halo / 1x1 + residual (ResBlock), 3x3x3 Conv3d; fwd + dgrad + wgrad + bias
+    gradients at <= 5e-5 max-normalised (the bf16 product path can only be held to ~3e-2), per launch AND end to end."""
+    from faceoff_b200.vqvae import Conv3dLatentPostnet, Decoder, Encoder, ResBlock
+    from oracle import faceoff_oracle as O
+
+    gen = torch.Generator().manual_seed(0)
+    torch.manual_seed(0)
+    cases = [
+        ("ResBlock(128, 32)", ResBlock(128, 32), lambda p, x: O.resblock(p, "m", x), torch.randn(2, 128, 16, 16, generator=gen)),
+        ("Encoder(6, 128, 2, 32, stride 4)", Encoder(6, 128, 2, 32, 4), lambda p, x: O.encoder(p, "m", x, 4),
+         torch.rand(2, 6, 64, 64, generator=gen) * 2 - 1),
+        ("Encoder(128, 128, 2, 32, stride 2)", Encoder(128, 128, 2, 32, 2), lambda p, x: O.encoder(p, "m", x, 2),
+         torch.randn(2, 128, 16, 16, generator=gen)),
+        ("Encoder(128, 128, 0, 32, stride 2)", Encoder(128, 128, 0, 32, 2), lambda p, x: O.encoder(p, "m", x, 2, n_res_block=0),
+         torch.randn(2, 128, 16, 16, generator=gen)),
+        ("Decoder(64, 64, 128, 2, 32, stride 2)", Decoder(64, 64, 128, 2, 32, 2), lambda p, x: O.decoder(p, "m", x, 2),
+         torch.randn(2, 64, 8, 8, generator=gen)),
+        ("Decoder(128, 6, 128, 2, 32, stride 4)", Decoder(128, 6, 128, 2, 32, 4), lambda p, x: O.decoder(p, "m", x, 4),
+         torch.randn(2, 128, 16, 16, generator=gen)),
+        ("Conv3dLatentPostnet(128) 2x3x8x8", Conv3dLatentPostnet(128), lambda p, x: O.conv3d_postnet(p, "m", x),
+         torch.randn(2, 128, 3, 8, 8, generator=gen)),
+        ("Conv3dLatentPostnet(128) 1x4x16x16", Conv3dLatentPostnet(128), lambda p, x: O.conv3d_postnet(p, "m", x),
+         torch.randn(1, 128, 4, 16, 16, generator=gen)),
+    ]
+    bad = {}
+    for name, mod, ref, x in cases:
+        print(name)
+        b = _precise_module_check(mod, ref, x)
+        if b:
+            bad[name] = b
+    assert not bad, bad
+
+
 @pytest.mark.parametrize("tag", ["vqvae_1x4x64", "vqvae_2x3x64_lpips"])
 def test_precise_mode_every_gradient_vs_fp64_oracle(tag):
     """The verification mode (faceoff_b200.ops.precise_mode: activations as hi|lo bf16 pairs through the SAME planner and
-    tcgen05 kernels, 3 MMAs per product) against the oracle in fp64: EVERY parameter gradient max-normalised <= 1e-4,
-    printed next to the error of the reference's own fp32 arithmetic (|ref_fp32 - fp64|); losses, reconstruction and EMA
-    codebooks at 1e-5 / 1e-4; indices identical.  This is the check that discriminates: a wrong tap, a dropped residual
-    gradient or a mis-scaled bias gradient is orders of magnitude above 1e-4."""
+    tcgen05 kernels, 3 MMAs per product) against the oracle in fp64 on the golden training steps:
+      * forward: indices identical, losses rtol 1e-5 (LPIPS 1e-4), reconstruction max-normalised 1e-4, EMA codebooks 2e-5;
+      * every tensor-core launch verified in place against torch fp64 on its actual operands (<= 5e-5);
+      * EVERY parameter gradient max-normalised <= 1e-4 against the fp64 oracle evaluated on the same piecewise-linear
+        branch (audited ReLU gate / pooling-winner overrides, tests/gate_consistent.py), printed next to the plain
+        comparison and to the error of the reference's own fp32 arithmetic (|ref_fp32 - fp64|).
+    A wrong tap, a dropped residual gradient or a mis-scaled bias gradient is orders of magnitude above 1e-4."""
     from faceoff_b200 import ops
+    from gate_consistent import GateRecorder
+    from op_verifier import OpVerifier
     from oracle import faceoff_oracle as O
 
     g = _golden()[tag]
@@ -686,19 +770,28 @@ def test_precise_mode_every_gradient_vs_fp64_oracle(tag):
             vql = VQLPIPS()
         vql.load_state_dict({"perceptual_loss." + k: v for k, v in lp.items()}, strict=True)
         vql = vql.cuda()
-    with ops.precise_mode():
+    with ops.precise_mode(), OpVerifier() as ver, GateRecorder() as rec:
         dec, diff, id_t, id_b = model.forward_with_ids(img.cuda(), clips=cfg["n_clips"])
-        rec = dec[:, :3]
-        recon = torch.nn.functional.mse_loss(rec, gt.cuda())
+        rec_ = dec[:, :3]
+        recon = torch.nn.functional.mse_loss(rec_, gt.cuda())
         loss = recon + diff.mean()
         perc = None
         if vql is not None:
-            perc = vql(gt.cuda(), rec)
+            perc = vql(gt.cuda(), rec_)
             loss = loss + perc
         loss.backward()
     torch.cuda.synchronize()
+    w_err, w_desc = ver.worst()
+    print(f"{tag}: per-launch verifier: {len(ver.records)} tensor-core launches, worst {w_err:.1e} ({w_desc})")
+    assert w_err <= 5e-5, (w_err, w_desc)
     o64 = O.train_step(p, img, gt, n_clips=cfg["n_clips"], lp=lp, dtype=torch.float64)
     o32 = O.train_step(p, img, gt, n_clips=cfg["n_clips"], lp=lp, dtype=torch.float32)
+    rec.install()
+    try:
+        o64g = O.train_step(p, img, gt, n_clips=cfg["n_clips"], lp=lp, dtype=torch.float64)
+    finally:
+        rec.uninstall()
+    print(f"{tag}: " + rec.summary())
     assert torch.equal(id_t.cpu(), o64["id_t"]) and torch.equal(id_b.cpu(), o64["id_b"]), "indices differ from the fp64 oracle"
     assert torch.equal(id_t.cpu(), g["id_t"].long()) and torch.equal(id_b.cpu(), g["id_b"].long())
     rel = lambda a, b: abs(a - b) / abs(b)   # noqa: E731
@@ -709,25 +802,28 @@ def test_precise_mode_every_gradient_vs_fp64_oracle(tag):
         assert rel(perc.item(), o64["perceptual_loss"].item()) < 1e-4, (perc.item(), o64["perceptual_loss"].item())
     assert maxnorm_err(dec.detach().cpu().double(), o64["dec"]) < 1e-4
     worst = 0.0
+    print(f"  {'parameter':42s} |ours-fp64| same branch   |ours-fp64| plain   |ref_fp32-fp64|")
     for k, v in model.named_parameters():
-        ref = o64["grads"][k]
-        e_ours = ((v.grad.cpu().double() - ref).abs().max() / (ref.abs().max() + 1e-300)).item()
-        e_ref32 = ((o32["grads"][k].double() - ref).abs().max() / (ref.abs().max() + 1e-300)).item()
-        print(f"  {k:42s} |ours-fp64| {e_ours:.2e}   |ref_fp32-fp64| {e_ref32:.2e}")
-        worst = max(worst, e_ours)
-        assert e_ours <= 1e-4, (k, e_ours, e_ref32)
-    print(f"{tag}: worst max-normalised gradient error vs fp64: {worst:.2e}")
+        e_same = maxnorm_err64(v.grad.cpu(), o64g["grads"][k])
+        e_plain = maxnorm_err64(v.grad.cpu(), o64["grads"][k])
+        e_ref32 = maxnorm_err64(o32["grads"][k], o64["grads"][k])
+        print(f"  {k:42s} {e_same:.2e}                {e_plain:.2e}            {e_ref32:.2e}")
+        worst = max(worst, e_same)
+    print(f"{tag}: worst max-normalised gradient error vs the fp64 oracle (same branch): {worst:.2e}")
+    assert worst <= 1e-4
     for q in ("quantize_t", "quantize_b"):
         for i, name in enumerate(("embed", "cluster_size", "embed_avg")):
             got = getattr(getattr(model, q), name).cpu().double()
-            torch.testing.assert_close(got, o64["new_buffers"][q][i], rtol=2e-5, atol=1e-6)
+            # (embed_avg = 0.99 old + 0.01 sum can cancel: the fp32 rounding is relative to the terms, hence the atol)
+            torch.testing.assert_close(got, o64["new_buffers"][q][i], rtol=2e-5, atol=5e-6)
 
 
 def test_precise_mode_lpips_value_and_input_gradient():
-    """LPIPS alone in the verification mode: value rtol 1e-4, input gradient max-normalised 2e-3 vs the fp64 oracle (the
-    bf16 product path can only be held to cosine > 0.98 here, see test_lpips_matches_reference_golden)."""
+    """LPIPS alone in the verification mode: value rtol 1e-4, input gradient max-normalised 1e-4 vs the fp64 oracle on the
+    same branch (the bf16 product path can only be held to cosine > 0.98 here, see test_lpips_matches_reference_golden)."""
     from faceoff_b200 import ops
     from faceoff_b200.lpips import LPIPS
+    from gate_consistent import GateRecorder
     from oracle import faceoff_oracle as O
 
     g = _golden()["lpips_3x64"]
@@ -739,20 +835,32 @@ def test_precise_mode_lpips_value_and_input_gradient():
     m = m.cuda().eval()
     a = g["a"].cuda()
     b = g["b"].cuda().requires_grad_(True)
-    with ops.precise_mode():
+    with ops.precise_mode(), GateRecorder() as rec:
         val = m(a, b)
         val.mean().backward()
     torch.cuda.synchronize()
     lp64 = {k: v.double() for k, v in lp.items()}
-    b64 = g["b"].double().requires_grad_(True)
-    v64 = O.lpips_forward(lp64, g["a"].double(), b64)
-    v64.mean().backward()
-    torch.testing.assert_close(val.detach().cpu().double(), v64.detach(), rtol=1e-4, atol=1e-8)
-    e = maxnorm_err(b.grad.cpu().double(), b64.grad)
-    e32 = maxnorm_err(g["grad_b"].double(), b64.grad)
-    nw = ((b.grad.cpu().double() - b64.grad).norm() / b64.grad.norm()).item()
-    print(f"precise LPIPS: input-gradient max-normalised err {e:.2e} (reference fp32: {e32:.2e}), norm-wise {nw:.2e}")
-    assert e < 2e-3 and nw < 2e-3
+
+    def run64():
+        b64 = g["b"].double().requires_grad_(True)
+        v64 = O.lpips_forward(lp64, g["a"].double(), b64)
+        v64.mean().backward()
+        return v64.detach(), b64.grad
+
+    v_plain, g_plain = run64()
+    rec.install()
+    try:
+        v_same, g_same = run64()
+    finally:
+        rec.uninstall()
+    print("precise LPIPS: " + rec.summary())
+    torch.testing.assert_close(val.detach().cpu().double(), v_plain, rtol=1e-4, atol=1e-8)
+    e_same = maxnorm_err64(b.grad.cpu(), g_same)
+    e_plain = maxnorm_err64(b.grad.cpu(), g_plain)
+    e32 = maxnorm_err64(g["grad_b"], g_plain)
+    print(f"precise LPIPS: input-gradient max-normalised err same branch {e_same:.2e}, plain {e_plain:.2e} "
+          f"(reference fp32 vs fp64: {e32:.2e})")
+    assert e_same <= 1e-4
 
 
 def test_two_rank_data_parallel_matches_single_process():
