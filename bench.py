@@ -376,12 +376,17 @@ def run_ours(args):
         del m1, d1
         torch.cuda.empty_cache()
 
-    # ---------------- synthetic inputs (pinned host copies for the end-to-end leg) ----------------
+    # ---------------- synthetic inputs ----------------
+    # The loader's product is uint8 HWC frames (source face, background, ground truth: TemporalAlignment/dataset.py:235-249);
+    # the end-to-end leg ships THOSE over PCIe from pinned memory (9 bytes per pixel) and normalises / concatenates on the
+    # GPU (faceoff_b200.data.process_data_u8 == utils.process_data + ToTensor + Normalize, bit-exact), SURVEY 8(f4).
+    from faceoff_b200.data import process_data_u8
+
     g = torch.Generator().manual_seed(1234 + rank)
-    host_img = [torch.empty(F_, 6, args.res, args.res).uniform_(-1, 1, generator=g).pin_memory() for _ in range(2)]
-    host_gt = [torch.empty(F_, 3, args.res, args.res).uniform_(-1, 1, generator=g).pin_memory() for _ in range(2)]
-    img = host_img[0].to(dev)
-    gt = host_gt[0].to(dev)
+    host_u8 = [[torch.randint(0, 256, (F_, args.res, args.res, 3), generator=g, dtype=torch.uint8).pin_memory()
+                for _ in range(3)] for _ in range(2)]          # 2 batches x (source, background, ground truth)
+    img, _, gt = process_data_u8(*host_u8[0], device=dev)
+    torch.cuda.synchronize()
 
     def measure(lpips: bool, steps: int, warmup: int, sample_clocks: bool):
         """Device-resident timing + (optionally) the end-to-end leg of one configuration on a fresh model replica."""
@@ -422,7 +427,8 @@ def run_ours(args):
         # ---- end-to-end: host buffers in, loss out, copies inside the timed region ----
         if not args.no_e2e:
             copy_stream = torch.cuda.Stream(device=dev)
-            dbuf = [(torch.empty_like(img), torch.empty_like(gt)) for _ in range(2)]
+            dbuf = [[torch.empty_like(t, device=dev) for t in host_u8[0]] for _ in range(2)]
+            fbuf = (torch.empty_like(img), torch.empty_like(gt))       # normalised fp32 inputs of the running step
             ready = [torch.cuda.Event() for _ in range(2)]
             consumed = [torch.cuda.Event() for _ in range(2)]
 
@@ -430,8 +436,8 @@ def run_ours(args):
                 b = i % 2
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(consumed[b])
-                    dbuf[b][0].copy_(host_img[b], non_blocking=True)
-                    dbuf[b][1].copy_(host_gt[b], non_blocking=True)
+                    for d_, h_ in zip(dbuf[b], host_u8[b]):
+                        d_.copy_(h_, non_blocking=True)
                     ready[b].record(copy_stream)
 
             loss_host = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -445,8 +451,9 @@ def run_ours(args):
                         prefetch(i + 1)
                     b = i % 2
                     torch.cuda.current_stream().wait_event(ready[b])
-                    loss = step(dbuf[b][0], dbuf[b][1])
+                    img_d, _, gt_d = process_data_u8(*dbuf[b], out_img=fbuf[0], out_gt=fbuf[1])
                     consumed[b].record()
+                    loss = step(img_d, gt_d)
                     loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
                 torch.cuda.synchronize()
 
@@ -460,9 +467,11 @@ def run_ours(args):
             barrier()
             e_ms = max_over_ranks(e0.elapsed_time(e1))
             res["e2e"] = {"value": args.clips * steps / (e_ms / 1e3), "unit": "clips/s",
-                          "h2d_bytes_per_step": (host_img[0].numel() + host_gt[0].numel()) * 4 * world,
+                          "h2d_bytes_per_step": sum(t.numel() for t in host_u8[0]) * world,
+                          "input": "uint8 HWC frames (source, background, ground truth) from pinned memory; normalise + "
+                                   "concat on the GPU (process_data_u8)",
                           "d2h_bytes_per_step": 4 * world, "wall_s": time.perf_counter() - t0}
-            del dbuf
+            del dbuf, fbuf
         res["peak_mem_gb"] = torch.cuda.max_memory_allocated(dev) / 2 ** 30
         del model, net, step
         torch.cuda.empty_cache()

@@ -721,6 +721,16 @@ extern "C" int fo_unpack_nchw(const void* x, float* out, int n, int c, int hw, i
   CUDA_TRY(launch_unpack_nchw(x, out, n, c, hw, cs, (cudaStream_t)stream));
   return FO_OK;
 }
+extern "C" int fo_u8hwc_to_nchw(const void* x, float* out, int n, int hw, int c_total, int c_off, float mean, float stdv,
+                                fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (hw % 4 != 0 || c_off < 0 || c_off + 3 > c_total) return fail(FO_ERR_INVALID, "u8hwc_to_nchw: hw %% 4 == 0 and c_off + 3 <= c_total required");
+  if ((reinterpret_cast<uintptr_t>(x) & 3) != 0 || (reinterpret_cast<uintptr_t>(out) & 15) != 0)
+    return fail(FO_ERR_INVALID, "u8hwc_to_nchw: input must be 4-byte and output 16-byte aligned");
+  if ((size_t)n * hw == 0) return FO_OK;
+  CUDA_TRY(launch_u8hwc_to_nchw(x, out, n, hw, c_total, c_off, mean, stdv, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
 extern "C" int fo_relu(const void* x, void* y, size_t numel, fo_stream_t stream) {
   REQUIRE_INIT();
   if (numel % 8 != 0) return fail(FO_ERR_INVALID, "relu: numel must be a multiple of 8");

@@ -297,6 +297,31 @@ __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __
   }
 }
 
+// ---------------------------------------------------------------- uint8 frames -> normalised fp32 planes
+// The reference's loader turns each uint8 HWC frame into a tensor with torchvision's ToTensor (x / 255, HWC -> CHW) and
+// Normalize(0.5, 0.5) ((v - 0.5) / 0.5) on the CPU (TemporalAlignment/dataset.py:235-249) and concatenates source and
+// background on the channel axis (utils.py:29-38).  Here the uint8 frames cross PCIe (4x fewer bytes) and this kernel does
+// the same arithmetic, in the same order and rounding (IEEE division, subtraction, division), into channels
+// c_off..c_off+2 of an NCHW tensor [n, c_total, hw].  4 pixels (12 bytes) per thread, 16-byte stores per plane.
+__global__ void u8hwc_to_nchw_kernel(const uint32_t* __restrict__ x, float* __restrict__ out, int hw4, size_t total4,
+                                     int c_total, int c_off, float mean, float stdv) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t n = i / hw4, p4 = i % hw4;
+    const uint32_t w0 = __ldg(x + 3 * i), w1 = __ldg(x + 3 * i + 1), w2 = __ldg(x + 3 * i + 2);
+    // bytes: r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+    const uint32_t b[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
+                            w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                            w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+    float v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)b[k], 255.f), mean), stdv);
+    float* o = out + (n * c_total + c_off) * (size_t)hw4 * 4 + p4 * 4;
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch)
+      *reinterpret_cast<float4*>(o + (size_t)ch * hw4 * 4) = make_float4(v[ch], v[3 + ch], v[6 + ch], v[9 + ch]);
+  }
+}
+
 // ---------------------------------------------------------------- im2col / col2im for the 6-channel 4x4 stride-2 layers
 // The first Conv2d (6->64, k4 s2 p1) and the last ConvTranspose2d (64->6) have too few channels for an efficient
 // implicit GEMM (32-byte TMA rows, N=16 MMAs).  Their image-side operand is therefore laid out as an explicit
@@ -525,6 +550,13 @@ cudaError_t launch_adam(const void* table, const void* chunks, int n_chunks, flo
   return cudaGetLastError();
 }
 
+cudaError_t launch_u8hwc_to_nchw(const void* x, float* out, int n, int hw, int c_total, int c_off, float mean, float stdv,
+                                 int num_sms, cudaStream_t st) {
+  const size_t total4 = (size_t)n * (hw / 4);
+  u8hwc_to_nchw_kernel<<<grid_for(total4, 256, num_sms, 16), 256, 0, st>>>((const uint32_t*)x, out, hw / 4, total4, c_total,
+                                                                           c_off, mean, stdv);
+  return cudaGetLastError();
+}
 cudaError_t launch_relu(const void* x, void* y, size_t numel, int num_sms, cudaStream_t st) {
   const size_t nvec = numel / 8;
   relu_kernel<<<grid_for(nvec, 256, num_sms), 256, 0, st>>>((const uint4*)x, (uint4*)y, nvec);

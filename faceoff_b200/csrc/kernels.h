@@ -42,6 +42,8 @@ cudaError_t launch_pack_nchw(const float* x, void* out, int n, int c, int hw, in
                              const float* scale, int num_sms, cudaStream_t st);
 cudaError_t launch_unpack_nchw(const void* x, float* out, int n, int c, int hw, int cs, cudaStream_t st);
 cudaError_t launch_relu(const void* x, void* y, size_t numel, int num_sms, cudaStream_t st);
+cudaError_t launch_u8hwc_to_nchw(const void* x, float* out, int n, int hw, int c_total, int c_off, float mean, float stdv,
+                                 int num_sms, cudaStream_t st);
 cudaError_t launch_adam(const void* table, const void* chunks, int n_chunks, float lr, float beta1, float beta2,
                         float eps, float weight_decay, float bias_c1, float sqrt_bias_c2, float grad_scale, int num_sms,
                         cudaStream_t st);

@@ -455,6 +455,19 @@ def chansum_nchw(x: torch.Tensor, c: int, out: torch.Tensor, accumulate: bool = 
     _count(1)
 
 
+def u8hwc_to_nchw(x: torch.Tensor, out: torch.Tensor, c_off: int = 0, mean: float = 0.5, std: float = 0.5):
+    """uint8 frames [N, H, W, 3] -> out[:, c_off:c_off+3] = ((x / 255) - mean) / std, out fp32 NCHW [N, C, H, W]."""
+    lib = L.load()
+    assert x.dtype == torch.uint8 and x.is_cuda and x.is_contiguous() and x.dim() == 4 and x.shape[-1] == 3
+    n, h, w, _ = x.shape
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] == n and tuple(out.shape[2:]) == (h, w)
+    with _Timed("hbm/u8hwc_to_nchw", 15.0 * n * h * w):
+        L.check(lib.fo_u8hwc_to_nchw(x.data_ptr(), out.data_ptr(), n, h * w, out.shape[1], c_off, mean, std, _stream()),
+                "fo_u8hwc_to_nchw")
+    _count(1)
+    return out
+
+
 def relu(x: torch.Tensor) -> torch.Tensor:
     if PRECISE:
         c = x.shape[-1] // 2

@@ -132,6 +132,13 @@ int fo_pack_nchw(const float* x, void* out, int n, int c, int hw, int cs, const 
                  fo_stream_t stream);
 /* channels-last bf16 [n, hw, cs] -> NCHW fp32 [n, c, hw] */
 int fo_unpack_nchw(const void* x, float* out, int n, int c, int hw, int cs, fo_stream_t stream);
+/* Input pipeline on the GPU: uint8 HWC frames [n, hw, 3] -> channels c_off..c_off+2 of an fp32 NCHW tensor
+ * [n, c_total, hw] as ((x / 255) - mean) / std -- torchvision ToTensor + Normalize(0.5, 0.5) of the reference's loader
+ * (TemporalAlignment/dataset.py:235-249), bit-exact (IEEE fp32 division / subtraction in the same order); calling it for
+ * the source frames (c_off 0) and the background frames (c_off 3) of a 6-channel tensor is utils.process_data's
+ * torch.cat([source, background]) (utils.py:29-38).  hw must be a multiple of 4. */
+int fo_u8hwc_to_nchw(const void* x, float* out, int n, int hw, int c_total, int c_off, float mean, float stdv,
+                     fo_stream_t stream);
 /* y = relu(x) on bf16 */
 int fo_relu(const void* x, void* y, size_t numel, fo_stream_t stream);
 /* out[c] (+)= sum_rows x[row][c_off + c], x bf16 [rows, cs]  (bias gradients) */

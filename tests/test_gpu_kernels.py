@@ -166,6 +166,35 @@ def test_pack_unpack_nchw_roundtrip():
     assert torch.equal(ops.unpack_nchw(p, 6).cpu(), x.bfloat16().float())
 
 
+def test_process_data_u8_bit_exact_vs_torchvision_transforms():
+    """uint8 frames -> normalised fp32 on the GPU == the reference loader's ToTensor + Normalize(0.5, 0.5)
+    (TemporalAlignment/dataset.py:235-249) followed by utils.process_data's channel concat (utils.py:29-38), bit for bit.
+    All 256 byte values occur."""
+    from faceoff_b200.data import process_data_u8
+
+    gen = torch.Generator().manual_seed(0)
+    T, H, W = 3, 16, 24
+    frames = [torch.randint(0, 256, (T, H, W, 3), generator=gen, dtype=torch.uint8) for _ in range(3)]
+    frames[0].view(-1)[:256] = torch.arange(256, dtype=torch.uint8)
+
+    def reference(fr):       # torchvision.transforms.functional.to_tensor + normalize, per frame, then vstack
+        try:
+            from torchvision import transforms
+
+            tf = transforms.Compose([transforms.ToPILImage(), transforms.ToTensor(),
+                                     transforms.Normalize((0.5, 0.5, 0.5), (0.5, 0.5, 0.5))])
+            return torch.vstack([tf(f.numpy()).unsqueeze(0) for f in fr])
+        except ImportError:  # no PIL: the same two functional steps written out
+            t = fr.permute(0, 3, 1, 2).to(torch.float32).div(255)
+            return t.sub_(0.5).div_(0.5)
+
+    src, bg, gtf = (reference(f) for f in frames)
+    img_ref = torch.cat([src, bg], 1)
+    img, S, gt = process_data_u8(frames[0], frames[1], frames[2], device="cuda")
+    assert S == T and img.shape == (T, 6, H, W) and gt.shape == (T, 3, H, W)
+    assert torch.equal(img.cpu(), img_ref) and torch.equal(gt.cpu(), gtf)
+
+
 # ------------------------------------------------------------------------------------------------ quantiser sweep
 @pytest.mark.parametrize("dim,n_embed", SWEEP)
 def test_vq_assign_bit_exact_on_the_codebook_sweep(dim, n_embed):
