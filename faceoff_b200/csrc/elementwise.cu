@@ -379,35 +379,63 @@ im2col4x4s2_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out,
 // 3x3 pad-1 im2col for c <= 3 input channels (first VGG16 conv of LPIPS, reference models/lpips.py:119-127) with the
 // ScalingLayer folded in: out[n][y][x][(ky*3+kx)*3 + ch] = (x[ch][y+ky-1][x+kx-1] - shift[ch]) / scale[ch], zero outside
 // the image and for k >= 27 (K padded to 32 -> 64-byte rows, one K=32 GEMM step instead of nine 32-byte-row TMA boxes).
-__global__ void im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, int h, int w,
-                                 const float* __restrict__ shift, const float* __restrict__ scale) {
-  __shared__ float sm[3][3][68];
-  const int n = blockIdx.z, y = blockIdx.y, x0 = blockIdx.x * 64;
-  for (int i = threadIdx.x; i < 3 * 3 * 66; i += blockDim.x) {
-    const int col = i % 66, r = (i / 66) % 3, cc = i / (66 * 3);
-    const int iy = y - 1 + r, ix = x0 - 1 + col;
-    float v = 0.f;
-    if (cc < c && iy >= 0 && iy < h && ix >= 0 && ix < w) {
-      v = __ldg(x + (((size_t)n * c + cc) * h + iy) * w + ix);
-      if (shift != nullptr) v = (v - shift[cc]) / scale[cc];
-    }
-    sm[cc][r][col] = v;
+// Block = 256 threads = a strip of 256 pixels x kIm2Rows image rows.  Load phase: one coalesced row load per (channel,
+// input row) into shared memory (scaling applied once per loaded element).  Store phase: a thread owns ONE 16-byte piece
+// (8 of the 32 k values; the 8 shared-memory offsets are computed once) and walks over pixels, so that a warp instruction
+// writes 8 pixels x 64 B = 512 contiguous bytes.
+constexpr int kIm2Rows = 4;
+__global__ void __launch_bounds__(256)
+im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, int c, int h, int w,
+                 const float* __restrict__ shift, const float* __restrict__ scale) {
+  constexpr int P = 260;   // row pitch in floats (258 used)
+  __shared__ float sm[3 * (kIm2Rows + 2) * P];
+  const int n = blockIdx.z, y0 = blockIdx.y * kIm2Rows, x0 = blockIdx.x * 256;
+  const int tid = threadIdx.x;
+  for (int cr = 0; cr < 3 * (kIm2Rows + 2); ++cr) {
+    const int cc = cr / (kIm2Rows + 2), r = cr % (kIm2Rows + 2);
+    const int iy = y0 - 1 + r;
+    const bool row_ok = cc < c && iy >= 0 && iy < h;
+    const float* xr = x + (((size_t)n * c + (cc < c ? cc : 0)) * h + (row_ok ? iy : 0)) * w;
+    const float sh = (shift != nullptr && cc < c) ? shift[cc] : 0.f, sc = (scale != nullptr && cc < c) ? scale[cc] : 1.f;
+    auto fetch = [&](int j) {           // shared-memory column j <-> image column x0 - 1 + j
+      const int ix = x0 - 1 + j;
+      float v = 0.f;
+      if (row_ok && ix >= 0 && ix < w) {
+        v = __ldg(xr + ix);
+        if (shift != nullptr) v = (v - sh) / sc;
+      }
+      sm[cr * P + j] = v;
+    };
+    fetch(tid + 1);
+    if (tid < 2) fetch(tid == 0 ? 0 : 257);
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < 64 * 4; i += blockDim.x) {
-    const int px = i >> 2, piece = i & 3;
-    if (x0 + px >= w) continue;
-    float v[8];
+  const int piece = tid & 3, pq = tid >> 2;
+  int offs[8];
+  bool live[8];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const int k = piece * 8 + e;
-      const int tap = k / 3, cc = k % 3;
-      v[e] = k < 27 ? sm[cc][tap / 3][px + tap % 3] : 0.f;
+  for (int e = 0; e < 8; ++e) {
+    const int k = piece * 8 + e;
+    const int tap = k / 3, cc = k % 3;
+    live[e] = k < 27;
+    offs[e] = live[e] ? (cc * (kIm2Rows + 2) + tap / 3) * P + tap % 3 : 0;
+  }
+  for (int rr = 0; rr < kIm2Rows; ++rr) {
+    const int y = y0 + rr;
+    if (y >= h) break;
+    __nv_bfloat16* orow = out + (((size_t)n * h + y) * w + x0) * 32;
+#pragma unroll
+    for (int k4 = 0; k4 < 4; ++k4) {
+      const int px = pq + 64 * k4;
+      if (x0 + px >= w) continue;
+      float v[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = live[e] ? sm[offs[e] + rr * P + px] : 0.f;
+      uint4 o;
+      o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+      o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+      reinterpret_cast<uint4*>(orow + (size_t)px * 32)[piece] = o;
     }
-    uint4 o;
-    o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-    o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-    reinterpret_cast<uint4*>(out + (((size_t)n * h + y) * w + x0 + px) * 32)[piece] = o;
   }
 }
 
@@ -613,7 +641,7 @@ cudaError_t launch_im2col4x4s2(const float* x, void* out, int n, int ca, int c, 
 }
 cudaError_t launch_im2col3x3(const float* x, void* out, int n, int c, int h, int w, const float* shift,
                              const float* scale, cudaStream_t st) {
-  dim3 grid((w + 63) / 64, h, n);
+  dim3 grid((w + 255) / 256, (h + kIm2Rows - 1) / kIm2Rows, n);
   im2col3x3_kernel<<<grid, 256, 0, st>>>(x, (__nv_bfloat16*)out, c, h, w, shift, scale);
   return cudaGetLastError();
 }
