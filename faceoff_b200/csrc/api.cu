@@ -210,7 +210,7 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   p.MT = 1;
   p.TPS = 1;
   bool halo = false;
-  const int smem_avail = kMaxDynSmem - 2048 - 1024 - 8 * 32 * 80;
+  const int smem_avail = kMaxDynSmem - 3328 - 1024 - 8 * 32 * 80;
   const int n_e_plan = (c->mask != nullptr ? 1 : 0) + (c->addend != nullptr ? 1 : 0);
   const bool want_prefetch = n_e_plan > 0 && !nchw && c->out_f32 == nullptr && p.NT % 32 == 0;
   const int e_one_plan = n_e_plan * 128 * (p.NT * 2 + 16);
@@ -257,6 +257,16 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     p.tile_step[d] = box[d];
     p.tile_cnt[d] = (ext[d] + box[d] - 1) / box[d];
     p.lim[d] = ext[d];
+  }
+  {   // the 32 rows of one epilogue warp form an aligned sub-box of the tile (all extents are powers of two)
+    int rem = 32;
+    for (int d = 0; d < 4; ++d) {
+      const int sdim = box[d] < rem ? box[d] : rem;
+      p.e_box[d] = sdim;
+      rem /= sdim;
+    }
+    p.e_cols = p.NT % 64 == 0 ? 64 : 32;
+    if (rem != 1) p.e_cols = 0;   // (cannot happen with power-of-two boxes) -> no operand prefetch
   }
   p.sub_off = 128 * rowb;
   p.tap_off = halo ? box[0] * rowb : 0;
@@ -405,10 +415,10 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   }
   const int stage_bytes = (p.a_bytes + p.TPS * (p.NT / (p.cta_pair ? 2 : 1)) * rowb + 1023) & ~1023;
   // shared memory: pipeline stages + (as far as it fits next to two stages) the epilogue's prefetched addend / mask rows
-  const int avail = kMaxDynSmem - 2048 - 1024 - 8 * 32 * 80;
+  const int avail = kMaxDynSmem - 3328 - 1024 - 8 * 32 * 80;
   const int e_tensor = p.MT * 128 * (p.NT * 2 + 16);   // one operand, all sub-tiles
   p.e_bufs = 0; p.e_mask = 0; p.e_add = 0;
-  if (!nchw && c->out_f32 == nullptr && p.NT % 32 == 0 && !c->split_out) {
+  if (!nchw && c->out_f32 == nullptr && p.NT % 32 == 0 && !c->split_out && p.e_cols != 0 && c->out_cs % 8 == 0) {
     int room = avail - 2 * stage_bytes;
     if (c->addend != nullptr && room >= e_tensor) { p.e_add = 1; room -= e_tensor; }
     if (c->mask != nullptr && room >= e_tensor) { p.e_mask = 1; room -= e_tensor; }
@@ -468,6 +478,29 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
     if (rc != FO_OK) return rc;
   }
   for (int s = c->n_src; s < kMaxAMaps; ++s) out->maps.a[s] = out->maps.a[0];
+  // epilogue operand maps (mask / addend have the layout of the bf16 outputs): tile domain = map dims 1..4, element
+  // strides = the epilogue's out_stride; UP form: one map per sub-pixel group (base shifted by out_off[g])
+  for (int which = 0; which < 2; ++which) {
+    const void* base = which == 0 ? c->mask : c->addend;
+    const bool on = p.e_bufs > 0 && (which == 0 ? p.e_mask : p.e_add);
+    for (int g = 0; g < kMaxGroups; ++g) {
+      if (!on || g >= p.groups) { out->maps.e[which][g] = out->maps.a[0]; continue; }
+      uint64_t dims[5], str[5];
+      uint32_t bx[5];
+      dims[0] = (uint64_t)ocs; str[0] = 1; bx[0] = (uint32_t)p.e_cols;
+      uint64_t fallback = (uint64_t)ocs;
+      for (int d = 0; d < 4; ++d) {
+        dims[d + 1] = (uint64_t)p.lim[d];
+        // a dummy dimension (extent 1) carries stride 0 in out_stride: give it any legal stride
+        str[d + 1] = p.out_stride[d] > 0 ? (uint64_t)p.out_stride[d] : fallback;
+        if (p.out_stride[d] > 0) fallback = (uint64_t)p.out_stride[d] * (uint64_t)p.lim[d];
+        bx[d + 1] = (uint32_t)p.e_box[d];
+      }
+      int rc = encode_map(&out->maps.e[which][g], (const uint8_t*)base + (size_t)p.out_off[g] * 2, 5, dims, str, bx,
+                          p.e_cols * 2);
+      if (rc != FO_OK) return rc;
+    }
+  }
   {
     uint64_t dims[2] = {(uint64_t)out->ktot, (uint64_t)out->npad};
     uint64_t str[2] = {1, (uint64_t)out->ktot};

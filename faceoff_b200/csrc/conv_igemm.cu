@@ -189,10 +189,18 @@ __device__ __forceinline__ void stage_store_rows(__nv_bfloat16* dst, int col0, c
   __syncwarp();
 }
 
-__device__ __forceinline__ void load_prefetched(const uint8_t* erow, int cbytes, uint32_t (&w)[16]) {
+// Prefetched mask / addend tile of one warp: [column block][32 rows][e_cols * 2 bytes], written by TMA with the 128-byte
+// (e_cols = 64) or 64-byte (e_cols = 32) swizzle.  Lane L reads the 32 channels starting at column ccol of ITS row L:
+// four 16-byte chunks whose physical position is chunk ^ (row & 7) resp. chunk ^ ((row >> 1) & 3) -- conflict-free.
+__device__ __forceinline__ void load_prefetched(const uint8_t* ebase, int ccol, int e_cols, int lane, uint32_t (&w)[16]) {
+  const int rowb = e_cols * 2;
+  const int cb = ccol / e_cols;
+  const uint8_t* row = ebase + cb * (32 * rowb) + lane * rowb;
+  const int k0 = (ccol % e_cols) >> 3;                       // first logical 16-byte chunk inside the row
+  const int sw = e_cols == 64 ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    const uint4 v = *reinterpret_cast<const uint4*>(erow + cbytes + q * 16);
+    const uint4 v = *reinterpret_cast<const uint4*>(row + (((k0 + q) ^ sw) << 4));
     w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
   }
 }
@@ -203,6 +211,7 @@ __device__ __forceinline__ void epilogue_chunk32_coalesced(const ConvParams& p, 
                                                            const bool (&rvalid)[4], uint8_t* stg, int lane,
                                                            const uint8_t* e_mask, const uint8_t* e_add,
                                                            const float* s_bias) {
+  // e_mask / e_add: base of this warp's prefetched tile (see load_prefetched), or null
   float f[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
@@ -218,7 +227,7 @@ __device__ __forceinline__ void epilogue_chunk32_coalesced(const ConvParams& p, 
   }
   uint32_t w[16];
   if (p.mask != nullptr) {
-    if (e_mask != nullptr) load_prefetched(e_mask, ccol * 2, w);
+    if (e_mask != nullptr) load_prefetched(e_mask, ccol, p.e_cols, lane, w);
     else stage_load_rows(p.mask, col0, roff, rvalid, stg, lane, w);
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -227,7 +236,7 @@ __device__ __forceinline__ void epilogue_chunk32_coalesced(const ConvParams& p, 
     }
   }
   if (p.addend != nullptr) {
-    if (e_add != nullptr) load_prefetched(e_add, ccol * 2, w);
+    if (e_add != nullptr) load_prefetched(e_add, ccol, p.e_cols, lane, w);
     else stage_load_rows(p.addend, col0, roff, rvalid, stg, lane, w);
 #pragma unroll
     for (int e = 0; e < 16; ++e) {
@@ -281,10 +290,12 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   uint64_t* empty_bar = bars + p.stages;      // [stages]
   uint64_t* tfull_bar = bars + 2 * p.stages;  // [2]
   uint64_t* tempty_bar = tfull_bar + 2;       // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* e_bar = tempty_bar + 2;           // [8 epilogue warps][2 slots]: operand prefetch (TMA) completion
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(e_bar + 16);
   float* s_bias = reinterpret_cast<float*>(tmem_ptr + 4);        // [256] bias of the (single) N tile
   uint8_t* stg_all = reinterpret_cast<uint8_t*>(s_bias + 256);   // 8 epilogue warps x 32 rows x 80 B
-  uint8_t* e_all = stg_all + 8 * 32 * kStgPitch;                // prefetched mask / addend rows (see epilogue)
+  uint8_t* e_all = stg_all + 8 * 32 * kStgPitch;                // prefetched mask / addend tiles (see epilogue)
+  e_all += (1024u - (smem_u32(e_all) & 1023u)) & 1023u;         // TMA destinations with the 128-byte swizzle
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -295,6 +306,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     if (lane == 0) {
       for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&maps.a[i]);
       tma_prefetch_desc(&maps.b);
+      if (p.e_bufs > 0)
+        for (int i = 0; i < 2 * kMaxGroups; ++i) tma_prefetch_desc(&maps.e[i / kMaxGroups][i % kMaxGroups]);
     }
     __syncwarp();
     if (CG == 2) {
@@ -309,6 +322,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
+    for (int i = 0; i < 16; ++i) mbar_init(&e_bar[i], 1);
     for (int b = 0; b < 2; ++b) {
       mbar_init(&tfull_bar[b], 1);
       mbar_init(&tempty_bar[b], 4 * p.MT * CG);   // CG == 2: the epilogue warps of both CTAs arrive at rank 0
@@ -443,93 +457,92 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     // rows of every such tile into shared memory with cp.async BEFORE waiting for the accumulator, i.e. overlapped with
     // the MMAs of the tile (fully coalesced: 16 lanes x 16 B per row), and later reads its own row back (pitch
     // NT*2+16 B: conflict-free).
-    const int e_pitch = p.NT * 2 + 16;
-    const int e_warp_bytes = 32 * e_pitch;
+    const int e_tile_bytes = 32 * p.NT * 2;      // one operand, this warp's 32 rows
     const int n_e = p.e_mask + p.e_add;
     const bool prefetch = coalesced && p.e_bufs > 0 && n_e > 0;
-    // layout: [depth slot][e_buf][tensor][warp quarter][32 rows][pitch]; ebuf below = slot * e_bufs + sub-tile
-    auto e_ptr = [&](int ebuf, int tensor) -> uint8_t* {
-      return e_all + ((size_t)(ebuf * n_e + tensor) * 4 + quarter) * e_warp_bytes;
+    const int ew = (my_m << 2) | quarter;         // this warp's index among the (up to) 8 epilogue warps
+    // layout: [depth slot][epilogue warp (4 * MT of them)][tensor][column block][32 rows][e_cols * 2 B]
+    auto e_ptr = [&](int slot, int tensor) -> uint8_t* {
+      return e_all + ((size_t)(slot * 4 * p.MT + ew) * n_e + tensor) * e_tile_bytes;
     };
-    const bool ahead = prefetch && p.e_depth == 2;   // rows of tile i+1 are fetched while tile i is processed
-    const int pieces = p.NT * 2 / 16;            // 16-byte pieces per row
-    auto issue_prefetch = [&](int ebuf, long long my_off, bool my_valid, int ncol0) {
-      // lane L owns row L of this warp; rows are fetched cooperatively, 32/pieces... rows per instruction
-      for (int idx = lane; idx < 32 * pieces; idx += 32) {
-        const int r = idx / pieces, pc = idx % pieces;
-        const long long o = __shfl_sync(0xffffffffu, my_off, r);
-        const bool ok = __shfl_sync(0xffffffffu, (int)my_valid, r) != 0;
+    const bool ahead = prefetch && p.e_depth == 2;   // tiles of step i+1 are fetched while step i is processed
+    // One lane asks the TMA unit for the warp's rows of every prefetched operand (NT / e_cols boxes each); rows outside
+    // the tensor arrive as zeros (gate closed / nothing added; the stores of those rows are predicated anyway).
+    // (the previous cp.async version spent ~45 instructions per 16 bytes on index arithmetic and shuffles: ncu)
+    const int rg0 = my_m * 128 + quarter * 32;      // first row of this warp inside a tile
+    const int eb1 = rg0 % p.box[0];
+    const int eb2 = (rg0 / p.box[0]) % p.box[1];
+    const int eb3 = (rg0 / (p.box[0] * p.box[1])) % p.box[2];
+    const int eb4 = rg0 / (p.box[0] * p.box[1] * p.box[2]);
+    uint32_t e_phase = 0;                           // bit s: parity to wait for on slot s
+    auto issue_prefetch = [&](int slot, int g, const int (&base)[4], int ncol0) {
+      if (lane == 0) {
+        uint64_t* bar = &e_bar[ew * 2 + slot];
+        mbar_expect_tx(bar, n_e * e_tile_bytes);
         int t = 0;
-        if (p.e_mask) {
-          if (ok) cp_async16(e_ptr(ebuf, t) + r * e_pitch + pc * 16, p.mask + o + ncol0 + pc * 8);
-          ++t;
-        }
-        if (p.e_add) {
-          if (ok) cp_async16(e_ptr(ebuf, t) + r * e_pitch + pc * 16, p.addend + o + ncol0 + pc * 8);
+        for (int which = 0; which < 2; ++which) {
+          if (!(which == 0 ? p.e_mask : p.e_add)) continue;
+          uint8_t* dst = e_ptr(slot, t++);
+          for (int cb = 0; cb * p.e_cols < p.NT; ++cb)
+            tma_load_5d(dst + cb * (32 * p.e_cols * 2), &maps.e[which][g], bar, ncol0 + cb * p.e_cols, base[0] + eb1,
+                        base[1] + eb2, base[2] + eb3, base[3] + eb4);
         }
       }
-      cp_async_commit();
+      __syncwarp();
     };
+    // position of this lane's row inside a tile: the same for every tile
+    const int rg_ = my_m * 128 + row;
+    const int rb1 = rg_ % p.box[0];
+    const int rb2 = (rg_ / p.box[0]) % p.box[1];
+    const int rb3 = (rg_ / (p.box[0] * p.box[1])) % p.box[2];
+    const int rb4 = rg_ / (p.box[0] * p.box[1] * p.box[2]);
     auto row_geometry = [&](const int (&base)[4], int g, int m, long long& off, bool& valid) {
-      const int rg = m * 128 + row;
-      const int b1 = rg % p.box[0];
-      const int b2 = (rg / p.box[0]) % p.box[1];
-      const int b3 = (rg / (p.box[0] * p.box[1])) % p.box[2];
-      const int b4 = rg / (p.box[0] * p.box[1] * p.box[2]);
-      const int c1 = base[0] + b1, c2 = base[1] + b2, c3 = base[2] + b3, c4 = base[3] + b4;
+      (void)m;
+      const int c1 = base[0] + rb1, c2 = base[1] + rb2, c3 = base[2] + rb3, c4 = base[3] + rb4;
       valid = (c1 < p.lim[0]) && (c2 < p.lim[1]) && (c3 < p.lim[2]) && (c4 < p.lim[3]);
       off = p.out_off[g] + c1 * p.out_stride[0] + c2 * p.out_stride[1] + c3 * p.out_stride[2] + c4 * p.out_stride[3];
     };
     int it = 0;
     const uint32_t tempty_remote[2] = {CG == 2 ? mapa_u32(&tempty_bar[0], 0) : 0u,
                                        CG == 2 ? mapa_u32(&tempty_bar[1], 0) : 0u};
-    if (ahead && tile0 < p.total_tiles) {   // first tile's rows
-      int g, nt, base[4];
-      decode_tile(p, tile0, g, nt, base);
-      long long off;
-      bool valid;
-      row_geometry(base, g, my_m, off, valid);
-      issue_prefetch(my_m, off, valid, nt * p.NT);
+    // geometry of the tile decoded last (the prefetch of tile i+1 already needs it: carried into the next iteration)
+    int cg = 0, cnt_ = 0, cbase[4] = {0, 0, 0, 0};
+    long long coff = 0;
+    bool cvalid = false;
+    if (tile0 < p.total_tiles) {
+      decode_tile(p, tile0, cg, cnt_, cbase);
+      row_geometry(cbase, cg, my_m, coff, cvalid);
+      if (ahead) issue_prefetch(0, cg, cbase, cnt_ * p.NT);   // first tile's rows
     }
     for (int tile = tile0; tile < p.total_tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      int g, nt, base[4];
-      decode_tile(p, tile, g, nt, base);
+      const int g = cg, nt = cnt_;
+      int base[4] = {cbase[0], cbase[1], cbase[2], cbase[3]};
       const int ncol0 = nt * p.NT;
-      long long off;
-      bool valid;
-      row_geometry(base, g, my_m, off, valid);
-      const int ebuf = (ahead ? (it & 1) * p.e_bufs : 0) + my_m;
-      bool next_in_flight = false;
-      if (ahead) {
+      const long long off = coff;
+      const bool valid = cvalid;
+      const int eslot = ahead ? (it & 1) : 0;
+      {
         const int tn = tile + gridDim.x;
-        if (tn < p.total_tiles) {   // the other slot was last read by this warp in the previous tile
-          int gn, ntn, basen[4];
-          decode_tile(p, tn, gn, ntn, basen);
-          long long offn;
-          bool validn;
-          row_geometry(basen, gn, my_m, offn, validn);
-          issue_prefetch(((it + 1) & 1) * p.e_bufs + my_m, offn, validn, ntn * p.NT);
-          next_in_flight = true;
+        if (tn < p.total_tiles) {
+          decode_tile(p, tn, cg, cnt_, cbase);
+          row_geometry(cbase, cg, my_m, coff, cvalid);
+          if (ahead) issue_prefetch((it + 1) & 1, cg, cbase, cnt_ * p.NT);   // slot last read by this warp one tile ago
         }
-      } else if (prefetch) {
-        issue_prefetch(ebuf, off, valid, ncol0);   // buffer was last read by this warp in the previous tile
       }
+      if (!ahead && prefetch) issue_prefetch(0, g, base, ncol0);   // buffer was last read by this warp in the previous tile
       mbar_wait_ns(&tfull_bar[buf], (it >> 1) & 1, p.backoff_ns);
       tc_fence_after();
       {
         const int m = my_m;
-        if (prefetch) {
-          if (next_in_flight) cp_async_wait_but_one();
-          else cp_async_wait_all();
-          __syncwarp();
-        }
         const uint8_t* e_mask = nullptr;
         const uint8_t* e_add = nullptr;
         if (prefetch) {
+          mbar_wait(&e_bar[ew * 2 + eslot], (e_phase >> eslot) & 1u);
+          e_phase ^= 1u << eslot;
           int t = 0;
-          if (p.e_mask) e_mask = e_ptr(ebuf, t++) + lane * e_pitch;
-          if (p.e_add) e_add = e_ptr(ebuf, t) + lane * e_pitch;
+          if (p.e_mask) e_mask = e_ptr(eslot, t++);
+          if (p.e_add) e_add = e_ptr(eslot, t);
         }
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (buf * p.MT + m) * p.NT;
         // rows handled by this lane in the transposed (coalesced) accesses
@@ -580,7 +593,7 @@ size_t conv_smem_bytes(const ConvParams& p) {
   const int rowb = p.KC * 2;
   const int stage_bytes = (p.a_bytes + p.TPS * (p.NT / (p.cta_pair ? 2 : 1)) * rowb + 1023) & ~1023;
   const int n_e = p.e_mask + p.e_add;
-  return (size_t)p.stages * stage_bytes + (2 * p.stages + 4) * 8 + 16 + 1024 + 8 * 32 * 80 +
+  return (size_t)p.stages * stage_bytes + (2 * p.stages + 4 + 16) * 8 + 16 + 1024 + 8 * 32 * 80 + 1024 +
          (size_t)p.e_bufs * (p.e_depth > 1 ? p.e_depth : 1) * n_e * 128 * (p.NT * 2 + 16) + 1024;
 }
 

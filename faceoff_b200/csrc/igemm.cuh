@@ -39,6 +39,8 @@ struct ConvParams {
   int e_bufs;         // epilogue operand prefetch: 0 = off, else MT (one buffer set per M sub-tile / warp group)
   int e_depth;        // 1: rows of a tile are fetched while its MMAs run; 2: one tile ahead (double-buffered)
   int e_mask, e_add;  // which of the two epilogue operands are prefetched (shared memory permitting)
+  int e_box[4];       // extents on map dims 1..4 of the 32 rows owned by one epilogue warp (an aligned sub-box of the tile)
+  int e_cols;         // channels per prefetch box: 64 (128-byte rows, 128B swizzle) or 32 (64-byte rows, 64B swizzle)
   int n_tiles;        // N tiles of width NT
   int NT;             // columns per N tile (multiple of 16, <= 256)
   int KC;             // channels per K step: 16 / 32 / 64  (row bytes 32 / 64 / 128 = swizzle mode)
@@ -65,6 +67,7 @@ struct ConvParams {
 struct ConvMaps {
   CUtensorMap a[kMaxAMaps];
   CUtensorMap b;
+  CUtensorMap e[2][kMaxGroups];   // epilogue operand maps ([0] mask, [1] addend; one per sub-pixel group), see e_bufs
 };
 
 // wgrad_igemm: dW[g][m][n] = sum_pixels P[pix][m] * Q[pix (+) shift_g][n]; both operands MN-major.
