@@ -38,6 +38,11 @@ class ConvDesc(C.Structure):
     ]
 
 
+class DConvDesc(C.Structure):
+    _fields_ = [(k, C.c_int) for k in ("n", "cin", "id", "ih", "iw", "cout", "od", "oh", "ow", "kd", "kh", "kw", "sd", "sh",
+                                       "sw", "pd", "ph", "pw")]
+
+
 class WgradDesc(C.Structure):
     _fields_ = [
         ("form", C.c_int), ("ndim", C.c_int), ("ksize", C.c_int),
@@ -112,6 +117,20 @@ _SIGS = {
     "fo_maxpool2_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fo_maxpool2_bwd_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
                                       C.c_void_p]),
+    "fo_dconv_fwd": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_dconv_dgrad": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_dconv_wgrad": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_instnorm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_int,
+                                  C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_instnorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int,
+                                  C.c_void_p, C.c_void_p]),
+    "fo_lrelu": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]),
+    "fo_lrelu_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p]),
+    "fo_avgpool3": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong] + [C.c_int] * 10 + [C.c_void_p]),
+    "fo_avgpool3_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_longlong] + [C.c_int] * 10 + [C.c_void_p]),
+    "fo_ralsgan": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p]),
+    "fo_ralsgan_bwd": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                 C.c_void_p]),
     "fo_mse": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
     "fo_adam_chunk_elems": (C.c_int, []),
     "fo_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float,

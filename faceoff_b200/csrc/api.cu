@@ -927,6 +927,112 @@ extern "C" int fo_lpips_tap_bwd_split(const void* f0, const void* f1, const floa
   CUDA_TRY(launch_lpips_tap_bwd(f0, f1, w, g, n, hw, c, d_f0, addend, g_num_sms, (cudaStream_t)stream, 1));
   return FO_OK;
 }
+// ------------------------------------------------------------------------------------------ discriminators (8(f1))
+static int to_dconv(const fo_dconv_t* d, DConvParams* p) {
+  if (d->n < 1 || d->cin < 1 || d->cout < 1 || d->kd < 1 || d->kh < 1 || d->kw < 1 || d->sd < 1 || d->sh < 1 || d->sw < 1)
+    return fail(FO_ERR_INVALID, "dconv: bad geometry");
+  if (d->od != (d->id + 2 * d->pd - d->kd) / d->sd + 1 || d->oh != (d->ih + 2 * d->ph - d->kh) / d->sh + 1 ||
+      d->ow != (d->iw + 2 * d->pw - d->kw) / d->sw + 1)
+    return fail(FO_ERR_INVALID, "dconv: output extents do not match (i + 2p - k) / s + 1");
+  if ((long long)d->n * d->od * d->oh * d->ow > 0x7fffffffLL || (long long)d->n * d->id * d->ih * d->iw > 0x7fffffffLL)
+    return fail(FO_ERR_INVALID, "dconv: more than 2^31 positions");
+  p->n = d->n; p->cin = d->cin; p->id = d->id; p->ih = d->ih; p->iw = d->iw;
+  p->cout = d->cout; p->od = d->od; p->oh = d->oh; p->ow = d->ow;
+  p->kd = d->kd; p->kh = d->kh; p->kw = d->kw; p->sd = d->sd; p->sh = d->sh; p->sw = d->sw;
+  p->pd = d->pd; p->ph = d->ph; p->pw = d->pw;
+  return FO_OK;
+}
+extern "C" int fo_dconv_fwd(const fo_dconv_t* d, const float* x, const float* w, const float* bias, float* y,
+                            fo_stream_t stream) {
+  REQUIRE_INIT();
+  DConvParams p;
+  int rc = to_dconv(d, &p);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_dconv_fwd(p, x, w, bias, y, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_dconv_dgrad(const fo_dconv_t* d, const float* dy, const float* w, float* dx, fo_stream_t stream) {
+  REQUIRE_INIT();
+  DConvParams p;
+  int rc = to_dconv(d, &p);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_dconv_dgrad(p, dy, w, dx, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_dconv_wgrad(const fo_dconv_t* d, const float* x, const float* dy, float* dw, float* dbias,
+                              fo_stream_t stream) {
+  REQUIRE_INIT();
+  DConvParams p;
+  int rc = to_dconv(d, &p);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_dconv_wgrad(p, x, dy, dw, dbias, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_instnorm_fwd(const float* x, float* y, int n, int c, long long plane, float eps, float slope, int training,
+                               float momentum, float* running_mean, float* running_var, float* save, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (n < 1 || c < 1 || plane < 1 || slope == 0.f) return fail(FO_ERR_INVALID, "instnorm: bad arguments");
+  if (!training && (running_mean == nullptr || running_var == nullptr))
+    return fail(FO_ERR_INVALID, "instnorm: eval mode needs the running statistics");
+  CUDA_TRY(launch_instnorm_fwd(x, y, n, c, plane, eps, slope, training, momentum, running_mean, running_var, save,
+                               (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_instnorm_bwd(const float* y, const float* dy, float* dx, int n, int c, long long plane, float slope,
+                               int training, const float* save, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (n < 1 || c < 1 || plane < 1 || slope == 0.f || save == nullptr) return fail(FO_ERR_INVALID, "instnorm_bwd: bad arguments");
+  CUDA_TRY(launch_instnorm_bwd(y, dy, dx, n, c, plane, slope, training, save, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_lrelu(const float* x, float* y, size_t numel, float slope, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (numel == 0) return FO_OK;
+  CUDA_TRY(launch_lrelu(x, y, numel, slope, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_lrelu_bwd(const float* y, const float* dy, float* dx, size_t numel, float slope, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (numel == 0) return FO_OK;
+  CUDA_TRY(launch_lrelu_bwd(y, dy, dx, numel, slope, (cudaStream_t)stream));
+  return FO_OK;
+}
+static int check_pool(int id, int ih, int iw, int od, int oh, int ow, int kd, int sd, int sh, int sw) {
+  if ((kd != 1 && kd != 3) || sd < 1 || sh < 1 || sw < 1) return fail(FO_ERR_INVALID, "avgpool3: kd must be 1 or 3");
+  if (od != (id + 2 * (kd / 2) - kd) / sd + 1 || oh != (ih + 2 - 3) / sh + 1 || ow != (iw + 2 - 3) / sw + 1)
+    return fail(FO_ERR_INVALID, "avgpool3: output extents do not match");
+  return FO_OK;
+}
+extern "C" int fo_avgpool3(const float* x, float* y, long long planes, int id, int ih, int iw, int od, int oh, int ow, int kd,
+                           int sd, int sh, int sw, fo_stream_t stream) {
+  REQUIRE_INIT();
+  int rc = check_pool(id, ih, iw, od, oh, ow, kd, sd, sh, sw);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_avgpool3(x, y, planes, id, ih, iw, od, oh, ow, kd, sd, sh, sw, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_avgpool3_bwd(const float* dy, float* dx, long long planes, int id, int ih, int iw, int od, int oh, int ow,
+                               int kd, int sd, int sh, int sw, fo_stream_t stream) {
+  REQUIRE_INIT();
+  int rc = check_pool(id, ih, iw, od, oh, ow, kd, sd, sh, sw);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_avgpool3_bwd(dy, dx, planes, id, ih, iw, od, oh, ow, kd, sd, sh, sw, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_ralsgan(const float* a, int n, const float* b, int m, float target, float* out, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (n < 1 || m < 1) return fail(FO_ERR_INVALID, "ralsgan: empty prediction");
+  CUDA_TRY(launch_ralsgan(a, n, b, m, target, out, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_ralsgan_bwd(const float* a, int n, int m, float target, const float* fwd, const float* g, float* da,
+                              float* db, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (n < 1 || m < 1) return fail(FO_ERR_INVALID, "ralsgan: empty prediction");
+  CUDA_TRY(launch_ralsgan_bwd(a, n, m, target, fwd, g, da, db, (cudaStream_t)stream));
+  return FO_OK;
+}
+
 // ------------------------------------------------------------------------------------------ verification mode helpers
 extern "C" int fo_split_f32(const float* x, int n, int c, int hw, long long sn, long long sc, long long sp, void* out,
                             int cp, fo_stream_t stream) {

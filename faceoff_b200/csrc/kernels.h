@@ -92,6 +92,30 @@ cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int
 cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
                                  void* d_f0, const void* addend, int num_sms, cudaStream_t st, int split = 0);
 
+// disc.cu (MoCoGAN-HD discriminators): fp32 NCDHW direct convolution + norm / pool / loss kernels
+struct DConvParams {
+  int n, cin, id, ih, iw;       // input  [n, cin, id, ih, iw]   (2-D: id = 1)
+  int cout, od, oh, ow;         // output [n, cout, od, oh, ow]
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+};
+cudaError_t launch_dconv_fwd(const DConvParams& p, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+cudaError_t launch_dconv_dgrad(const DConvParams& p, const float* dy, const float* w, float* dx, cudaStream_t st);
+cudaError_t launch_dconv_wgrad(const DConvParams& p, const float* x, const float* dy, float* dw, float* dbias, int num_sms,
+                               cudaStream_t st);
+cudaError_t launch_instnorm_fwd(const float* x, float* y, int n, int c, long long plane, float eps, float slope, int training,
+                                float momentum, float* running_mean, float* running_var, float* save, cudaStream_t st);
+cudaError_t launch_instnorm_bwd(const float* y, const float* dy, float* dx, int n, int c, long long plane, float slope,
+                                int training, const float* save, cudaStream_t st);
+cudaError_t launch_lrelu(const float* x, float* y, size_t n, float slope, cudaStream_t st);
+cudaError_t launch_lrelu_bwd(const float* y, const float* dy, float* dx, size_t n, float slope, cudaStream_t st);
+cudaError_t launch_avgpool3(const float* x, float* y, long long planes, int id, int ih, int iw, int od, int oh, int ow, int kd,
+                            int sd, int sh, int sw, cudaStream_t st);
+cudaError_t launch_avgpool3_bwd(const float* dy, float* dx, long long planes, int id, int ih, int iw, int od, int oh, int ow,
+                                int kd, int sd, int sh, int sw, cudaStream_t st);
+cudaError_t launch_ralsgan(const float* a, int n, const float* b, int m, float target, float* out, cudaStream_t st);
+cudaError_t launch_ralsgan_bwd(const float* a, int n, int m, float target, const float* fwd, const float* g, float* da,
+                               float* db, cudaStream_t st);
+
 // precise.cu (verification mode)
 cudaError_t launch_split_f32(const float* x, int n, int c, int hw, long long sn, long long sc, long long sp, void* out,
                              int cp, cudaStream_t st);

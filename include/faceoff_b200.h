@@ -236,6 +236,45 @@ int fo_mse(const float* a, const float* b, int n, int ca, int c, int hw, float* 
 int fo_mse_grad(const float* a, const float* b, int n, int ca, int c, int hw, const float* gscale, float scale,
                 float* grad, fo_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * MoCoGAN-HD discriminator step (reference TemporalAlignment/models/mocoganhd_content_disc.py:8-165,
+ * mocoganhd_video_disc.py:8-176, mocoganhd_losses.py:109-126, disc_trainers/train_vqvae_perceptual_mocoganhd_disc.py:160-333).
+ * fp32 tensors in the PyTorch-native NC(D)HW layout.  Replaces, for this path, torch's conv2d / conv3d (+ autograd),
+ * instance_norm, leaky_relu, avg_pool2d / avg_pool3d and the MSELoss of the relativistic average LSGAN.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int n, cin, id, ih, iw; /* input  [n, cin, id, ih, iw] (2-D convolution: id = kd = sd = 1, pd = 0) */
+  int cout, od, oh, ow;   /* output [n, cout, od, oh, ow], o = (i + 2 p - k) / s + 1 (checked) */
+  int kd, kh, kw, sd, sh, sw, pd, ph, pw;
+} fo_dconv_t;
+/* y = conv(x, w) + bias;  w [cout, cin, kd, kh, kw], bias [cout] or NULL */
+int fo_dconv_fwd(const fo_dconv_t* d, const float* x, const float* w, const float* bias, float* y, fo_stream_t stream);
+/* dx = gradient of the convolution w.r.t. its input */
+int fo_dconv_dgrad(const fo_dconv_t* d, const float* dy, const float* w, float* dx, fo_stream_t stream);
+/* dw (overwritten) = gradient w.r.t. the weight, dbias (overwritten, optional) = sum of dy over n and positions */
+int fo_dconv_wgrad(const fo_dconv_t* d, const float* x, const float* dy, float* dw, float* dbias, fo_stream_t stream);
+/* InstanceNorm (affine=False) fused with LeakyReLU(slope) (slope = 1: no activation): y = lrelu((x - mean) / sqrt(var + eps)),
+ * per (n, c) plane of `plane` elements.  training != 0: instance statistics; running_mean / running_var (optional)
+ * are updated with `momentum` like nn.InstanceNorm*d(track_running_stats=True) (unbiased variance, averaged over n).
+ * training == 0: the running statistics are used.  save [2 * n * c] receives (mean, rstd) for the backward kernel. */
+int fo_instnorm_fwd(const float* x, float* y, int n, int c, long long plane, float eps, float slope, int training,
+                    float momentum, float* running_mean, float* running_var, float* save, fo_stream_t stream);
+int fo_instnorm_bwd(const float* y, const float* dy, float* dx, int n, int c, long long plane, float slope, int training,
+                    const float* save, fo_stream_t stream);
+int fo_lrelu(const float* x, float* y, size_t numel, float slope, fo_stream_t stream);
+int fo_lrelu_bwd(const float* y, const float* dy, float* dx, size_t numel, float slope, fo_stream_t stream);
+/* AvgPool with kernel (kd, 3, 3), kd in {1, 3}, stride (sd, sh, sw), padding (kd / 2, 1, 1), count_include_pad=False
+ * (reference mocoganhd_content_disc.py:74-77, mocoganhd_video_disc.py:80-89).  x [planes, id, ih, iw]. */
+int fo_avgpool3(const float* x, float* y, long long planes, int id, int ih, int iw, int od, int oh, int ow, int kd, int sd,
+                int sh, int sw, fo_stream_t stream);
+int fo_avgpool3_bwd(const float* dy, float* dx, long long planes, int id, int ih, int iw, int od, int oh, int ow, int kd,
+                    int sd, int sh, int sw, fo_stream_t stream);
+/* Relativistic average LSGAN term (mocoganhd_losses.py:109-126): out[0] = mean((a - mean(b) - target)^2), out[1] = mean(b).
+ * Backward: da [n] and db [m] (either may be NULL) for the upstream gradient *g (device scalar). */
+int fo_ralsgan(const float* a, int n, const float* b, int m, float target, float* out, fo_stream_t stream);
+int fo_ralsgan_bwd(const float* a, int n, int m, float target, const float* fwd, const float* g, float* da, float* db,
+                   fo_stream_t stream);
+
 /* Optimizer step (reference optim.Adam(model.parameters(), lr=3e-4), train_faceoff_perceptual.py:190,
  * torch.optim.Adam semantics without amsgrad): one launch over all parameter tensors.
  * table_dev : DEVICE array of n tensors; chunks_dev : DEVICE array of n_chunks (tensor index, chunk index) int pairs, a

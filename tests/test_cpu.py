@@ -347,3 +347,35 @@ def test_launch_spawns_world2(tmp_path):
         dist.launch(lambda: None, 2, n_machine=2, dist_url="auto")
     with pytest.raises(ValueError):
         dist.launch(lambda: None, 2, n_machine=2, dist_url="file:///tmp/x")
+
+
+# ---------------------------------------------------------------------------------------------- discriminators (8(f1))
+@pytest.mark.parametrize("kind", ["img", "vid"])
+def test_disc_oracle_and_dropin_init_vs_reference_golden(kind):
+    """oracle/disc_oracle.py against the committed outputs of the reference discriminators, run on the state_dict of the
+    DROP-IN module built from the same seed (which must reproduce the reference's initial weights: checksums)."""
+    from faceoff_b200.mocoganhd import content_disc, video_disc
+    from oracle import disc_oracle as DO
+
+    g = torch.load(os.path.join(HERE, "golden", "golden_disc.pt"), map_location="cpu")[kind]
+    torch.manual_seed(g["seed_model"])
+    m = content_disc.ModelD_img(3, "instance", 2, 1e-4) if kind == "img" else video_disc.ModelD_3d(3, "instance", 2, 1e-4, False, 12)
+    sd = m.state_dict()
+    assert set(k for k, v in sd.items() if v.dtype.is_floating_point) == set(g["param_checksums"])
+    for k, (s_, a_) in g["param_checksums"].items():
+        assert abs(sd[k].double().sum().item() - s_) < 1e-9 and abs(sd[k].double().abs().sum().item() - a_) < 1e-9 * a_ + 1e-12, k
+    gen = torch.Generator().manual_seed(g["seed_data"])
+    x_real = torch.rand(g["shape"], generator=gen) * 2 - 1
+    x_fake = torch.rand(g["shape"], generator=gen) * 2 - 1
+    ns = {}
+    loss, d_real, d_fake = DO.disc_loss(sd, x_real, x_fake, 2 if kind == "img" else 3, n_frames=11, new_stats=ns)
+    torch.testing.assert_close(loss, g["d_loss"], rtol=1e-6, atol=1e-8)
+    for got, ref in zip(d_real, g["pred_real"]):
+        torch.testing.assert_close(got[-1], ref, rtol=1e-5, atol=1e-6)
+    for k, ref in g["stats_after"].items():
+        if "num_batches" not in k:
+            torch.testing.assert_close(ns[k], ref, rtol=1e-5, atol=1e-7)
+    # the drop-in refuses to compute on the CPU
+    from faceoff_b200 import _lib
+    with pytest.raises((_lib.FaceoffB200Error, RuntimeError)):
+        m(x_real)

@@ -1,0 +1,167 @@
+"""GPU parity tests of the MoCoGAN-HD discriminator step (BASELINE configs[4]) -- ``pytest -m gpu``.
+The CUDA path (faceoff_b200.mocoganhd, csrc/disc.cu through the C ABI) against the committed outputs of the UNMODIFIED
+reference classes (tests/golden/golden_disc.pt) and against the oracle.  fp32 path: rtol 1e-4."""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = os.path.join(HERE, "golden", "golden_disc.pt")
+
+
+def _build(kind):
+    from faceoff_b200.mocoganhd import content_disc, video_disc
+
+    g = torch.load(GOLDEN, map_location="cpu")[kind]
+    torch.manual_seed(g["seed_model"])
+    m = content_disc.ModelD_img(3, "instance", 2, 1e-4) if kind == "img" else video_disc.ModelD_3d(3, "instance", 2, 1e-4, False, 12)
+    for k, v in m.state_dict().items():     # same seed => the reference's initial weights (checksums from the reference)
+        if v.dtype.is_floating_point:
+            s, a = g["param_checksums"][k]
+            assert abs(v.double().sum().item() - s) <= 1e-9 + 1e-12 * abs(a) and abs(v.double().abs().sum().item() - a) <= 1e-9 * a + 1e-12, k
+    gen = torch.Generator().manual_seed(g["seed_data"])
+    x_real = torch.rand(g["shape"], generator=gen) * 2 - 1
+    x_fake = torch.rand(g["shape"], generator=gen) * 2 - 1
+    return g, m, x_real, x_fake
+
+
+@pytest.mark.parametrize("kind", ["img", "vid"])
+def test_discriminator_step_matches_reference_golden(kind):
+    """Discriminator step (trainer :240-300): fake then real forward in training mode, relativistic average LSGAN loss,
+    backward: patch predictions, loss, every parameter gradient, InstanceNorm running statistics."""
+    from faceoff_b200.mocoganhd import losses
+
+    g, m, x_real, x_fake = _build(kind)
+    sd0 = {k: v.clone() for k, v in m.state_dict().items()}
+    m = m.cuda().train()
+    crit = losses.Relativistic_Average_LSGAN()
+    d_fake = m(x_fake.cuda())
+    d_real = m(x_real.cuda())
+    d_loss = (crit(d_real, d_fake, True) + crit(d_fake, d_real, False)) * 0.5
+    m.zero_grad()
+    d_loss.backward()
+    torch.cuda.synchronize()
+    assert len(d_real) == 2 and len(d_real[0]) == 5
+    for got, ref in zip(d_real, g["pred_real"]):
+        torch.testing.assert_close(got[-1].detach().cpu(), ref, rtol=1e-4, atol=1e-6)
+    for got, ref in zip(d_fake, g["pred_fake"]):
+        torch.testing.assert_close(got[-1].detach().cpu(), ref, rtol=1e-4, atol=1e-6)
+    torch.testing.assert_close(d_real[1][1].detach().cpu()[:, :4], g["feat_real_scale0_layer1"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(d_loss.detach().cpu(), g["d_loss"], rtol=1e-5, atol=1e-7)
+    worst = 0.0
+    for k, p in m.named_parameters():
+        n_ref = g["grad_norms"][k].item()
+        rel = abs(p.grad.norm().item() - n_ref) / (n_ref + 1e-30)
+        worst = max(worst, rel)
+        sl = p.grad.flatten()[:64].cpu()
+        torch.testing.assert_close(sl, g["grad_slices"][k], rtol=2e-3, atol=1e-5 * n_ref + 1e-12)
+    print(f"{kind}: worst gradient-norm relative error {worst:.2e}")
+    assert worst < 1e-4
+    for k, ref in g["stats_after"].items():
+        got = m.state_dict()[k].cpu()
+        if "num_batches" in k:
+            assert got.item() == ref.item(), k
+        else:
+            torch.testing.assert_close(got, ref, rtol=1e-4, atol=1e-6)
+    # generator-side loss and its gradient w.r.t. the fake input, from the initial state (trainer :208-227)
+    m.load_state_dict(sd0)
+    xf = x_fake.cuda().requires_grad_(True)
+    df = m(xf)
+    dr = m(x_real.cuda())
+    g_loss = (crit(df, dr, True) + crit(dr, df, False)) * 0.5
+    g_loss.backward()
+    torch.testing.assert_close(g_loss.detach().cpu(), g["g_loss"], rtol=1e-5, atol=1e-7)
+    ref_gx = g["grad_x_fake"]
+    err = ((xf.grad.cpu() - ref_gx).abs().max() / ref_gx.abs().max()).item()
+    print(f"{kind}: d(G loss)/d(x_fake) max-normalised error {err:.2e}")
+    assert err < 1e-4
+
+
+@pytest.mark.parametrize("kind", ["img", "vid"])
+def test_discriminator_eval_mode_uses_running_statistics(kind):
+    from oracle import disc_oracle as DO
+
+    g, m, x_real, _ = _build(kind)
+    sd = {k: v.clone() for k, v in m.state_dict().items()}
+    for k in sd:    # non-trivial running statistics
+        if k.endswith("running_mean"):
+            sd[k] = torch.linspace(-0.01, 0.01, sd[k].numel())
+        if k.endswith("running_var"):
+            sd[k] = torch.linspace(0.5, 1.5, sd[k].numel()) * 1e-3
+    m.load_state_dict(sd)
+    m = m.cuda().eval()
+    with torch.no_grad():
+        out = m(x_real.cuda())
+    ref = DO.multiscale_forward(sd, x_real, 2 if kind == "img" else 3, n_frames=11, training=False)
+    for a, b in zip(out, ref):
+        for u, v in zip(a, b):
+            torch.testing.assert_close(u.cpu(), v, rtol=1e-4, atol=1e-5)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v.cpu(), sd[k]), f"eval forward modified {k}"
+
+
+@pytest.mark.parametrize("shape,cout,k,s,p", [((2, 5, 17, 13), 7, 4, 2, 2), ((1, 6, 9, 9), 64, 4, 1, 2), ((1, 3, 5, 11, 9), 4, 4, 2, 2),
+                                              ((2, 4, 3, 6, 7), 5, 4, 1, 2), ((1, 70, 8, 8), 130, 3, 1, 1)])
+def test_dconv_forward_dgrad_wgrad_vs_torch_fp64(shape, cout, k, s, p):
+    """The direct convolution kernels on odd sizes / ragged channel counts (tiles of 64 are partially filled) vs torch fp64."""
+    from faceoff_b200.mocoganhd import layers
+
+    gen = torch.Generator().manual_seed(sum(shape) + cout)
+    nd = len(shape) - 2
+    conv = (layers.Conv2d if nd == 2 else layers.Conv3d)(shape[1], cout, k, stride=s, padding=p).cuda()
+    x = torch.randn(shape, generator=gen).cuda().requires_grad_(True)
+    y = conv(x)
+    go = torch.randn(y.shape, generator=gen).cuda()
+    y.backward(go)
+    x64 = x.detach().double().cpu().requires_grad_(True)
+    w64 = conv.weight.detach().double().cpu().requires_grad_(True)
+    b64 = conv.bias.detach().double().cpu().requires_grad_(True)
+    r = (F.conv2d if nd == 2 else F.conv3d)(x64, w64, b64, stride=s, padding=p)
+    r.backward(go.double().cpu())
+    torch.testing.assert_close(y.detach().cpu().double(), r.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(x.grad.cpu().double(), x64.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(conv.weight.grad.cpu().double(), w64.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(conv.bias.grad.cpu().double(), b64.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_avgpool_instnorm_lrelu_vs_torch():
+    from faceoff_b200.mocoganhd import layers
+
+    gen = torch.Generator().manual_seed(0)
+    for shape, mod, ref in (((2, 3, 9, 11), layers.AvgPool2d(3, stride=2, padding=[1, 1], count_include_pad=False),
+                             lambda t: F.avg_pool2d(t, 3, 2, [1, 1], count_include_pad=False)),
+                            ((1, 2, 5, 8, 7), layers.AvgPool3d(3, stride=[1, 2, 2], padding=[1, 1, 1], count_include_pad=False),
+                             lambda t: F.avg_pool3d(t, 3, [1, 2, 2], [1, 1, 1], count_include_pad=False)),
+                            ((1, 2, 6, 8, 8), layers.AvgPool3d(3, stride=2, padding=[1, 1, 1], count_include_pad=False),
+                             lambda t: F.avg_pool3d(t, 3, 2, [1, 1, 1], count_include_pad=False))):
+        x = torch.randn(shape, generator=gen)
+        xc = x.cuda().requires_grad_(True)
+        y = mod(xc)
+        go = torch.randn(y.shape, generator=gen)
+        y.backward(go.cuda())
+        xr = x.double().requires_grad_(True)
+        r = ref(xr)
+        r.backward(go.double())
+        torch.testing.assert_close(y.detach().cpu().double(), r.detach(), rtol=1e-5, atol=1e-6)
+        torch.testing.assert_close(xc.grad.cpu().double(), xr.grad, rtol=1e-5, atol=1e-6)
+    # InstanceNorm (training, running statistics) followed by LeakyReLU
+    norm = layers.InstanceNorm3d(5, affine=False, track_running_stats=True).cuda().train()
+    act = layers.LeakyReLU(0.2, True)
+    x = torch.randn(2, 5, 3, 6, 7, generator=gen) * 3 + 1
+    xc = x.cuda().requires_grad_(True)
+    y = act(norm(xc))
+    go = torch.randn(y.shape, generator=gen)
+    y.backward(go.cuda())
+    xr = x.double().requires_grad_(True)
+    rm, rv = torch.zeros(5, dtype=torch.float64), torch.ones(5, dtype=torch.float64)
+    r = F.leaky_relu(F.instance_norm(xr, rm, rv, use_input_stats=True, momentum=0.1, eps=1e-5), 0.2)
+    r.backward(go.double())
+    torch.testing.assert_close(y.detach().cpu().double(), r.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(xc.grad.cpu().double(), xr.grad, rtol=1e-3, atol=1e-5)
+    torch.testing.assert_close(norm.running_mean.cpu().double(), rm, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(norm.running_var.cpu().double(), rv, rtol=1e-5, atol=1e-6)
+    assert norm.num_batches_tracked.item() == 1
