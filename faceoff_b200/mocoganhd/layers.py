@@ -128,8 +128,7 @@ class _InstanceNormMixin:
         if self.affine:
             raise L.FaceoffB200Error("InstanceNorm: affine=True is not used by the reference discriminators")
         use_running = (not self.training) and self.track_running_stats
-        if self.training and self.track_running_stats and self.num_batches_tracked is not None:
-            self.num_batches_tracked.add_(1)
+        # (nn.InstanceNorm*d never advances num_batches_tracked -- only BatchNorm's forward does -- so neither does this)
         momentum = 0.1 if self.momentum is None else self.momentum
         rm = self.running_mean if self.track_running_stats else None
         rv = self.running_var if self.track_running_stats else None
