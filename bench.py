@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-eager", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-disc-step", action="store_true")
     ap.add_argument("--cpu-clip-frames", type=int, default=T_FRAMES)
     ap.add_argument("--eager-clips", type=int, default=4)
     return ap.parse_args()
@@ -510,8 +511,64 @@ def run_ours(args):
                 "largest_layer_class": None if best[0] is None else dict(best[1], layer_class=best[0]),
                 "ncu_evidence": evd}
 
+    def disc_step_bench(steps=5, warmup=3):
+        """BASELINE configs[4] addendum: the MoCoGAN-HD discriminator step of one clip at full size (trainer
+        disc_trainers/train_vqvae_perceptual_mocoganhd_disc.py:240-300): video discriminator on the 11 frame pairs
+        [1, 6, 11, 256, 256] (fake + real forward, relativistic average LSGAN, backward) and image discriminator on one
+        frame pair [1, 6, 256, 256].  First implementation: fp32 CUDA-core kernels (csrc/disc.cu)."""
+        from faceoff_b200.mocoganhd import content_disc, losses, video_disc
+
+        torch.manual_seed(0)
+        d3 = video_disc.ModelD_3d(3, "instance", 2, 1e-4, False, 12).to(dev).train()
+        d2 = content_disc.ModelD_img(3, "instance", 2, 1e-4).to(dev).train()
+        crit = losses.Relativistic_Average_LSGAN()
+        gq = torch.Generator().manual_seed(3)
+        v_real = (torch.rand(1, 6, 11, args.res, args.res, generator=gq) * 2 - 1).to(dev)
+        v_fake = (torch.rand(1, 6, 11, args.res, args.res, generator=gq) * 2 - 1).to(dev)
+        i_real, i_fake = v_real[:, :, 0].contiguous(), v_fake[:, :, 0].contiguous()
+
+        def conv_flops(m, x_shape):
+            tot, shp = 0.0, x_shape
+            for j in range(5):
+                w = getattr(m.netD, f"scale1_layer{j}")[0].weight
+                s = 2 if j < 3 else 1
+                sp = [(v + 4 - 4) // s + 1 for v in shp]
+                tot += 2.0 * w.numel() * float(torch.tensor(sp).prod())
+                shp = sp
+            return tot
+
+        fl3 = conv_flops(d3, [11, args.res, args.res]) + conv_flops(d3, [11, args.res // 2, args.res // 2])
+        fl2 = conv_flops(d2, [args.res, args.res]) + conv_flops(d2, [args.res // 2, args.res // 2])
+        flops = (fl3 + fl2) * 2 * 3      # fake + real, forward + data gradient + weight gradient (upper bound: the first layer has no dgrad)
+
+        def one():
+            for d, fake, real in ((d3, v_fake, v_real), (d2, i_fake, i_real)):
+                o_f, o_r = d(fake), d(real)
+                loss = (crit(o_r, o_f, True) + crit(o_f, o_r, False)) * 0.5
+                d.optim.zero_grad()
+                loss.backward()
+            return loss
+
+        for _ in range(warmup):
+            one()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            one()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        return {"workload": "MoCoGAN-HD discriminator step, 1 clip: D_3d on [1,6,11,256,256] + D_img on [1,6,256,256], "
+                            "fake+real forward, RA-LSGAN, backward (configs[4] component, SURVEY 8(f1))",
+                "ms_per_step": ms, "algorithmic_tflop_per_step": flops / 1e12, "tflops": flops / ms / 1e9,
+                "dtype": "f32 (CUDA cores; tcgen05 forms for k4 / pad 2 / odd sizes are the listed next step)",
+                "steps": steps, "warmup": warmup}
+
     cpu_baseline = None
     extra = {}
+    if rank == 0 and world == 1 and not args.no_disc_step:
+        extra["disc_step"] = disc_step_bench()
     if rank == 0 and world == 1:
         if not args.no_cpu_baseline:
             sec, cores = cpu_train_step_time(args.cpu_clip_frames, args.res, headline_lpips, steps=3, warmup=1)

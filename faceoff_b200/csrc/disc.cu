@@ -4,7 +4,7 @@
 // AvgPool(3, stride 2, pad 1, count_include_pad=False) between the scales, relativistic average LSGAN loss.
 //
 // First implementation of this row: fp32 NCDHW (PyTorch-native layout, no conversions), the convolutions are tiled
-// fp32 implicit GEMMs on the CUDA cores (64 x 64 x 16 tiles, 4 x 4 outputs per thread, operands gathered on the fly with
+// fp32 implicit GEMMs on the CUDA cores (128 x 128 x 8 tiles, 8 x 8 outputs per thread, operands gathered on the fly with
 // zero padding).  The discriminators see ONE 2-frame pair / 11-frame clip per step (~0.15 TFLOP forward), so this path is
 // ~3 % of the FLOPs of the batch-32 VQVAE+LPIPS step; moving these (odd-sized, pad-2, k4) forms onto the tcgen05 planner
 // is listed as the next step in DESIGN.md.  Everything is exact fp32 arithmetic (parity rtol 1e-4 vs the reference).
@@ -24,92 +24,146 @@ __device__ __forceinline__ void decode_pos(int m, const DConvParams& p, bool out
 
 // MODE 0 (forward):  C[m = output position][n = co] = sum_k x[pos (+) tap][ci] * w[co][ci][tap],   k = (ci, tap)
 // MODE 1 (dgrad):    C[m = input position][n = ci]  = sum_k dy[(pos + pad - tap) / stride][co] * w[co][ci][tap], k = (co, tap)
+// 128 x 128 x 8 tiles, 256 threads, 8 x 8 outputs per thread (64 FMAs per 16 shared-memory operand reads).  The k -> (channel,
+// tap) decode of a K slice is done once per slice by 8 threads into shared memory; every loader thread owns a fixed tile
+// row (its position is decoded once), so a gathered element costs three adds, the bounds test and one address.
 template <int MODE>
 __global__ void __launch_bounds__(256)
 dconv_gemm_kernel(const DConvParams p, const float* __restrict__ a_src, const float* __restrict__ wgt,
                   const float* __restrict__ bias, float* __restrict__ out) {
-  constexpr int BM = 64, BN = 64, BK = 16;
+  constexpr int BM = 128, BN = 128, BK = 8;
   __shared__ float As[BK][BM + 4];
   __shared__ float Bs[BK][BN + 4];
+  __shared__ int kt_ch[BK], kt_d[BK], kt_h[BK], kt_w[BK], kt_tap[BK];
   const int taps = p.kd * p.kh * p.kw;
-  const int M = MODE == 0 ? p.n * p.od * p.oh * p.ow : p.n * p.id * p.ih * p.iw;
+  // dgrad of a strided convolution: an input position only receives the taps t = (i + p) mod s (per dimension).  The
+  // input positions are therefore split into sd*sh*sw residue classes (blockIdx.z); within a class the K loop runs over the
+  // matching taps only (1/8 of them for a stride-2 Conv3d) instead of multiplying zeros.
+  int cd_ = 0, ch_ = 0, cw_ = 0, Jd = 1, Jh = 1, Jw = 1, t0d = 0, t0h = 0, t0w = 0, Td = p.kd, Th = p.kh, Tw = p.kw;
+  if (MODE == 1) {
+    const int cls = blockIdx.z;
+    cw_ = cls % p.sw; ch_ = (cls / p.sw) % p.sh; cd_ = cls / (p.sw * p.sh);
+    Jd = cd_ < p.id ? (p.id - cd_ + p.sd - 1) / p.sd : 0;
+    Jh = ch_ < p.ih ? (p.ih - ch_ + p.sh - 1) / p.sh : 0;
+    Jw = cw_ < p.iw ? (p.iw - cw_ + p.sw - 1) / p.sw : 0;
+    t0d = (cd_ + p.pd) % p.sd; t0h = (ch_ + p.ph) % p.sh; t0w = (cw_ + p.pw) % p.sw;
+    Td = t0d < p.kd ? (p.kd - t0d + p.sd - 1) / p.sd : 0;
+    Th = t0h < p.kh ? (p.kh - t0h + p.sh - 1) / p.sh : 0;
+    Tw = t0w < p.kw ? (p.kw - t0w + p.sw - 1) / p.sw : 0;
+  }
+  const int ctaps = MODE == 0 ? taps : Td * Th * Tw;      // taps walked by the K loop
+  const int M = MODE == 0 ? p.n * p.od * p.oh * p.ow : p.n * Jd * Jh * Jw;
   const int N = MODE == 0 ? p.cout : p.cin;
-  const int K = (MODE == 0 ? p.cin : p.cout) * taps;
+  const int K = (MODE == 0 ? p.cin : p.cout) * ctaps;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  if (m0 >= M) return;
   const int tid = threadIdx.x;
-  // A loads: this thread always fetches row (tid % 64) of the tile, k = tid / 64 + 4 j
-  const int am = m0 + (tid & 63);
-  int an = 0, ad = 0, ah = 0, aw = 0;
+  // loaders: thread t fetches tile row / column (t % 128) for k = t / 128 + 2 j, j = 0..3
+  const int lrow = tid & 127, kq = tid >> 7;
+  const int am = m0 + lrow;
   const bool am_ok = am < M;
-  if (am_ok) decode_pos(am, p, MODE == 0, an, ad, ah, aw);
-  // B loads: column (tid % 64), k = tid / 64 + 4 j
-  const int bn = n0 + (tid & 63);
-  const int kq = tid >> 6;
-  const int tx = tid & 15, ty = tid >> 4;      // 16 x 16 threads, 4 x 4 outputs each
-  float acc[4][4];
+  int an = 0, ad = 0, ah = 0, aw = 0;
+  auto decode_m = [&](int m, int& n, int& d, int& h, int& w) {
+    if (MODE == 0) {
+      decode_pos(m, p, true, n, d, h, w);
+    } else {   // position inside the residue class -> input coordinates
+      w = cw_ + p.sw * (m % Jw); m /= Jw;
+      h = ch_ + p.sh * (m % Jh); m /= Jh;
+      d = cd_ + p.sd * (m % Jd);
+      n = m / Jd;
+    }
+  };
+  if (am_ok) decode_m(am, an, ad, ah, aw);
+  // base coordinates of the gather: forward o * s - p (+ tap); dgrad (i + p - t0) / s (- tap index inside the class)
+  const int bd = MODE == 0 ? ad * p.sd - p.pd : (ad + p.pd - t0d) / p.sd;
+  const int bh = MODE == 0 ? ah * p.sh - p.ph : (ah + p.ph - t0h) / p.sh;
+  const int bw = MODE == 0 ? aw * p.sw - p.pw : (aw + p.pw - t0w) / p.sw;
+  const long long src_plane = MODE == 0 ? (long long)p.id * p.ih * p.iw : (long long)p.od * p.oh * p.ow;
+  const int src_c = MODE == 0 ? p.cin : p.cout;
+  const float* a_img = a_src + (long long)an * src_c * src_plane;
+  const int bn = n0 + lrow;
+  const bool bn_ok = bn < N;
+  const int tx = tid & 15, ty = tid >> 4;      // 16 x 16 threads, 8 x 8 outputs each (rows ty*8.., columns tx*8..)
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  const long long in_plane = MODE == 0 ? (long long)p.id * p.ih * p.iw : (long long)p.od * p.oh * p.ow;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   for (int k0 = 0; k0 < K; k0 += BK) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int kl = kq + 4 * j, k = k0 + kl;
-      float av = 0.f, bv = 0.f;
+    if (tid < BK) {
+      const int k = k0 + tid;
+      int ch = -1, td = 0, th = 0, tw = 0, tap = 0;
       if (k < K) {
-        const int ch = k / taps, tap = k % taps;
-        const int tw = tap % p.kw, th = (tap / p.kw) % p.kh, td = tap / (p.kw * p.kh);
-        if (am_ok) {
-          if (MODE == 0) {
-            const int id = ad * p.sd - p.pd + td, ih = ah * p.sh - p.ph + th, iw = aw * p.sw - p.pw + tw;
-            if (id >= 0 && id < p.id && ih >= 0 && ih < p.ih && iw >= 0 && iw < p.iw)
-              av = __ldg(a_src + ((long long)an * p.cin + ch) * in_plane + ((long long)id * p.ih + ih) * p.iw + iw);
-          } else {
-            const int qd = ad + p.pd - td, qh = ah + p.ph - th, qw = aw + p.pw - tw;
-            if (qd >= 0 && qh >= 0 && qw >= 0 && qd % p.sd == 0 && qh % p.sh == 0 && qw % p.sw == 0) {
-              const int od = qd / p.sd, oh = qh / p.sh, ow = qw / p.sw;
-              if (od < p.od && oh < p.oh && ow < p.ow)
-                av = __ldg(a_src + ((long long)an * p.cout + ch) * in_plane + ((long long)od * p.oh + oh) * p.ow + ow);
-            }
-          }
-        }
-        if (bn < N) {
-          // weight [cout][cin][taps]: forward B[k = (ci, tap)][n = co]; dgrad B[k = (co, tap)][n = ci]
-          bv = MODE == 0 ? __ldg(wgt + ((long long)bn * p.cin + ch) * taps + tap)
-                         : __ldg(wgt + ((long long)ch * p.cin + bn) * taps + tap);
+        ch = k / ctaps;
+        const int ct = k % ctaps;
+        if (MODE == 0) {
+          tap = ct;
+          tw = ct % p.kw;
+          th = (ct / p.kw) % p.kh;
+          td = ct / (p.kw * p.kh);
+        } else {   // tap index inside the class -> filter tap t0 + s * t'
+          tw = ct % Tw;
+          th = (ct / Tw) % Th;
+          td = ct / (Tw * Th);
+          tap = ((t0d + p.sd * td) * p.kh + (t0h + p.sh * th)) * p.kw + (t0w + p.sw * tw);
         }
       }
-      As[kl][tid & 63] = av;
-      Bs[kl][tid & 63] = bv;
+      kt_ch[tid] = ch; kt_d[tid] = td; kt_h[tid] = th; kt_w[tid] = tw; kt_tap[tid] = tap;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int kl = kq + 2 * j;
+      const int ch = kt_ch[kl];
+      float av = 0.f, bv = 0.f;
+      if (ch >= 0) {
+        if (am_ok) {
+          if (MODE == 0) {
+            const int id = bd + kt_d[kl], ih = bh + kt_h[kl], iw = bw + kt_w[kl];
+            if ((unsigned)id < (unsigned)p.id && (unsigned)ih < (unsigned)p.ih && (unsigned)iw < (unsigned)p.iw)
+              av = __ldg(a_img + (long long)ch * src_plane + ((long long)id * p.ih + ih) * p.iw + iw);
+          } else {
+            const int od = bd - kt_d[kl], oh = bh - kt_h[kl], ow = bw - kt_w[kl];
+            if ((unsigned)od < (unsigned)p.od && (unsigned)oh < (unsigned)p.oh && (unsigned)ow < (unsigned)p.ow)
+              av = __ldg(a_img + (long long)ch * src_plane + ((long long)od * p.oh + oh) * p.ow + ow);
+          }
+        }
+        if (bn_ok) {
+          // weight [cout][cin][taps]: forward B[k = (ci, tap)][n = co]; dgrad B[k = (co, tap)][n = ci]
+          bv = MODE == 0 ? __ldg(wgt + ((long long)bn * p.cin + ch) * taps + kt_tap[kl])
+                         : __ldg(wgt + ((long long)ch * p.cin + bn) * taps + kt_tap[kl]);
+        }
+      }
+      As[kl][lrow] = av;
+      Bs[kl][lrow] = bv;
     }
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float a[4], b[4];
+      float a[8], b[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
   const long long out_plane = MODE == 0 ? (long long)p.od * p.oh * p.ow : (long long)p.id * p.ih * p.iw;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int m = m0 + ty * 8 + i;
     if (m >= M) continue;
     int n, d, h, w;
-    decode_pos(m, p, MODE == 0, n, d, h, w);
+    decode_m(m, n, d, h, w);
     const int W = MODE == 0 ? p.ow : p.iw, H = MODE == 0 ? p.oh : p.ih;
     const long long sp = ((long long)d * H + h) * W + w;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = n0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int c = n0 + tx * 8 + j;
       if (c >= N) continue;
       float v = acc[i][j];
       if (MODE == 0 && bias != nullptr) v += bias[c];
@@ -118,45 +172,54 @@ dconv_gemm_kernel(const DConvParams p, const float* __restrict__ a_src, const fl
   }
 }
 
-// weight gradient: dw[co][k = (ci, tap)] += sum_pos dy[pos][co] * x[pos (+) tap][ci]; positions split over blockIdx.z
+// weight gradient: dw[co][k = (ci, tap)] += sum_pos dy[pos][co] * x[pos (+) tap][ci]; positions split over blockIdx.z.
+// 128 (co) x 128 (k) x 8 (positions) tiles; a loader thread owns one k column (its (ci, tap) decoded once) resp. one co
+// row; the 8 positions of a slice are decoded once per slice into shared memory.
 __global__ void __launch_bounds__(256)
 dconv_wgrad_kernel(const DConvParams p, const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw,
                    int pos_per_split) {
-  constexpr int BM = 64, BN = 64, BK = 16;
+  constexpr int BM = 128, BN = 128, BK = 8;
   __shared__ float As[BK][BM + 4];   // [pos][co]
   __shared__ float Bs[BK][BN + 4];   // [pos][k]
+  __shared__ int pt_n[BK], pt_d[BK], pt_h[BK], pt_w[BK];
   const int taps = p.kd * p.kh * p.kw;
   const int K = p.cin * taps;
   const int P = p.n * p.od * p.oh * p.ow;
   const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
   const int r_begin = blockIdx.z * pos_per_split, r_end = min(P, r_begin + pos_per_split);
   const int tid = threadIdx.x;
-  const int col = tid & 63, rq = tid >> 6;
+  const int col = tid & 127, rq = tid >> 7;
   const int co = m0 + col;
   const int k = n0 + col;
-  const bool k_ok = k < K;
+  const bool k_ok = k < K, co_ok = co < p.cout;
   const int ci = k_ok ? k / taps : 0, tap = k_ok ? k % taps : 0;
-  const int tw = tap % p.kw, th = (tap / p.kw) % p.kh, td = tap / (p.kw * p.kh);
+  const int tw = tap % p.kw - p.pw, th = (tap / p.kw) % p.kh - p.ph, td = tap / (p.kw * p.kh) - p.pd;
   const int tx = tid & 15, ty = tid >> 4;
   const long long oplane = (long long)p.od * p.oh * p.ow, iplane = (long long)p.id * p.ih * p.iw;
-  float acc[4][4];
+  float acc[8][8];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
   for (int r0 = r_begin; r0 < r_end; r0 += BK) {
+    if (tid < BK) {
+      const int r = r0 + tid;
+      int n = -1, d = 0, h = 0, w = 0;
+      if (r < r_end) decode_pos(r, p, true, n, d, h, w);
+      pt_n[tid] = n; pt_d[tid] = d; pt_h[tid] = h; pt_w[tid] = w;
+    }
+    __syncthreads();
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int rl = rq + 4 * j, r = r0 + rl;
+      const int rl = rq + 2 * j;
+      const int n = pt_n[rl];
       float av = 0.f, bv = 0.f;
-      if (r < r_end) {
-        int n, d, h, w;
-        decode_pos(r, p, true, n, d, h, w);
-        const long long sp = ((long long)d * p.oh + h) * p.ow + w;
-        if (co < p.cout) av = __ldg(dy + ((long long)n * p.cout + co) * oplane + sp);
+      if (n >= 0) {
+        const int d = pt_d[rl], h = pt_h[rl], w = pt_w[rl];
+        if (co_ok) av = __ldg(dy + ((long long)n * p.cout + co) * oplane + ((long long)d * p.oh + h) * p.ow + w);
         if (k_ok) {
-          const int id = d * p.sd - p.pd + td, ih = h * p.sh - p.ph + th, iw = w * p.sw - p.pw + tw;
-          if (id >= 0 && id < p.id && ih >= 0 && ih < p.ih && iw >= 0 && iw < p.iw)
+          const int id = d * p.sd + td, ih = h * p.sh + th, iw = w * p.sw + tw;
+          if ((unsigned)id < (unsigned)p.id && (unsigned)ih < (unsigned)p.ih && (unsigned)iw < (unsigned)p.iw)
             bv = __ldg(x + ((long long)n * p.cin + ci) * iplane + ((long long)id * p.ih + ih) * p.iw + iw);
         }
       }
@@ -166,25 +229,25 @@ dconv_wgrad_kernel(const DConvParams p, const float* __restrict__ x, const float
     __syncthreads();
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
-      float a[4], b[4];
+      float a[8], b[8];
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[kk][ty * 8]), a1 = *reinterpret_cast<const float4*>(&As[kk][ty * 8 + 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8]), b1 = *reinterpret_cast<const float4*>(&Bs[kk][tx * 8 + 4]);
+      a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+      b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+      for (int i = 0; i < 8; ++i)
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int c = m0 + ty * 4 + i;
+  for (int i = 0; i < 8; ++i) {
+    const int c = m0 + ty * 8 + i;
     if (c >= p.cout) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int kk = n0 + tx * 4 + j;
+    for (int j = 0; j < 8; ++j) {
+      const int kk = n0 + tx * 8 + j;
       if (kk < K) atomicAdd(dw + (long long)c * K + kk, acc[i][j]);
     }
   }
@@ -428,13 +491,14 @@ static int nblocks(size_t total, int per_block = 256, int cap = 148 * 16) {
 }
 cudaError_t launch_dconv_fwd(const DConvParams& p, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
   const long long M = (long long)p.n * p.od * p.oh * p.ow;
-  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p.cout + 63) / 64));
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((p.cout + 127) / 128));
   dconv_gemm_kernel<0><<<grid, 256, 0, st>>>(p, x, w, bias, y);
   return cudaGetLastError();
 }
 cudaError_t launch_dconv_dgrad(const DConvParams& p, const float* dy, const float* w, float* dx, cudaStream_t st) {
-  const long long M = (long long)p.n * p.id * p.ih * p.iw;
-  dim3 grid((unsigned)((M + 63) / 64), (unsigned)((p.cin + 63) / 64));
+  // one residue class of input positions per blockIdx.z; grid.x covers the largest class (class (0, 0, 0))
+  const long long M = (long long)p.n * ((p.id + p.sd - 1) / p.sd) * ((p.ih + p.sh - 1) / p.sh) * ((p.iw + p.sw - 1) / p.sw);
+  dim3 grid((unsigned)((M + 127) / 128), (unsigned)((p.cin + 127) / 128), (unsigned)(p.sd * p.sh * p.sw));
   dconv_gemm_kernel<1><<<grid, 256, 0, st>>>(p, dy, w, nullptr, dx);
   return cudaGetLastError();
 }
@@ -445,15 +509,15 @@ cudaError_t launch_dconv_wgrad(const DConvParams& p, const float* x, const float
   const int P = p.n * p.od * p.oh * p.ow;
   cudaError_t e = cudaMemsetAsync(dw, 0, sizeof(float) * p.cout * K, st);
   if (e != cudaSuccess) return e;
-  const int tiles = (int)(((p.cout + 63) / 64) * ((K + 63) / 64));
+  const int tiles = (int)(((p.cout + 127) / 128) * ((K + 127) / 128));
   int splits = (4 * num_sms + tiles - 1) / tiles;
   const int max_splits = (P + 255) / 256;
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   int per = (P + splits - 1) / splits;
-  per = (per + 15) / 16 * 16;
+  per = (per + 7) / 8 * 8;
   splits = (P + per - 1) / per;
-  dim3 grid((unsigned)((p.cout + 63) / 64), (unsigned)((K + 63) / 64), (unsigned)splits);
+  dim3 grid((unsigned)((p.cout + 127) / 128), (unsigned)((K + 127) / 128), (unsigned)splits);
   dconv_wgrad_kernel<<<grid, 256, 0, st>>>(p, x, dy, dw, per);
   if ((e = cudaGetLastError()) != cudaSuccess) return e;
   if (dbias != nullptr) {
