@@ -588,7 +588,21 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
       for (int d = 0; d < 4; ++d) box[d] = b2[d];
     }
   }
-  if (!p.halo) choose_box(ext, 64, box);
+  if (!p.halo) {
+    // 128 pixels per stage whenever the tile exists and two stages fit (see WgradParams::kpix); FO_WG_KPIX=64 forces the
+    // small stages (experiments)
+    const char* kp = getenv("FO_WG_KPIX");
+    int b2[4];
+    choose_box(ext, 128, b2);
+    const int q_loads_max = s1 ? (g->ksize == 3 ? 3 : 1) : 4;
+    const int stage128 = (p.p_chunks * 128 * p.p_rowb + q_loads_max * p.q_chunks * 128 * p.q_rowb + 1023) & ~1023;
+    if (!(kp && atoi(kp) == 64) && b2[3] == 1 && b2[0] * b2[1] * b2[2] == 128 && 2 * stage128 <= kMaxDynSmem - 2048 - 8192) {
+      p.kpix = 128;
+      for (int d = 0; d < 4; ++d) box[d] = b2[d];
+    } else {
+      choose_box(ext, 64, box);
+    }
+  }
   p.total_ptiles = 1;
   for (int d = 0; d < 4; ++d) {
     p.tile_step[d] = box[d];
@@ -602,14 +616,21 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
   // taps; slot order = pass-major.  tap_index maps a slot to the PyTorch filter tap.
   int nt = 0;
   FinalizeParams& f = out->fin;
+  const char* wg_env = getenv("FO_WG_GROUP");   // experiments only: 0 = one MMA per tap, no merged passes
+  const bool grouping = !(wg_env && atoi(wg_env) == 0);
+  const int avail_smem = kMaxDynSmem - 2048 - 8192;   // 8 KB: all-ones tile of the fused bias gradient + alignment
+  const int p_bytes = p.p_chunks * p.kpix * p.p_rowb, q_bytes = p.q_chunks * p.q_box_bytes;
   if (s1) {
     const int k = g->ksize, pad = (k - 1) / 2;
     if (k != 1 && k != 3) return fail(FO_ERR_INVALID, "wgrad ksize unsupported");
     const int kd_n = g->ndim == 3 ? k : 1;
     const int sg = g->q_shift_sign < 0 ? -1 : 1;
     if (p.halo) {
-      // pass = (kd, kw); the three slots of a pass are the vertical offsets -1, 0, +1 read from one box that starts one
-      // row above the tile; slot j serves filter row kh with sg * (kh - pad) == j - 1
+      // pass = (kd, kw); the three slots of a filter column kw are the vertical offsets -1, 0, +1 read from one box that
+      // starts one row above the tile; slot j serves filter row kh with sg * (kh - pad) == j - 1.
+      // Narrow Q sides (9 accumulators of NC columns fit in TMEM next to the bias column): the three filter columns
+      // share a pass too -- three Q boxes per stage, P is read once instead of three times.
+      const bool merge_kw = grouping && g->ndim == 2 && 9 * nc + 16 <= 512 && 2 * ((p_bytes + 3 * q_bytes + 1023) & ~1023) <= avail_smem;
       for (int kd = 0; kd < kd_n; ++kd)
         for (int kw = 0; kw < k; ++kw)
           for (int j = 0; j < k; ++j) {
@@ -620,6 +641,8 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
             f.tap_index[nt] = (int8_t)((kd * k + kh) * k + kw);
             ++nt;
           }
+      p.taps_per_load = 3;
+      p.q_loads = merge_kw ? 3 : 1;
     } else {
       for (int kd = 0; kd < kd_n; ++kd)
         for (int kh = 0; kh < k; ++kh)
@@ -630,8 +653,9 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
             f.tap_index[nt] = (int8_t)nt;
             ++nt;
           }
+      p.taps_per_load = 1;
+      p.q_loads = k == 1 ? 1 : 3;
     }
-    p.taps_per_pass = k == 1 ? 1 : 3;
   } else {
     for (int ky = 0; ky < 4; ++ky)
       for (int kx = 0; kx < 4; ++kx) {
@@ -641,13 +665,22 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
         f.tap_index[nt] = (int8_t)nt;
         ++nt;
       }
-    p.taps_per_pass = 4;
+    p.taps_per_load = 1;
+    p.q_loads = 4;
+  }
+  p.taps_per_pass = p.q_loads * p.taps_per_load;
+  // taps that share one MMA: a whole halo box (3 taps, one image row apart) or all the boxes of a stage (q_bytes apart);
+  // needs one chunk per tap (NC <= 64) and N = G * NC <= 256
+  p.mma_group = 1;
+  if (grouping && p.q_chunks == 1) {
+    int gsz = p.taps_per_load > 1 ? p.taps_per_load : p.q_loads;
+    while (gsz > 1 && (gsz * nc > 256 || (p.taps_per_load > 1 ? p.taps_per_load : p.q_loads) % gsz != 0)) --gsz;
+    p.mma_group = gsz;
   }
   out->taps = nt;
   p.passes = nt / p.taps_per_pass;
-  const int p_bytes = p.p_chunks * p.kpix * p.p_rowb, q_bytes = p.q_chunks * p.q_box_bytes;
-  const int stage_bytes = (p_bytes + (p.halo ? 1 : p.taps_per_pass) * q_bytes + 1023) & ~1023;
-  int stages = (kMaxDynSmem - 2048 - 8192) / stage_bytes;   // 8 KB: all-ones tile of the fused bias gradient + alignment
+  const int stage_bytes = (p_bytes + p.q_loads * q_bytes + 1023) & ~1023;
+  int stages = avail_smem / stage_bytes;
   if (stages > 6) stages = 6;
   if (stages < 2) return fail(FO_ERR_INVALID, "wgrad stage does not fit");
   p.stages = stages;

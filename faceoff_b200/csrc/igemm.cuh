@@ -71,7 +71,7 @@ struct ConvMaps {
 };
 
 // wgrad_igemm: dW[g][m][n] = sum_pixels P[pix][m] * Q[pix (+) shift_g][n]; both operands MN-major.
-constexpr int kMaxWgTaps = 4;  // accumulators resident in TMEM per CTA pass (4 x 128 columns)
+constexpr int kMaxWgTaps = 9;  // accumulators resident in TMEM per CTA pass (taps_per_pass * NC <= 512 columns)
 struct WgTap {
   int16_t c0;
   int8_t d1, d2, d3;
@@ -88,11 +88,18 @@ struct WgradParams {
   int NC;                // Q-side channels per tap (UMMA N), multiple of 16, <= 128
   int q_chunks;
   int q_rowb;
-  int kpix;              // pixels per pipeline stage (64 or 128); kpix/16 MMAs per tap
-  int halo;              // 1: the taps of a pass are the 3 vertical taps read from ONE Q box of R+2 image rows
+  int kpix;              // pixels per pipeline stage (64 or 128); kpix/16 MMAs per tap group.  128 whenever two stages
+                         // fit: a stage costs ~1.4 k cycles of fixed hand-shake latency whatever its size (measured: 1x1
+                         // layers 4.2 -> 5.7 TB/s, 4x4 stride-2 layers 2.13 -> 1.15 ms when going from 64 to 128 pixels)
+  int halo;              // 1: ONE Q box of R+2 image rows holds the 3 vertical taps of a filter column
   int q_tap_off;         // halo: byte offset between consecutive taps inside the Q box (one image row)
   int q_box_bytes;       // bytes of one Q chunk box
   int taps_per_pass;     // <= kMaxWgTaps
+  int q_loads;           // Q boxes fetched per stage (each q_chunks TMA operations)
+  int taps_per_load;     // taps served by one Q box: 3 with halo, else 1 (taps_per_pass = q_loads * taps_per_load)
+  int mma_group;         // G consecutive taps share ONE MMA of N = G * NC columns: their Q boxes lie at a uniform byte
+                         // stride in the stage, which an MN-major descriptor expresses as the chunk stride (LBO); the
+                         // narrow-N layers (NC <= 64) otherwise pay the A-operand read (64 cycles per MMA) once per tap
   int passes;
   int splits;            // split-K factor over pixel tiles
   int total_ptiles;      // prod(tile_cnt)

@@ -13,7 +13,8 @@
 // resident in TMEM) and a contiguous range of kpix-pixel tiles; per tile it loads P once and Q either once per
 // tap, or (3x3(x3) filters, "halo") ONCE as a box of R+2 image rows whose three vertical taps are read through
 // descriptors offset by one image row -- the same operand-reuse trick as conv_igemm.cu, which turns the kernel from
-// TMA-bound into MMA-bound.  Partials go to partial[split][slot][m][n]; wgrad_finalize (elementwise.cu) reduces the
+// TMA-bound into MMA-bound.  Narrow Q sides (NC <= 64) would pay the A-operand read of an MMA (64 cycles whatever N
+// is) once per tap: there `mma_group` taps share one MMA of N = G * NC columns (see WgradParams::mma_group).  Partials go to partial[split][slot][m][n]; wgrad_finalize (elementwise.cu) reduces the
 // splits in a fixed order (deterministic) and scatters into the PyTorch weight layout.
 #include "common.cuh"
 #include "igemm.cuh"
@@ -31,7 +32,7 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
   const int q_chunk_bytes = p.q_box_bytes;
   const int p_bytes = p.p_chunks * p_chunk_bytes;
   const int q_bytes = p.q_chunks * q_chunk_bytes;  // per Q load group (per tap, or per stage with halo)
-  const int q_loads = p.halo ? 1 : p.taps_per_pass;
+  const int q_loads = p.q_loads;
   const int stage_bytes = (p_bytes + q_loads * q_bytes + 1023) & ~1023;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full_bar = bars;
@@ -93,8 +94,8 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int t = t_begin; t < t_end; ++t) {
-        int base[4];
+      const int p_cw = p.p_rowb / 2, q_cw = p.q_rowb / 2;
+      auto tile_base = [&](int t, int (&base)[4]) {
         int r = t;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
@@ -102,16 +103,18 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
           base[d] = (r % c) * p.tile_step[d];
           r /= c;
         }
+      };
+      for (int t = t_begin; t < t_end; ++t) {
+        int base[4];
+        tile_base(t, base);
         mbar_wait_ns(&empty_bar[stage], phase ^ 1, p.backoff_ns);
         uint8_t* sp = smem + (size_t)stage * stage_bytes;
         mbar_expect_tx(&full_bar[stage], p_bytes + q_loads * q_bytes);
-        const int p_cw = p.p_rowb / 2;
         for (int c = 0; c < p.p_chunks; ++c)
           tma_load_5d(sp + c * p_chunk_bytes, &maps.p, &full_bar[stage], p.p_c0 + c * p_cw, base[0], base[1], base[2],
                       base[3]);
-        const int q_cw = p.q_rowb / 2;
         for (int tp = 0; tp < q_loads; ++tp) {
-          const WgTap w = taps[tp];
+          const WgTap w = taps[tp * p.taps_per_load];
           uint8_t* sq = sp + p_bytes + tp * q_bytes;
           for (int c = 0; c < p.q_chunks; ++c)
             tma_load_5d(sq + c * q_chunk_bytes, &maps.q[w.map], &full_bar[stage], w.c0 + c * q_cw, base[0] + w.d1,
@@ -121,10 +124,14 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    const uint32_t idesc = make_idesc_bf16(128, p.NC, 1, 1);
+    // G taps per MMA (N = G * NC): the taps' Q data lie tap_stride bytes apart (inside a halo box: one image row; else
+    // one Q box), which the MN-major descriptor takes as the stride between its NC-wide chunks
+    const int G = p.mma_group, tpl = p.taps_per_load;
+    const uint32_t tap_stride = tpl > 1 ? (uint32_t)p.q_tap_off : (uint32_t)q_bytes;
+    const uint32_t idesc = make_idesc_bf16(128, p.NC * G, 1, 1);
     const uint64_t a_desc_base = make_smem_desc(0, p.p_rowb, p.p_chunks > 1 ? p_chunk_bytes : 0);
-    const uint64_t b_desc_base = make_smem_desc(0, p.q_rowb, p.q_chunks > 1 ? q_chunk_bytes : 0);
-    const uint32_t q16 = (p.halo ? p.q_tap_off : q_bytes) >> 4, pk16 = (16 * p.p_rowb) >> 4, qk16 = (16 * p.q_rowb) >> 4;
+    const uint64_t b_desc_base = make_smem_desc(0, p.q_rowb, p.q_chunks > 1 ? q_chunk_bytes : G > 1 ? tap_stride : 0);
+    const uint32_t qload16 = q_bytes >> 4, qtap16 = p.q_tap_off >> 4, pk16 = (16 * p.p_rowb) >> 4, qk16 = (16 * p.q_rowb) >> 4;
     const int n_taps = p.dbg_skip_mma ? 0 : p.taps_per_pass;
     const int kk_n = p.kpix / 16;
     const uint32_t idesc_bias = make_idesc_bf16(128, 16, 1, 1);
@@ -138,8 +145,8 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
         const uint32_t sp = smem_u32(smem + (size_t)stage * stage_bytes);
         const uint64_t a0 = a_desc_base + ((sp & 0x3FFFF) >> 4);
         const uint64_t b0 = b_desc_base + (((sp + p_bytes) & 0x3FFFF) >> 4);
-        for (int tp = 0; tp < n_taps; ++tp) {
-          const uint64_t bt = b0 + (uint32_t)(tp * q16);
+        for (int tp = 0; tp < n_taps; tp += G) {
+          const uint64_t bt = b0 + (uint32_t)((tp / tpl) * qload16 + (tp % tpl) * qtap16);
           const uint32_t dt = tmem_base + tp * p.NC;
           // 16 pixels per MMA = two 8-row swizzle groups = 16 * rowb bytes
           umma_bf16(dt, a0, bt, idesc, i != 0);
@@ -216,7 +223,7 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
 size_t wgrad_smem_bytes(const WgradParams& p) {
   const int p_bytes = p.p_chunks * p.kpix * p.p_rowb;
   const int q_bytes = p.q_chunks * p.q_box_bytes;
-  const int stage_bytes = (p_bytes + (p.halo ? 1 : p.taps_per_pass) * q_bytes + 1023) & ~1023;
+  const int stage_bytes = (p_bytes + p.q_loads * q_bytes + 1023) & ~1023;
   return (size_t)p.stages * stage_bytes + (2 * p.stages + 1) * 8 + 16 + 1024 + 1024 + 128 * 32;
 }
 

@@ -97,6 +97,27 @@ def main():
         dwt = torch.empty(128, 64, 4, 4, device=dev)
         ms = timeit(lambda: ops.wgrad(ops.FORM_DOWN, 2, 4, (xl, 128, 0), (dyh, 64, 0), dwt, m_axis=0))
         print(f"wgrad4x4s2 128x64 (dec convT 128->64 @64): {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    if which in ("wgrad_small", "all"):
+        F_ = clips * T
+        dy = torch.randn(F_, 64, 64, 128, device=dev).to(torch.bfloat16)
+        h = torch.randn(F_, 64, 64, 32, device=dev).to(torch.bfloat16)
+        x64 = torch.randn(F_, 64, 64, 64, device=dev).to(torch.bfloat16)
+        dw = torch.empty(128, 32, 1, 1, device=dev)
+        db = torch.zeros(128, device=dev)
+        ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 2, 1, (dy, 128, 0), (h, 32, 0), dw, m_axis=0, dbias=db))
+        gb = (dy.numel() + h.numel()) * 2 / 1e9
+        print(f"wgrad1x1 128x32 @64 (+bias): {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        dw = torch.empty(128, 64, 1, 1, device=dev)
+        ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 2, 1, (dy, 128, 0), (x64, 64, 0), dw, m_axis=0, dbias=db))
+        gb = (dy.numel() + x64.numel()) * 2 / 1e9
+        print(f"wgrad1x1 128x64 @64 (+bias): {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        dw = torch.empty(128, 64, 3, 3, device=dev)
+        fl = 2.0 * F_ * 64 * 64 * 128 * 64 * 9
+        ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 2, 3, (dy, 128, 0), (x64, 64, 0), dw, m_axis=0, dbias=db))
+        print(f"wgrad3x3 128x64 @64 (+bias): {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        dw = torch.empty(128, 128, 3, 3, device=dev)
+        ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 2, 3, (dy, 128, 0), (dy, 128, 0), dw, m_axis=0, dbias=db))
+        print(f"wgrad3x3 128x128 @64 (+bias): {ms:.3f} ms  {2 * fl / ms / 1e9:.1f} TFLOP/s")
     if which in ("wgrad3d", "all"):
         x = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)
         dy = torch.randn(clips, T, 64, 64, 128, device=dev).to(torch.bfloat16)
