@@ -341,7 +341,15 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // One lane per TMA operation of a stage (lanes 0 .. a_ops-1: the A box, the next TPS lanes: the B tiles): the
+    // operands of every operation are computed in parallel and the operations are issued back to back.  A single
+    // thread issuing them one after the other is a dependent chain of ~230 cycles per operation, which bounded the
+    // layers whose stages are short (4x4 stride-2: 2 operations per 512 MMA cycles); see also wgrad_igemm.cu.
+    const int n_ops = p.a_ops + p.TPS;
+    if (lane < n_ops) {
+      const bool is_a = lane < p.a_ops;
+      const int j = lane - p.a_ops;                 // B tile index (tap) of this lane
+      const int a_op_bytes = a_bytes / p.a_ops;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < p.total_tiles; tile += gridDim.x) {
@@ -354,28 +362,27 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
           uint8_t* sa = smem + (size_t)stage * stage_bytes;
           uint8_t* sb = sa + a_bytes;
           if (p.dbg_skip_mma == 2) {   // debug: MMAs over whatever is in shared memory, no loads
-            mbar_arrive(&full_bar[stage]);
+            if (lane == 0) mbar_arrive(&full_bar[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             continue;
           }
           const KStep s = ks[k];
-          const int a_op_bytes = a_bytes / p.a_ops;
           if (CG == 2) {
             // both CTAs' loads complete on rank 0's barrier, which rank 0 arms for the bytes of the pair
-            if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * (a_bytes + p.TPS * b_bytes));
+            if (cta_rank == 0 && lane == 0) mbar_expect_tx(&full_bar[stage], 2 * (a_bytes + p.TPS * b_bytes));
             const uint32_t fb = mapa_u32(&full_bar[stage], 0);
-            for (int o = 0; o < p.a_ops; ++o)
-              tma_load_5d_pair(sa + o * a_op_bytes, &maps.a[s.map], fb, s.c0, base[0] + s.d1,
-                               base[1] + s.d2 + o * p.a_op_rows, base[2] + s.d3, base[3]);
-            for (int j = 0; j < p.TPS; ++j)
+            if (is_a)
+              tma_load_5d_pair(sa + lane * a_op_bytes, &maps.a[s.map], fb, s.c0, base[0] + s.d1,
+                               base[1] + s.d2 + lane * p.a_op_rows, base[2] + s.d3, base[3]);
+            else
               tma_load_2d_pair(sb + j * b_bytes, &maps.b, fb, kcol0 + (k * p.TPS + j) * p.KC,
                                nt * p.NT + (int)cta_rank * (p.NT / 2));
           } else {
-            mbar_expect_tx(&full_bar[stage], a_bytes + p.TPS * b_bytes);
-            for (int o = 0; o < p.a_ops; ++o)
-              tma_load_5d(sa + o * a_op_bytes, &maps.a[s.map], &full_bar[stage], s.c0, base[0] + s.d1,
-                          base[1] + s.d2 + o * p.a_op_rows, base[2] + s.d3, base[3]);
-            for (int j = 0; j < p.TPS; ++j)
+            if (lane == 0) mbar_expect_tx(&full_bar[stage], a_bytes + p.TPS * b_bytes);
+            if (is_a)
+              tma_load_5d(sa + lane * a_op_bytes, &maps.a[s.map], &full_bar[stage], s.c0, base[0] + s.d1,
+                          base[1] + s.d2 + lane * p.a_op_rows, base[2] + s.d3, base[3]);
+            else
               tma_load_2d(sb + j * b_bytes, &maps.b, &full_bar[stage], kcol0 + (k * p.TPS + j) * p.KC, nt * p.NT);
           }
           if (++stage == p.stages) { stage = 0; phase ^= 1; }

@@ -90,39 +90,61 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   const WgTap* taps = p.taps + pass * p.taps_per_pass;
 
-  if (warp == 0) {
+  // ---------------------------------------------------------------- producers
+  // One elected thread issuing every TMA operation of a stage is a serial chain of ~230 cycles per operation (tap table
+  // reads, uniform-register moves, UTMALDG) plus the tile decode: measured 1.4 k cycles per 3-operation stage whatever the
+  // number of stages in flight -- the 1x1 and stride-2 layers were bound by this thread, not by memory.  So the work is
+  // spread: warp 0 arms the barrier and loads P, the (otherwise idle) epilogue warps 2.. load one Q box each, and the tile
+  // coordinates are carried incrementally (no divisions per tile).
+  const int q_role = warp - 2;   // Q box fetched by this warp (epilogue warps), if < q_loads
+  if ((warp == 0 || (q_role >= 0 && q_role < q_loads)) && n_my > 0) {
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       const int p_cw = p.p_rowb / 2, q_cw = p.q_rowb / 2;
-      auto tile_base = [&](int t, int (&base)[4]) {
-        int r = t;
+      int idx[4], base[4];
+      {
+        int r = t_begin;
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
-          int c = p.tile_cnt[d];
-          base[d] = (r % c) * p.tile_step[d];
+          const int c = p.tile_cnt[d];
+          idx[d] = r % c;
           r /= c;
+          base[d] = idx[d] * p.tile_step[d];
         }
-      };
+      }
+      const WgTap w = taps[(warp == 0 ? 0 : q_role) * p.taps_per_load];
+      const CUtensorMap* qmap = &maps.q[w.map];
+      const int q_off = p_bytes + (warp == 0 ? 0 : q_role) * q_bytes;
+      const int tx_bytes = p_bytes + q_loads * q_bytes;
       for (int t = t_begin; t < t_end; ++t) {
-        int base[4];
-        tile_base(t, base);
         mbar_wait_ns(&empty_bar[stage], phase ^ 1, p.backoff_ns);
         uint8_t* sp = smem + (size_t)stage * stage_bytes;
-        mbar_expect_tx(&full_bar[stage], p_bytes + q_loads * q_bytes);
-        for (int c = 0; c < p.p_chunks; ++c)
-          tma_load_5d(sp + c * p_chunk_bytes, &maps.p, &full_bar[stage], p.p_c0 + c * p_cw, base[0], base[1], base[2],
-                      base[3]);
-        for (int tp = 0; tp < q_loads; ++tp) {
-          const WgTap w = taps[tp * p.taps_per_load];
-          uint8_t* sq = sp + p_bytes + tp * q_bytes;
+        if (warp == 0) {
+          mbar_expect_tx(&full_bar[stage], tx_bytes);
+          for (int c = 0; c < p.p_chunks; ++c)
+            tma_load_5d(sp + c * p_chunk_bytes, &maps.p, &full_bar[stage], p.p_c0 + c * p_cw, base[0], base[1], base[2],
+                        base[3]);
+        } else {
+          uint8_t* sq = sp + q_off;
           for (int c = 0; c < p.q_chunks; ++c)
-            tma_load_5d(sq + c * q_chunk_bytes, &maps.q[w.map], &full_bar[stage], w.c0 + c * q_cw, base[0] + w.d1,
-                        base[1] + w.d2, base[2] + w.d3, base[3]);
+            tma_load_5d(sq + c * q_chunk_bytes, qmap, &full_bar[stage], w.c0 + c * q_cw, base[0] + w.d1, base[1] + w.d2,
+                        base[2] + w.d3, base[3]);
         }
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        // next tile: odometer over the tile grid
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+          if (++idx[d] < p.tile_cnt[d]) { base[d] += p.tile_step[d]; break; }
+          idx[d] = 0;
+          base[d] = 0;
+        }
       }
     }
+    __syncwarp();
+  }
+  if (warp == 0) {
+    // nothing else: warp 0 only produces
   } else if (warp == 1) {
     // G taps per MMA (N = G * NC): the taps' Q data lie tap_stride bytes apart (inside a halo box: one image row; else
     // one Q box), which the MN-major descriptor takes as the stride between its NC-wide chunks
