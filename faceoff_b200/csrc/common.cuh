@@ -164,8 +164,13 @@ __device__ __forceinline__ uint32_t mapa_u32(const void* p, uint32_t rank) {
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_u32(p)), "r"(rank));
   return r;
 }
+// Remote arrive (the peer CTA's epilogue warps release rank 0's accumulator buffer).  Default semantics (.release at CTA
+// scope): what the arrive publishes are this warp's completed tcgen05.ld reads, already ordered by tcgen05.wait::ld +
+// tcgen05.fence::before_thread_sync.  The former `.release.cluster` form compiled to MEMBAR.ALL.CTA + ERRBAR in front of the
+// arrive, i.e. every epilogue warp drained all of its global stores once per tile (24 % of the stall samples of the VGG
+// 64->64 launch, ncu source page).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
                                                  int c1) {

@@ -97,6 +97,29 @@ def main():
         dwt = torch.empty(128, 64, 4, 4, device=dev)
         ms = timeit(lambda: ops.wgrad(ops.FORM_DOWN, 2, 4, (xl, 128, 0), (dyh, 64, 0), dwt, m_axis=0))
         print(f"wgrad4x4s2 128x64 (dec convT 128->64 @64): {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+    if which in ("vgg", "all"):
+        F_ = clips * T
+        x = torch.randn(F_, 256, 256, 64, device=dev).to(torch.bfloat16).relu_()
+        w = torch.randn(64, 64, 3, 3, device=dev) * 0.03
+        b = torch.zeros(64, device=dev)
+        fl = 2.0 * F_ * 256 * 256 * 64 * 64 * 9
+        ms = timeit(lambda: ops.conv(ops.FORM_S1, 2, 3, [(x, 64, 0)], w, 0, 64, bias=b, want_raw=False, want_relu=True))
+        print(f"vgg conv3x3 64->64 @256 fwd: {ms:.3f} ms  {fl / ms / 1e9:.1f} TFLOP/s")
+        col = torch.randn(F_, 256, 256, 32, device=dev).to(torch.bfloat16)
+        w1 = torch.randn(64, 32, 1, 1, device=dev) * 0.1
+        ms = timeit(lambda: ops.conv(ops.FORM_S1, 2, 1, [(col, 32, 0)], w1, 0, 64, bias=b, want_raw=False, want_relu=True))
+        gb = (col.numel() + x.numel()) * 2 / 1e9
+        print(f"vgg first conv (im2col K=32 -> 64) @256: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        w3 = torch.randn(64, 3, 3, 3, device=dev) * 0.1
+        ms = timeit(lambda: ops.conv(ops.FORM_S1_DGRAD, 2, 3, [(x, 64, 0)], w3, 1, 3, f32="nchw"))
+        print(f"vgg first conv dgrad 64->3 @256: {ms:.3f} ms")
+        del x, col
+        x2 = torch.randn(F_, 128, 128, 64, device=dev).to(torch.bfloat16).relu_()
+        w2 = torch.randn(128, 64, 3, 3, device=dev) * 0.03
+        b2 = torch.zeros(128, device=dev)
+        fl2 = 2.0 * F_ * 128 * 128 * 64 * 128 * 9
+        ms = timeit(lambda: ops.conv(ops.FORM_S1, 2, 3, [(x2, 64, 0)], w2, 0, 128, bias=b2, want_raw=False, want_relu=True))
+        print(f"vgg conv3x3 64->128 @128 fwd: {ms:.3f} ms  {fl2 / ms / 1e9:.1f} TFLOP/s")
     if which in ("wgrad_small", "all"):
         F_ = clips * T
         dy = torch.randn(F_, 64, 64, 128, device=dev).to(torch.bfloat16)
