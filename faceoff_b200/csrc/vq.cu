@@ -132,31 +132,45 @@ __device__ __forceinline__ void vq_halve(float (&s)[16], int lane, int off) {
 // bf16-rounded-up half band of a row: cx/2 with cx = kVqBand * |x| (the row's entry of the augmented K slice)
 __device__ __forceinline__ __nv_bfloat16 vq_half_band(float x2) { return __float2bfloat16_ru(0.5f * kVqBand * sqrtf(x2)); }
 
-// Scan 32 accumulator columns.  Thanks to the augmented K slice the accumulator IS v_k = -(lower bound of code k's
-// distance)/2, so a code costs one LOP3 (column tag in the 5 low mantissa bits) and ~2.5 FMNMX for the running two largest.
-__device__ __forceinline__ void vq_scan32(const uint32_t (&v)[32], uint32_t tag_mask, float& r1, float& r2, int& ridx,
-                                          int code0) {
-  float a1 = -kVqBig, a2 = -kVqBig, b1 = -kVqBig, b2 = -kVqBig;
+// Scan 32 accumulator columns of one row.  Thanks to the augmented K slice the accumulator IS v_k = -(lower bound of code
+// k's distance)/2, so no per-code arithmetic is needed: what remains is finding the largest v, its column, and whether any
+// OTHER code lies within the winner's error band.  FMNMX and LOP3 share the ALU pipe (one warp instruction per two cycles
+// per scheduler), and a running top-2 costs ~3.5 such operations per code -- with two epilogue warps per scheduler that
+// was MORE than the tensor time of a code tile.  So the runner-up is not tracked: per code
+//   ALU pipe : tag the column into 5 mantissa bits (LOP3) and a 3-input max tree (0.5 FMNMX3)            ~1.5 ops
+//   FMA pipe : count the codes above thr = v_max - band(max) with a saturated FMA (exactly 0 or 1) + add     2 ops
+// The two pipes issue in parallel.  When the running maximum moves by more than the new winner's band the count restarts
+// (every earlier code is then certainly out of reach); when it moves by less, the old maximum stays counted and the
+// row ends up flagged -- which is exactly right.  count == 1 <=> the winner is certain.
+constexpr float kVqCountScale = 1.152921504606847e18f;   // 2^60: (t - thr) * 2^60 saturates to exactly 0 or 1
+constexpr float kVqTagSlack = 1.6e-5f;                   // 4x the value shift of two index tags (2 * 2^-19 relative)
+__device__ __forceinline__ float vq_max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+__device__ __forceinline__ float vq_threshold(float m1, float band1) { return fmaf(-kVqTagSlack, fabsf(m1), m1 - band1); }
+__device__ __forceinline__ void vq_scan32(const uint32_t (&v)[32], uint32_t tag_mask, float& m1, int& midx, float& cnt,
+                                          float cxp, const float* sEN, int code0) {
+  float t[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) {
-    // tag_mask lives in a register so that (v & mask) | j is ONE LOP3 (a single immediate per instruction)
-    const float t = __uint_as_float((v[j] & tag_mask) | (uint32_t)j);
-    if (j & 1) {
-      const float mn = fminf(b1, t);
-      b1 = fmaxf(b1, t);
-      b2 = fmaxf(b2, mn);
-    } else {
-      const float mn = fminf(a1, t);
-      a1 = fmaxf(a1, t);
-      a2 = fmaxf(a2, mn);
-    }
+  for (int j = 0; j < 32; ++j) t[j] = __uint_as_float((v[j] & tag_mask) | (uint32_t)j);   // ONE LOP3 each (mask in a register)
+  float a[11];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) a[i] = vq_max3(t[3 * i], t[3 * i + 1], t[3 * i + 2]);
+  a[10] = fmaxf(t[30], t[31]);
+  const float m = fmaxf(vq_max3(vq_max3(a[0], a[1], a[2]), vq_max3(a[3], a[4], a[5]), vq_max3(a[6], a[7], a[8])),
+                        fmaxf(a[9], a[10]));
+  const bool changed = m > m1;
+  const float old = m1;
+  m1 = fmaxf(m1, m);
+  midx = changed ? code0 + (int)(__float_as_uint(m) & 31u) : midx;
+  const float thr = vq_threshold(m1, cxp * sEN[midx]);
+  cnt = (changed && old < thr) ? 0.f : cnt;
+  const float thr_s = -thr * kVqCountScale;
+  float c0 = 0.f, c1 = 0.f;
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    c0 += __saturatef(fmaf(t[j], kVqCountScale, thr_s));
+    c1 += __saturatef(fmaf(t[j + 1], kVqCountScale, thr_s));
   }
-  const float m1 = fmaxf(a1, b1);
-  const float m2 = fmaxf(fminf(a1, b1), fmaxf(a2, b2));
-  const bool gt = m1 > r1;
-  r2 = fmaxf(fmaxf(r2, m2), fminf(r1, m1));
-  ridx = gt ? code0 + (int)(__float_as_uint(m1) & 31u) : ridx;
-  r1 = fmaxf(r1, m1);
+  cnt += c0 + c1;
 }
 
 template <int DIM>
@@ -397,12 +411,15 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
     const uint32_t tag_mask = 0xffffffe0u | ((uint32_t)p.n_tiles >> 30);
     int it = 0, acc_it = 0;
     for (int rt = blockIdx.x; rt < p.row_tiles; rt += gridDim.x, ++it) {
-      float r1 = -kVqBig, r2 = -kVqBig;
+      float m1 = -kVqBig, cnt = 0.f;
       int ridx = 0;
+      // written before a_full, which precedes t_full; same rounding as the loader's augmented row
+      float cxp = 0.f;
       for (int nt = 0; nt < p.n_tiles; ++nt, ++acc_it) {
         const int tb = acc_it & 1;
         mbar_wait(&t_full[tb], (acc_it >> 1) & 1);
         tc_fence_after();
+        if (nt == 0) cxp = 2.f * __bfloat162float(vq_half_band(sX2[(it & 3) * 128 + row]));
         const int c0 = half * (kVqNT / 2);
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + tb * kVqNT + c0;
         const int code0 = nt * kVqNT + c0;
@@ -411,46 +428,50 @@ vq_assign_kernel(const __grid_constant__ VqAssignParams p, const __grid_constant
         tmem_ld32(taddr, va);
         tmem_ld_wait32(va);
         tmem_ld32(taddr + 32, vb);
-        vq_scan32(va, tag_mask, r1, r2, ridx, code0);
+        vq_scan32(va, tag_mask, m1, ridx, cnt, cxp, sEN, code0);
         tmem_ld_wait32(vb);
         tmem_ld32(taddr + 64, va);
-        vq_scan32(vb, tag_mask, r1, r2, ridx, code0 + 32);
+        vq_scan32(vb, tag_mask, m1, ridx, cnt, cxp, sEN, code0 + 32);
         tmem_ld_wait32(va);
         tmem_ld32(taddr + 96, vb);
-        vq_scan32(va, tag_mask, r1, r2, ridx, code0 + 64);
+        vq_scan32(va, tag_mask, m1, ridx, cnt, cxp, sEN, code0 + 64);
         tmem_ld_wait32(vb);
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&t_empty[tb]);   // the accumulator is in registers: release it before the last scan
-        vq_scan32(vb, tag_mask, r1, r2, ridx, code0 + 96);
+        vq_scan32(vb, tag_mask, m1, ridx, cnt, cxp, sEN, code0 + 96);
       }
-      // hand the upper column half over to the lower one (named barrier 1: the 256 epilogue threads)
+      // hand the upper column half over to the lower one.  The upper half only ARRIVES on named barrier 1 (256 = the
+      // epilogue threads) and goes on with the next row tile; sMerge is double-buffered by row-tile parity, and a warp
+      // cannot be two row tiles ahead of its partner (both must release every accumulator before it is reused).
       float* mg = sMerge + ((it & 1) * 128 + row) * 4;
       if (half == 1) {
-        mg[0] = r1; mg[1] = r2; mg[2] = __int_as_float(ridx);
+        mg[0] = m1; mg[1] = cnt; mg[2] = __int_as_float(ridx);
+        asm volatile("bar.arrive 1, 256;" ::: "memory");
+        continue;
       }
       asm volatile("bar.sync 1, 256;" ::: "memory");
-      if (half == 1) continue;
+      float lose;   // the best value of the half that did not win
       {
-        const float o1 = mg[0], o2 = mg[1];
+        const float o1 = mg[0], ocnt = mg[1];
         const int oi = __float_as_int(mg[2]);
-        const bool gt = o1 > r1;
-        r2 = fmaxf(fmaxf(r2, o2), fminf(r1, o1));
+        const bool gt = o1 > m1;
+        lose = fminf(o1, m1);
+        cnt = gt ? ocnt : cnt;
         ridx = gt ? oi : ridx;
-        r1 = fmaxf(r1, o1);
+        m1 = fmaxf(m1, o1);
       }
       const size_t grow = (size_t)rt * 128 + row;
       if (grow < p.rows) {
         p.embed_ind[grow] = ridx;
-        // written before a_full, which precedes t_full; same rounding as the loader's augmented row
-        const float cxp = 2.f * __bfloat162float(vq_half_band(sX2[(it & 3) * 128 + row]));
         const float band1 = cxp * sEN[ridx];
-        // the index tag moved each value by < 2^-18 of its magnitude
-        const float slack = 7.7e-6f * (fabsf(r1) + fabsf(r2));
-        if (!(r1 - r2 > band1 + slack)) {   // ambiguous within the error bound (also catches NaN rows)
+        const float thr = vq_threshold(m1, band1);
+        // certain iff the winner is the only code above its threshold in its own half and the other half stays below it
+        // (the negations also catch NaN rows: every comparison fails, the count is 0)
+        if (!(cnt == 1.f) || !(lose < thr)) {
           const int slot = atomicAdd(p.flag_count, 1);
           p.flag_rows[slot] = (int)grow;   // capacity = rows
-          p.flag_u[slot] = -2.f * r1 + 2.f * band1 + 2.f * slack;
+          p.flag_u[slot] = -2.f * m1 + 2.f * band1 + 2.f * kVqTagSlack * fabsf(m1);
         }
       }
     }
