@@ -8,7 +8,10 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <memory>
 #include <mutex>
+#include <string>
+#include <unordered_map>
 
 #include "../../include/faceoff_b200.h"
 #include "kernels.h"
@@ -531,12 +534,36 @@ extern "C" int fo_conv_pack_weights(const fo_conv_t* c, const float* weight, int
   return FO_OK;
 }
 
+// Plans (tile geometry, K-step table, encoded tensor maps) are cached per thread, keyed on the descriptor bytes: PyTorch's
+// caching allocator hands out the same addresses every step, so in steady state a launch costs one hash lookup instead of
+// the planner, ~6 getenv calls and up to 15 cuTensorMapEncodeTiled calls.  (The forward runs on the main thread, the
+// backward on the autograd thread: two caches, no lock.)  Descriptors come zero-initialised from the bindings, so the
+// padding bytes compare equal.
+template <typename Plan>
+struct PlanCache {
+  std::unordered_map<std::string, std::unique_ptr<Plan>> map;
+  template <typename Desc, typename Fn>
+  int get(const Desc* d, Fn&& build, Plan** out) {
+    std::string key(reinterpret_cast<const char*>(d), sizeof(Desc));
+    auto it = map.find(key);
+    if (it != map.end()) { *out = it->second.get(); return FO_OK; }
+    std::unique_ptr<Plan> plan(new Plan);
+    const int rc = build(plan.get());
+    if (rc != FO_OK) return rc;
+    if (map.size() >= 4096) map.clear();   // shapes / addresses keep changing: start over rather than grow without bound
+    *out = plan.get();
+    map.emplace(std::move(key), std::move(plan));
+    return FO_OK;
+  }
+};
+
 extern "C" int fo_conv_run(const fo_conv_t* c, fo_stream_t stream) {
   REQUIRE_INIT();
-  static thread_local ConvPlan plan;
-  int rc = plan_conv(c, &plan, true);
+  static thread_local PlanCache<ConvPlan> cache;
+  ConvPlan* plan = nullptr;
+  int rc = cache.get(c, [&](ConvPlan* pl) { return plan_conv(c, pl, true); }, &plan);
   if (rc != FO_OK) return rc;
-  CUDA_TRY(launch_conv_igemm(plan.p, plan.maps, g_num_sms, (cudaStream_t)stream));
+  CUDA_TRY(launch_conv_igemm(plan->p, plan->maps, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
 
@@ -745,17 +772,21 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
 
 extern "C" size_t fo_wgrad_workspace_bytes(const fo_wgrad_t* g) {
   if (fo_init() != FO_OK) return 0;
-  static thread_local WgradPlan plan;
-  if (plan_wgrad(g, &plan, false) != FO_OK) return 0;
+  static thread_local PlanCache<WgradPlan> cache;   // (the query precedes the run and carries no workspace yet: its own cache)
+  WgradPlan* planp = nullptr;
+  if (cache.get(g, [&](WgradPlan* pl) { return plan_wgrad(g, pl, false); }, &planp) != FO_OK) return 0;
+  const WgradPlan& plan = *planp;
   return (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float) +
          (size_t)plan.p.passes * plan.p.splits * plan.p.MC * sizeof(float);
 }
 
 extern "C" int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream) {
   REQUIRE_INIT();
-  static thread_local WgradPlan plan;
-  int rc = plan_wgrad(g, &plan, true);
+  static thread_local PlanCache<WgradPlan> cache;
+  WgradPlan* planp = nullptr;
+  int rc = cache.get(g, [&](WgradPlan* pl) { return plan_wgrad(g, pl, true); }, &planp);
   if (rc != FO_OK) return rc;
+  WgradPlan& plan = *planp;
   const size_t main_bytes = (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float);
   const size_t need = main_bytes + (size_t)plan.p.passes * plan.p.splits * plan.p.MC * sizeof(float);
   if (g->workspace == nullptr || g->workspace_bytes < need)

@@ -34,12 +34,62 @@ __device__ __forceinline__ void load_pix(const __nv_bfloat16* p, int lpp, int su
     }
   }
 }
+// Both kernels were instruction bound, not memory bound (~130 / ~230 issue slots per 16-byte vector pair: IEEE sqrt and
+// division sequences, scalar FMAs, per-element selects).  Now: packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2, sm_100),
+// sqrt.approx + rcp.approx (2 MUFU; relative error ~2^-22, far inside the 1e-5 parity bound), the packed bf16 vectors stay
+// in registers until used, U pixels per thread and iteration.
+template <int VPL, bool SPLIT>
+struct PixRaw {
+  uint4 hi[VPL];
+  uint4 lo[SPLIT ? VPL : 1];
+};
+template <int VPL, bool SPLIT>
+__device__ __forceinline__ void load_raw(const __nv_bfloat16* p, int lpp, int sub, int c, PixRaw<VPL, SPLIT>& r) {
+  const uint4* q = reinterpret_cast<const uint4*>(p);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    r.hi[i] = __ldg(q + i * lpp + sub);
+    if (SPLIT) r.lo[i] = __ldg(q + c / 8 + i * lpp + sub);
+  }
+}
+// channel pairs (2e, 2e+1) of vector i -> v[i * 4 + e]
+template <int VPL, bool SPLIT>
+__device__ __forceinline__ void unpack_raw(const PixRaw<VPL, SPLIT>& r, float2 (&v)[VPL * 4]) {
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const uint32_t w[4] = {r.hi[i].x, r.hi[i].y, r.hi[i].z, r.hi[i].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[i * 4 + e] = make_float2(bf16lo(w[e]), bf16hi(w[e]));
+    if (SPLIT) {
+      const uint32_t wl[4] = {r.lo[i].x, r.lo[i].y, r.lo[i].z, r.lo[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[i * 4 + e] = __fadd2_rn(v[i * 4 + e], make_float2(bf16lo(wl[e]), bf16hi(wl[e])));
+    }
+  }
+}
 __device__ __forceinline__ float group_sum(float s, int lpp) {
   for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
   return s;
 }
+__device__ __forceinline__ float sqrt_fast(float x) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+template <int N>
+__device__ __forceinline__ float sum_sq(const float2 (&v)[N]) {
+  float2 s = __fmul2_rn(v[0], v[0]);
+#pragma unroll
+  for (int j = 1; j < N; ++j) s = __ffma2_rn(v[j], v[j], s);
+  return s.x + s.y;
+}
 
-template <int VPL, bool SPLIT>
+template <int VPL, bool SPLIT, int U>
 __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
                                  const float* __restrict__ w, int hw, int c, int lpp, float* __restrict__ out) {
   __shared__ float red[32];
@@ -47,35 +97,41 @@ __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __n
   const int ppw = 32 / lpp;                        // pixels per warp
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % lpp, pw = lane / lpp;
-  float wv[VPL * 8];
+  float2 wv[VPL * 4];
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) wv[i * 8 + e] = __ldg(w + (i * lpp + sub) * 8 + e);
-  float acc = 0.f;
+    for (int e = 0; e < 4; ++e)
+      wv[i * 4 + e] = make_float2(__ldg(w + (i * lpp + sub) * 8 + 2 * e), __ldg(w + (i * lpp + sub) * 8 + 2 * e + 1));
+  float2 acc2 = make_float2(0.f, 0.f);
   const int pix_per_block = (blockDim.x >> 5) * ppw;
-  for (int p0 = blockIdx.x * pix_per_block; p0 < hw; p0 += gridDim.x * pix_per_block) {
-    const int pix = p0 + warp * ppw + pw;
-    const bool ok = pix < hw;
-    float a[VPL * 8], b[VPL * 8];
-    const size_t off = ((size_t)n * hw + (ok ? pix : 0)) * c * (SPLIT ? 2 : 1);
-    load_pix<VPL, SPLIT>(f0 + off, lpp, sub, c, a);
-    load_pix<VPL, SPLIT>(f1 + off, lpp, sub, c, b);
-    float s0 = 0.f, s1 = 0.f;
+  for (int p0 = blockIdx.x * pix_per_block * U; p0 < hw; p0 += gridDim.x * pix_per_block * U) {
+    PixRaw<VPL, SPLIT> ra[U], rb[U];
+    bool ok[U];
 #pragma unroll
-    for (int j = 0; j < VPL * 8; ++j) { s0 += a[j] * a[j]; s1 += b[j] * b[j]; }
-    s0 = group_sum(s0, lpp);
-    s1 = group_sum(s1, lpp);
-    const float i0 = 1.f / (sqrtf(s0) + kLpipsEps), i1 = 1.f / (sqrtf(s1) + kLpipsEps);
-    float d = 0.f;
-#pragma unroll
-    for (int j = 0; j < VPL * 8; ++j) {
-      const float t = a[j] * i0 - b[j] * i1;
-      d += wv[j] * t * t;
+    for (int u = 0; u < U; ++u) {
+      const int pix = p0 + u * pix_per_block + warp * ppw + pw;
+      ok[u] = pix < hw;
+      const size_t off = ((size_t)n * hw + (ok[u] ? pix : 0)) * c * (SPLIT ? 2 : 1);
+      load_raw<VPL, SPLIT>(f0 + off, lpp, sub, c, ra[u]);
+      load_raw<VPL, SPLIT>(f1 + off, lpp, sub, c, rb[u]);
     }
-    if (ok) acc += d;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float2 a[VPL * 4], b[VPL * 4];
+      unpack_raw<VPL, SPLIT>(ra[u], a);
+      unpack_raw<VPL, SPLIT>(rb[u], b);
+      const float s0 = group_sum(sum_sq(a), lpp), s1 = group_sum(sum_sq(b), lpp);
+      const float i0 = rcp_fast(sqrt_fast(s0) + kLpipsEps), i1 = ok[u] ? -rcp_fast(sqrt_fast(s1) + kLpipsEps) : 0.f;
+      const float2 i0v = make_float2(ok[u] ? i0 : 0.f, ok[u] ? i0 : 0.f), i1v = make_float2(i1, i1);
+#pragma unroll
+      for (int j = 0; j < VPL * 4; ++j) {
+        const float2 t = __ffma2_rn(a[j], i0v, __fmul2_rn(b[j], i1v));   // a/n0 - b/n1 (0 for pixels past the end)
+        acc2 = __ffma2_rn(__fmul2_rn(wv[j], t), t, acc2);
+      }
+    }
   }
-  acc = warp_sum(acc);
+  float acc = warp_sum(acc2.x + acc2.y);
   if (lane == 0) red[warp] = acc;
   __syncthreads();
   if (threadIdx.x == 0) {
@@ -88,7 +144,7 @@ __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __n
 // d/df0 of the tap value, times g[n], gated by the ReLU that produced f0, plus optional addend (pool gradient).
 //   a = f0/n0, n0 = |f0| + eps ;  u_c = (2/hw) w_c (a_c - b_c)
 //   dL/df0_j = u_j / n0 - (sum_c u_c f0_c) f0_j / (n0^2 |f0|)
-template <int VPL, bool SPLIT>
+template <int VPL, bool SPLIT, int U>
 __global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
                                      const float* __restrict__ w, const float* __restrict__ g, int hw, int c, int lpp,
                                      __nv_bfloat16* __restrict__ d_f0, const __nv_bfloat16* __restrict__ addend) {
@@ -96,67 +152,79 @@ __global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const
   const int ppw = 32 / lpp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = lane % lpp, pw = lane / lpp;
-  float wv[VPL * 8];
+  const float gn = g[n] * 2.f / (float)hw;
+  float2 gw[VPL * 4];   // (2 g / hw) w_c
 #pragma unroll
   for (int i = 0; i < VPL; ++i)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) wv[i * 8 + e] = __ldg(w + (i * lpp + sub) * 8 + e);
-  const float gn = g[n] * 2.f / (float)hw;
+    for (int e = 0; e < 4; ++e)
+      gw[i * 4 + e] = make_float2(gn * __ldg(w + (i * lpp + sub) * 8 + 2 * e), gn * __ldg(w + (i * lpp + sub) * 8 + 2 * e + 1));
   const int pix_per_block = (blockDim.x >> 5) * ppw;
-  for (int p0 = blockIdx.x * pix_per_block; p0 < hw; p0 += gridDim.x * pix_per_block) {
-    const int pix = p0 + warp * ppw + pw;
-    const bool ok = pix < hw;
-    float a[VPL * 8], b[VPL * 8];
-    const size_t off = ((size_t)n * hw + (ok ? pix : 0)) * c * (SPLIT ? 2 : 1);
-    load_pix<VPL, SPLIT>(f0 + off, lpp, sub, c, a);
-    load_pix<VPL, SPLIT>(f1 + off, lpp, sub, c, b);
-    float s0 = 0.f, s1 = 0.f;
+  for (int p0 = blockIdx.x * pix_per_block * U; p0 < hw; p0 += gridDim.x * pix_per_block * U) {
+    // all loads of the U pixels first (f0, f1, pool-gradient addend)
+    PixRaw<VPL, SPLIT> ra[U], rb[U], rad[U];
+    bool ok[U];
+    size_t off[U];
 #pragma unroll
-    for (int j = 0; j < VPL * 8; ++j) { s0 += a[j] * a[j]; s1 += b[j] * b[j]; }
-    s0 = group_sum(s0, lpp);
-    s1 = group_sum(s1, lpp);
-    const float r0 = sqrtf(s0);
-    const float n0 = r0 + kLpipsEps;
-    const float i0 = 1.f / n0, i1 = 1.f / (sqrtf(s1) + kLpipsEps);
-    float u[VPL * 8];
-    float dot = 0.f;
-#pragma unroll
-    for (int j = 0; j < VPL * 8; ++j) {
-      u[j] = gn * wv[j] * (a[j] * i0 - b[j] * i1);
-      dot += u[j] * a[j];
+    for (int u = 0; u < U; ++u) {
+      const int pix = p0 + u * pix_per_block + warp * ppw + pw;
+      ok[u] = pix < hw;
+      off[u] = ((size_t)n * hw + (ok[u] ? pix : 0)) * c * (SPLIT ? 2 : 1);
+      load_raw<VPL, SPLIT>(f0 + off[u], lpp, sub, c, ra[u]);
+      load_raw<VPL, SPLIT>(f1 + off[u], lpp, sub, c, rb[u]);
+      if (addend != nullptr) load_raw<VPL, SPLIT>(addend + off[u], lpp, sub, c, rad[u]);
     }
-    dot = group_sum(dot, lpp);
-    const float k2 = r0 > 0.f ? dot * i0 * i0 / r0 : 0.f;
-    float ad[VPL * 8];
-    if (addend != nullptr) {
-      load_pix<VPL, SPLIT>(addend + off, lpp, sub, c, ad);
-    } else {
 #pragma unroll
-      for (int j = 0; j < VPL * 8; ++j) ad[j] = 0.f;
-    }
-    if (ok) {
-      uint4* dst = reinterpret_cast<uint4*>(d_f0 + off);
+    for (int u = 0; u < U; ++u) {
+      float2 a[VPL * 4], b[VPL * 4];
+      unpack_raw<VPL, SPLIT>(ra[u], a);
+      unpack_raw<VPL, SPLIT>(rb[u], b);
+      const float s0 = group_sum(sum_sq(a), lpp), s1 = group_sum(sum_sq(b), lpp);
+      const float r0 = sqrt_fast(s0);
+      const float i0 = rcp_fast(r0 + kLpipsEps), i1 = -rcp_fast(sqrt_fast(s1) + kLpipsEps);
+      const float2 i0v = make_float2(i0, i0), i1v = make_float2(i1, i1);
+      float2 uu[VPL * 4];
+      float2 dot2 = make_float2(0.f, 0.f);
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
-        float o[8];
+      for (int j = 0; j < VPL * 4; ++j) {
+        uu[j] = __fmul2_rn(gw[j], __ffma2_rn(a[j], i0v, __fmul2_rn(b[j], i1v)));
+        dot2 = __ffma2_rn(uu[j], a[j], dot2);
+      }
+      const float dot = group_sum(dot2.x + dot2.y, lpp);
+      const float k2 = r0 > 0.f ? -dot * i0 * i0 * rcp_fast(r0) : 0.f;
+      const float2 k2v = make_float2(k2, k2);
+      float2 ad[VPL * 4];
+      if (addend != nullptr) {
+        unpack_raw<VPL, SPLIT>(rad[u], ad);
+      } else {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int j = i * 8 + e;
-          const float gr = u[j] * i0 - k2 * a[j];
-          o[e] = a[j] > 0.f ? gr + ad[j] : 0.f;   // ReLU gate of the tap (addend is already gated)
-        }
-        uint4 ov;
-        ov.x = pack_bf16x2(o[0], o[1]); ov.y = pack_bf16x2(o[2], o[3]);
-        ov.z = pack_bf16x2(o[4], o[5]); ov.w = pack_bf16x2(o[6], o[7]);
-        dst[i * lpp + sub] = ov;
-        if (SPLIT) {   // lo = bf16(value - hi)
-          const uint32_t wv2[4] = {ov.x, ov.y, ov.z, ov.w};
-          uint4 ol;
-          ol.x = pack_bf16x2(o[0] - bf16lo(wv2[0]), o[1] - bf16hi(wv2[0]));
-          ol.y = pack_bf16x2(o[2] - bf16lo(wv2[1]), o[3] - bf16hi(wv2[1]));
-          ol.z = pack_bf16x2(o[4] - bf16lo(wv2[2]), o[5] - bf16hi(wv2[2]));
-          ol.w = pack_bf16x2(o[6] - bf16lo(wv2[3]), o[7] - bf16hi(wv2[3]));
-          dst[c / 8 + i * lpp + sub] = ol;
+        for (int j = 0; j < VPL * 4; ++j) ad[j] = make_float2(0.f, 0.f);
+      }
+      if (ok[u]) {
+        uint4* dst = reinterpret_cast<uint4*>(d_f0 + off[u]);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          float2 o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int j = i * 4 + e;
+            // u / n0 - k f0 + addend, gated by the ReLU of the tap (the addend is already gated)
+            const float2 gr = __ffma2_rn(uu[j], i0v, __ffma2_rn(k2v, a[j], ad[j]));
+            o[e] = make_float2(a[j].x > 0.f ? gr.x : 0.f, a[j].y > 0.f ? gr.y : 0.f);
+          }
+          uint4 ov;
+          ov.x = pack_bf16x2(o[0].x, o[0].y); ov.y = pack_bf16x2(o[1].x, o[1].y);
+          ov.z = pack_bf16x2(o[2].x, o[2].y); ov.w = pack_bf16x2(o[3].x, o[3].y);
+          dst[i * lpp + sub] = ov;
+          if (SPLIT) {   // lo = bf16(value - hi)
+            const uint32_t wv2[4] = {ov.x, ov.y, ov.z, ov.w};
+            uint4 ol;
+            ol.x = pack_bf16x2(o[0].x - bf16lo(wv2[0]), o[0].y - bf16hi(wv2[0]));
+            ol.y = pack_bf16x2(o[1].x - bf16lo(wv2[1]), o[1].y - bf16hi(wv2[1]));
+            ol.z = pack_bf16x2(o[2].x - bf16lo(wv2[2]), o[2].y - bf16hi(wv2[2]));
+            ol.w = pack_bf16x2(o[3].x - bf16lo(wv2[3]), o[3].y - bf16hi(wv2[3]));
+            dst[c / 8 + i * lpp + sub] = ol;
+          }
         }
       }
     }
@@ -181,10 +249,10 @@ cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int
   if (bx < 1) bx = 1;
   dim3 grid(bx, n);
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
-  if (vpl == 1 && !split) lpips_tap_kernel<1, false><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
-  else if (vpl == 2 && !split) lpips_tap_kernel<2, false><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
-  else if (vpl == 1) lpips_tap_kernel<1, true><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
-  else if (vpl == 2) lpips_tap_kernel<2, true><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  if (vpl == 1 && !split) lpips_tap_kernel<1, false, 2><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  else if (vpl == 2 && !split) lpips_tap_kernel<2, false, 2><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  else if (vpl == 1) lpips_tap_kernel<1, true, 1><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  else if (vpl == 2) lpips_tap_kernel<2, true, 1><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -202,10 +270,10 @@ cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w,
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
   __nv_bfloat16* d = (__nv_bfloat16*)d_f0;
   const __nv_bfloat16* ad = (const __nv_bfloat16*)addend;
-  if (vpl == 1 && !split) lpips_tap_bwd_kernel<1, false><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
-  else if (vpl == 2 && !split) lpips_tap_bwd_kernel<2, false><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
-  else if (vpl == 1) lpips_tap_bwd_kernel<1, true><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
-  else if (vpl == 2) lpips_tap_bwd_kernel<2, true><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
+  if (vpl == 1 && !split) lpips_tap_bwd_kernel<1, false, 2><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 2 && !split) lpips_tap_bwd_kernel<2, false, 1><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 1) lpips_tap_bwd_kernel<1, true, 1><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 2) lpips_tap_bwd_kernel<2, true, 1><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
