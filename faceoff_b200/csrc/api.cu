@@ -407,6 +407,9 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   // CTA pairs (cta_group::2): two neighbouring position tiles share every B tile; needs an even tile count per
   // (group, n-tile) so that both CTAs of a pair always have work with the same K-step list
   p.pos_tiles = p.tile_cnt[0] * p.tile_cnt[1] * p.tile_cnt[2] * p.tile_cnt[3];
+  p.fd_pos = make_fastdiv(p.pos_tiles);
+  p.fd_nt = make_fastdiv(p.n_tiles);
+  for (int d = 0; d < 4; ++d) p.fd_cnt[d] = make_fastdiv(p.tile_cnt[d]);
   {
     // worth it for the long-K layers (3x3 / 4x4 / 3x3x3 filters over >= 64 channels); the short 1x1 layers are bound by
     // their epilogue and only pay for the pair's extra synchronisation.  FO_CTA_PAIR=0 disables, =2 forces (debug).

@@ -36,20 +36,19 @@ __device__ __forceinline__ void decode_tile(const ConvParams& p, int tile, int& 
   int t;
   if (p.cta_pair) {
     // position tile fastest: tiles 2i and 2i+1 (the two CTAs of a pair) share the n-tile and the group
-    t = tile % p.pos_tiles;
-    const int rest = tile / p.pos_tiles;
-    nt = rest % p.n_tiles;
-    t += (rest / p.n_tiles) * p.pos_tiles;
+    int rest;
+    p.fd_pos.divmod(tile, rest, t);
+    int gq;
+    p.fd_nt.divmod(rest, gq, nt);
+    t += gq * p.pos_tiles;
   } else {
     // n-tile fastest so CTAs that share an A tile run concurrently and hit L2
-    nt = tile % p.n_tiles;
-    t = tile / p.n_tiles;
+    p.fd_nt.divmod(tile, t, nt);
   }
 #pragma unroll
   for (int d = 0; d < 4; ++d) {
-    int c = p.tile_cnt[d];
-    int i = t % c;
-    t /= c;
+    int i;
+    p.fd_cnt[d].divmod(t, t, i);
     base[d] = i * p.tile_step[d];
   }
   g = t;
@@ -193,10 +192,12 @@ __device__ __forceinline__ void stage_store_rows(__nv_bfloat16* dst, int col0, c
 // (e_cols = 64) or 64-byte (e_cols = 32) swizzle.  Lane L reads the 32 channels starting at column ccol of ITS row L:
 // four 16-byte chunks whose physical position is chunk ^ (row & 7) resp. chunk ^ ((row >> 1) & 3) -- conflict-free.
 __device__ __forceinline__ void load_prefetched(const uint8_t* ebase, int ccol, int e_cols, int lane, uint32_t (&w)[16]) {
+  // e_cols is 64 or 32: shifts, not divisions (this runs once per operand and 32-column chunk)
+  const int sh = e_cols == 64 ? 6 : 5;
   const int rowb = e_cols * 2;
-  const int cb = ccol / e_cols;
+  const int cb = ccol >> sh;
   const uint8_t* row = ebase + cb * (32 * rowb) + lane * rowb;
-  const int k0 = (ccol % e_cols) >> 3;                       // first logical 16-byte chunk inside the row
+  const int k0 = (ccol & (e_cols - 1)) >> 3;                 // first logical 16-byte chunk inside the row
   const int sw = e_cols == 64 ? (lane & 7) : ((lane >> 1) & 3);
 #pragma unroll
   for (int q = 0; q < 4; ++q) {

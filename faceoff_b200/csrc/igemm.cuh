@@ -18,6 +18,29 @@ struct KStep {
   int16_t pad;
 };
 
+// Division by a launch-time constant as multiply-high + shift (dividends < 2^31): the tile decode runs once per tile in the
+// producer and in every epilogue warp, where a hardware-less integer division costs ~25 dependent instructions.
+struct FastDiv {
+  uint32_t mul, shr, div;
+#if defined(__CUDACC__)
+  __device__ __forceinline__ void divmod(int n, int& q, int& r) const {
+    q = div == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr);
+    r = n - q * (int)div;
+  }
+#endif
+};
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f;
+  f.div = (uint32_t)d;
+  if (d <= 1) { f.div = 1; f.mul = 0; f.shr = 0; return f; }
+  int lg = 0;
+  while ((1u << lg) < (uint32_t)d) ++lg;           // ceil(log2 d)
+  const unsigned p = 31 + lg;
+  f.mul = (uint32_t)(((1ull << p) + (uint32_t)d - 1) / (uint32_t)d);
+  f.shr = p - 32;
+  return f;
+}
+
 // conv_igemm: D[128 pixels, NT] = sum_k A_k[128, KC] * W_k[NT, KC]^T   (+ fused epilogue)
 struct ConvParams {
   // M tiling: a tile is a box of box[0] x box[1] x box[2] x box[3] positions on map dims 1..4, product 128*MT
@@ -36,6 +59,7 @@ struct ConvParams {
   int backoff_ns;     // sleep between mbarrier probes of the long waits (0 = plain polling)
   int cta_pair;       // 1: CTA pairs (cluster of 2, tcgen05 cta_group::2): tiles 2i / 2i+1 share every B tile
   int pos_tiles;      // position tiles per (group, n-tile) = product of tile_cnt
+  FastDiv fd_pos, fd_nt, fd_cnt[4];   // dividers by pos_tiles, n_tiles, tile_cnt[d]
   int e_bufs;         // epilogue operand prefetch: 0 = off, else MT (one buffer set per M sub-tile / warp group)
   int e_depth;        // 1: rows of a tile are fetched while its MMAs run; 2: one tile ahead (double-buffered)
   int e_mask, e_add;  // which of the two epilogue operands are prefetched (shared memory permitting)
