@@ -515,8 +515,9 @@ def run_ours(args):
         """BASELINE configs[4] addendum: the MoCoGAN-HD discriminator step of one clip at full size (trainer
         disc_trainers/train_vqvae_perceptual_mocoganhd_disc.py:240-300): video discriminator on the 11 frame pairs
         [1, 6, 11, 256, 256] (fake + real forward, relativistic average LSGAN, backward) and image discriminator on one
-        frame pair [1, 6, 256, 256].  First implementation: fp32 CUDA-core kernels (csrc/disc.cu)."""
-        from faceoff_b200.mocoganhd import content_disc, losses, video_disc
+        frame pair [1, 6, 256, 256].  Timed in both convolution modes: the product path (im2col + split-bf16 GEMMs on the
+        tcgen05 kernel, csrc/disc_gemm.cu) and the exact-fp32 FFMA kernels (csrc/disc.cu)."""
+        from faceoff_b200.mocoganhd import content_disc, layers, losses, video_disc
 
         torch.manual_seed(0)
         d3 = video_disc.ModelD_3d(3, "instance", 2, 1e-4, False, 12).to(dev).train()
@@ -549,20 +550,30 @@ def run_ours(args):
                 loss.backward()
             return loss
 
-        for _ in range(warmup):
-            one()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            one()
-        e1.record()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / steps
+        def timed():
+            for _ in range(warmup):
+                one()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                one()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / steps
+
+        ms = timed()
+        layers.TENSOR_CORE = False
+        try:
+            ms32 = timed()
+        finally:
+            layers.TENSOR_CORE = True
         return {"workload": "MoCoGAN-HD discriminator step, 1 clip: D_3d on [1,6,11,256,256] + D_img on [1,6,256,256], "
                             "fake+real forward, RA-LSGAN, backward (configs[4] component, SURVEY 8(f1))",
                 "ms_per_step": ms, "algorithmic_tflop_per_step": flops / 1e12, "tflops": flops / ms / 1e9,
-                "dtype": "f32 (CUDA cores; tcgen05 forms for k4 / pad 2 / odd sizes are the listed next step)",
+                "dtype": "split-bf16 (hi|lo) GEMMs on tcgen05 with fp32 accumulation over an explicit im2col matrix: 3 MMAs per "
+                         "algorithmic product, ~2e-5 against fp64 (tests/test_gpu_disc.py)",
+                "fp32_ffma_mode": {"ms_per_step": ms32, "tflops": flops / ms32 / 1e9},
                 "steps": steps, "warmup": warmup}
 
     cpu_baseline = None

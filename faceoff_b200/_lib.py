@@ -35,6 +35,7 @@ class ConvDesc(C.Structure):
         ("wpacked", C.c_void_p), ("bias", C.c_void_p), ("mask", C.c_void_p), ("addend", C.c_void_p),
         ("out_bf16", C.c_void_p), ("out_relu", C.c_void_p), ("out_f32", C.c_void_p),
         ("out_cs", C.c_int), ("out_f32_nchw", C.c_int), ("relu_f32", C.c_int), ("split_out", C.c_int),
+        ("out_f32_accumulate", C.c_int),
     ]
 
 
@@ -120,6 +121,10 @@ _SIGS = {
     "fo_dconv_fwd": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fo_dconv_dgrad": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fo_dconv_wgrad": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fo_dconv_im2col_pairs": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "fo_dconv_im2col_t": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fo_dconv_col2im": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_longlong, C.c_void_p, C.c_void_p]),
+    "fo_dconv_dbias": (C.c_int, [C.POINTER(DConvDesc), C.c_void_p, C.c_void_p, C.c_void_p]),
     "fo_instnorm_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_float, C.c_int,
                                   C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fo_instnorm_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_longlong, C.c_float, C.c_int,

@@ -327,8 +327,8 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   bool ok = true;
   auto push_stage = [&](int map, int c0, int d1, int d2, int d3) {
     if (n_stage >= kMaxKSteps) { ok = false; return; }
-    ks[n_stage].c0 = (int16_t)c0; ks[n_stage].d1 = (int8_t)d1; ks[n_stage].d2 = (int8_t)d2; ks[n_stage].d3 = (int8_t)d3;
-    ks[n_stage].map = (uint8_t)map; ks[n_stage].pad = 0;
+    ks[n_stage].c0 = c0; ks[n_stage].d1 = (int8_t)d1; ks[n_stage].d2 = (int8_t)d2; ks[n_stage].d3 = (int8_t)d3;
+    ks[n_stage].map = (uint8_t)map;
     ++n_stage;
   };
   auto push_pack = [&](int tap, int wk0, int valid) {
@@ -455,6 +455,8 @@ static int plan_conv(const fo_conv_t* c, ConvPlan* out, bool need_maps) {
   p.out_relu = (__nv_bfloat16*)c->out_relu;
   p.out_f32 = c->out_f32;
   p.relu_f32 = c->relu_f32;
+  p.acc_f32 = c->out_f32_accumulate;
+  if (p.acc_f32 && c->out_f32 == nullptr) return fail(FO_ERR_INVALID, "out_f32_accumulate needs out_f32");
   p.split_off = 0;
   if (c->split_out) {
     if (nchw || (c->out_cs & 31) != 0 || c->out_cs / 2 < out->npad)
@@ -1033,6 +1035,45 @@ extern "C" int fo_dconv_wgrad(const fo_dconv_t* d, const float* x, const float* 
   int rc = to_dconv(d, &p);
   if (rc != FO_OK) return rc;
   CUDA_TRY(launch_dconv_wgrad(p, x, dy, dw, dbias, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_dconv_im2col_pairs(const fo_dconv_t* d, const float* x, void* col, int kp, int parts, fo_stream_t stream) {
+  REQUIRE_INIT();
+  DConvParams p = {};
+  int rc = to_dconv(d, &p);
+  if (rc != FO_OK) return rc;
+  if (kp % 8 != 0 || kp < d->cin * d->kd * d->kh * d->kw) return fail(FO_ERR_INVALID, "im2col_pairs: kp must be a multiple of 8 and >= K");
+  if (parts != 2 && parts != 3) return fail(FO_ERR_INVALID, "im2col_pairs: parts must be 2 or 3");
+  CUDA_TRY(launch_dim2col_pairs(p, x, col, kp, parts, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_dconv_im2col_t(const fo_dconv_t* d, const float* x, void* out, int kp, int pc, int chunks,
+                                 fo_stream_t stream) {
+  REQUIRE_INIT();
+  DConvParams p = {};
+  int rc = to_dconv(d, &p);
+  if (rc != FO_OK) return rc;
+  if (pc < 8 || pc % 8 != 0 || (long long)pc * chunks < (long long)d->n * d->od * d->oh * d->ow)
+    return fail(FO_ERR_INVALID, "im2col_t: pc (multiple of 8) * chunks must cover all positions");
+  if (kp < d->cin * d->kd * d->kh * d->kw) return fail(FO_ERR_INVALID, "im2col_t: kp < K");
+  CUDA_TRY(launch_dim2col_t(p, x, out, kp, pc, chunks, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_dconv_col2im(const fo_dconv_t* d, const float* dcol, long long ld, float* dx, fo_stream_t stream) {
+  REQUIRE_INIT();
+  DConvParams p;
+  int rc = to_dconv(d, &p);
+  if (rc != FO_OK) return rc;
+  if (ld < (long long)d->cin * d->kd * d->kh * d->kw) return fail(FO_ERR_INVALID, "col2im: ld < K");
+  CUDA_TRY(launch_dcol2im(p, dcol, ld, dx, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" int fo_dconv_dbias(const fo_dconv_t* d, const float* dy, float* dbias, fo_stream_t stream) {
+  REQUIRE_INIT();
+  DConvParams p = {};
+  int rc = to_dconv(d, &p);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_dconv_dbias(dy, p.n, p.cout, p.od * p.oh * p.ow, dbias, (cudaStream_t)stream));
   return FO_OK;
 }
 extern "C" int fo_instnorm_fwd(const float* x, float* y, int n, int c, long long plane, float eps, float slope, int training,

@@ -102,6 +102,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
 #pragma unroll
       for (int q = 0; q < NCH / 4; ++q) {
         float4 o = make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        if (p.acc_f32) {
+          const float4 old = op[q];
+          o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+        }
         if (p.relu_f32) {
           o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
         }
@@ -111,8 +115,10 @@ __device__ __forceinline__ void epilogue_chunk(const ConvParams& p, const uint32
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
         if (col0 + j < p.c_store) {
-          float o = p.relu_f32 ? fmaxf(f[j], 0.f) : f[j];
-          p.out_f32[off + (long long)(col0 + j) * p.out_cstride] = o;
+          float* dst = p.out_f32 + off + (long long)(col0 + j) * p.out_cstride;
+          float o = f[j];
+          if (p.acc_f32) o += *dst;
+          *dst = p.relu_f32 ? fmaxf(o, 0.f) : o;
         }
       }
     }

@@ -12,10 +12,9 @@ constexpr int kMaxGroups = 4;     // sub-pixel (parity) classes of a stride-2 tr
 
 // One K step of the implicit GEMM: which activation map, which channel chunk, which spatial shift.
 struct KStep {
-  int16_t c0;      // coordinate on map dim 0 (channels)
+  int32_t c0;      // coordinate on map dim 0 (channels; the GEMM forms of the discriminator path reach > 2^15)
   int8_t d1, d2, d3;  // coordinate deltas on map dims 1..3
   uint8_t map;     // A-operand tensor map index
-  int16_t pad;
 };
 
 // Division by a launch-time constant as multiply-high + shift (dividends < 2^31): the tile decode runs once per tile in the
@@ -84,6 +83,7 @@ struct ConvParams {
   __nv_bfloat16* out_relu;       // relu(result) or null
   float* out_f32;                // raw result in fp32 (channel stride out_cstride) or null
   int relu_f32;                  // apply relu to out_f32 too
+  int acc_f32;                   // out_f32 += result (K split over several launches: the discriminator GEMMs)
   int split_off;                 // > 0: bf16 tensors of the epilogue are hi|lo pairs, lo part split_off channels after hi
   KStep ksteps[kMaxKSteps];
 };

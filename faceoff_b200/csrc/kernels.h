@@ -102,6 +102,13 @@ cudaError_t launch_dconv_fwd(const DConvParams& p, const float* x, const float* 
 cudaError_t launch_dconv_dgrad(const DConvParams& p, const float* dy, const float* w, float* dx, cudaStream_t st);
 cudaError_t launch_dconv_wgrad(const DConvParams& p, const float* x, const float* dy, float* dw, float* dbias, int num_sms,
                                cudaStream_t st);
+// disc_gemm.cu: data movement of the tensor-core (im2col + split-bf16 GEMM) path of the discriminator convolutions
+cudaError_t launch_dim2col_pairs(const DConvParams& p, const float* x, void* col, int kp, int parts, int num_sms,
+                                 cudaStream_t st);
+cudaError_t launch_dim2col_t(const DConvParams& p, const float* x, void* out, int kp, int pc, int chunks, int num_sms,
+                             cudaStream_t st);
+cudaError_t launch_dcol2im(const DConvParams& p, const float* dcol, long long ld, float* dx, int num_sms, cudaStream_t st);
+cudaError_t launch_dconv_dbias(const float* dy, int n, int c, int plane, float* dbias, cudaStream_t st);
 cudaError_t launch_instnorm_fwd(const float* x, float* y, int n, int c, long long plane, float eps, float slope, int training,
                                 float momentum, float* running_mean, float* running_var, float* save, cudaStream_t st);
 cudaError_t launch_instnorm_bwd(const float* y, const float* dy, float* dx, int n, int c, long long plane, float slope,

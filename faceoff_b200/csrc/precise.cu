@@ -1,7 +1,8 @@
-// Verification mode ("split" activations): helpers that move fp32 values in and out of the hi|lo bf16 pair layout
+// Split ("hi|lo") activations: helpers that move fp32 values in and out of the hi|lo bf16 pair layout
 // (hi = bf16(v) in channels [0, cp), lo = bf16(v - hi) in [cp, 2cp); see fo_conv_t.split_out in include/faceoff_b200.h),
 // and fp32 channels-last max-pool kernels for the LPIPS trunk in that mode.  Test infrastructure for tight parity checks
-// of the tensor-core kernels against an fp64 CPU restatement; never used by the product (bf16) path.
+// of the tensor-core kernels against an fp64 CPU restatement; the split kernel also feeds the split-bf16 GEMMs of the
+// discriminator path (faceoff_b200/mocoganhd/layers.py).  Never used by the bf16 VQVAE / LPIPS path.
 #include "common.cuh"
 #include "kernels.h"
 

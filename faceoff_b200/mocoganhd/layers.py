@@ -42,6 +42,107 @@ def _desc(x_shape, w_shape, stride, padding):
     return d, (x_shape[0], w_shape[0]) + out_sp
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Tensor-core path (default): im2col + GEMMs on the tcgen05 implicit-GEMM kernel (1x1 form) in hi|lo split-bf16 arithmetic
+# (x_hi w_hi + x_lo w_hi + x_hi w_lo, fp32 accumulation in TMEM; see csrc/disc_gemm.cu).  K = Cin * taps is padded to a
+# multiple of 128 (kp).  Accuracy against fp64 convolutions (tests/test_gpu_disc.py): y ~2e-5, dx ~5e-6, dw ~1e-5
+# max-normalised -- the forward figure is set by the tensor core's fp32 accumulation over K / 16 chained MMAs, not by the
+# split (a three-term split measured the same 2e-5), against ~2e-6 for the FFMA kernels of csrc/disc.cu.  Those remain
+# selectable (TENSOR_CORE = False: exact-fp32 parity mode, 4.5x slower); the reference itself runs these convolutions
+# through cuDNN, whose default on Ampere-and-later GPUs is TF32 (~1e-3).
+# ---------------------------------------------------------------------------------------------------------------------
+_KCH = 4096      # K (or position) chunk of one GEMM launch: 3 x 4096 / 64 = 192 of the planner's 256 K steps
+TENSOR_CORE = True
+TC_PARTS = {"fwd": True, "dgrad": True, "wgrad": True}   # experiments: which of the three GEMMs take the tensor-core path
+
+
+def _geom(d):
+    K = d.cin * d.kd * d.kh * d.kw
+    return d.n, d.cout, d.od * d.oh * d.ow, K, (K + 127) // 128 * 128
+
+
+def _use_tc(d) -> bool:
+    return TENSOR_CORE and d.cin * d.kd * d.kh * d.kw >= 64
+
+
+def _w2(w, cout, K, kp):
+    """the parameter as the [cout, kp] GEMM operand (zero columns for k >= K)"""
+    w2 = w.detach().reshape(cout, K)
+    if kp != K:
+        w2 = torch.nn.functional.pad(w2, (0, kp - K))
+    return w2
+
+
+def _tc_forward(x, w, b, d, out_shape):
+    from .. import ops
+    lib = L.load()
+    n, cout, P, K, kp = _geom(d)
+    col = torch.empty((n, 1, P, 2 * kp), dtype=torch.bfloat16, device=x.device)
+    L.check(lib.fo_dconv_im2col_pairs(C.byref(d), x.data_ptr(), col.data_ptr(), kp, 2, _stream()), "fo_dconv_im2col_pairs")
+    _count(1)
+    y = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+    bias = None
+    if b is not None:
+        bias = torch.zeros(ops.pad16(cout), dtype=torch.float32, device=x.device)
+        bias[:cout] = b.detach()
+    for k0 in range(0, kp, _KCH):
+        kc = min(_KCH, kp - k0)
+        ops.conv(ops.FORM_S1, 2, 1, [(col, kc, k0)],
+                 lambda k0=k0, kc=kc: _w2(w, cout, K, kp)[:, k0:k0 + kc].contiguous().view(cout, kc, 1, 1),
+                 0, cout, bias=bias if k0 == 0 else None, want_raw=False, f32="nchw", precise=True, out_f32=y,
+                 f32_accumulate=k0 > 0, wkey=(w, ("dfwd", k0)))
+    return y
+
+
+def _tc_dgrad(dy, w, d, x_shape):
+    from .. import ops
+    lib = L.load()
+    n, cout, P, K, kp = _geom(d)
+    cp = ops.pad16(cout)
+    # dy [n, cout, P] -> pairs channels-last [n * P, 2 * cp]
+    dyp = torch.empty((n, 1, P, 2 * cp), dtype=torch.bfloat16, device=dy.device)
+    L.check(lib.fo_split_f32(dy.data_ptr(), n, cout, P, cout * P, P, 1, dyp.data_ptr(), cp, _stream()), "fo_split_f32")
+    _count(1)
+    dcol = torch.empty((n, 1, P, kp), dtype=torch.float32, device=dy.device)
+    ops.conv(ops.FORM_S1, 2, 1, [(dyp, cout, 0)], lambda: _w2(w, cout, K, kp).contiguous().view(cout, kp, 1, 1), 1, kp,
+             want_raw=False, f32="cl", out_cs=kp, precise=True, out_f32=dcol, wkey=(w, "ddgrad"))
+    dx = torch.empty(x_shape, dtype=torch.float32, device=dy.device)
+    L.check(lib.fo_dconv_col2im(C.byref(d), dcol.data_ptr(), kp, dx.data_ptr(), _stream()), "fo_dconv_col2im")
+    _count(1)
+    return dx
+
+
+def _tc_wgrad(x, dy, w, d, has_bias):
+    from .. import ops
+    lib = L.load()
+    n, cout, P, K, kp = _geom(d)
+    rows = n * P
+    chunks = (rows + _KCH - 1) // _KCH
+    pp = chunks * _KCH
+    # im2col^T, already packed as the (hi | hi | lo) weight operand of each position chunk
+    colT = torch.empty((chunks, kp, 3 * _KCH), dtype=torch.bfloat16, device=x.device)
+    L.check(lib.fo_dconv_im2col_t(C.byref(d), x.data_ptr(), colT.data_ptr(), kp, _KCH, chunks, _stream()), "fo_dconv_im2col_t")
+    _count(1)
+    # dy^T [cout, n * P] as the activation operand ("pixels" = output channels, "channels" = positions)
+    dyt = dy if n == 1 else dy.view(n, cout, P).permute(1, 0, 2).reshape(cout, rows).contiguous()
+    cpix = ops.pad16(cout) if cout < 16 else cout
+    dyp = torch.empty((1, 1, cpix, 2 * pp), dtype=torch.bfloat16, device=x.device)
+    if cpix != cout:
+        dyp.zero_()
+    L.check(lib.fo_split_f32(dyt.data_ptr(), 1, rows, cout, 0, 1, rows, dyp.data_ptr(), pp, _stream()), "fo_split_f32")
+    _count(1)
+    dw = torch.empty((1, 1, cpix, kp), dtype=torch.float32, device=x.device)
+    for i in range(chunks):
+        ops.conv(ops.FORM_S1, 2, 1, [(dyp, _KCH, i * _KCH)], None, 0, kp, want_raw=False, f32="cl", out_cs=kp,
+                 precise=True, out_f32=dw, f32_accumulate=i > 0, wpacked=colT[i], wkey=(w, "unused"))
+    db = None
+    if has_bias:
+        db = torch.empty(cout, dtype=torch.float32, device=x.device)
+        L.check(lib.fo_dconv_dbias(C.byref(d), dy.data_ptr(), db.data_ptr(), _stream()), "fo_dconv_dbias")
+        _count(1)
+    return dw.view(cpix, kp)[:cout, :K].reshape(w.shape), db
+
+
 class _ConvFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, w, b, stride, padding):
@@ -50,10 +151,15 @@ class _ConvFn(torch.autograd.Function):
         x = x.contiguous()
         wd = w.detach().contiguous()
         d, out_shape = _desc(x.shape, w.shape, stride, padding)
-        y = torch.empty(out_shape, dtype=torch.float32, device=x.device)
-        L.check(lib.fo_dconv_fwd(C.byref(d), x.data_ptr(), wd.data_ptr(), None if b is None else b.detach().data_ptr(),
-                                 y.data_ptr(), _stream()), "fo_dconv_fwd")
-        _count(1)
+        ctx.tc = _use_tc(d)
+        ctx.w_param = w     # the parameter object keys the packed-weight cache (version-checked) in forward and backward
+        if ctx.tc and TC_PARTS["fwd"]:
+            y = _tc_forward(x, w, b, d, out_shape)
+        else:
+            y = torch.empty(out_shape, dtype=torch.float32, device=x.device)
+            L.check(lib.fo_dconv_fwd(C.byref(d), x.data_ptr(), wd.data_ptr(), None if b is None else b.detach().data_ptr(),
+                                     y.data_ptr(), _stream()), "fo_dconv_fwd")
+            _count(1)
         ctx.save_for_backward(x, wd)
         ctx.d, ctx.has_bias = d, b is not None
         return y
@@ -66,15 +172,21 @@ class _ConvFn(torch.autograd.Function):
         d = ctx.d
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = torch.empty_like(x)
-            L.check(lib.fo_dconv_dgrad(C.byref(d), dy.data_ptr(), w.data_ptr(), dx.data_ptr(), _stream()), "fo_dconv_dgrad")
-            _count(1)
+            if ctx.tc and TC_PARTS["dgrad"]:
+                dx = _tc_dgrad(dy, ctx.w_param, d, x.shape)
+            else:
+                dx = torch.empty_like(x)
+                L.check(lib.fo_dconv_dgrad(C.byref(d), dy.data_ptr(), w.data_ptr(), dx.data_ptr(), _stream()), "fo_dconv_dgrad")
+                _count(1)
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
-            dw = torch.empty_like(w)
-            db = torch.empty(w.shape[0], dtype=torch.float32, device=w.device) if ctx.has_bias else None
-            L.check(lib.fo_dconv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
-                                       None if db is None else db.data_ptr(), _stream()), "fo_dconv_wgrad")
-            _count(2)
+            if ctx.tc and TC_PARTS["wgrad"]:
+                dw, db = _tc_wgrad(x, dy, ctx.w_param, d, ctx.has_bias)
+            else:
+                dw = torch.empty_like(w)
+                db = torch.empty(w.shape[0], dtype=torch.float32, device=w.device) if ctx.has_bias else None
+                L.check(lib.fo_dconv_wgrad(C.byref(d), x.data_ptr(), dy.data_ptr(), dw.data_ptr(),
+                                           None if db is None else db.data_ptr(), _stream()), "fo_dconv_wgrad")
+                _count(2)
         return dx, dw, db, None, None
 
 

@@ -196,20 +196,24 @@ def out_spatial(form: int, shape: Sequence[int]) -> Tuple[int, ...]:
     return tuple(shape)
 
 
-def packed_weights(desc: ConvDesc, weight: torch.Tensor, n_axis: int, n_scale: Optional[torch.Tensor], key_extra,
-                   wkey=None) -> torch.Tensor:
+def packed_weights(desc: ConvDesc, weight, n_axis: int, n_scale: Optional[torch.Tensor], key_extra,
+                   wkey=None, cache: bool = True) -> torch.Tensor:
     """bf16 K-step-ordered copy of ``weight``, cached per (parameter storage, version, role).  ``wkey`` =
     (source parameter, tag) must be given when ``weight`` is a temporary derived from a parameter (its own
-    data_ptr/version say nothing about staleness)."""
+    data_ptr/version say nothing about staleness); ``weight`` may then be a callable that builds the temporary (only
+    called on a miss).  ``cache=False``: the operand is an activation playing the weight role (never cached)."""
     lib = L.load()
-    src_t, tag = (weight, None) if wkey is None else wkey
-    key = (src_t.data_ptr(), tag, desc.form, desc.ndim, desc.ksize, n_axis, key_extra, _p(n_scale))
-    ver = src_t._version
-    hit = _wcache.get(key)
-    # the entry is only valid for the SAME live tensor object: addresses (and version counters) are recycled by the
-    # caching allocator once a parameter dies
-    if hit is not None and hit[0] == ver and hit[2]() is src_t:
-        return hit[1]
+    if cache:
+        src_t, tag = (weight, None) if wkey is None else wkey
+        key = (src_t.data_ptr(), tag, desc.form, desc.ndim, desc.ksize, n_axis, key_extra, _p(n_scale))
+        ver = src_t._version
+        hit = _wcache.get(key)
+        # the entry is only valid for the SAME live tensor object: addresses (and version counters) are recycled by the
+        # caching allocator once a parameter dies
+        if hit is not None and hit[0] == ver and hit[2]() is src_t:
+            return hit[1]
+    if callable(weight):
+        weight = weight()
     nbytes = lib.fo_conv_wpacked_bytes(C.byref(desc))
     if nbytes == 0:
         raise L.FaceoffB200Error("fo_conv_wpacked_bytes: " + lib.fo_last_error().decode())
@@ -218,7 +222,8 @@ def packed_weights(desc: ConvDesc, weight: torch.Tensor, n_axis: int, n_scale: O
     L.check(lib.fo_conv_pack_weights(C.byref(desc), weight.data_ptr(), weight.shape[0], weight.shape[1], n_axis,
                                      _p(n_scale), wp.data_ptr(), _stream()), "fo_conv_pack_weights")
     _count(1)
-    _wcache[key] = (ver, wp, weakref.ref(src_t))
+    if cache:
+        _wcache[key] = (ver, wp, weakref.ref(src_t))
     return wp
 
 
@@ -226,32 +231,63 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
          bias: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
          addend: Optional[torch.Tensor] = None, want_raw: bool = True, want_relu: bool = False,
          f32: Optional[str] = None, relu_f32: bool = False, n_scale: Optional[torch.Tensor] = None,
-         out_cs: Optional[int] = None, out_raw: Optional[torch.Tensor] = None, wkey=None):
+         out_cs: Optional[int] = None, out_raw: Optional[torch.Tensor] = None, wkey=None,
+         precise: Optional[bool] = None, out_f32: Optional[torch.Tensor] = None, f32_accumulate: bool = False,
+         cache_weights: bool = True, wpacked: Optional[torch.Tensor] = None):
     """Run one implicit-GEMM convolution.  Returns (raw_bf16|None, relu_bf16|None, f32|None).
 
     f32: None | 'cl' (channels-last fp32 [.., out_cs]) | 'nchw' (fp32 [N, cout, H, W]).
+    precise: None = the module-level verification switch; True = hi|lo split-bf16 arithmetic for THIS call (the
+    fp32-accurate GEMMs of the discriminator path, faceoff_b200.mocoganhd).  out_f32 / f32_accumulate: write (or add)
+    the fp32 result into an existing tensor (a GEMM whose K dimension is split over several launches).
+    wpacked: the weight operand already in the packed layout of this descriptor (``weight`` is then ignored).
     """
     lib = L.load()
-    precise = PRECISE
+    precise = PRECISE if precise is None else precise
     if precise:
-        # (hi, lo, hi) sources against (w_hi, w_hi, w_lo) weights; the K axis of the weight is the one that is not N
+        # precise = True / 2: (hi, lo, hi) sources against (w_hi, w_hi, w_lo) weights -- 16 mantissa bits per operand.
+        # precise = 3: operands split into three bf16 terms (24 bits), the six products of total order <= 2:
+        #   x0 w0 + x0 w1 + x1 w0 + x0 w2 + x1 w1 + x2 w0   (fp32-accurate; one logical source only: 6 tensor maps).
+        # The K axis of the weight is the one that is not N.
+        three = precise == 3
         k_axis = 1 - n_axis
-        w_hi = weight.detach().bfloat16().float()
-        w_lo = weight.detach() - w_hi
-        srcs3, parts, o = [], [], 0
+        w_src = weight
+        logical = list(srcs)
+        assert not three or len(logical) == 1
+        x_sel = (0, 0, 1, 0, 1, 2) if three else (0, 1, 0)
+        w_sel = (0, 1, 0, 2, 1, 0) if three else (0, 0, 1)
+
+        def weight():   # built only when the packed-weight cache misses
+            ws = (w_src() if callable(w_src) else w_src).detach()
+            terms, r = [], ws
+            for _ in range(3 if three else 2):
+                t_ = r.bfloat16().float()
+                terms.append(t_)
+                r = r - t_
+            parts, o = [], 0
+            for (_, c, _) in logical:
+                parts += [terms[j].narrow(k_axis, o, c) for j in w_sel]
+                o += c
+            return torch.cat(parts, k_axis).contiguous()
+
+        srcs3 = []
         for (t, c, off) in srcs:
-            half = t.shape[-1] // 2
-            srcs3 += [(t, c, off), (t, c, off + half), (t, c, off)]
-            parts += [w_hi.narrow(k_axis, o, c), w_hi.narrow(k_axis, o, c), w_lo.narrow(k_axis, o, c)]
-            o += c
-        wkey = (weight, "precise") if wkey is None else (wkey[0], ("precise", wkey[1]))
-        weight = torch.cat(parts, k_axis).contiguous()
+            part = t.shape[-1] // (3 if three else 2)
+            srcs3 += [(t, c, off + j * part) for j in x_sel]
+        assert wkey is not None or not callable(w_src), "a lazily built weight needs a cache key"
+        wkey = (w_src, "precise") if wkey is None else (wkey[0], ("precise", precise, wkey[1]))
         logical_srcs, srcs = srcs, srcs3
         assert n_scale is None
     d = _conv_desc(form, ndim, ksize, srcs, cout)
     # the packed column order depends on the planner's tiling mode, which depends on the geometry
     key_extra = tuple((s[1], s[0].shape[-1], s[2]) for s in srcs) + (cout, d.n, d.d, d.h, d.w)
-    wp = packed_weights(d, weight, n_axis, n_scale, key_extra, wkey)
+    if wpacked is not None:
+        need = lib.fo_conv_wpacked_bytes(C.byref(d))
+        assert wpacked.dtype == torch.bfloat16 and wpacked.is_contiguous() and wpacked.numel() * 2 == need, \
+            (wpacked.shape, need)
+        wp = wpacked
+    else:
+        wp = packed_weights(d, weight, n_axis, n_scale, key_extra, wkey, cache=cache_weights)
     d.wpacked = wp.data_ptr()
     t0 = srcs[0][0]
     lead = out_spatial(form, t0.shape[:-1])
@@ -259,7 +295,8 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
     dev = t0.device
     raw = relu = of32 = None
     if f32 == "nchw":
-        of32 = torch.empty((lead[0], cout, lead[1], lead[2]), dtype=torch.float32, device=dev)
+        of32 = out_f32 if out_f32 is not None else torch.empty((lead[0], cout, lead[1], lead[2]), dtype=torch.float32, device=dev)
+        assert of32.is_contiguous() and of32.numel() == lead[0] * cout * lead[1] * lead[2]
         d.out_f32_nchw = 1
     else:
         if want_raw:
@@ -267,7 +304,8 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
         if want_relu:
             relu = torch.empty((*lead, ocs), dtype=torch.bfloat16, device=dev)
         if f32 == "cl":
-            of32 = torch.empty((*lead, ocs), dtype=torch.float32, device=dev)
+            of32 = out_f32 if out_f32 is not None else torch.empty((*lead, ocs), dtype=torch.float32, device=dev)
+            assert of32.is_contiguous() and of32.numel() == ocs * t0.numel() // t0.shape[-1]
     if precise and (raw is not None or relu is not None or mask is not None or addend is not None):
         assert ocs == 2 * pad16(cout) and f32 is None, "verification mode: bf16 epilogue tensors are hi|lo pairs"
         d.split_out = 1
@@ -282,6 +320,7 @@ def conv(form: int, ndim: int, ksize: int, srcs: Sequence[SrcT], weight: torch.T
     d.addend = _p(addend)
     d.out_bf16, d.out_relu, d.out_f32 = _p(raw), _p(relu), _p(of32)
     d.relu_f32 = int(relu_f32)
+    d.out_f32_accumulate = int(f32_accumulate)
     if bias is not None:
         assert bias.dtype == torch.float32 and bias.numel() >= pad16(cout), "bias must be fp32 padded to 16"
     for t in (mask, addend):

@@ -88,6 +88,9 @@ typedef struct {
    * the convolution to ~2^-16 relative accuracy, which lets parity tests compare gradients with an fp64 CPU restatement at 1e-4
    * instead of the bf16 tolerance.  0 = off (the product path). */
   int split_out;
+  /* out_f32 += result instead of out_f32 = result: a GEMM whose K dimension is split over several launches (the
+   * discriminator convolutions below).  0 = overwrite. */
+  int out_f32_accumulate;
 } fo_conv_t;
 
 /* Bytes of packed-weight workspace needed for this descriptor. */
@@ -253,6 +256,19 @@ int fo_dconv_fwd(const fo_dconv_t* d, const float* x, const float* w, const floa
 int fo_dconv_dgrad(const fo_dconv_t* d, const float* dy, const float* w, float* dx, fo_stream_t stream);
 /* dw (overwritten) = gradient w.r.t. the weight, dbias (overwritten, optional) = sum of dy over n and positions */
 int fo_dconv_wgrad(const fo_dconv_t* d, const float* x, const float* dy, float* dw, float* dbias, fo_stream_t stream);
+/* Tensor-core path of the same convolutions: im2col + GEMMs on fo_conv_run (1x1 form) in the hi|lo split-bf16 arithmetic
+ * (split_out / verification mode: fp32-accurate).  These four only move data; k = ((ci * kd + a) * kh + b) * kw + c.
+ *   fo_dconv_im2col_pairs : col [n * P, parts * kp] bf16, term j = bf16(v - sum of the earlier terms) in [j kp, (j+1) kp);
+ *                           parts = 2 (16 mantissa bits) or 3 (24 bits: the forward GEMM); kp % 8 == 0, kp >= K
+ *   fo_dconv_im2col_t     : the transposed matrix as the WEIGHT operand of the weight-gradient GEMM, already in
+ *                           fo_conv_run's packed layout for the sources (hi, lo, hi): out [chunks][kp][3 * pc] bf16 =
+ *                           (hi | hi | lo), chunk = (n * P + pos) / pc, zero past the last position and for k >= K
+ *   fo_dconv_col2im       : dx (NCDHW) = gather of dcol [n * P, ld] fp32 over the taps that reach each input element
+ *   fo_dconv_dbias        : dbias [cout] = sum of dy over n and positions */
+int fo_dconv_im2col_pairs(const fo_dconv_t* d, const float* x, void* col, int kp, int parts, fo_stream_t stream);
+int fo_dconv_im2col_t(const fo_dconv_t* d, const float* x, void* out, int kp, int pc, int chunks, fo_stream_t stream);
+int fo_dconv_col2im(const fo_dconv_t* d, const float* dcol, long long ld, float* dx, fo_stream_t stream);
+int fo_dconv_dbias(const fo_dconv_t* d, const float* dy, float* dbias, fo_stream_t stream);
 /* InstanceNorm (affine=False) fused with LeakyReLU(slope) (slope = 1: no activation): y = lrelu((x - mean) / sqrt(var + eps)),
  * per (n, c) plane of `plane` elements.  training != 0: instance statistics; running_mean / running_var (optional)
  * are updated with `momentum` like nn.InstanceNorm*d(track_running_stats=True) (unbiased variance, averaged over n).

@@ -1,6 +1,14 @@
 """GPU parity tests of the MoCoGAN-HD discriminator step (BASELINE configs[4]) -- ``pytest -m gpu``.
-The CUDA path (faceoff_b200.mocoganhd, csrc/disc.cu through the C ABI) against the committed outputs of the UNMODIFIED
-reference classes (tests/golden/golden_disc.pt) and against the oracle.  fp32 path: rtol 1e-4."""
+The CUDA path (faceoff_b200.mocoganhd through the C ABI) against the committed outputs of the UNMODIFIED reference classes
+(tests/golden/golden_disc.pt) and against the oracle, in both convolution modes:
+
+* ``tensor`` (default product path): im2col + split-bf16 GEMMs on the tcgen05 kernel (csrc/disc_gemm.cu).  Per layer
+  ~2e-5 / 5e-6 / 1e-5 (y / dx / dw, max-normalised against fp64).  End to end the predictions and losses hold the same
+  1e-4 as the fp32 mode; individual weight-gradient ELEMENTS may move by up to a few per cent of the tensor's maximum,
+  because a forward difference of 2e-5 puts some LeakyReLU inputs on the other side of zero (the fp32 mode itself is 1.6e-3
+  away from an fp64 run on one of these tensors: tests/gpu_disc_fp64_check.py) -- the norms of the gradients still agree
+  to 2e-3.
+* ``fp32``: the FFMA kernels of csrc/disc.cu, rtol 1e-4 throughout."""
 import os
 
 import pytest
@@ -19,6 +27,20 @@ def _mn(a, b):
     return ((a.double() - b.double()).abs().max() / (b.double().abs().max() + 1e-300)).item()
 
 
+import contextlib  # noqa: E402
+
+
+@contextlib.contextmanager
+def _mode(mode):
+    from faceoff_b200.mocoganhd import layers
+    old = layers.TENSOR_CORE
+    layers.TENSOR_CORE = mode == "tensor"
+    try:
+        yield
+    finally:
+        layers.TENSOR_CORE = old
+
+
 def _build(kind):
     from faceoff_b200.mocoganhd import content_disc, video_disc
 
@@ -35,12 +57,19 @@ def _build(kind):
     return g, m, x_real, x_fake
 
 
+@pytest.mark.parametrize("mode", ["tensor", "fp32"])
 @pytest.mark.parametrize("kind", ["img", "vid"])
-def test_discriminator_step_matches_reference_golden(kind):
+def test_discriminator_step_matches_reference_golden(kind, mode):
     """Discriminator step (trainer :240-300): fake then real forward in training mode, relativistic average LSGAN loss,
     backward: patch predictions, loss, every parameter gradient, InstanceNorm running statistics."""
+    with _mode(mode):
+        _golden_step(kind, mode)
+
+
+def _golden_step(kind, mode):
     from faceoff_b200.mocoganhd import losses
 
+    tensor = mode == "tensor"
     g, m, x_real, x_fake = _build(kind)
     sd0 = {k: v.clone() for k, v in m.state_dict().items()}
     m = m.cuda().train()
@@ -56,7 +85,7 @@ def test_discriminator_step_matches_reference_golden(kind):
         assert _mn(got[-1].detach().cpu(), ref) < 2e-4
     for got, ref in zip(d_fake, g["pred_fake"]):
         assert _mn(got[-1].detach().cpu(), ref) < 2e-4
-    assert _mn(d_real[1][1].detach().cpu()[:, :4], g["feat_real_scale0_layer1"]) < 1e-4
+    assert _mn(d_real[1][1].detach().cpu()[:, :4], g["feat_real_scale0_layer1"]) < (2e-4 if tensor else 1e-4)
     torch.testing.assert_close(d_loss.detach().cpu(), g["d_loss"], rtol=1e-4, atol=1e-7)
     worst = 0.0
     for k, p in m.named_parameters():
@@ -71,9 +100,12 @@ def test_discriminator_step_matches_reference_golden(kind):
         rel = abs(p.grad.norm().item() - n_ref) / (n_ref + 1e-30)
         worst = max(worst, rel)
         sl = p.grad.flatten()[:64].cpu()
-        assert (sl - g["grad_slices"][k]).abs().max().item() <= 1e-3 * g["grad_slices"][k].abs().max().item() + 1e-5 * n_ref, k
-    print(f"{kind}: worst gradient-norm relative error {worst:.2e}")
-    assert worst < 5e-4
+        err = (sl - g["grad_slices"][k]).abs().max().item()
+        # tensor mode: single elements move when a LeakyReLU gate flips (module docstring); the norm check above holds both
+        assert err <= (5e-2 if tensor else 1e-3) * g["grad_slices"][k].abs().max().item() + 1e-5 * n_ref, \
+            (k, err, g["grad_slices"][k].abs().max().item(), n_ref, rel)
+    print(f"{kind} [{mode}]: worst gradient-norm relative error {worst:.2e}")
+    assert worst < (2e-3 if tensor else 5e-4)
     for k, ref in g["stats_after"].items():
         got = m.state_dict()[k].cpu()
         if "num_batches" in k:
@@ -90,12 +122,18 @@ def test_discriminator_step_matches_reference_golden(kind):
     torch.testing.assert_close(g_loss.detach().cpu(), g["g_loss"], rtol=1e-4, atol=1e-7)
     ref_gx = g["grad_x_fake"]
     err = ((xf.grad.cpu() - ref_gx).abs().max() / ref_gx.abs().max()).item()
-    print(f"{kind}: d(G loss)/d(x_fake) max-normalised error {err:.2e}")
-    assert err < 5e-4
+    print(f"{kind} [{mode}]: d(G loss)/d(x_fake) max-normalised error {err:.2e}")
+    assert err < (2e-2 if tensor else 5e-4)
 
 
+@pytest.mark.parametrize("mode", ["tensor", "fp32"])
 @pytest.mark.parametrize("kind", ["img", "vid"])
-def test_discriminator_eval_mode_uses_running_statistics(kind):
+def test_discriminator_eval_mode_uses_running_statistics(kind, mode):
+    with _mode(mode):
+        _eval_mode(kind)
+
+
+def _eval_mode(kind):
     from oracle import disc_oracle as DO
 
     g, m, x_real, _ = _build(kind)
@@ -115,10 +153,20 @@ def test_discriminator_eval_mode_uses_running_statistics(kind):
         assert torch.equal(v.cpu(), sd[k]), f"eval forward modified {k}"
 
 
+@pytest.mark.parametrize("mode", ["tensor", "fp32"])
 @pytest.mark.parametrize("shape,cout,k,s,p", [((2, 5, 17, 13), 7, 4, 2, 2), ((1, 6, 9, 9), 64, 4, 1, 2), ((1, 3, 5, 11, 9), 4, 4, 2, 2),
-                                              ((2, 4, 3, 6, 7), 5, 4, 1, 2), ((1, 70, 8, 8), 130, 3, 1, 1)])
-def test_dconv_forward_dgrad_wgrad_vs_torch_fp64(shape, cout, k, s, p):
-    """The direct convolution kernels on odd sizes / ragged channel counts (tiles of 64 are partially filled) vs torch fp64."""
+                                              ((2, 4, 3, 6, 7), 5, 4, 1, 2), ((1, 70, 8, 8), 130, 3, 1, 1),
+                                              ((1, 64, 33, 33), 128, 4, 2, 2), ((2, 32, 3, 17, 17), 64, 4, 1, 2),
+                                              ((1, 256, 18, 18), 1, 4, 1, 2), ((1, 6, 5, 64, 64), 64, 4, 2, 2)])
+def test_dconv_forward_dgrad_wgrad_vs_torch_fp64(shape, cout, k, s, p, mode):
+    """Both convolution paths on odd sizes / ragged channel counts (partially filled tiles, K padded to 128, several K and
+    position chunks, 1-channel outputs) vs torch fp64.  fp32 mode: rtol 1e-4.  tensor mode: max-normalised 6e-5 / 2e-5 /
+    6e-5 for y / dx / dw (the tensor core's chained fp32 accumulation)."""
+    with _mode(mode):
+        _dconv_vs_fp64(shape, cout, k, s, p, mode)
+
+
+def _dconv_vs_fp64(shape, cout, k, s, p, mode):
     from faceoff_b200.mocoganhd import layers
 
     gen = torch.Generator().manual_seed(sum(shape) + cout)
@@ -133,6 +181,12 @@ def test_dconv_forward_dgrad_wgrad_vs_torch_fp64(shape, cout, k, s, p):
     b64 = conv.bias.detach().double().cpu().requires_grad_(True)
     r = (F.conv2d if nd == 2 else F.conv3d)(x64, w64, b64, stride=s, padding=p)
     r.backward(go.double().cpu())
+    if mode == "tensor":
+        assert _mn(y.detach().cpu(), r.detach()) < 6e-5
+        assert _mn(x.grad.cpu(), x64.grad) < 2e-5
+        assert _mn(conv.weight.grad.cpu(), w64.grad) < 6e-5
+        assert _mn(conv.bias.grad.cpu(), b64.grad) < 1e-5
+        return
     torch.testing.assert_close(y.detach().cpu().double(), r.detach(), rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(x.grad.cpu().double(), x64.grad, rtol=1e-4, atol=1e-5)
     torch.testing.assert_close(conv.weight.grad.cpu().double(), w64.grad, rtol=1e-4, atol=1e-4)
