@@ -69,7 +69,8 @@ def main():
 
     def same_on_all_ranks(model, what):
         for k, v in model.named_buffers():
-            mine = v.detach().cpu()
+            # NCCL gathers device tensors (one GPU per rank), gloo host tensors (both ranks on cuda:0)
+            mine = v.detach().clone() if multi_gpu else v.detach().cpu()
             lst = [torch.empty_like(mine) for _ in range(world)]
             dist.all_gather(lst, mine)
             assert all(torch.equal(lst[0], t) for t in lst), f"{what}: buffer {k} differs across ranks"
