@@ -939,14 +939,16 @@ extern "C" int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, c
                             &map_x, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
+extern "C" size_t fo_vq_gather_scratch_bytes(int dim, int n_embed) { return vq_gather_scratch_bytes(dim, n_embed); }
 extern "C" int fo_vq_gather_stats(const float* x, const int64_t* embed_ind, size_t rows, int dim, int n_embed,
                                   const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
-                                  float* embed_sum, fo_stream_t stream) {
+                                  float* embed_sum, float* scratch, fo_stream_t stream) {
   REQUIRE_INIT();
   if (dim % 4 != 0) return fail(FO_ERR_INVALID, "vq: dim must be a multiple of 4");
   if (rows == 0) return FO_OK;
+  if (scratch != nullptr && (reinterpret_cast<uintptr_t>(scratch) & 15) != 0) return fail(FO_ERR_INVALID, "vq: scratch must be 16-byte aligned");
   CUDA_TRY(launch_vq_gather_stats(x, embed_ind, rows, dim, n_embed, e_t, q_f32, q_bf16, diff_sum, counts, embed_sum,
-                                  g_num_sms, (cudaStream_t)stream));
+                                  scratch, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
 extern "C" int fo_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts,

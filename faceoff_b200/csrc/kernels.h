@@ -78,7 +78,8 @@ cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, 
 cudaError_t init_vq();
 cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t rows, int dim, int n_embed,
                                    const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
-                                   float* embed_sum, int num_sms, cudaStream_t st);
+                                   float* embed_sum, float* scratch, int num_sms, cudaStream_t st);
+size_t vq_gather_scratch_bytes(int dim, int n_embed);
 cudaError_t launch_vq_ema(float* embed, float* cluster_size, float* embed_avg, const float* counts,
                           const float* embed_sum, int dim, int n_embed, float decay, float one_minus_decay, float eps,
                           cudaStream_t st);

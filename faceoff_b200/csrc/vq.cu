@@ -14,6 +14,8 @@
 //                 w.r.t. the reference outside true near-ties.
 //  vq_gather_stats gather + straight-through + commitment loss + EMA statistics in one pass (:55-61,77-78).
 //  vq_ema         EMA + renormalisation (:66-75).     vq_backward   grad of :77-78.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -666,7 +668,8 @@ __global__ void __launch_bounds__(512)
 vq_gather_stats_kernel(const float* __restrict__ x, const long long* __restrict__ ind, size_t rows,
                                        int dim, int n_embed, const float* __restrict__ e_t, float* __restrict__ q_f32,
                                        __nv_bfloat16* __restrict__ q_bf16, float* __restrict__ diff_sum,
-                                       float* __restrict__ counts, float* __restrict__ embed_sum) {
+                                       float* __restrict__ counts, float* __restrict__ embed_sum,
+                                       float* __restrict__ sum_t) {
   extern __shared__ float sm[];  // SMEM_STATS: [n_embed*dim] sums, [n_embed] counts
   __shared__ float red[32];
   const bool stats = counts != nullptr;
@@ -694,6 +697,12 @@ vq_gather_stats_kernel(const float* __restrict__ x, const long long* __restrict_
       float* d = s_sum + (size_t)k * dim + q * 4;
       atomicAdd(d + 0, a.x); atomicAdd(d + 1, a.y); atomicAdd(d + 2, a.z); atomicAdd(d + 3, a.w);
       if (q == 0) atomicAdd(s_cnt + k, cnt);
+    } else if (sum_t != nullptr) {
+      // codebooks whose statistics do not fit in shared memory: one 16-byte vector atomic per lane into a TRANSPOSED
+      // scratch [n_embed][dim] (the dim floats of a code are contiguous: 2-4 lines per flushed run instead of dim lines
+      // n_embed floats apart); vq_stats_transpose_add folds it into embed_sum afterwards
+      atomicAdd(reinterpret_cast<float4*>(sum_t + (size_t)k * dim) + q, a);
+      if (q == 0) atomicAdd(counts + k, cnt);
     } else {
       const int d0 = q * 4;
       atomicAdd(embed_sum + (size_t)(d0 + 0) * n_embed + k, a.x);
@@ -776,12 +785,38 @@ vq_gather_stats_kernel(const float* __restrict__ x, const long long* __restrict_
   }
 }
 
+// embed_sum[d][k] += sum_t[k][d]   (tiny: n_embed * dim floats; tiled through shared memory, both sides coalesced)
+__global__ void vq_stats_transpose_add_kernel(const float* __restrict__ sum_t, float* __restrict__ embed_sum, int dim,
+                                              int n_embed) {
+  __shared__ float tile[32][33];
+  const int k0 = blockIdx.x * 32, d0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int k = k0 + r, d = d0 + threadIdx.x;
+    tile[r][threadIdx.x] = (k < n_embed && d < dim) ? sum_t[(size_t)k * dim + d] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int d = d0 + r, k = k0 + threadIdx.x;
+    if (d < dim && k < n_embed) embed_sum[(size_t)d * n_embed + k] += tile[threadIdx.x][r];
+  }
+}
+
+size_t vq_gather_scratch_bytes(int dim, int n_embed) {
+  const size_t smem = (size_t)n_embed * (dim + 1) * sizeof(float);
+  static const char* force = getenv("FO_VQ_SMEM_STATS");
+  return (smem <= 200 * 1024 && !(force && atoi(force) == 0)) ? 0 : (size_t)n_embed * dim * sizeof(float);
+}
+
 cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t rows, int dim, int n_embed,
                                    const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
-                                   float* embed_sum, int num_sms, cudaStream_t st) {
-  const size_t smem = (size_t)n_embed * (dim + 1) * sizeof(float);
+                                   float* embed_sum, float* scratch, int num_sms, cudaStream_t st) {
+  size_t smem = (size_t)n_embed * (dim + 1) * sizeof(float);
   const size_t total = rows * (dim / 4);
   size_t blocks = (total + 255) / 256;
+  {
+    static const char* force = getenv("FO_VQ_SMEM_STATS");   // experiments only: 0 = always the global vector-atomic path
+    if (force && atoi(force) == 0 && scratch != nullptr) smem = (size_t)1 << 30;
+  }
   if (smem <= 200 * 1024) {
     static bool configured = false;
     if (!configured) {
@@ -793,11 +828,21 @@ cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t ro
     if (blocks > (size_t)num_sms) blocks = num_sms;  // one CTA per SM (smem-limited)
     vq_gather_stats_kernel<true><<<(int)blocks, 512, smem, st>>>(x, (const long long*)ind, rows, dim, n_embed, e_t,
                                                                    q_f32, (__nv_bfloat16*)q_bf16, diff_sum, counts,
-                                                                   embed_sum);
+                                                                   embed_sum, nullptr);
   } else {
+    const bool use_t = scratch != nullptr && counts != nullptr && dim % 4 == 0;
+    if (use_t) {
+      cudaError_t e = cudaMemsetAsync(scratch, 0, (size_t)n_embed * dim * sizeof(float), st);
+      if (e != cudaSuccess) return e;
+    }
     if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
     vq_gather_stats_kernel<false><<<(int)blocks, 256, 0, st>>>(x, (const long long*)ind, rows, dim, n_embed, e_t, q_f32,
-                                                                (__nv_bfloat16*)q_bf16, diff_sum, counts, embed_sum);
+                                                                (__nv_bfloat16*)q_bf16, diff_sum, counts, embed_sum,
+                                                                use_t ? scratch : nullptr);
+    if (use_t) {
+      dim3 grid((n_embed + 31) / 32, (dim + 31) / 32), block(32, 8);
+      vq_stats_transpose_add_kernel<<<grid, block, 0, st>>>(scratch, embed_sum, dim, n_embed);
+    }
   }
   return cudaGetLastError();
 }

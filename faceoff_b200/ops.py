@@ -603,8 +603,10 @@ def vq_gather_stats(x: torch.Tensor, ind: torch.Tensor, e_t: torch.Tensor, diff_
     q16 = torch.empty((rows, dim), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
     # algorithmic bytes per row: read x 4D + index 8, write q 4D (+ 2D for the bf16 copy)
     with _Timed("hbm/vq_gather_stats", rows * (4.0 * dim + 8 + (4.0 * dim if want_f32 else 0) + (2.0 * dim if want_bf16 else 0))):
+        need = lib.fo_vq_gather_scratch_bytes(dim, n_embed) if counts is not None else 0
+        scratch = workspace(need, x.device, "vq_stats") if need else None
         L.check(lib.fo_vq_gather_stats(x.data_ptr(), ind.data_ptr(), rows, dim, n_embed, e_t.data_ptr(), _p(q32),
-                                       _p(q16), diff_sum.data_ptr(), _p(counts), _p(embed_sum), _stream()),
+                                       _p(q16), diff_sum.data_ptr(), _p(counts), _p(embed_sum), _p(scratch), _stream()),
                 "fo_vq_gather_stats")
     _count(1)
     if precise_pairs:

@@ -189,10 +189,14 @@ size_t fo_vq_assign_workspace_bytes(size_t rows, int dim);
 /* Gather + straight-through + commitment loss + EMA statistics (:55-61,77-78), one pass:
  *   quantize = x + (E[:, ind] - x)         -> q_f32 (optional) and q_bf16 (optional, channels-last copy)
  *   diff_sum += sum (E[:, ind] - x)^2      (caller divides by rows*dim)
- *   counts[k] += #rows assigned to k ; embed_sum[d][k] += sum of x rows assigned to k   (if counts != NULL) */
+ *   counts[k] += #rows assigned to k ; embed_sum[d][k] += sum of x rows assigned to k   (if counts != NULL)
+ * scratch: fo_vq_gather_scratch_bytes(dim, n_embed) bytes (0 when the per-CTA statistics fit in shared memory), 16-byte
+ * aligned, or NULL.  Large codebooks accumulate into it in transposed order with 16-byte vector atomics and fold it into
+ * embed_sum at the end; with NULL they fall back to scalar atomics on embed_sum (same result, slower). */
+size_t fo_vq_gather_scratch_bytes(int dim, int n_embed);
 int fo_vq_gather_stats(const float* x, const int64_t* embed_ind, size_t rows, int dim, int n_embed,
                        const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,
-                       float* embed_sum, fo_stream_t stream);
+                       float* embed_sum, float* scratch, fo_stream_t stream);
 /* EMA update + renormalisation (:66-75), in place on the three buffers; counts / embed_sum are the
  * (all-reduced) statistics.  one_minus_decay is passed separately because the reference forms ``alpha = 1 - decay`` in
  * double precision before rounding it to fp32 (1.f - 0.99f differs from (float)0.01 by 1e-6 relative). */
