@@ -890,6 +890,15 @@ extern "C" int fo_im2col3x3(const float* x, void* out, int n, int c, int h, int 
   CUDA_TRY(launch_im2col3x3(x, out, n, c, h, w, shift, scale, (cudaStream_t)stream));
   return FO_OK;
 }
+extern "C" int fo_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias,
+                                 const float* shift, const float* scale, void* out_relu, fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (n < 1 || h < 1 || w < 1) return fail(FO_ERR_INVALID, "vgg_first_conv: bad extents");
+  if ((shift == nullptr) != (scale == nullptr)) return fail(FO_ERR_INVALID, "vgg_first_conv: shift and scale go together");
+  if ((reinterpret_cast<uintptr_t>(out_relu) & 15) != 0) return fail(FO_ERR_INVALID, "vgg_first_conv: output must be 16-byte aligned");
+  CUDA_TRY(launch_vgg_first_conv(x, n, h, w, weight, bias, shift, scale, out_relu, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
 extern "C" int fo_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi,
                               fo_stream_t stream) {
   REQUIRE_INIT();

@@ -66,6 +66,10 @@ cudaError_t launch_col2im4x4s2(const void* col, const float* bias, float* out, i
 cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, float* out, int accumulate, int num_sms,
                                 cudaStream_t st);
 
+// small_cin.cu
+cudaError_t launch_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias,
+                                  const float* shift, const float* scale, void* out, int num_sms, cudaStream_t st);
+
 // vq.cu
 cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
                            cudaStream_t st);

@@ -190,16 +190,20 @@ def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, t
                           param_grad=False)
             cur_relu = True
         elif kind == "conv" and first:
-            # first conv (3 -> 64): explicit im2col (K = 27 -> 32) + 1x1 GEMM; 3-channel 32-byte TMA rows are slow
+            # first conv (3 -> 64): one kernel from the fp32 NCHW image (ScalingLayer folded in, A tile built in shared
+            # memory, weights resident); no im2col matrix in HBM (csrc/small_cin.cu)
             first = False
             w = tape.params[prefix + key + ".weight"]
             b = tape.params[prefix + key + ".bias"]
-            col = ops.im2col3x3(x, shift, scale)
-            w2 = torch.zeros(ch, 32, dtype=torch.float32, device=w.device)
-            w2[:, :27] = w.detach().permute(0, 2, 3, 1).reshape(ch, 27)
-            _, act, _ = ops.conv(FORM_S1, 2, 1, [(col, 32, 0)], w2.view(ch, 32, 1, 1), 0, ch, bias=b,
-                                 want_raw=False, want_relu=True, wkey=(w, "im2col3x3"))
-            del col
+            if ch == 64 and x.shape[1] == 3:
+                act = ops.vgg_first_conv(x.contiguous(), w.detach().contiguous(), b.detach(), shift, scale)
+            else:   # other widths: explicit im2col (K = 27 -> 32) + 1x1 GEMM
+                col = ops.im2col3x3(x, shift, scale)
+                w2 = torch.zeros(ch, 32, dtype=torch.float32, device=w.device)
+                w2[:, :27] = w.detach().permute(0, 2, 3, 1).reshape(ch, 27)
+                _, act, _ = ops.conv(FORM_S1, 2, 1, [(col, 32, 0)], w2.view(ch, 32, 1, 1), 0, ch, bias=b,
+                                     want_raw=False, want_relu=True, wkey=(w, "im2col3x3"))
+                del col
             cur = Node(ch, act=act)
 
             def first_bwd(node=cur, w=w):

@@ -470,6 +470,21 @@ def im2col3x3(x: torch.Tensor, shift: Optional[torch.Tensor] = None, scale: Opti
     return out
 
 
+def vgg_first_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, shift: Optional[torch.Tensor] = None,
+                   scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """relu(conv3x3((x - shift) / scale, weight) + bias): NCHW fp32 [N, 3, H, W] -> bf16 channels-last [N, H, W, 64]."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous() and x.shape[1] == 3
+    assert tuple(weight.shape) == (64, 3, 3, 3) and weight.is_contiguous() and bias.numel() >= 64
+    n, _, h, w = x.shape
+    out = torch.empty((n, h, w, 64), dtype=torch.bfloat16, device=x.device)
+    with _Timed("hbm/vgg_first_conv", n * h * w * (12.0 + 128.0)):
+        L.check(lib.fo_vgg_first_conv(x.data_ptr(), n, h, w, weight.data_ptr(), bias.data_ptr(), _p(shift), _p(scale),
+                                      out.data_ptr(), _stream()), "fo_vgg_first_conv")
+    _count(1)
+    return out
+
+
 def col2im4x4s2(col: torch.Tensor, bias: Optional[torch.Tensor], c: int) -> torch.Tensor:
     """bf16 [N, Hi, Wi, 128] (k = tap*8 + co) -> NCHW fp32 [N, c, 2Hi, 2Wi] (+ bias)."""
     lib = L.load()

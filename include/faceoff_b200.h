@@ -157,6 +157,12 @@ int fo_im2col4x4s2(const float* x, void* out, int n, int ca, int c, int h, int w
  * with the ScalingLayer (x - shift) / scale folded in (reference models/lpips.py:96-103,119). */
 int fo_im2col3x3(const float* x, void* out, int n, int c, int h, int w, const float* shift, const float* scale,
                  fo_stream_t stream);
+/* The same layer in one kernel (the product path): ScalingLayer + Conv2d(3 -> 64, 3x3, pad 1) + ReLU from the fp32 NCHW
+ * image x [n, 3, h, w] to the bf16 channels-last activation out_relu [n, h, w, 64]; weight [64, 3, 3, 3] / bias [64] are
+ * the PyTorch parameters (reference models/lpips.py:96-103,119-127).  The A tile is built in shared memory, no im2col
+ * matrix reaches HBM. */
+int fo_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias, const float* shift,
+                      const float* scale, void* out_relu, fo_stream_t stream);
 /* Inverse scatter for the last ConvTranspose2d: col bf16 [n, hi, wi, 128] (k = tap*8 + co) + bias -> NCHW fp32
  * [n, c, 2hi, 2wi]. */
 int fo_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, fo_stream_t stream);

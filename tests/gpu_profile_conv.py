@@ -111,6 +111,12 @@ def main():
         gb = (col.numel() + x.numel()) * 2 / 1e9
         print(f"vgg first conv (im2col K=32 -> 64) @256: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
         w3 = torch.randn(64, 3, 3, 3, device=dev) * 0.1
+        img = torch.rand(F_, 3, 256, 256, device=dev)
+        sh3, sc3 = torch.tensor([-.03, -.088, -.188], device=dev), torch.tensor([.458, .448, .45], device=dev)
+        ms = timeit(lambda: ops.vgg_first_conv(img, w3, b, sh3, sc3))
+        gb = (img.numel() * 4 + x.numel() * 2) / 1e9
+        print(f"vgg first conv fused (3 -> 64) @256: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        del img
         ms = timeit(lambda: ops.conv(ops.FORM_S1_DGRAD, 2, 3, [(x, 64, 0)], w3, 1, 3, f32="nchw"))
         print(f"vgg first conv dgrad 64->3 @256: {ms:.3f} ms")
         del x, col

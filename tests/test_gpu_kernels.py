@@ -141,6 +141,26 @@ def test_im2col3x3_with_scaling_layer():
     assert col[..., 27:].abs().max().item() == 0.0
 
 
+@pytest.mark.parametrize("n,h,w,scaled", [(2, 6, 256, True), (1, 5, 128, True), (3, 3, 200, False), (1, 1, 384, True)])
+def test_vgg_first_conv_fused_kernel(n, h, w, scaled):
+    """ScalingLayer + Conv2d(3 -> 64, 3x3, pad 1) + ReLU in one kernel (csrc/small_cin.cu, reference models/lpips.py:96-103,
+    119-127) against fp64 on the operands the tensor core sees (scaled image and weights rounded to bf16): products are
+    exact, accumulation fp32, output one bf16 rounding.  Widths that are not multiples of the 128-pixel tile included."""
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(n * 1000 + h * 10 + w)
+    x = torch.rand(n, 3, h, w, generator=gen) * 2 - 1
+    wt = torch.randn(64, 3, 3, 3, generator=gen) * 0.2
+    b = torch.randn(64, generator=gen) * 0.1
+    shift = torch.tensor([-.030, -.088, -.188])
+    scale = torch.tensor([.458, .448, .450])
+    got = ops.vgg_first_conv(x.cuda(), wt.cuda(), b.cuda(), shift.cuda() if scaled else None, scale.cuda() if scaled else None)
+    xs = ((x - shift.view(1, 3, 1, 1)) / scale.view(1, 3, 1, 1)) if scaled else x
+    ref = F.conv2d(xs.bfloat16().double(), wt.bfloat16().double(), b.double(), padding=1).relu().permute(0, 2, 3, 1)
+    assert got.shape == (n, h, w, 64) and got.dtype == torch.bfloat16
+    _one_ulp_close(got, ref, extra=2e-6)
+
+
 @pytest.mark.parametrize("rows,cs,c_off,c", [(4096, 128, 0, 128), (1000, 192, 64, 64), (7, 32, 0, 6), (70000, 64, 0, 64)])
 def test_colsum_bias_gradient(rows, cs, c_off, c):
     from faceoff_b200 import ops
