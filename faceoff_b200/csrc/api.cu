@@ -612,7 +612,14 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
   p.halo = 0;
   if (s1 && g->ksize == 3) {
     int b2[4];
-    choose_box(ext, 128, b2);
+    // narrow, tall tiles: the halo'd Q box has R + 2 image rows for R rows of pixels, and this kernel's 3x3(x3) forms are
+    // bound by L2->SM traffic (Conv3d: P 32 KB + Q box per 1536 MMA cycles) -- 16 x 8 pixels read 1.25x, 64 x 2 read 2x
+    int boxw = 16;
+    {
+      const char* e = getenv("FO_WG_BOXW");   // experiments only
+      if (e && atoi(e) >= 8) boxw = atoi(e);
+    }
+    choose_box(ext, 128, b2, boxw);
     if (b2[2] == 1 && b2[3] == 1 && b2[0] * b2[1] == 128 && b2[0] <= ext[0] && b2[1] <= ext[1] &&
         (b2[0] * p.q_rowb) % 1024 == 0 && (b2[0] * p.p_rowb) % 1024 == 0) {
       p.kpix = 128;
