@@ -132,6 +132,16 @@ def test_library_exports_every_header_symbol():
     assert set(syms) == set(_lib.EXPORTED_SYMBOLS)
 
 
+def test_fastdiv_magic_numbers(tmp_path):
+    """Host logic of the conv kernels' tile decode: the multiply-high divider (csrc/igemm.cuh make_fastdiv) equals integer
+    division for every divisor 1..4096 (+ a spread up to 2e6) over dividends covering [0, 2^31)."""
+    exe = str(tmp_path / "fastdiv_check")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.run(["g++", "-O2", "-I", cuda_inc, os.path.join(ROOT, "tests", "fastdiv_check.cpp"), "-o", exe], check=True)
+    res = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=120)
+    assert res.returncode == 0 and "bad=0" in res.stdout, res.stdout
+
+
 def test_no_cpu_fallback_fails_loudly():
     """Without a GPU every op must raise (no silent eager/CPU path)."""
     if torch.cuda.is_available():
