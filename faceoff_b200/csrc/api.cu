@@ -906,6 +906,33 @@ extern "C" int fo_vgg_first_conv(const float* x, int n, int h, int w, const floa
   CUDA_TRY(launch_vgg_first_conv(x, n, h, w, weight, bias, shift, scale, out_relu, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
+static int s2_check(int n, int ca, int c, int H, int W) {
+  if (n < 1 || (c != 3 && c != 6) || ca < c || H < 2 || W < 2 || ((H | W) & 1))
+    return fail(FO_ERR_INVALID, "s2conv: needs c in {3, 6}, ca >= c and even H, W (got c=%d ca=%d H=%d W=%d)", c, ca, H, W);
+  return FO_OK;
+}
+extern "C" int fo_s2conv(const float* x, int n, int ca, int c, int H, int W, const float* weight, const float* bias,
+                         const void* mask, const void* addend, void* out, int relu, fo_stream_t stream) {
+  REQUIRE_INIT();
+  int rc = s2_check(n, ca, c, H, W);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_s2conv(x, n, ca, c, H, W, weight, bias, mask, addend, out, relu, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
+extern "C" size_t fo_s2wgrad_workspace_bytes(void) {
+  if (fo_init() != FO_OK) return 0;
+  return (size_t)s2_grid(g_num_sms) * 128 * 64 * sizeof(float);
+}
+extern "C" int fo_s2wgrad(const float* x, int n, int ca, int c, int H, int W, const void* y, float* dweight, int accumulate,
+                          float* dbias, int dbias_accumulate, void* workspace, size_t workspace_bytes, fo_stream_t stream) {
+  REQUIRE_INIT();
+  int rc = s2_check(n, ca, c, H, W);
+  if (rc != FO_OK) return rc;
+  if (workspace == nullptr || workspace_bytes < fo_s2wgrad_workspace_bytes()) return fail(FO_ERR_INVALID, "s2wgrad: workspace too small");
+  CUDA_TRY(launch_s2wgrad(x, n, ca, c, H, W, y, dweight, accumulate, dbias, dbias_accumulate, (float*)workspace, g_num_sms,
+                          (cudaStream_t)stream));
+  return FO_OK;
+}
 extern "C" int fo_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi,
                               fo_stream_t stream) {
   REQUIRE_INIT();

@@ -70,6 +70,12 @@ cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, fl
 cudaError_t launch_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias,
                                   const float* shift, const float* scale, void* out, int num_sms, cudaStream_t st);
 
+int s2_grid(int num_sms);
+cudaError_t launch_s2conv(const float* x, int n, int ca, int c, int H, int W, const float* weight, const float* bias,
+                          const void* mask, const void* addend, void* out, int relu, int num_sms, cudaStream_t st);
+cudaError_t launch_s2wgrad(const float* x, int n, int ca, int c, int H, int W, const void* y, float* dweight, int accumulate,
+                           float* dbias, int dbias_accumulate, float* workspace, int num_sms, cudaStream_t st);
+
 // vq.cu
 cudaError_t launch_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e_t, float* e_norm2,
                            cudaStream_t st);

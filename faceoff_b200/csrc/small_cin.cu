@@ -9,6 +9,8 @@
 // vq_assign's loader), the weights stay resident in shared memory, ONE tcgen05 MMA pair produces the tile in TMEM, and the
 // epilogue stages bias + ReLU + bf16 in shared memory so that the 16 KB of the tile (128 consecutive pixels x 64 channels)
 // leave as fully coalesced 16-byte stores.  No pipeline inside the CTA: several CTAs per SM overlap each other's phases.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.h"
 
@@ -189,6 +191,464 @@ vgg_first_conv_kernel(const FirstConvParams p) {
     tc_fence_after();
     tmem_dealloc(tmem, 128);
   }
+}
+
+// =====================================================================================================================
+// Image-side layers of the VQVAE (reference models/vqvae_conv3d_latent.py:109 first Conv2d(6 -> 64, 4, stride 2, pad 1);
+// :154-156 last ConvTranspose2d(64 -> 6, 4, stride 2, pad 1)) WITHOUT an explicit im2col matrix.  Two kernels share one tile
+// builder: the [128 output pixels x K] im2col tile (k = ch * 16 + ky * 4 + kx, the order of the PyTorch weight; K = 16 * C
+// <= 128, two 64-wide chunks of 128-byte rows, 128B swizzle) is assembled in shared memory straight from the image rows:
+// a thread owns one output pixel and half of the C * 4 image rows; per row it loads the aligned pair (2x, 2x + 1) with one
+// 8-byte load and takes its outer taps (2x - 1, 2x + 2) from the neighbouring lanes by shuffle (lanes 0 / 31 load them).
+//   s2conv_kernel   D[pixel, 64] = tile x W^T : the first conv's forward (bias + ReLU) and -- with the transposed-conv weight,
+//                   whose layout [64, C, 4, 4] is exactly a Conv2d weight -- the last layer's DATA gradient (ReLU gate of the
+//                   layer input, optional addend).  The tile is the K-major A operand.
+//   s2wgrad_kernel  dW^T[k, 64] = sum_pixels tile^T x Y : both layers' WEIGHT gradients (Y = dy of the first conv / the input
+//                   activation of the last layer).  The same tile is the MN-major A operand (M = k), Y the MN-major B operand;
+//                   the accumulator stays in TMEM over all tiles of a (persistent) CTA; pad slot k = 16 * C holds 1.0, so
+//                   that row of the result is the column sum of Y = the bias gradient.
+// Phases of a tile run back to back inside a CTA (the image rows of the next tile are already in flight during the epilogue
+// / the MMAs); three CTAs per SM overlap each other.
+// =====================================================================================================================
+constexpr int kS2Threads = 256;
+
+struct S2Params {
+  const float* x;          // image-side tensor [n, ca, H, W] fp32 (first c channels used)
+  int n, ca, c, H, W;      // H, W even; output grid (H/2, W/2)
+  int tiles_x;             // ceil((W/2) / 128)
+  int total_tiles;         // n * (H/2) * tiles_x
+  FastDiv fd_tx, fd_ho;    // dividers by tiles_x and H/2
+  // s2conv
+  const float* weight;     // [64, c, 4, 4] fp32
+  const float* bias;       // [64] or null
+  const __nv_bfloat16* mask;    // [n, H/2, W/2, 64] or null: result zeroed where mask <= 0
+  const __nv_bfloat16* addend;  // same layout or null
+  __nv_bfloat16* out;      // [n, H/2, W/2, 64]
+  int relu;                // apply ReLU to the result (first conv) -- the data-gradient form writes the raw value
+  // s2wgrad
+  const __nv_bfloat16* y;  // [n, H/2, W/2, 64] bf16
+  float* partial;          // [gridDim.x][128][64] fp32
+};
+
+struct S2Tile { int n, oy, ox0; };
+__device__ __forceinline__ S2Tile s2_decode(const S2Params& p, int tile) {
+  int ty, tx;
+  p.fd_tx.divmod(tile, ty, tx);
+  S2Tile t;
+  p.fd_ho.divmod(ty, t.n, t.oy);
+  t.ox0 = tx * 128;
+  return t;
+}
+
+// Image values of one output pixel for the 2 * C image rows of one half of the tile row: half h owns the filter rows
+// ky = 2h, 2h + 1 of every channel, i.e. the 16-byte unit u = 2 * ch + h (k = 8u .. 8u + 7 = ch * 16 + ky * 4 + kx)
+template <int C>
+struct S2Rows {
+  float2 mid[2 * C];   // [ch * 2 + (ky & 1)]: input columns 2x, 2x + 1
+  float edge[2 * C];   // lane 0: column 2x - 1; lane 31: column 2x + 2 (other lanes get them from their neighbours)
+};
+
+template <int C>
+__device__ __forceinline__ void s2_load_rows(const S2Params& p, const S2Tile& t, int px, int half, int lane, S2Rows<C>& rw) {
+  const int ix = 2 * (t.ox0 + px);
+  const bool okm = ix < p.W;
+  const int ex = lane == 0 ? ix - 1 : ix + 2;
+  const bool oke = (lane == 0 || lane == 31) && (unsigned)ex < (unsigned)p.W;
+  const int iy0 = 2 * t.oy - 1 + 2 * half;                   // H even: only iy0 = -1 (half 0) and iy0 + 1 = H (half 1) fall outside
+  const bool ok0 = iy0 >= 0, ok1 = iy0 + 1 < p.H;
+  const bool m0 = ok0 && okm, m1 = ok1 && okm, e0 = ok0 && oke, e1 = ok1 && oke;
+  const size_t plane = (size_t)p.H * p.W;
+  const float* r0 = p.x + (size_t)t.n * p.ca * plane + (size_t)(ok0 ? iy0 : 0) * p.W;
+  const float* r1 = p.x + (size_t)t.n * p.ca * plane + (size_t)(ok1 ? iy0 + 1 : 0) * p.W;
+#pragma unroll
+  for (int ch = 0; ch < C; ++ch) {
+    rw.mid[2 * ch] = m0 ? __ldg(reinterpret_cast<const float2*>(r0 + ix)) : make_float2(0.f, 0.f);
+    rw.mid[2 * ch + 1] = m1 ? __ldg(reinterpret_cast<const float2*>(r1 + ix)) : make_float2(0.f, 0.f);
+    rw.edge[2 * ch] = e0 ? __ldg(r0 + ex) : 0.f;
+    rw.edge[2 * ch + 1] = e1 ? __ldg(r1 + ex) : 0.f;
+    r0 += plane;
+    r1 += plane;
+  }
+}
+
+template <int C>
+__device__ __forceinline__ void s2_build_tile(const S2Rows<C>& rw, uint8_t* sT, int px, int half, int lane) {
+  uint8_t* row = sT + px * 128;
+  const int sw = (px & 7) ^ half;          // unit u = 2 ch + half sits at slot (u & 7) ^ (px & 7) of chunk u >> 3 = ch >> 2
+#pragma unroll
+  for (int ch = 0; ch < C; ++ch) {
+    uint32_t w[4];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const float2 m = rw.mid[2 * ch + h];
+      float left = __shfl_up_sync(0xffffffffu, m.y, 1);
+      float right = __shfl_down_sync(0xffffffffu, m.x, 1);
+      if (lane == 0) left = rw.edge[2 * ch + h];
+      if (lane == 31) right = rw.edge[2 * ch + h];
+      w[2 * h] = pack_bf16x2(left, m.x);
+      w[2 * h + 1] = pack_bf16x2(m.y, right);
+    }
+    *reinterpret_cast<uint4*>(row + (ch >> 2) * (128 * 128) + ((((2 * ch) & 7) ^ sw) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+}
+// Units 2C .. 15 of every tile row are constant: zero, and 1.0 at k = 16 * C when ONES (the bias-gradient row of s2wgrad)
+template <int C, bool ONES>
+__device__ __forceinline__ void s2_fill_pad(uint8_t* sT, int tid) {
+  for (int i = tid; i < 128 * (16 - 2 * C); i += kS2Threads) {
+    const int px = i / (16 - 2 * C), u = 2 * C + i % (16 - 2 * C);
+    const uint4 v = make_uint4((ONES && u == 2 * C) ? 0x00003F80u : 0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4*>(sT + (u >> 3) * (128 * 128) + px * 128 + (((u & 7) ^ (px & 7)) << 4)) = v;
+  }
+}
+
+// EPI: the epilogue has a mask and / or an addend.  Their tiles are then fetched with coalesced 16-byte loads while the MMAs
+// run, the accumulator (+ bias) is staged in fp32, and the gate / sum / single bf16 rounding happen in the store phase.
+template <int C, bool EPI, int OCC>
+__global__ void __launch_bounds__(kS2Threads, OCC)
+s2conv_kernel(const S2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sT = smem;                               // 2 x [128 x 128 B] tile
+  // output staging: bf16 [128 x 128 B] over the chunk the MMAs of this C do not need to survive (C = 6: chunk 0, rewritten
+  // by every tile; C = 3: chunk 1, never read), or fp32 [128 x 256 B] over both (EPI; the constant pad units are refilled)
+  uint8_t* sOut = EPI ? sT : sT + (C == 3 ? 128 * 128 : 0);
+  uint8_t* sB = sT + 2 * 128 * 128;                 // 2 x [64 x 128 B] weights (k chunks), 128B swizzle
+  float* sBias = reinterpret_cast<float*>(sB + 2 * 64 * 128);   // [64]
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sBias + 64);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp & 1, px = (warp >> 1) * 32 + lane;
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 64);
+    tmem_relinquish();
+  } else if (tid == 32) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (int i = tid; i < 64 * 128; i += kS2Threads) {
+    const int co = i >> 7, k = i & 127;
+    const float v = k < 16 * C ? p.weight[co * 16 * C + k] : 0.f;
+    const uint32_t off = (uint32_t)(k >> 6) * (64 * 128) + co * 128 + (((((uint32_t)k & 63) >> 3) ^ ((uint32_t)co & 7)) << 4) + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(v);
+  }
+  if (tid < 64) sBias[tid] = p.bias != nullptr ? p.bias[tid] : 0.f;
+  s2_fill_pad<C, false>(sT, tid);
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t idesc = make_idesc_bf16(128, 64, 0, 0);
+  const uint64_t a_desc = make_smem_desc(smem_u32(sT), 128, 16);
+  const uint64_t b_desc = make_smem_desc(smem_u32(sB), 128, 16);
+  constexpr int kK16 = (16 * C + 15) / 16;          // 16-wide K slices that hold data (6 for C = 6)
+  uint32_t phase = 0;
+  const int Wo = p.W / 2, Ho = p.H / 2;
+
+  S2Rows<C> rw;
+  S2Tile t_next = s2_decode(p, blockIdx.x);
+  if ((int)blockIdx.x < p.total_tiles) s2_load_rows<C>(p, t_next, px, half, lane, rw);
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    const S2Tile t = t_next;
+    const size_t pix0 = ((size_t)t.n * Ho + t.oy) * Wo + t.ox0;
+    const int live_rows = Wo - t.ox0 < 128 ? Wo - t.ox0 : 128;
+    s2_build_tile<C>(rw, sT, px, half, lane);
+    if (EPI && C == 6) s2_fill_pad<C, false>(sT, tid);   // the fp32 staging tile of the previous iteration covered them
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < kK16; ++j) {
+        const uint32_t off16 = (uint32_t)((j >> 2) * (128 * 128) + (j & 3) * 32) >> 4;
+        const uint32_t boff16 = (uint32_t)((j >> 2) * (64 * 128) + (j & 3) * 32) >> 4;
+        umma_bf16(tmem, a_desc + off16, b_desc + boff16, idesc, j != 0);
+      }
+      umma_commit(bar);
+    }
+    __syncwarp();
+    // coalesced epilogue operands: thread -> (row, 16-byte chunk) = i >> 3, i & 7 for i = tid + 256 * j
+    uint4 em[4], ea[4];
+    if (EPI) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = tid + j * kS2Threads;
+        const bool live = (i >> 3) < live_rows;
+        em[j] = ea[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (p.mask != nullptr && live) em[j] = __ldg(reinterpret_cast<const uint4*>(p.mask + pix0 * 64) + i);
+        if (p.addend != nullptr && live) ea[j] = __ldg(reinterpret_cast<const uint4*>(p.addend + pix0 * 64) + i);
+      }
+    }
+    mbar_wait(bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // ---- epilogue: warp w -> TMEM lane quarter w % 4 (lane = pixel), column half w / 4
+    {
+      const int quarter = warp & 3, hcol = warp >> 2;
+      const int row = quarter * 32 + lane;
+      uint32_t v[32];
+      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + hcol * 32, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 b0 = *reinterpret_cast<const float4*>(sBias + hcol * 32 + q * 8);
+        const float4 b1 = *reinterpret_cast<const float4*>(sBias + hcol * 32 + q * 8 + 4);
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + bb[e];
+        const int chunk = hcol * 4 + q;       // 8 channels
+        if (EPI) {                            // fp32 rows of 256 B = 16 units; unit ^ (row & 7) keeps quarter-warps conflict-free
+          uint8_t* r = sOut + row * 256;
+          *reinterpret_cast<float4*>(r + (((2 * chunk) ^ (row & 7)) << 4)) = make_float4(f[0], f[1], f[2], f[3]);
+          *reinterpret_cast<float4*>(r + (((2 * chunk + 1) ^ (row & 7)) << 4)) = make_float4(f[4], f[5], f[6], f[7]);
+        } else {
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+          *reinterpret_cast<uint4*>(sOut + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
+        }
+      }
+      tc_fence_before();
+    }
+    __syncthreads();
+    if (tile + (int)gridDim.x < p.total_tiles) {      // in flight during the store phase
+      t_next = s2_decode(p, tile + gridDim.x);
+      s2_load_rows<C>(p, t_next, px, half, lane, rw);
+    }
+    {
+      uint4* dst = reinterpret_cast<uint4*>(p.out + pix0 * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = tid + j * kS2Threads;
+        const int row = i >> 3, chunk = i & 7;
+        if (row >= live_rows) continue;
+        if (EPI) {
+          const uint8_t* r = sOut + row * 256;
+          const float4 lo = *reinterpret_cast<const float4*>(r + (((2 * chunk) ^ (row & 7)) << 4));
+          const float4 hi = *reinterpret_cast<const float4*>(r + (((2 * chunk + 1) ^ (row & 7)) << 4));
+          float f[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+          if (p.mask != nullptr) {
+            const uint32_t w[4] = {em[j].x, em[j].y, em[j].z, em[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (!(bf16lo(w[e]) > 0.f)) f[2 * e] = 0.f;
+              if (!(bf16hi(w[e]) > 0.f)) f[2 * e + 1] = 0.f;
+            }
+          }
+          {
+            const uint32_t w[4] = {ea[j].x, ea[j].y, ea[j].z, ea[j].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { f[2 * e] += bf16lo(w[e]); f[2 * e + 1] += bf16hi(w[e]); }
+          }
+          if (p.relu) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+          }
+          uint4 o;
+          o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+          dst[i] = o;
+        } else {
+          dst[i] = *reinterpret_cast<const uint4*>(sOut + row * 128 + ((chunk ^ (row & 7)) << 4));
+        }
+      }
+    }
+    __syncthreads();          // the staging tile overlays sT, which the next iteration rewrites
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 64);
+  }
+}
+
+template <int C>
+__global__ void __launch_bounds__(kS2Threads, 3)
+s2wgrad_kernel(const S2Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sT = smem;                               // 2 x [128 pixels x 128 B]: MN-major A operand, M = k
+  uint8_t* sY = sT + 2 * 128 * 128;                 // [128 pixels x 128 B]: MN-major B operand, N = 64
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sY + 128 * 128);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bar + 1);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp & 1, px = (warp >> 1) * 32 + lane;
+  if (warp == 0) {
+    tmem_alloc(tmem_ptr, 64);
+    tmem_relinquish();
+  } else if (tid == 32) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  s2_fill_pad<C, true>(sT, tid);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
+  const uint64_t a_desc = make_smem_desc(smem_u32(sT), 128, 128 * 128);   // LBO = distance between the two 64-wide M chunks
+  const uint64_t b_desc = make_smem_desc(smem_u32(sY), 128, 0);
+  uint32_t phase = 0;
+  const int Wo = p.W / 2, Ho = p.H / 2;
+  // contiguous range of tiles per CTA
+  const int per = (p.total_tiles + gridDim.x - 1) / gridDim.x;
+  const int t_begin = blockIdx.x * per;
+  const int t_end = t_begin + per < p.total_tiles ? t_begin + per : p.total_tiles;
+  bool first = true;
+  for (int tile = t_begin; tile < t_end; ++tile) {
+    const S2Tile t = s2_decode(p, tile);
+    S2Rows<C> rw;
+    s2_load_rows<C>(p, t, px, half, lane, rw);
+    uint4 yv[4];    // Y tile: 128 pixels x 128 B, coalesced 16-byte loads; pixels past the row end are zero
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(p.y + (((size_t)t.n * Ho + t.oy) * Wo + t.ox0) * 64);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = tid + j * kS2Threads;
+        yv[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (t.ox0 + (i >> 3) < Wo) yv[j] = __ldg(src + i);
+      }
+    }
+    if (!first) {                       // the previous tile's MMAs still read sT / sY while this tile's loads are in flight
+      mbar_wait(bar, phase);
+      phase ^= 1;
+      tc_fence_after();
+    }
+    s2_build_tile<C>(rw, sT, px, half, lane);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = tid + j * kS2Threads;
+      const int row = i >> 3, chunk = i & 7;
+      *reinterpret_cast<uint4*>(sY + row * 128 + ((chunk ^ (row & 7)) << 4)) = yv[j];
+    }
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk)    // 16 pixels per MMA = 16 rows of 128 B
+        umma_bf16(tmem, a_desc + (uint32_t)((kk * 16 * 128) >> 4), b_desc + (uint32_t)((kk * 16 * 128) >> 4), idesc, !(first && kk == 0));
+      umma_commit(bar);
+    }
+    __syncwarp();
+    first = false;
+  }
+  if (!first) {
+    mbar_wait(bar, phase);
+    tc_fence_after();
+  }
+  // partial[cta][k][n]: warps -> lane quarters (k rows) w % 4, column halves w / 4
+  {
+    const int quarter = warp & 3, hcol = warp >> 2;
+    const int row = quarter * 32 + lane;
+    uint32_t v[32];
+    if (!first) {
+      tmem_ld32(tmem + ((uint32_t)(quarter * 32) << 16) + hcol * 32, v);
+      tmem_ld_wait();
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 0u;
+    }
+    float4* dst = reinterpret_cast<float4*>(p.partial + ((size_t)blockIdx.x * 128 + row) * 64 + hcol * 32);
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]), __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 64);
+  }
+}
+
+// One block per k: dweight[n64][k] (+)= sum_cta partial[cta][k][n64] for k < 16 * C;  dbias[n64] (+)= the same sum at k = 16 * C
+__global__ void __launch_bounds__(1024)
+s2wgrad_finalize_kernel(const float* __restrict__ partial, int ctas, int c, float* __restrict__ dweight, int accumulate,
+                        float* __restrict__ dbias, int dbias_accumulate) {
+  __shared__ float red[16][64];
+  const int k = blockIdx.x, n = threadIdx.x & 63, part = threadIdx.x >> 6;
+  float s = 0.f;
+  for (int j = part; j < ctas; j += 16) s += partial[((size_t)j * 128 + k) * 64 + n];
+  red[part][n] = s;
+  __syncthreads();
+  if (part != 0) return;
+#pragma unroll
+  for (int j = 1; j < 16; ++j) s += red[j][n];
+  if (k < 16 * c) {
+    float* d = dweight + (size_t)n * 16 * c + k;
+    *d = accumulate ? *d + s : s;
+  } else if (dbias != nullptr) {
+    dbias[n] = dbias_accumulate ? dbias[n] + s : s;
+  }
+}
+
+static size_t s2_smem_bytes(bool wgrad) {
+  return (wgrad ? 3 * 128 * 128 : 2 * 128 * 128 + 2 * 64 * 128 + 64 * sizeof(float)) + 64 + 1024;
+}
+static int s2_occ() {   // resident CTAs per SM the conv kernel is compiled for (experiment knob FO_S2_OCC = 2 | 3)
+  static int occ = 0;
+  if (occ == 0) {
+    const char* e = getenv("FO_S2_OCC");
+    occ = (e != nullptr && atoi(e) == 3) ? 3 : 2;
+  }
+  return occ;
+}
+int s2_grid(int num_sms) { return num_sms * 3; }
+
+static S2Params s2_params(const float* x, int n, int ca, int c, int H, int W) {
+  S2Params p = {};
+  p.x = x; p.n = n; p.ca = ca; p.c = c; p.H = H; p.W = W;
+  p.tiles_x = (W / 2 + 127) / 128;
+  p.total_tiles = n * (H / 2) * p.tiles_x;
+  p.fd_tx = make_fastdiv(p.tiles_x);
+  p.fd_ho = make_fastdiv(H / 2);
+  return p;
+}
+
+template <typename K>
+static cudaError_t s2_launch(K kernel, const S2Params& p, int grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  kernel<<<grid, kS2Threads, smem, st>>>(p);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_s2conv(const float* x, int n, int ca, int c, int H, int W, const float* weight, const float* bias,
+                          const void* mask, const void* addend, void* out, int relu, int num_sms, cudaStream_t st) {
+  if ((long long)n * (H / 2) * ((W / 2 + 127) / 128) > 0x7fffffffLL) return cudaErrorInvalidValue;
+  S2Params p = s2_params(x, n, ca, c, H, W);
+  p.weight = weight; p.bias = bias; p.mask = (const __nv_bfloat16*)mask; p.addend = (const __nv_bfloat16*)addend;
+  p.out = (__nv_bfloat16*)out; p.relu = relu;
+  const size_t smem = s2_smem_bytes(false);
+  const int occ = s2_occ();
+  const int grid = p.total_tiles < num_sms * occ ? p.total_tiles : num_sms * occ;
+  const bool epi = mask != nullptr || addend != nullptr;
+#define S2CONV(C_, E_) (occ == 3 ? s2_launch(s2conv_kernel<C_, E_, 3>, p, grid, smem, st) : s2_launch(s2conv_kernel<C_, E_, 2>, p, grid, smem, st))
+  if (c == 6) return epi ? S2CONV(6, true) : S2CONV(6, false);
+  if (c == 3) return epi ? S2CONV(3, true) : S2CONV(3, false);
+#undef S2CONV
+  return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_s2wgrad(const float* x, int n, int ca, int c, int H, int W, const void* y, float* dweight, int accumulate,
+                           float* dbias, int dbias_accumulate, float* workspace, int num_sms, cudaStream_t st) {
+  if ((long long)n * (H / 2) * ((W / 2 + 127) / 128) > 0x7fffffffLL) return cudaErrorInvalidValue;
+  S2Params p = s2_params(x, n, ca, c, H, W);
+  p.y = (const __nv_bfloat16*)y; p.partial = workspace;
+  const size_t smem = s2_smem_bytes(true);
+  const int grid = p.total_tiles < s2_grid(num_sms) ? p.total_tiles : s2_grid(num_sms);
+  cudaError_t e;
+  if (c == 6) e = s2_launch(s2wgrad_kernel<6>, p, grid, smem, st);
+  else if (c == 3) e = s2_launch(s2wgrad_kernel<3>, p, grid, smem, st);
+  else return cudaErrorInvalidValue;
+  if (e != cudaSuccess) return e;
+  s2wgrad_finalize_kernel<<<16 * c + 1, 1024, 0, st>>>(workspace, grid, c, dweight, accumulate, dbias, dbias_accumulate);
+  return cudaGetLastError();
 }
 
 cudaError_t launch_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias,

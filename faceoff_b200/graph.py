@@ -219,11 +219,35 @@ def conv_op(tape: Tape, form: int, ksize: int, srcs: Sequence[View], wname: str,
     return out
 
 
+def _s2_direct(img: torch.Tensor, c_img: int, c_feat: int) -> bool:
+    """The image-side stride-2 layers run without an im2col matrix when the shapes are the kernels' (csrc/small_cin.cu)."""
+    return (not ops.PRECISE and c_img in (3, 6) and c_feat == 64 and img.dtype == torch.float32 and img.dim() == 4
+            and img.shape[2] % 2 == 0 and img.shape[3] % 2 == 0)
+
+
 def first_conv_op(tape: Tape, x_nchw: torch.Tensor, wname: str, cin: int, cout: int) -> Node:
     """Conv2d(cin<=8 -> cout, 4, stride 2, pad 1) + ReLU on the raw fp32 NCHW input (reference
-    models/vqvae_conv3d_latent.py:109): explicit im2col (K = 16 taps x 8 = 128) + a 1x1 GEMM on the tcgen05 kernel.
-    The input needs no gradient."""
+    models/vqvae_conv3d_latent.py:109).  The input needs no gradient.  3 / 6 input channels and 64 output channels (the
+    reference's configuration): the kernels of csrc/small_cin.cu build the im2col tile in shared memory, forward and
+    weight gradient read the image itself.  Otherwise (and in verification mode, whose activations are hi|lo pairs):
+    explicit im2col (K = 16 taps x 8 = 128) + a 1x1 GEMM on the tcgen05 kernel."""
     w = tape.params[wname + ".weight"]          # [cout, cin, 4, 4]
+    if _s2_direct(x_nchw, cin, cout):
+        act = ops.s2conv(x_nchw, cin, w.detach(), tape.params[wname + ".bias"].detach(), relu=True)
+        out = Node(cout, act=act)
+
+        def backward_direct():
+            gt, g_off = out.g
+            if g_off != 0 or gt.shape[-1] != cout:
+                gt = gt[..., g_off:g_off + cout].contiguous()
+            gw, acc_w = tape.grad_buffer(wname + ".weight")
+            gb, acc_b = tape.grad_buffer(wname + ".bias")
+            ops.s2wgrad(x_nchw, cin, gt.view(act.shape), gw, accumulate=acc_w, dbias=gb, dbias_accumulate=acc_b)
+            tape.grad_ready(wname + ".weight")
+            tape.grad_ready(wname + ".bias")
+
+        tape.record(backward_direct)
+        return out
     b = _padded_bias(tape, wname + ".bias", cout)
     col = ops.im2col4x4s2(x_nchw, cin)          # [F, H/2, W/2, 128]
     w2 = torch.zeros(cout, 16, 8, dtype=torch.float32, device=w.device)
@@ -274,6 +298,22 @@ def last_convT_op(tape: Tape, src: View, wname: str, cout: int) -> Node:
         assert g is not None, "no gradient reached the reconstruction"
         gb, acc = tape.grad_buffer(wname + ".bias")
         ops.chansum_nchw(g, cout, gb, accumulate=acc)
+        nd = src.node
+        if _s2_direct(g, cout, cin) and g.is_contiguous() and x.is_contiguous() and x.shape[-1] == cin and nd.cs == cin:
+            # both gradients straight from the fp32 NCHW output gradient (no im2col matrix): the ConvTranspose2d weight
+            # [cin, cout, 4, 4] is the Conv2d weight of its own data gradient
+            gw, acc = tape.grad_buffer(wname + ".weight")
+            xa = x.view(g.shape[0], g.shape[2] // 2, g.shape[3] // 2, cin)
+            ops.s2wgrad(g, cout, xa, gw, accumulate=acc)
+            tape.grad_ready(wname + ".weight")
+            tape.grad_ready(wname + ".bias")
+            addend = None
+            if nd.g is not None:
+                addend = nd.g[0] if (nd.g[1] == 0 and nd.g[0].shape[-1] == cin) else nd.g[0][..., nd.g[1]:nd.g[1] + cin].contiguous()
+                addend = addend.view(xa.shape)
+            dx = ops.s2conv(g, cout, w.detach(), None, mask=nd.act.view(xa.shape) if src.relu else None, addend=addend)
+            nd.g = (dx.view(x.shape), 0)
+            return
         dcol = ops.im2col4x4s2(g, cout)         # [F, h, w, 128]
         dw2 = torch.empty(128, cin, 1, 1, dtype=torch.float32, device=w.device)
         ops.wgrad(FORM_S1, 2, 1, (dcol, 128, 0), (x, cin, 0), dw2, m_axis=0)

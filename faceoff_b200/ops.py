@@ -485,6 +485,42 @@ def vgg_first_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, sh
     return out
 
 
+def s2conv(x: torch.Tensor, c: int, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+           mask: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
+    """Conv2d(c -> 64, 4, stride 2, pad 1) of the fp32 NCHW tensor x [N, Ca, H, W] (first c channels) without an im2col
+    matrix -> bf16 channels-last [N, H/2, W/2, 64]; epilogue: + bias, ReLU gate by ``mask``, + ``addend``, optional ReLU."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
+    n, ca, h, w = x.shape
+    assert tuple(weight.shape) == (64, c, 4, 4) and weight.dtype == torch.float32 and weight.is_contiguous()
+    out = torch.empty((n, h // 2, w // 2, 64), dtype=torch.bfloat16, device=x.device)
+    for t in (mask, addend):
+        assert t is None or (t.dtype == torch.bfloat16 and t.is_contiguous() and tuple(t.shape) == tuple(out.shape))
+    nbytes = n * h * w * 4.0 * c + out.numel() * 2.0 * (1 + (mask is not None) + (addend is not None))
+    with _Timed("hbm/s2conv", nbytes):
+        L.check(lib.fo_s2conv(x.data_ptr(), n, ca, c, h, w, weight.data_ptr(), _p(bias), _p(mask), _p(addend),
+                              out.data_ptr(), int(relu), _stream()), "fo_s2conv")
+    _count(1)
+    return out
+
+
+def s2wgrad(x: torch.Tensor, c: int, y: torch.Tensor, dweight: torch.Tensor, accumulate: bool = False,
+            dbias: Optional[torch.Tensor] = None, dbias_accumulate: bool = False):
+    """dweight [64, c, 4, 4] (+)= sum_pixels y (x) im2col4x4s2(x); dbias [64] (+)= sum_pixels y.  x fp32 NCHW, y bf16
+    channels-last [N, H/2, W/2, 64]."""
+    lib = L.load()
+    assert x.dtype == torch.float32 and x.dim() == 4 and x.is_contiguous()
+    n, ca, h, w = x.shape
+    assert y.dtype == torch.bfloat16 and y.is_contiguous() and tuple(y.shape) == (n, h // 2, w // 2, 64)
+    assert tuple(dweight.shape) == (64, c, 4, 4) and dweight.dtype == torch.float32 and dweight.is_contiguous()
+    need = lib.fo_s2wgrad_workspace_bytes()
+    ws = workspace(need, x.device, "s2wgrad")
+    with _Timed("hbm/s2wgrad", n * h * w * 4.0 * c + y.numel() * 2.0):
+        L.check(lib.fo_s2wgrad(x.data_ptr(), n, ca, c, h, w, y.data_ptr(), dweight.data_ptr(), int(accumulate), _p(dbias),
+                               int(dbias_accumulate), ws.data_ptr(), ws.numel(), _stream()), "fo_s2wgrad")
+    _count(2)
+
+
 def col2im4x4s2(col: torch.Tensor, bias: Optional[torch.Tensor], c: int) -> torch.Tensor:
     """bf16 [N, Hi, Wi, 128] (k = tap*8 + co) -> NCHW fp32 [N, c, 2Hi, 2Wi] (+ bias)."""
     lib = L.load()

@@ -163,6 +163,20 @@ int fo_im2col3x3(const float* x, void* out, int n, int c, int h, int w, const fl
  * matrix reaches HBM. */
 int fo_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias, const float* shift,
                       const float* scale, void* out_relu, fo_stream_t stream);
+/* Image-side layers of the VQVAE without an im2col matrix (csrc/small_cin.cu; reference models/vqvae_conv3d_latent.py:109
+ * first Conv2d(c -> 64, 4, stride 2, pad 1), :154-156 last ConvTranspose2d(64 -> c, 4, stride 2, pad 1)); c in {3, 6}.
+ * x: fp32 NCHW [n, ca, H, W] (first c channels used), H and W even; all bf16 tensors are channels-last [n, H/2, W/2, 64].
+ *   fo_s2conv : out = f(conv4x4s2(x, weight [64, c, 4, 4]) + bias), f = (mask > 0 ? . : 0) + addend, then ReLU if relu != 0.
+ *               First conv forward: bias, relu = 1.  Data gradient of the last ConvTranspose2d w.r.t. its 64-channel input:
+ *               x = the fp32 NCHW output gradient, weight = the ConvTranspose2d parameter [64, c, 4, 4] as it is,
+ *               mask = the layer input (ReLU gate), relu = 0.
+ *   fo_s2wgrad: dweight [64, c, 4, 4] (+)= sum_pixels y[pixel, :] (x) im2col(x)[pixel, :], dbias [64] (+)= sum_pixels y
+ *               (dbias may be NULL).  First conv: y = dy.  Last ConvTranspose2d: y = the layer input, x = the output gradient. */
+int fo_s2conv(const float* x, int n, int ca, int c, int H, int W, const float* weight, const float* bias, const void* mask,
+              const void* addend, void* out, int relu, fo_stream_t stream);
+size_t fo_s2wgrad_workspace_bytes(void);
+int fo_s2wgrad(const float* x, int n, int ca, int c, int H, int W, const void* y, float* dweight, int accumulate, float* dbias,
+               int dbias_accumulate, void* workspace, size_t workspace_bytes, fo_stream_t stream);
 /* Inverse scatter for the last ConvTranspose2d: col bf16 [n, hi, wi, 128] (k = tap*8 + co) + bias -> NCHW fp32
  * [n, c, 2hi, 2wi]. */
 int fo_col2im4x4s2(const void* col, const float* bias, float* out, int n, int c, int hi, int wi, fo_stream_t stream);

@@ -126,6 +126,32 @@ def main():
         fl2 = 2.0 * F_ * 128 * 128 * 64 * 128 * 9
         ms = timeit(lambda: ops.conv(ops.FORM_S1, 2, 3, [(x2, 64, 0)], w2, 0, 128, bias=b2, want_raw=False, want_relu=True))
         print(f"vgg conv3x3 64->128 @128 fwd: {ms:.3f} ms  {fl2 / ms / 1e9:.1f} TFLOP/s")
+    if which in ("s2", "all"):
+        F_ = clips * T
+        img = torch.randn(F_, 6, 256, 256, device=dev)
+        w6 = torch.randn(64, 6, 4, 4, device=dev) * 0.1
+        b = torch.zeros(64, device=dev)
+        act = torch.randn(F_, 128, 128, 64, device=dev).to(torch.bfloat16)
+        gb = (img.numel() * 4 + act.numel() * 2) / 1e9
+        ms = timeit(lambda: ops.s2conv(img, 6, w6, b, relu=True))
+        print(f"s2conv 6->64 @256 fwd (no im2col): {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        ms = timeit(lambda: ops.s2conv(img, 6, w6, None, mask=act, addend=act))
+        print(f"s2conv dgrad form (+mask+addend): {ms:.3f} ms  {(gb + 2 * act.numel() * 2 / 1e9) / ms * 1e3:.0f} GB/s")
+        dw = torch.empty(64, 6, 4, 4, device=dev)
+        ms = timeit(lambda: ops.s2wgrad(img, 6, act, dw, dbias=b))
+        print(f"s2wgrad 64x6x4x4 (+bias): {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
+        ms = timeit(lambda: ops.im2col4x4s2(img, 6))
+        print(f"   (old) im2col4x4s2: {ms:.3f} ms")
+        col = ops.im2col4x4s2(img, 6)
+        w2 = torch.randn(64, 128, 1, 1, device=dev) * 0.1
+        ms = timeit(lambda: ops.conv(ops.FORM_S1, 2, 1, [(col, 128, 0)], w2, 0, 64, bias=b, want_raw=False, want_relu=True))
+        print(f"   (old) 1x1 GEMM K=128 -> 64: {ms:.3f} ms")
+        dw2 = torch.empty(64, 128, 1, 1, device=dev)
+        ms = timeit(lambda: ops.wgrad(ops.FORM_S1, 2, 1, (act, 64, 0), (col, 128, 0), dw2, m_axis=0, dbias=b))
+        print(f"   (old) wgrad1x1 64x128: {ms:.3f} ms")
+        ms = timeit(lambda: ops.conv(ops.FORM_S1_DGRAD, 2, 1, [(col, 128, 0)], w2.view(128, 64, 1, 1), 1, 64, mask=act, addend=act))
+        print(f"   (old) dgrad1x1 128 -> 64 (+mask+addend): {ms:.3f} ms")
+        del img, col, act
     if which in ("wgrad_small", "all"):
         F_ = clips * T
         dy = torch.randn(F_, 64, 64, 128, device=dev).to(torch.bfloat16)

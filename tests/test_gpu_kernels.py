@@ -161,6 +161,41 @@ def test_vgg_first_conv_fused_kernel(n, h, w, scaled):
     _one_ulp_close(got, ref, extra=2e-6)
 
 
+@pytest.mark.parametrize("n,c,ca,h,w", [(2, 6, 6, 8, 256), (1, 3, 3, 6, 512), (3, 6, 8, 4, 200), (2, 6, 6, 10, 16), (1, 6, 6, 2, 1024)])
+def test_s2conv_and_s2wgrad_without_im2col(n, c, ca, h, w):
+    """Image-side stride-2 layers without an im2col matrix (csrc/small_cin.cu) against fp64 on the bf16-rounded operands:
+    forward (+bias, ReLU), the gated / accumulated data-gradient form, and the weight + bias gradient.  Widths that are not
+    multiples of the 128-pixel tile, several tiles per row, more storage channels than used."""
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(n * 100 + c * 10 + h + w)
+    x = torch.randn(n, ca, h, w, generator=gen)
+    wt = torch.randn(64, c, 4, 4, generator=gen) * 0.1
+    b = torch.randn(64, generator=gen) * 0.1
+    xs = x[:, :c].bfloat16().double()
+    ref = F.conv2d(xs, wt.bfloat16().double(), None, stride=2, padding=1).permute(0, 2, 3, 1)      # [n, h/2, w/2, 64]
+    got = ops.s2conv(x.cuda(), c, wt.cuda(), b.cuda(), relu=True)
+    _one_ulp_close(got, (ref + b.double()).relu(), extra=2e-6)
+    mask = _bf16(n, h // 2, w // 2, 64, gen=gen)
+    add = _bf16(n, h // 2, w // 2, 64, gen=gen)
+    got = ops.s2conv(x.cuda(), c, wt.cuda(), None, mask=mask.cuda(), addend=add.cuda())
+    _one_ulp_close(got, torch.where(mask.double() > 0, ref, torch.zeros_like(ref)) + add.double(), extra=2e-6)
+    y = _bf16(n, h // 2, w // 2, 64, gen=gen)
+    dw = torch.full((64, c, 4, 4), 7.0).cuda()
+    db = torch.full((64,), -3.0).cuda()
+    ops.s2wgrad(x.cuda(), c, y.cuda(), dw, dbias=db)
+    cols = F.unfold(xs, kernel_size=4, stride=2, padding=1)                                          # [n, c*16, L]
+    dw_ref = torch.einsum("nlo,nkl->ok", y.double().reshape(n, -1, 64), cols).reshape(64, c, 4, 4)
+    abs_ref = torch.einsum("nlo,nkl->ok", y.double().abs().reshape(n, -1, 64), cols.abs()).reshape(64, c, 4, 4)
+    _within("dweight", (dw.cpu().double() - dw_ref).abs(), 1e-5 * dw_ref.abs() + 3e-7 * abs_ref + 1e-6)
+    db_ref = y.double().sum((0, 1, 2))
+    _within("dbias", (db.cpu().double() - db_ref).abs(), 1e-5 * db_ref.abs() + 3e-7 * y.double().abs().sum((0, 1, 2)) + 1e-6)
+    dw2, db2 = dw.clone(), db.clone()
+    ops.s2wgrad(x.cuda(), c, y.cuda(), dw2, accumulate=True, dbias=db2, dbias_accumulate=True)
+    torch.testing.assert_close(dw2, 2 * dw, rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(db2, 2 * db, rtol=1e-6, atol=1e-6)
+
+
 @pytest.mark.parametrize("rows,cs,c_off,c", [(4096, 128, 0, 128), (1000, 192, 64, 64), (7, 32, 0, 6), (70000, 64, 0, 64)])
 def test_colsum_bias_gradient(rows, cs, c_off, c):
     from faceoff_b200 import ops
