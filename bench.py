@@ -498,10 +498,14 @@ def run_ours(args):
         return res
 
     headline_lpips = bool(args.lpips)
-    main = measure(headline_lpips, args.steps, args.warmup, sample_clocks=True)
-    other = None
-    if not args.no_lpips_step and not headline_lpips:
-        other = measure(True, args.steps, max(3, args.warmup), sample_clocks=True)
+    import contextlib
+    # FO_BENCH_SIDE_STREAM=1 (experiments): run the steps on a non-default stream
+    side = torch.cuda.Stream(device=dev) if os.environ.get("FO_BENCH_SIDE_STREAM") == "1" else None
+    with (torch.cuda.stream(side) if side is not None else contextlib.nullcontext()):
+        main = measure(headline_lpips, args.steps, args.warmup, sample_clocks=True)
+        other = None
+        if not args.no_lpips_step and not headline_lpips:
+            other = measure(True, args.steps, max(3, args.warmup), sample_clocks=True)
 
     def roofline_of(m):
         """Dominant kernel = conv_igemm_kernel over EVERY launch of the step (tensor-bound and HBM-bound layers alike);

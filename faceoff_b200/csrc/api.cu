@@ -38,6 +38,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_encode = nullptr;
 static int g_num_sms = 0;
+namespace fo { int g_pdl = 1; }   // programmatic dependent launch (common.cuh); FO_PDL=0 turns it off
 static int g_pair_ok = 1;   // clusters of two CTAs can be scheduled on every TPC
 static std::once_flag g_once;
 static int g_init_rc = FO_ERR_NO_DEVICE;
@@ -61,6 +62,10 @@ static void do_init() {
     return;
   }
   g_num_sms = prop.multiProcessorCount;
+  {
+    const char* e = getenv("FO_PDL");
+    if (e != nullptr) fo::g_pdl = atoi(e) != 0;
+  }
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
@@ -809,10 +814,9 @@ extern "C" int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream) {
     plan.p.bias_partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(g->workspace) + main_bytes);
   }
   CUDA_TRY(launch_wgrad_igemm(plan.p, plan.maps, (cudaStream_t)stream));
-  CUDA_TRY(launch_wgrad_finalize(plan.fin, g_num_sms, (cudaStream_t)stream));
-  if (g->dbias != nullptr)
-    CUDA_TRY(launch_bias_finalize(plan.p.bias_partial, plan.p.passes * plan.p.splits, plan.p.MC, g->p.c, g->dbias, g->dbias_accumulate,
-                                  (cudaStream_t)stream));
+  // one launch: split reduction + scatter of the weight gradient, and the bias gradient's column-sum partials
+  CUDA_TRY(launch_wgrad_finalize(plan.fin, plan.p.bias_partial, plan.p.passes * plan.p.splits, g->p.c, g->dbias,
+                                 g->dbias_accumulate, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
 

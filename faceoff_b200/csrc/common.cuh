@@ -29,6 +29,47 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// A training step is ~230 back-to-back launches, most of them 20-200 us long at 4 clips per GPU: the launch gap and the
+// prologue of every kernel (tensor-map prefetch, TMEM allocation, barrier initialisation, block scheduling) add up to
+// several per cent of such a step.  Kernels launched through launch_k() carry the programmatic-stream-serialization
+// attribute: their CTAs may become resident while the preceding kernel of the stream is still draining, run their prologue,
+// and block in pdl_wait() until that kernel has COMPLETED and its writes are visible -- so every global-memory access of
+// such a kernel (TMA included) must come after pdl_wait().  pdl_trigger() at the top lets the next kernel do the same with
+// this one.  A kernel launched without the attribute sees both instructions as no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_pdl;   // api.cu: 1 unless FO_PDL=0 (experiments)
+
+// Launch `kernel` with the PDL attribute (plus a cluster dimension when cluster_x > 1).  The kernel MUST call pdl_wait().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, int cluster_x,
+                            Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (g_pdl) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 // ------------------------------------------------------------------ mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));

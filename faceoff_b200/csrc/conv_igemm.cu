@@ -309,6 +309,7 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * p.MT * p.NT) tmem_cols <<= 1;
 
+  pdl_trigger();   // the next kernel of the stream may start its prologue (common.cuh)
   if (warp == 0) {
     if (lane == 0) {
       for (int i = 0; i < kMaxAMaps; ++i) tma_prefetch_desc(&maps.a[i]);
@@ -336,6 +337,8 @@ conv_igemm_kernel(const __grid_constant__ ConvParams p, const __grid_constant__ 
     }
     fence_mbar_init();
   }
+  // everything above overlaps the tail of the preceding kernel; global memory is touched only from here on
+  pdl_wait();
   const bool bias_in_smem = p.bias != nullptr && p.n_tiles == 1;
   if (bias_in_smem)
     for (int i = threadIdx.x; i < p.NT; i += blockDim.x) s_bias[i] = p.bias[i];
@@ -616,22 +619,9 @@ cudaError_t launch_conv_igemm(const ConvParams& p, const ConvMaps& maps, int num
   int grid = p.total_tiles < num_sms ? p.total_tiles : num_sms;
   if (p.cta_pair) {
     grid &= ~1;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(grid);
-    cfg.blockDim = dim3(kConvThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<2>, p, maps);
+    return launch_k(conv_igemm_kernel<2>, dim3(grid), dim3(kConvThreads), smem, stream, 2, p, maps);
   }
-  conv_igemm_kernel<1><<<grid, kConvThreads, smem, stream>>>(p, maps);
-  return cudaGetLastError();
+  return launch_k(conv_igemm_kernel<1>, dim3(grid), dim3(kConvThreads), smem, stream, 1, p, maps);
 }
 
 cudaError_t init_conv_igemm() {

@@ -52,6 +52,8 @@ __global__ void pack_nchw_wide_kernel(const float* __restrict__ x, __nv_bfloat16
 template <int CS>
 __global__ void unpack_nchw_small_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int c, int hw,
                                          size_t total) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
     const size_t n = i / hw, px = i % hw;
     float v[CS];
@@ -70,6 +72,8 @@ __global__ void unpack_nchw_small_kernel(const __nv_bfloat16* __restrict__ x, fl
 
 __global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, int c, int hw,
                                    int cs) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   // block: 32 pixels x up to 32 channels per pass through smem
   __shared__ float tile[32][33];
   const int n = blockIdx.y;
@@ -91,6 +95,8 @@ __global__ void unpack_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* _
 }
 
 __global__ void relu_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, size_t nvec) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
     uint4 v = x[i];
     uint32_t w[4] = {v.x, v.y, v.z, v.w};
@@ -127,37 +133,100 @@ __global__ void pack_weights_kernel(const float* __restrict__ w, __nv_bfloat16* 
 }
 
 // ---------------------------------------------------------------- split-K reduce + scatter to PyTorch layout
-__global__ void wgrad_finalize_kernel(FinalizeParams fp) {
+// One launch reduces the weight partials AND (blocks past main_blocks) the bias column-sum partials of a wgrad_igemm launch.
+// Up to 148 splits per output element: a thread that walks them alone is a chain of ~40 dependent L2 round trips (the former
+// kernel: 18 us per launch whatever the batch, 11 us more for the bias -- 1.3 ms of every step, i.e. 12 % of a 4-clip
+// step).  Here the 8 warps of a block take the splits s = warp, warp + 8, ... of the same 32 consecutive elements (lanes along
+// n: coalesced), four independent accumulators each, and warp 0 adds the 8 sums in a fixed order: deterministic.
+__global__ void __launch_bounds__(256)
+wgrad_finalize_kernel(FinalizeParams fp, int main_blocks, const float* __restrict__ bias_part, int bias_rows,
+                      int bias_c, float* __restrict__ dbias, int dbias_accumulate) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
+  __shared__ float red[8][32];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if ((int)blockIdx.x >= main_blocks) {
+    // bias gradient: dbias[c] (+)= sum_rows bias_part[row][c]   (rows = passes * splits, row pitch = MC)
+    const int i = ((int)blockIdx.x - main_blocks) * 32 + lane;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (i < bias_c) {
+      const float* src = bias_part + i;
+      int r = w;
+      for (; r + 24 < bias_rows; r += 32) {
+        a0 += src[(size_t)r * fp.MC];
+        a1 += src[(size_t)(r + 8) * fp.MC];
+        a2 += src[(size_t)(r + 16) * fp.MC];
+        a3 += src[(size_t)(r + 24) * fp.MC];
+      }
+      for (; r < bias_rows; r += 8) a0 += src[(size_t)r * fp.MC];
+    }
+    red[w][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (w == 0 && i < bias_c) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += red[k][lane];
+      if (dbias_accumulate) dbias[i] += acc; else dbias[i] = acc;
+    }
+    return;
+  }
   const size_t per_tap = (size_t)fp.MC * fp.NC;
+  const size_t split_stride = (size_t)fp.taps * per_tap;
   const size_t total = (size_t)fp.taps * fp.m_real * fp.n_real;
-  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+  if (fp.splits <= 16) {
+    // few splits (many passes, e.g. Conv3d: 27 taps x 128 x 128 elements over 16 splits): one thread per element
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)main_blocks * blockDim.x) {
+      const int n = (int)(i % fp.n_real);
+      const int m = (int)((i / fp.n_real) % fp.m_real);
+      const int tap = (int)(i / ((size_t)fp.n_real * fp.m_real));
+      const float* src = fp.partial + (size_t)tap * per_tap + (size_t)m * fp.NC + n;
+      float acc = 0.f;
+      for (int sp = 0; sp < fp.splits; ++sp) acc += src[(size_t)sp * split_stride];
+      const int wt = fp.tap_index[tap];
+      const size_t idx = fp.m_axis == 0 ? ((size_t)m * fp.dimB + (fp.q_w_off + n)) * fp.taps + wt
+                                        : ((size_t)(fp.q_w_off + n) * fp.dimB + m) * fp.taps + wt;
+      if (fp.accumulate) fp.dweight[idx] += acc; else fp.dweight[idx] = acc;
+    }
+    return;
+  }
+  for (size_t base = (size_t)blockIdx.x * 32; base < total; base += (size_t)main_blocks * 32) {
+    const size_t i = base + lane;
     // n fastest for coalesced partial reads
     const int n = (int)(i % fp.n_real);
     const int m = (int)((i / fp.n_real) % fp.m_real);
     const int tap = (int)(i / ((size_t)fp.n_real * fp.m_real));
-    const float* src = fp.partial + (size_t)tap * per_tap + (size_t)m * fp.NC + n;
-    float acc = 0.f;
-    for (int s = 0; s < fp.splits; ++s) acc += src[(size_t)s * fp.taps * per_tap];
-    const int wt = fp.tap_index[tap];
-    const size_t idx = fp.m_axis == 0 ? ((size_t)m * fp.dimB + (fp.q_w_off + n)) * fp.taps + wt
-                                      : ((size_t)(fp.q_w_off + n) * fp.dimB + m) * fp.taps + wt;
-    if (fp.accumulate) fp.dweight[idx] += acc; else fp.dweight[idx] = acc;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (i < total) {
+      const float* src = fp.partial + (size_t)tap * per_tap + (size_t)m * fp.NC + n;
+      int sp = w;
+      for (; sp + 24 < fp.splits; sp += 32) {
+        a0 += src[(size_t)sp * split_stride];
+        a1 += src[(size_t)(sp + 8) * split_stride];
+        a2 += src[(size_t)(sp + 16) * split_stride];
+        a3 += src[(size_t)(sp + 24) * split_stride];
+      }
+      for (; sp < fp.splits; sp += 8) a0 += src[(size_t)sp * split_stride];
+    }
+    red[w][lane] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (w == 0 && i < total) {
+      float acc = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc += red[k][lane];
+      const int wt = fp.tap_index[tap];
+      const size_t idx = fp.m_axis == 0 ? ((size_t)m * fp.dimB + (fp.q_w_off + n)) * fp.taps + wt
+                                        : ((size_t)(fp.q_w_off + n) * fp.dimB + m) * fp.taps + wt;
+      if (fp.accumulate) fp.dweight[idx] += acc; else fp.dweight[idx] = acc;
+    }
+    __syncthreads();
   }
-}
-
-// bias gradient from the wgrad kernel's column-sum partials: out[c] (+)= sum_splits part[s][c]
-__global__ void bias_finalize_kernel(const float* __restrict__ part, int splits, int mc, int c, float* __restrict__ out,
-                                     int accumulate) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= c) return;
-  float s = 0.f;
-  for (int k = 0; k < splits; ++k) s += part[(size_t)k * mc + i];
-  if (accumulate) out[i] += s; else out[i] = s;
 }
 
 // ---------------------------------------------------------------- column sums (bias gradients)
 // x bf16 [rows, cs]; each block strides over rows; thread owns an 8-channel vector lane.
 __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, size_t rows, int cs, float* __restrict__ part) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   extern __shared__ float sm[];  // [rows_per_iter][cs]
   const int vecs = cs / 8;
   const int rpi = blockDim.x / vecs;  // rows per iteration
@@ -201,31 +270,33 @@ __global__ void colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, size_
     part[(size_t)blockIdx.x * cs + c] = s;
   }
 }
-// 32 channels per CTA, 8 slices of the partial rows per channel (coalesced over channels), fixed-order tree over slices
-__global__ void __launch_bounds__(256)
+// 32 channels per CTA, 32 slices of the partial rows per channel (coalesced over channels), eight independent loads in
+// flight per thread (the rows are ~1200 L2 round trips: the former 8-slice, 4-accumulator version took 30 us per launch
+// whatever the batch), fixed-order sums: deterministic
+__global__ void __launch_bounds__(1024)
 colsum_final_kernel(const float* __restrict__ part, int nblocks, int cs, int c_off, int c, float* __restrict__ out,
                     int accumulate) {
-  __shared__ float red[8][33];
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
+  __shared__ float red[32][33];
   const int ci = threadIdx.x & 31, sl = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + ci;
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   if (i < c) {
     const float* col = part + c_off + i;
     int b = sl;
-    for (; b + 24 < nblocks; b += 32) {
-      s0 += col[(size_t)b * cs];
-      s1 += col[(size_t)(b + 8) * cs];
-      s2 += col[(size_t)(b + 16) * cs];
-      s3 += col[(size_t)(b + 24) * cs];
+    for (; b + 7 * 32 < nblocks; b += 8 * 32) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) a[u] += col[(size_t)(b + u * 32) * cs];
     }
-    for (; b < nblocks; b += 8) s0 += col[(size_t)b * cs];
+    for (; b < nblocks; b += 32) a[0] += col[(size_t)b * cs];
   }
-  red[sl][ci] = (s0 + s1) + (s2 + s3);
+  red[sl][ci] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   __syncthreads();
   if (sl == 0 && i < c) {
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) s += red[k][ci];
+    for (int k = 0; k < 32; ++k) s += red[k][ci];
     if (accumulate) out[i] += s; else out[i] = s;
   }
 }
@@ -236,6 +307,8 @@ __device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 __global__ void maxpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int vecs) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int ho = h / 2, wo = w / 2;
   const size_t total = (size_t)n * ho * wo * vecs;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -273,6 +346,8 @@ __device__ __forceinline__ uint32_t pool_bwd_pair(uint32_t x, uint32_t y, uint32
 }
 __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
                                     uint4* __restrict__ dx, int n, int h, int w, int vecs) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int ho = h / 2, wo = w / 2;
   const size_t total = (size_t)n * ho * wo * vecs;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -305,6 +380,8 @@ __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __
 // c_off..c_off+2 of an NCHW tensor [n, c_total, hw].  4 pixels (12 bytes) per thread, 16-byte stores per plane.
 __global__ void u8hwc_to_nchw_kernel(const uint32_t* __restrict__ x, float* __restrict__ out, int hw4, size_t total4,
                                      int c_total, int c_off, float mean, float stdv) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total4; i += (size_t)gridDim.x * blockDim.x) {
     const size_t n = i / hw4, p4 = i % hw4;
     const uint32_t w0 = __ldg(x + 3 * i), w1 = __ldg(x + 3 * i + 1), w2 = __ldg(x + 3 * i + 2);
@@ -444,6 +521,8 @@ im2col3x3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, i
 __global__ void __launch_bounds__(256)
 col2im4x4s2_kernel(const __nv_bfloat16* __restrict__ col, const float* __restrict__ bias, float* __restrict__ out, int c,
                    int hi, int wi) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int ho = 2 * hi, wo = 2 * wi;
   const int ox = blockIdx.x * 256 + threadIdx.x;
   const int oy = blockIdx.y;
@@ -477,6 +556,8 @@ col2im4x4s2_kernel(const __nv_bfloat16* __restrict__ col, const float* __restric
 
 // out[c] (+)= sum over n, hw of x[n][c][hw]   (bias gradient of the last layer, NCHW fp32 gradient)
 __global__ void chansum_nchw_kernel(const float* __restrict__ x, int n, int ca, int c, int hw, float* __restrict__ out) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   __shared__ float red[32];
   const int cc = blockIdx.y;
   float acc = 0.f;
@@ -523,11 +604,11 @@ cudaError_t launch_pack_nchw(const float* x, void* out, int n, int c, int hw, in
 cudaError_t launch_unpack_nchw(const void* x, float* out, int n, int c, int hw, int cs, cudaStream_t st) {
   if (cs == 16) {
     const size_t total = (size_t)n * hw;
-    unpack_nchw_small_kernel<16><<<grid_for(total, 256, 148, 16), 256, 0, st>>>((const __nv_bfloat16*)x, out, c, hw, total);
+    (void)launch_k(unpack_nchw_small_kernel<16>, dim3(grid_for(total, 256, 148, 16)), dim3(256), 0, st, 1, (const __nv_bfloat16*)x, out, c, hw, total);
     return cudaGetLastError();
   }
   dim3 grid((hw + 31) / 32, n);
-  unpack_nchw_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)x, out, c, hw, cs);
+  (void)launch_k(unpack_nchw_kernel, grid, dim3(256), 0, st, 1, (const __nv_bfloat16*)x, out, c, hw, cs);
   return cudaGetLastError();
 }
 // ---------------------------------------------------------------- fused multi-tensor Adam
@@ -581,13 +662,13 @@ cudaError_t launch_adam(const void* table, const void* chunks, int n_chunks, flo
 cudaError_t launch_u8hwc_to_nchw(const void* x, float* out, int n, int hw, int c_total, int c_off, float mean, float stdv,
                                  int num_sms, cudaStream_t st) {
   const size_t total4 = (size_t)n * (hw / 4);
-  u8hwc_to_nchw_kernel<<<grid_for(total4, 256, num_sms, 16), 256, 0, st>>>((const uint32_t*)x, out, hw / 4, total4, c_total,
+  (void)launch_k(u8hwc_to_nchw_kernel, dim3(grid_for(total4, 256, num_sms, 16)), dim3(256), 0, st, 1, (const uint32_t*)x, out, hw / 4, total4, c_total,
                                                                            c_off, mean, stdv);
   return cudaGetLastError();
 }
 cudaError_t launch_relu(const void* x, void* y, size_t numel, int num_sms, cudaStream_t st) {
   const size_t nvec = numel / 8;
-  relu_kernel<<<grid_for(nvec, 256, num_sms), 256, 0, st>>>((const uint4*)x, (uint4*)y, nvec);
+  (void)launch_k(relu_kernel, dim3(grid_for(nvec, 256, num_sms)), dim3(256), 0, st, 1, (const uint4*)x, (uint4*)y, nvec);
   return cudaGetLastError();
 }
 cudaError_t launch_pack_weights(const float* w, void* out, const PackParams& pp, int num_sms, cudaStream_t st) {
@@ -595,15 +676,14 @@ cudaError_t launch_pack_weights(const float* w, void* out, const PackParams& pp,
   pack_weights_kernel<<<grid_for(total, 256, num_sms), 256, 0, st>>>(w, (__nv_bfloat16*)out, pp);
   return cudaGetLastError();
 }
-cudaError_t launch_wgrad_finalize(const FinalizeParams& fp, int num_sms, cudaStream_t st) {
+cudaError_t launch_wgrad_finalize(const FinalizeParams& fp, const float* bias_part, int bias_rows, int bias_c, float* dbias,
+                                  int dbias_accumulate, int num_sms, cudaStream_t st) {
   const size_t total = (size_t)fp.taps * fp.m_real * fp.n_real;
-  wgrad_finalize_kernel<<<grid_for(total, 256, num_sms), 256, 0, st>>>(fp);
-  return cudaGetLastError();
-}
-cudaError_t launch_bias_finalize(const float* part, int splits, int mc, int c, float* out, int accumulate,
-                                 cudaStream_t st) {
-  bias_finalize_kernel<<<(c + 127) / 128, 128, 0, st>>>(part, splits, mc, c, out, accumulate);
-  return cudaGetLastError();
+  size_t mb = fp.splits <= 16 ? (total + 255) / 256 : (total + 31) / 32;   // (thread | 8 warps x 32 lanes) per element(s)
+  if (mb > (size_t)num_sms * 8) mb = (size_t)num_sms * 8;
+  const int bias_blocks = dbias != nullptr ? (bias_c + 31) / 32 : 0;
+  return launch_k(wgrad_finalize_kernel, dim3((unsigned)mb + bias_blocks), dim3(256), 0, st, 1, fp, (int)mb, bias_part, bias_rows,
+                  bias_c, dbias, dbias_accumulate);
 }
 int colsum_blocks(int num_sms) { return num_sms * 8; }
 cudaError_t launch_colsum(const void* x, size_t rows, int cs, int c_off, int c, float* out, int accumulate,
@@ -614,22 +694,22 @@ cudaError_t launch_colsum(const void* x, size_t rows, int cs, int c_off, int c, 
   int nblocks = colsum_blocks(num_sms);
   const size_t need = (rows + rpi - 1) / rpi;
   if ((size_t)nblocks > need) nblocks = (int)(need ? need : 1);
-  colsum_partial_kernel<<<nblocks, threads, (size_t)rpi * cs * sizeof(float), st>>>((const __nv_bfloat16*)x, rows, cs,
+  (void)launch_k(colsum_partial_kernel, dim3(nblocks), dim3(threads), (size_t)rpi * cs * sizeof(float), st, 1, (const __nv_bfloat16*)x, rows, cs,
                                                                                      workspace);
-  colsum_final_kernel<<<(c + 31) / 32, 256, 0, st>>>(workspace, nblocks, cs, c_off, c, out, accumulate);
+  (void)launch_k(colsum_final_kernel, dim3((c + 31) / 32), dim3(1024), 0, st, 1, workspace, nblocks, cs, c_off, c, out, accumulate);
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool2(const void* x, void* y, int n, int h, int w, int cs, int num_sms, cudaStream_t st) {
   const int vecs = cs / 8;
   const size_t total = (size_t)n * (h / 2) * (w / 2) * vecs;
-  maxpool2_kernel<<<grid_for(total, 256, num_sms), 256, 0, st>>>((const uint4*)x, (uint4*)y, n, h, w, vecs);
+  (void)launch_k(maxpool2_kernel, dim3(grid_for(total, 256, num_sms)), dim3(256), 0, st, 1, (const uint4*)x, (uint4*)y, n, h, w, vecs);
   return cudaGetLastError();
 }
 cudaError_t launch_maxpool2_bwd(const void* x, const void* y, const void* dy, void* dx, int n, int h, int w, int cs,
                                 int num_sms, cudaStream_t st) {
   const int vecs = cs / 8;
   const size_t total = (size_t)n * (h / 2) * (w / 2) * vecs;
-  maxpool2_bwd_kernel<<<grid_for(total, 256, num_sms, 16), 256, 0, st>>>((const uint4*)x, (const uint4*)y,
+  (void)launch_k(maxpool2_bwd_kernel, dim3(grid_for(total, 256, num_sms, 16)), dim3(256), 0, st, 1, (const uint4*)x, (const uint4*)y,
                                                                         (const uint4*)dy, (uint4*)dx, n, h, w, vecs);
   return cudaGetLastError();
 }
@@ -649,7 +729,7 @@ cudaError_t launch_col2im4x4s2(const void* col, const float* bias, float* out, i
                                cudaStream_t st) {
   (void)num_sms;
   dim3 grid((2 * wi + 255) / 256, 2 * hi, n);
-  col2im4x4s2_kernel<<<grid, 256, 0, st>>>((const __nv_bfloat16*)col, bias, out, c, hi, wi);
+  (void)launch_k(col2im4x4s2_kernel, grid, dim3(256), 0, st, 1, (const __nv_bfloat16*)col, bias, out, c, hi, wi);
   return cudaGetLastError();
 }
 cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, float* out, int accumulate, int num_sms,
@@ -660,7 +740,7 @@ cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, fl
   }
   if (hw % 4 != 0) return cudaErrorInvalidValue;
   dim3 grid(num_sms * 2, c);
-  chansum_nchw_kernel<<<grid, 512, 0, st>>>(x, n, ca, c, hw, out);
+  (void)launch_k(chansum_nchw_kernel, grid, dim3(512), 0, st, 1, x, n, ca, c, hw, out);
   return cudaGetLastError();
 }
 

@@ -48,9 +48,8 @@ cudaError_t launch_adam(const void* table, const void* chunks, int n_chunks, flo
                         float eps, float weight_decay, float bias_c1, float sqrt_bias_c2, float grad_scale, int num_sms,
                         cudaStream_t st);
 cudaError_t launch_pack_weights(const float* w, void* out, const PackParams& pp, int num_sms, cudaStream_t st);
-cudaError_t launch_wgrad_finalize(const FinalizeParams& fp, int num_sms, cudaStream_t st);
-cudaError_t launch_bias_finalize(const float* part, int splits, int mc, int c, float* out, int accumulate,
-                                 cudaStream_t st);
+cudaError_t launch_wgrad_finalize(const FinalizeParams& fp, const float* bias_part, int bias_rows, int bias_c, float* dbias,
+                                  int dbias_accumulate, int num_sms, cudaStream_t st);
 int colsum_blocks(int num_sms);
 cudaError_t launch_colsum(const void* x, size_t rows, int cs, int c_off, int c, float* out, int accumulate,
                           float* workspace, int num_sms, cudaStream_t st);

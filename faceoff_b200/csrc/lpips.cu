@@ -92,6 +92,8 @@ __device__ __forceinline__ float sum_sq(const float2 (&v)[N]) {
 template <int VPL, bool SPLIT, int U>
 __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
                                  const float* __restrict__ w, int hw, int c, int lpp, float* __restrict__ out) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   __shared__ float red[32];
   const int n = blockIdx.y;
   const int ppw = 32 / lpp;                        // pixels per warp
@@ -148,6 +150,8 @@ template <int VPL, bool SPLIT, int U>
 __global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
                                      const float* __restrict__ w, const float* __restrict__ g, int hw, int c, int lpp,
                                      __nv_bfloat16* __restrict__ d_f0, const __nv_bfloat16* __restrict__ addend) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int n = blockIdx.y;
   const int ppw = 32 / lpp;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -249,10 +253,10 @@ cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int
   if (bx < 1) bx = 1;
   dim3 grid(bx, n);
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
-  if (vpl == 1 && !split) lpips_tap_kernel<1, false, 2><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
-  else if (vpl == 2 && !split) lpips_tap_kernel<2, false, 2><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
-  else if (vpl == 1) lpips_tap_kernel<1, true, 1><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
-  else if (vpl == 2) lpips_tap_kernel<2, true, 1><<<grid, threads, 0, st>>>(a, b, w, hw, c, lpp, out);
+  if (vpl == 1 && !split) (void)launch_k(lpips_tap_kernel<1, false, 2>, grid, dim3(threads), 0, st, 1, a, b, w, hw, c, lpp, out);
+  else if (vpl == 2 && !split) (void)launch_k(lpips_tap_kernel<2, false, 2>, grid, dim3(threads), 0, st, 1, a, b, w, hw, c, lpp, out);
+  else if (vpl == 1) (void)launch_k(lpips_tap_kernel<1, true, 1>, grid, dim3(threads), 0, st, 1, a, b, w, hw, c, lpp, out);
+  else if (vpl == 2) (void)launch_k(lpips_tap_kernel<2, true, 1>, grid, dim3(threads), 0, st, 1, a, b, w, hw, c, lpp, out);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -270,10 +274,10 @@ cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w,
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
   __nv_bfloat16* d = (__nv_bfloat16*)d_f0;
   const __nv_bfloat16* ad = (const __nv_bfloat16*)addend;
-  if (vpl == 1 && !split) lpips_tap_bwd_kernel<1, false, 2><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
-  else if (vpl == 2 && !split) lpips_tap_bwd_kernel<2, false, 1><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
-  else if (vpl == 1) lpips_tap_bwd_kernel<1, true, 1><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
-  else if (vpl == 2) lpips_tap_bwd_kernel<2, true, 1><<<grid, threads, 0, st>>>(a, b, w, g, hw, c, lpp, d, ad);
+  if (vpl == 1 && !split) (void)launch_k(lpips_tap_bwd_kernel<1, false, 2>, grid, dim3(threads), 0, st, 1, a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 2 && !split) (void)launch_k(lpips_tap_bwd_kernel<2, false, 1>, grid, dim3(threads), 0, st, 1, a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 1) (void)launch_k(lpips_tap_bwd_kernel<1, true, 1>, grid, dim3(threads), 0, st, 1, a, b, w, g, hw, c, lpp, d, ad);
+  else if (vpl == 2) (void)launch_k(lpips_tap_bwd_kernel<2, true, 1>, grid, dim3(threads), 0, st, 1, a, b, w, g, hw, c, lpp, d, ad);
   else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
@@ -285,6 +289,8 @@ template <bool GRAD>
 __global__ void __launch_bounds__(256)
 mse_kernel(const float4* __restrict__ a, const float4* __restrict__ b, int ca, int c, int hw4, size_t total4,
            float* __restrict__ out, const float* __restrict__ gscale, float scale, float4* __restrict__ grad) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   __shared__ float red[8];
   float acc = 0.f;
   const float g = GRAD ? __ldg(gscale) * scale : 0.f;
@@ -335,7 +341,7 @@ cudaError_t launch_mse(const float* a, const float* b, int n, int ca, int c, int
   size_t blocks = (total4 + 1023) / 1024;
   if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
   if (blocks < 1) blocks = 1;
-  mse_kernel<false><<<(int)blocks, 256, 0, st>>>((const float4*)a, (const float4*)b, ca, c, hw / 4, total4, sum_out,
+  (void)launch_k(mse_kernel<false>, dim3((int)blocks), dim3(256), 0, st, 1, (const float4*)a, (const float4*)b, ca, c, hw / 4, total4, sum_out,
                                                  nullptr, 0.f, nullptr);
   return cudaGetLastError();
 }
@@ -345,7 +351,7 @@ cudaError_t launch_mse_grad(const float* a, const float* b, int n, int ca, int c
   size_t blocks = (total4 + 1023) / 1024;
   if (blocks > (size_t)num_sms * 8) blocks = (size_t)num_sms * 8;
   if (blocks < 1) blocks = 1;
-  mse_kernel<true><<<(int)blocks, 256, 0, st>>>((const float4*)a, (const float4*)b, ca, c, hw / 4, total4, nullptr,
+  (void)launch_k(mse_kernel<true>, dim3((int)blocks), dim3(256), 0, st, 1, (const float4*)a, (const float4*)b, ca, c, hw / 4, total4, nullptr,
                                                 gscale, scale, (float4*)grad);
   return cudaGetLastError();
 }

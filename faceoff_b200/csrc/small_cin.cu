@@ -54,6 +54,8 @@ vgg_first_conv_kernel(const FirstConvParams p) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
+  pdl_trigger();   // programmatic dependent launch (common.cuh): global memory only after pdl_wait()
+  pdl_wait();
   // weights -> K-major bf16 tile, k = (ky * 3 + kx) * 3 + ch (zero for k >= 27)
   for (int i = tid; i < 64 * 32; i += kFcThreads) {
     const int co = i >> 5, k = i & 31;
@@ -325,6 +327,9 @@ s2conv_kernel(const S2Params p) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
+  pdl_trigger();   // programmatic dependent launch (common.cuh): global memory only after pdl_wait()
+  s2_fill_pad<C, false>(sT, tid);
+  pdl_wait();
   for (int i = tid; i < 64 * 128; i += kS2Threads) {
     const int co = i >> 7, k = i & 127;
     const float v = k < 16 * C ? p.weight[co * 16 * C + k] : 0.f;
@@ -332,7 +337,6 @@ s2conv_kernel(const S2Params p) {
     *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(v);
   }
   if (tid < 64) sBias[tid] = p.bias != nullptr ? p.bias[tid] : 0.f;
-  s2_fill_pad<C, false>(sT, tid);
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -484,10 +488,12 @@ s2wgrad_kernel(const S2Params p) {
     mbar_init(bar, 1);
     fence_mbar_init();
   }
+  pdl_trigger();   // programmatic dependent launch (common.cuh): global memory only after pdl_wait()
   s2_fill_pad<C, true>(sT, tid);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_ptr;
   const uint32_t idesc = make_idesc_bf16(128, 64, 1, 1);
   const uint64_t a_desc = make_smem_desc(smem_u32(sT), 128, 128 * 128);   // LBO = distance between the two 64-wide M chunks
@@ -571,6 +577,8 @@ __global__ void __launch_bounds__(1024)
 s2wgrad_finalize_kernel(const float* __restrict__ partial, int ctas, int c, float* __restrict__ dweight, int accumulate,
                         float* __restrict__ dbias, int dbias_accumulate) {
   __shared__ float red[16][64];
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
   const int k = blockIdx.x, n = threadIdx.x & 63, part = threadIdx.x >> 6;
   float s = 0.f;
   for (int j = part; j < ctas; j += 16) s += partial[((size_t)j * 128 + k) * 64 + n];
@@ -614,8 +622,7 @@ template <typename K>
 static cudaError_t s2_launch(K kernel, const S2Params& p, int grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kernel<<<grid, kS2Threads, smem, st>>>(p);
-  return cudaGetLastError();
+  return launch_k(kernel, dim3(grid), dim3(kS2Threads), smem, st, 1, p);
 }
 
 cudaError_t launch_s2conv(const float* x, int n, int ca, int c, int H, int W, const float* weight, const float* bias,
@@ -647,8 +654,8 @@ cudaError_t launch_s2wgrad(const float* x, int n, int ca, int c, int H, int W, c
   else if (c == 3) e = s2_launch(s2wgrad_kernel<3>, p, grid, smem, st);
   else return cudaErrorInvalidValue;
   if (e != cudaSuccess) return e;
-  s2wgrad_finalize_kernel<<<16 * c + 1, 1024, 0, st>>>(workspace, grid, c, dweight, accumulate, dbias, dbias_accumulate);
-  return cudaGetLastError();
+  return launch_k(s2wgrad_finalize_kernel, dim3(16 * c + 1), dim3(1024), 0, st, 1, workspace, grid, c, dweight, accumulate, dbias,
+                  dbias_accumulate);
 }
 
 cudaError_t launch_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias,
@@ -669,8 +676,7 @@ cudaError_t launch_vgg_first_conv(const float* x, int n, int h, int w, const flo
   long long grid = p.total_tiles;
   const long long cap = (long long)num_sms * 4;
   if (grid > cap) grid = cap;
-  vgg_first_conv_kernel<<<(int)grid, kFcThreads, smem, st>>>(p);
-  return cudaGetLastError();
+  return launch_k(vgg_first_conv_kernel, dim3((int)grid), dim3(kFcThreads), smem, st, 1, p);
 }
 
 }  // namespace fo

@@ -49,6 +49,7 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < p.taps_per_pass * p.NC + (p.bias_partial != nullptr ? 16 : 0)) tmem_cols <<= 1;
 
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
   const int split = blockIdx.x;
   const int pass = blockIdx.y;
   // the column-sum MMAs are spread round-robin over the passes (pass p takes pixel tiles i with i % passes == p) so no
@@ -86,6 +87,7 @@ wgrad_igemm_kernel(const __grid_constant__ WgradParams p, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();      // the preceding kernel has completed: global memory (TMA loads, partial stores) from here on
   // warp-uniform copy (the shuffle lets the compiler keep MMA operands in uniform registers)
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_ptr, 0);
   const WgTap* taps = p.taps + pass * p.taps_per_pass;
@@ -251,8 +253,7 @@ size_t wgrad_smem_bytes(const WgradParams& p) {
 
 cudaError_t launch_wgrad_igemm(const WgradParams& p, const WgradMaps& maps, cudaStream_t stream) {
   dim3 grid(p.splits, p.passes);
-  wgrad_igemm_kernel<<<grid, kWgThreads, wgrad_smem_bytes(p), stream>>>(p, maps);
-  return cudaGetLastError();
+  return launch_k(wgrad_igemm_kernel, grid, dim3(kWgThreads), wgrad_smem_bytes(p), stream, 1, p, maps);
 }
 
 cudaError_t init_wgrad_igemm() {
