@@ -964,8 +964,14 @@ extern "C" int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, c
                             const float* e_norm2, int64_t* embed_ind, int* n_flagged, void* workspace,
                             size_t workspace_bytes, fo_stream_t stream) {
   REQUIRE_INIT();
-  if (dim != 64 && dim != 128) return fail(FO_ERR_INVALID, "vq_assign: dim must be 64 or 128 (got %d)", dim);
-  if (n_embed % 16 != 0 || n_embed > 8192) return fail(FO_ERR_INVALID, "vq_assign: n_embed must be a multiple of 16, <= 8192");
+  if (dim <= 0 || n_embed <= 0) return fail(FO_ERR_INVALID, "vq_assign: dim and n_embed must be positive");
+  if (vq_assign_is_generic(dim, n_embed)) {
+    // any other codebook shape the reference's Quantize accepts: exact fp64 scan on CUDA cores (vq.cu)
+    if (dim > 1536) return fail(FO_ERR_INVALID, "vq_assign: dim %d above the generic kernel's 1536", dim);
+    if (rows == 0) return FO_OK;
+    CUDA_TRY(launch_vq_assign_generic(x, rows, dim, n_embed, e_t, embed_ind, n_flagged, g_num_sms, (cudaStream_t)stream));
+    return FO_OK;
+  }
   if (workspace_bytes < vq_assign_workspace_bytes(rows, dim)) return fail(FO_ERR_INVALID, "vq_assign workspace too small");
   if (rows == 0) return FO_OK;
   CUtensorMap map_e;

@@ -84,6 +84,9 @@ cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, 
                              const void* e_split, const float* e_norm2, int64_t* embed_ind, int* n_flagged,
                              void* workspace, const CUtensorMap* map_e, const CUtensorMap* map_x, int num_sms,
                              cudaStream_t st);
+bool vq_assign_is_generic(int dim, int n_embed);
+cudaError_t launch_vq_assign_generic(const float* x, size_t rows, int dim, int n_embed, const float* e_t, int64_t* embed_ind,
+                                     int* n_flagged, int num_sms, cudaStream_t st);
 cudaError_t init_vq();
 cudaError_t launch_vq_gather_stats(const float* x, const int64_t* ind, size_t rows, int dim, int n_embed,
                                    const float* e_t, float* q_f32, void* q_bf16, float* diff_sum, float* counts,

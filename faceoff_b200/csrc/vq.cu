@@ -654,6 +654,82 @@ cudaError_t launch_vq_assign(const float* x, size_t rows, int dim, int n_embed, 
   if (n_flagged != nullptr) e = cudaMemcpyAsync(n_flagged, p.flag_count, sizeof(int), cudaMemcpyDeviceToDevice, st);
   return e;
 }
+// Codebooks the tensor-core kernel is not specialised for (dim other than 64 / 128, n_embed not a multiple of 16 or above
+// 8192; the reference's Quantize takes any, models/vqvae_conv3d_latent.py:34-45): every row is scored against every code in
+// fp64 exactly like the flagged rows above (e^2 - 2 x e accumulated term by term, first minimum wins) -- bit-exact by
+// construction, CUDA cores only.  A CTA takes 8 rows at a time (dynamic shared memory [8][dim]); thread t scans codes t,
+// t + 128, ... and reads each code row once for the 8 rows.
+__global__ void __launch_bounds__(kVqRefineThreads)
+vq_assign_generic_kernel(const float* __restrict__ x, const float* __restrict__ e_t, size_t rows, int dim, int n_embed,
+                         long long* __restrict__ embed_ind) {
+  constexpr int R = kVqRefineRows;
+  extern __shared__ __align__(16) float sxg[];   // [R][dim]
+  __shared__ double s_best[R][kVqRefineThreads / 32];
+  __shared__ int s_idx[R][kVqRefineThreads / 32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (size_t r0 = (size_t)blockIdx.x * R; r0 < rows; r0 += (size_t)gridDim.x * R) {
+    __syncthreads();   // previous group fully consumed
+    for (int i = threadIdx.x; i < R * dim; i += kVqRefineThreads) {
+      const int r = i / dim, d = i % dim;
+      sxg[i] = r0 + r < rows ? x[(r0 + r) * dim + d] : 0.f;
+    }
+    __syncthreads();
+    double best[R];
+    int besti[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { best[r] = 1e300; besti[r] = 0x7fffffff; }
+    for (int k = threadIdx.x; k < n_embed; k += kVqRefineThreads) {
+      const float* er = e_t + (size_t)k * dim;
+      double acc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) acc[r] = 0.0;
+      for (int d = 0; d < dim; ++d) {
+        const double e = (double)__ldg(er + d);
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] += e * (e - 2.0 * (double)sxg[r * dim + d]);
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        if (acc[r] < best[r]) { best[r] = acc[r]; besti[r] = k; }   // k ascends: the first minimum is kept
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      double bv = best[r];
+      int bi = besti[r];
+      for (int o = 16; o > 0; o >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ob < bv || (ob == bv && oi < bi)) { bv = ob; bi = oi; }
+      }
+      if (lane == 0) { s_best[r][warp] = bv; s_idx[r][warp] = bi; }
+    }
+    __syncthreads();
+    if (threadIdx.x < R && r0 + threadIdx.x < rows) {
+      const int r = threadIdx.x;
+      double bv = s_best[r][0];
+      int bi = s_idx[r][0];
+#pragma unroll
+      for (int w = 1; w < kVqRefineThreads / 32; ++w)
+        if (s_best[r][w] < bv || (s_best[r][w] == bv && s_idx[r][w] < bi)) { bv = s_best[r][w]; bi = s_idx[r][w]; }
+      embed_ind[r0 + r] = bi == 0x7fffffff ? 0 : bi;   // a NaN row compares false everywhere: index 0 like the fast path
+    }
+  }
+}
+bool vq_assign_is_generic(int dim, int n_embed) { return (dim != 64 && dim != 128) || n_embed % 16 != 0 || n_embed > 8192; }
+cudaError_t launch_vq_assign_generic(const float* x, size_t rows, int dim, int n_embed, const float* e_t, int64_t* embed_ind,
+                                     int* n_flagged, int num_sms, cudaStream_t st) {
+  const size_t smem = (size_t)kVqRefineRows * dim * sizeof(float);
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;
+  size_t blocks = (rows + kVqRefineRows - 1) / kVqRefineRows;
+  if (blocks > (size_t)num_sms * 16) blocks = (size_t)num_sms * 16;
+  vq_assign_generic_kernel<<<(int)blocks, kVqRefineThreads, smem, st>>>(x, e_t, rows, dim, n_embed,
+                                                                        reinterpret_cast<long long*>(embed_ind));
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  if (n_flagged != nullptr) e = cudaMemsetAsync(n_flagged, 0, sizeof(int), st);
+  return e;
+}
+
 cudaError_t init_vq() {
   cudaError_t e = cudaFuncSetAttribute(vq_assign_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxDynSmem);
   if (e != cudaSuccess) return e;

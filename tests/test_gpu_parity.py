@@ -100,6 +100,43 @@ def test_vq_assign_bit_exact_vs_fp64(rows, dim, K):
     assert torch.equal(ind, ref), f"{(ind != ref).sum().item()} mismatches"
 
 
+@pytest.mark.parametrize("dim,K", [(32, 100), (96, 40), (64, 50), (256, 24)])
+def test_quantize_any_codebook_shape_vs_oracle(dim, K):
+    """The reference's Quantize takes any (dim, n_embed) (models/vqvae_conv3d_latent.py:34-45).  Shapes outside the
+    tensor-core kernel's (dim 64 / 128, n_embed % 16 == 0) run the exact fp64 scan (vq.cu vq_assign_generic_kernel): indices
+    bit-exact vs the fp64 argmin, outputs / EMA buffers / input gradient vs the oracle on the same seeded input."""
+    from faceoff_b200.vqvae import Quantize
+    from oracle import faceoff_oracle as O
+
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(3, 7, 5, dim, generator=gen)
+    q = Quantize(dim, K)
+    with torch.no_grad():
+        q.embed.copy_(torch.randn(dim, K, generator=gen))
+        q.embed_avg.copy_(q.embed)
+        q.cluster_size.copy_(torch.rand(K, generator=gen))
+    e0, c0, a0 = q.embed.clone(), q.cluster_size.clone(), q.embed_avg.clone()
+    gq = torch.randn(3, 7, 5, dim, generator=gen)
+    q = q.cuda().train()
+    xg = x.cuda().requires_grad_(True)
+    quant, diff, ind = q(xg)
+    (quant * gq.cuda()).sum().add(diff * 3.0).backward()
+    torch.cuda.synchronize()
+    xo = x.clone().requires_grad_(True)
+    oq, odiff, oind, obuf, _ = O.quantize_forward(xo, e0, c0, a0, training=True)
+    (oq * gq).sum().add(odiff * 3.0).backward()
+    d = (x.double().reshape(-1, dim).pow(2).sum(1, keepdim=True) - 2 * x.double().reshape(-1, dim) @ e0.double()
+         + e0.double().pow(2).sum(0, keepdim=True))
+    assert torch.equal(ind.cpu().reshape(-1), d.argmin(1)), "indices differ from the fp64 argmin"
+    assert torch.equal(ind.cpu(), oind)
+    torch.testing.assert_close(quant.detach().cpu(), oq.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(diff.detach().cpu(), odiff.detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(xg.grad.cpu(), xo.grad, rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(q.embed.cpu(), obuf[0], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(q.cluster_size.cpu(), obuf[1], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(q.embed_avg.cpu(), obuf[2], rtol=1e-5, atol=1e-6)
+
+
 def _load_vqvae(p):
     from faceoff_b200.vqvae import VQVAE
 
