@@ -384,7 +384,7 @@ def wgrad(form: int, ndim: int, ksize: int, p: SrcT, q: SrcT, dweight: torch.Ten
     if PROFILE is not None:
         kind = ("wgrad3d" if ndim == 3 else f"wgrad{ksize}x{ksize}" if form == FORM_S1 else "wgrad4x4s2") + f"_{p[1]}x{q[1]}"
         PROFILE.setdefault("wgrad_igemm/" + kind, []).append(PROFILE["wgrad_igemm"][-1])
-    _count(2 + (dbias is not None))
+    _count(2)      # wgrad_igemm + wgrad_finalize (which also reduces the bias partials)
 
 
 def colsum(x: torch.Tensor, c: int, out: torch.Tensor, c_off: int = 0, accumulate: bool = False, _raw: bool = False):
