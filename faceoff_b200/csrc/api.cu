@@ -732,6 +732,19 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
   if (splits < 1) splits = 1;
   if (splits > p.total_ptiles) splits = p.total_ptiles;
   p.splits = splits;
+  {
+    // accumulation chains (wgrad_igemm.cu): at most ~4096 accumulating MMAs per TMEM accumulator, then a new partial slot
+    int chain_mmas = 4096;
+    const char* e = getenv("FO_WG_CHAIN");   // experiments: 0 = one chain per CTA
+    if (e != nullptr) chain_mmas = atoi(e);
+    const int per = (p.total_ptiles + splits - 1) / splits;
+    const int mmas_per_tile = p.kpix / 16;
+    int n_flush = chain_mmas > 0 ? (per * mmas_per_tile + chain_mmas - 1) / chain_mmas : 1;
+    if (n_flush < 1) n_flush = 1;
+    p.n_flush = n_flush;
+    p.chain_tiles = (per + n_flush - 1) / n_flush;   // balanced chunks
+    if (p.chain_tiles < 1) p.chain_tiles = 1;
+  }
   p.partial = (float*)g->workspace;
   {
     const char* sk = getenv("FO_SKIP_MMA");
@@ -742,7 +755,7 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
     if (st && atoi(st) >= 2 && atoi(st) <= p.stages) p.stages = atoi(st);
   }
 
-  f.partial = p.partial; f.dweight = g->dweight; f.splits = splits; f.taps = nt; f.MC = mc; f.NC = nc;
+  f.partial = p.partial; f.dweight = g->dweight; f.splits = splits * p.n_flush; f.taps = nt; f.MC = mc; f.NC = nc;
   f.m_real = g->p.c; f.n_real = g->q.c; f.dimB = g->dimB; f.m_axis = g->m_axis; f.q_w_off = g->q_w_off;
   f.accumulate = g->accumulate;
   if (!need_maps) return FO_OK;
@@ -793,8 +806,8 @@ extern "C" size_t fo_wgrad_workspace_bytes(const fo_wgrad_t* g) {
   WgradPlan* planp = nullptr;
   if (cache.get(g, [&](WgradPlan* pl) { return plan_wgrad(g, pl, false); }, &planp) != FO_OK) return 0;
   const WgradPlan& plan = *planp;
-  return (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float) +
-         (size_t)plan.p.passes * plan.p.splits * plan.p.MC * sizeof(float);
+  const size_t slots = (size_t)plan.p.splits * plan.p.n_flush;
+  return slots * plan.taps * plan.p.MC * plan.p.NC * sizeof(float) + (size_t)plan.p.passes * slots * plan.p.MC * sizeof(float);
 }
 
 extern "C" int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream) {
@@ -804,8 +817,9 @@ extern "C" int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream) {
   int rc = cache.get(g, [&](WgradPlan* pl) { return plan_wgrad(g, pl, true); }, &planp);
   if (rc != FO_OK) return rc;
   WgradPlan& plan = *planp;
-  const size_t main_bytes = (size_t)plan.p.splits * plan.taps * plan.p.MC * plan.p.NC * sizeof(float);
-  const size_t need = main_bytes + (size_t)plan.p.passes * plan.p.splits * plan.p.MC * sizeof(float);
+  const size_t slots = (size_t)plan.p.splits * plan.p.n_flush;
+  const size_t main_bytes = slots * plan.taps * plan.p.MC * plan.p.NC * sizeof(float);
+  const size_t need = main_bytes + (size_t)plan.p.passes * slots * plan.p.MC * sizeof(float);
   if (g->workspace == nullptr || g->workspace_bytes < need)
     return fail(FO_ERR_INVALID, "wgrad workspace too small: %zu < %zu", g->workspace_bytes, need);
   plan.p.bias_partial = nullptr;
@@ -815,7 +829,7 @@ extern "C" int fo_wgrad_run(const fo_wgrad_t* g, fo_stream_t stream) {
   }
   CUDA_TRY(launch_wgrad_igemm(plan.p, plan.maps, (cudaStream_t)stream));
   // one launch: split reduction + scatter of the weight gradient, and the bias gradient's column-sum partials
-  CUDA_TRY(launch_wgrad_finalize(plan.fin, plan.p.bias_partial, plan.p.passes * plan.p.splits, g->p.c, g->dbias,
+  CUDA_TRY(launch_wgrad_finalize(plan.fin, plan.p.bias_partial, plan.p.passes * (int)slots, g->p.c, g->dbias,
                                  g->dbias_accumulate, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }

@@ -128,11 +128,14 @@ struct WgradParams {
   int splits;            // split-K factor over pixel tiles
   int total_ptiles;      // prod(tile_cnt)
   int stages;
+  int chain_tiles;       // pixel tiles accumulated into a TMEM accumulator before it is written out and restarted (see
+                         // wgrad_igemm.cu "accumulation chains"); a CTA's range is cut into n_flush such chunks
+  int n_flush;           // chunks per split = partial slots per split
   int p_c0;              // channel offset of the P side inside its map
   int dbg_skip_mma;      // debug: do not issue MMAs (pure TMA streaming rate)
   int backoff_ns;        // sleep between mbarrier probes of the long waits (0 = plain polling)
-  float* partial;        // [splits][passes*taps_per_pass][MC][NC] fp32
-  float* bias_partial;   // [passes][splits][MC] partial column sums of P (= bias gradient) or null
+  float* partial;        // [splits * n_flush][passes*taps_per_pass][MC][NC] fp32
+  float* bias_partial;   // [passes][splits * n_flush][MC] partial column sums of P (= bias gradient) or null
   WgTap taps[64];        // passes * taps_per_pass entries (padded entries have map = 255)
 };
 struct WgradMaps {
