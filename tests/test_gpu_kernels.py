@@ -315,3 +315,36 @@ def test_vq_gather_stats_ema_backward_on_the_codebook_sweep(dim, n_embed, skew):
     g32, _ = ops.vq_backward(gq.cuda(), 0, gd.cuda(), xs, inds, e_t)
     gref = gq.double() + 0.7 * 2 * (x.double() - qref.double()) / x.numel()
     torch.testing.assert_close(g32.cpu().double(), gref, rtol=1e-5, atol=1e-9)
+
+
+# ------------------------------------------------------------------------------------------------ weight gradients
+@pytest.mark.parametrize("clips", [1, 32])
+def test_wgrad_accumulation_chain_is_bounded(clips):
+    """Conv3d 128 -> 128 weight gradient at the BASELINE batch (32 clips x 30 x 64 x 64 positions in ONE launch) against an
+    fp64 GEMM of the same bf16 operands: centre tap dW[:, :, 1, 1, 1] = dy^T x.  The tensor core truncates when it adds to
+    its fp32 accumulator (csrc/wgrad_igemm.cu "accumulation chains"): without the chunked chains the 32-clip launch is
+    2.5e-4 short in norm (3.0e-4 max-normalised); with them it must stay below 1e-4, like a 1-clip launch.  Also checks
+    the fused bias gradient (column sums of dy) at rtol 1e-5."""
+    from faceoff_b200 import ops
+    from faceoff_b200.ops import FORM_S1
+
+    dev = torch.device("cuda", 0)
+    g = torch.Generator(device=dev).manual_seed(3)
+    x = torch.randn(clips, 30, 64, 64, 128, device=dev, generator=g).to(torch.bfloat16)
+    dy = (torch.randn(clips, 30, 64, 64, 128, device=dev, generator=g) * 1e-3).to(torch.bfloat16)
+    ref = torch.zeros(128, 128, dtype=torch.float64, device=dev)
+    bref = torch.zeros(128, dtype=torch.float64, device=dev)
+    for c in range(clips):
+        d = dy[c].reshape(-1, 128).double()
+        ref += d.t() @ x[c].reshape(-1, 128).double()
+        bref += d.sum(0)
+    dw = torch.empty(128, 128, 3, 3, 3, dtype=torch.float32, device=dev)
+    db = torch.empty(128, dtype=torch.float32, device=dev)
+    ops.wgrad(FORM_S1, 3, 3, (dy, 128, 0), (x, 128, 0), dw, m_axis=0, dbias=db)
+    torch.cuda.synchronize()
+    a = dw[:, :, 1, 1, 1].double()
+    e_max = ((a - ref).abs().max() / ref.abs().max()).item()
+    e_norm = ((a.norm() - ref.norm()) / ref.norm()).item()
+    print(f"wgrad3d {clips} clips: max-normalised err {e_max:.3e}, norm rel err {e_norm:+.3e}")
+    assert e_max < 1e-4 and abs(e_norm) < 1e-4
+    assert ((db.double() - bref).abs().max() / bref.abs().max()).item() < 1e-4
