@@ -201,7 +201,9 @@ int fo_vq_prep(const float* embed, int dim, int n_embed, void* e_split, float* e
                fo_stream_t stream);
 /* Nearest-code assignment (:48-54).  x fp32 [rows, dim].  embed_ind int64 [rows].
  * e_t / e_split / e_norm2 come from fo_vq_prep.  Tensor-core distances (bf16 split, error-bounded per code) + exact
- * (fp64-accumulated) re-evaluation of the rows that are ambiguous within the bound; n_flagged (device int32, optional) counts those rows. */
+ * (fp64-accumulated) re-evaluation of the rows that are ambiguous within the bound; n_flagged (device int32, optional) counts those rows.
+ * That kernel takes dim 64 / 128 and n_embed % 16 == 0, <= 8192; every other shape the reference's Quantize accepts (:34-45;
+ * dim <= 1536) is scored exactly in fp64 on CUDA cores (same first-minimum rule, n_flagged = 0, workspace unused). */
 int fo_vq_assign(const float* x, size_t rows, int dim, int n_embed, const float* e_t, const void* e_split,
                  const float* e_norm2, int64_t* embed_ind, int* n_flagged, void* workspace, size_t workspace_bytes,
                  fo_stream_t stream);
