@@ -924,6 +924,20 @@ extern "C" int fo_vgg_first_conv(const float* x, int n, int h, int w, const floa
   CUDA_TRY(launch_vgg_first_conv(x, n, h, w, weight, bias, shift, scale, out_relu, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
+extern "C" int fo_vgg_first_dgrad(const void* dy, int n, int h, int w, const float* weight, const float* scale, float* dx,
+                                  fo_stream_t stream) {
+  REQUIRE_INIT();
+  if (n < 1 || h < 1 || w < 1) return fail(FO_ERR_INVALID, "vgg_first_dgrad: bad extents");
+  // dy: bf16 channels-last [n, h, w, 64]; one TMA box = 8 rows x 32 pixels x 64 channels (out-of-range pixels read as zero)
+  CUtensorMap map;
+  const uint64_t dims[5] = {64, (uint64_t)w, (uint64_t)h, (uint64_t)n, 1};
+  const uint64_t str[5] = {1, 64, (uint64_t)w * 64, (uint64_t)h * w * 64, (uint64_t)n * h * w * 64};
+  const uint32_t bx[5] = {64, 32, 8, 1, 1};
+  int rc = encode_map(&map, dy, 5, dims, str, bx, 128);
+  if (rc != FO_OK) return rc;
+  CUDA_TRY(launch_vgg_first_dgrad(&map, n, h, w, weight, scale, dx, g_num_sms, (cudaStream_t)stream));
+  return FO_OK;
+}
 static int s2_check(int n, int ca, int c, int H, int W) {
   if (n < 1 || (c != 3 && c != 6) || ca < c || H < 2 || W < 2 || ((H | W) & 1))
     return fail(FO_ERR_INVALID, "s2conv: needs c in {3, 6}, ca >= c and even H, W (got c=%d ca=%d H=%d W=%d)", c, ca, H, W);

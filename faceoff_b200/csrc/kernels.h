@@ -69,6 +69,9 @@ cudaError_t launch_chansum_nchw(const float* x, int n, int ca, int c, int hw, fl
 cudaError_t launch_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias,
                                   const float* shift, const float* scale, void* out, int num_sms, cudaStream_t st);
 
+cudaError_t launch_vgg_first_dgrad(const CUtensorMap* map_dy, int n, int h, int w, const float* weight, const float* scale,
+                                   float* dx, int num_sms, cudaStream_t st);
+
 int s2_grid(int num_sms);
 cudaError_t launch_s2conv(const float* x, int n, int ca, int c, int H, int W, const float* weight, const float* bias,
                           const void* mask, const void* addend, void* out, int relu, int num_sms, cudaStream_t st);

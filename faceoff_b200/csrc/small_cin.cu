@@ -196,6 +196,175 @@ vgg_first_conv_kernel(const FirstConvParams p) {
 }
 
 // =====================================================================================================================
+// Data gradient of the first VGG conv (Conv2d 3 -> 64, 3x3, pad 1; reference models/lpips.py:119-127 slice1, the gradient
+// that leaves the LPIPS trunk towards the decoder).  As an implicit GEMM it is the worst shape there is: N = 3 (padded to
+// 16) output channels against K = 9 taps x 64, i.e. 36 MMAs of 128 x 16 x 16 per 128 pixels, each paying the 64-cycle
+// A-operand read -- 5.3 ms per 960 frames for 0.2 TFLOP (+ 0.4 ms to unpack the bf16 channels-last result to NCHW).
+// Here the taps move from K to N:
+//     T[p][tap][c] = sum_co dy[p][co] * W[co][c][tap]          ONE K = 64 GEMM per pixel tile, N = 9 taps x (3 + 1 pad) = 36 (48)
+//     dx[q][c]     = sum_tap T[q - shift(tap)][tap][c]         shift-add inside the tile
+// A CTA takes a T tile of 8 rows x 32 columns of pixels (TMA box with halo, out-of-range pixels zero-filled = the padding;
+// two M = 128 MMAs x 4 K steps), copies the 36 accumulator columns to shared memory (fp32), and every thread then sums the
+// nine shifted 16-byte (tap) entries of one of the 6 x 30 interior output pixels and writes fp32 NCHW directly, divided by
+// the ScalingLayer's scale.  The next tile's TMA load is issued as soon as the MMAs have consumed the current one.
+constexpr int kDgThreads = 256;
+constexpr int kDgTR = 8, kDgTC = 32;          // T tile (pixels)
+constexpr int kDgOR = kDgTR - 2, kDgOC = kDgTC - 2;   // outputs per tile
+constexpr int kDgPitch = 36;                  // floats per T pixel: 9 taps x 4
+constexpr int kDgBRows = 40;                  // B rows kept in shared memory (N = 48: rows 40..47 alias sT, their columns are unused)
+struct FirstDgradParams {
+  const float* weight;   // [64][3][3][3]
+  const float* scale;    // [3] or null: dx /= scale[c]
+  float* dx;             // fp32 NCHW [n][3][h][w]
+  int n, h, w, tiles_x, tiles_y, total_tiles;
+  FastDiv fd_tx, fd_ty;
+};
+
+__global__ void __launch_bounds__(kDgThreads, 3)
+vgg_first_dgrad_kernel(const FirstDgradParams p, const __grid_constant__ CUtensorMap map_dy) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* sA = smem;                                    // [256 pixels x 128 B] dy tile, 128B swizzle (TMA)
+  uint8_t* sB = sA + kDgTR * kDgTC * 128;                // [40 (48) x 128 B] W2[n = tap * 4 + c][co], 128B swizzle
+  float* sT = reinterpret_cast<float*>(sB + kDgBRows * 128);   // [256 pixels][36]
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sT + kDgTR * kDgTC * kDgPitch);
+  uint64_t* mma_bar = full_bar + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(mma_bar + 1);
+  float* sScale = reinterpret_cast<float*>(tmem_ptr + 2);      // [3]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    if (lane == 0) tma_prefetch_desc(&map_dy);
+    __syncwarp();
+    tmem_alloc(tmem_ptr, 128);
+    tmem_relinquish();
+  } else if (tid == 32) {
+    mbar_init(full_bar, 1);
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+  }
+  pdl_trigger();   // programmatic dependent launch (common.cuh): global memory only after pdl_wait()
+  pdl_wait();
+  for (int i = tid; i < kDgBRows * 64; i += kDgThreads) {
+    const int n = i >> 6, k = i & 63, tap = n >> 2, c = n & 3;
+    const float v = (tap < 9 && c < 3) ? p.weight[(k * 3 + c) * 9 + tap] : 0.f;
+    const uint32_t off = (uint32_t)n * 128 + ((((uint32_t)k >> 3) ^ ((uint32_t)n & 7)) << 4) + (k & 7) * 2;
+    *reinterpret_cast<__nv_bfloat16*>(sB + off) = __float2bfloat16(v);
+  }
+  if (tid < 3) sScale[tid] = p.scale != nullptr ? p.scale[tid] : 1.f;
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_ptr;
+  const uint32_t idesc = make_idesc_bf16(128, 48, 0, 0);
+  const uint64_t a_desc = make_smem_desc(smem_u32(sA), 128, 16);
+  const uint64_t b_desc = make_smem_desc(smem_u32(sB), 128, 16);
+  auto decode = [&](int tile, int& n, int& y0, int& x0) {
+    int rest, tx, ty;
+    p.fd_tx.divmod(tile, rest, tx);
+    p.fd_ty.divmod(rest, n, ty);
+    y0 = ty * kDgOR;
+    x0 = tx * kDgOC;
+  };
+  auto issue = [&](int tile) {   // one thread: the T tile starts one pixel above / left of its first output
+    int n, y0, x0;
+    decode(tile, n, y0, x0);
+    mbar_expect_tx(full_bar, kDgTR * kDgTC * 128);
+    tma_load_5d(sA, &map_dy, full_bar, 0, x0 - 1, y0 - 1, n, 0);
+  };
+  if (tid == 0 && (int)blockIdx.x < p.total_tiles) issue(blockIdx.x);
+  uint32_t phase = 0;
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int n, y0, x0;
+    decode(tile, n, y0, x0);
+    if (tid == 0) {
+      mbar_wait(full_bar, phase);
+      tc_fence_after();
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          umma_bf16(tmem + m * 64, a_desc + (uint32_t)((m * 128 * 128 + j * 32) >> 4), b_desc + (uint32_t)((j * 32) >> 4), idesc,
+                    j != 0);
+      umma_commit(mma_bar);
+    }
+    __syncwarp();
+    mbar_wait(mma_bar, phase);
+    phase ^= 1;
+    tc_fence_after();
+    // the MMAs have consumed sA: fetch the next tile while this one is post-processed
+    if (tid == 0 && tile + (int)gridDim.x < p.total_tiles) issue(tile + gridDim.x);
+    // ---- accumulators -> sT: warp w owns M tile w / 4, TMEM lane quarter w % 4 (lane = pixel)
+    {
+      const int quarter = warp & 3, m = warp >> 2;
+      float* dst = sT + (m * 128 + quarter * 32 + lane) * kDgPitch;
+#pragma unroll
+      for (int c0 = 0; c0 < 48; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem + ((uint32_t)(quarter * 32) << 16) + m * 64 + c0, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (c0 + 4 * q < kDgPitch)
+            *reinterpret_cast<float4*>(dst + c0 + 4 * q) = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                                                       __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+      }
+      tc_fence_before();
+    }
+    __syncthreads();
+    // ---- shift-add: thread -> one interior pixel, nine 16-byte reads (pixel pitch 144 B: conflict-free quarter-warps)
+    if (tid < kDgOR * kDgOC) {
+      const int r = tid / kDgOC, cc = tid - r * kDgOC;
+      const int y = y0 + r, x = x0 + cc;
+      if (y < p.h && x < p.w) {
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const float4 t = *reinterpret_cast<const float4*>(sT + ((r + 2 - ky) * kDgTC + (cc + 2 - kx)) * kDgPitch + (ky * 3 + kx) * 4);
+            a0 += t.x; a1 += t.y; a2 += t.z;
+          }
+        float* o = p.dx + (((size_t)n * 3) * p.h + y) * p.w + x;
+        const size_t plane = (size_t)p.h * p.w;
+        o[0] = a0 / sScale[0];
+        o[plane] = a1 / sScale[1];
+        o[2 * plane] = a2 / sScale[2];
+      }
+    }
+    __syncthreads();   // sT and the accumulators are rewritten by the next iteration
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 128);
+  }
+}
+
+cudaError_t launch_vgg_first_dgrad(const CUtensorMap* map_dy, int n, int h, int w, const float* weight, const float* scale,
+                                   float* dx, int num_sms, cudaStream_t st) {
+  FirstDgradParams p;
+  p.weight = weight; p.scale = scale; p.dx = dx; p.n = n; p.h = h; p.w = w;
+  p.tiles_x = (w + kDgOC - 1) / kDgOC;
+  p.tiles_y = (h + kDgOR - 1) / kDgOR;
+  const long long total = (long long)n * p.tiles_x * p.tiles_y;
+  if (total > 0x7fffffffLL) return cudaErrorInvalidValue;
+  p.total_tiles = (int)total;
+  p.fd_tx = make_fastdiv(p.tiles_x);
+  p.fd_ty = make_fastdiv(p.tiles_y);
+  const size_t smem = (size_t)kDgTR * kDgTC * 128 + kDgBRows * 128 + (size_t)kDgTR * kDgTC * kDgPitch * sizeof(float) + 16 + 8 + 16 + 1008;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t e = cudaFuncSetAttribute(vgg_first_dgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    configured = true;
+  }
+  const int grid = p.total_tiles < num_sms * 3 ? p.total_tiles : num_sms * 3;
+  return launch_k(vgg_first_dgrad_kernel, dim3(grid), dim3(kDgThreads), smem, st, 1, p, *map_dy);
+}
+
+// =====================================================================================================================
 // Image-side layers of the VQVAE (reference models/vqvae_conv3d_latent.py:109 first Conv2d(6 -> 64, 4, stride 2, pad 1);
 // :154-156 last ConvTranspose2d(64 -> 6, 4, stride 2, pad 1)) WITHOUT an explicit im2col matrix.  Two kernels share one tile
 // builder: the [128 output pixels x K] im2col tile (k = ch * 16 + ky * 4 + kx, the order of the PyTorch weight; K = 16 * C

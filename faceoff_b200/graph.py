@@ -21,7 +21,7 @@ from .ops import FORM_DOWN, FORM_S1, FORM_S1_DGRAD, FORM_UP, pad16
 
 
 class Node:
-    __slots__ = ("raw", "act", "c", "g", "f32", "gdec")
+    __slots__ = ("raw", "act", "c", "g", "f32", "gdec", "g32")
 
     def __init__(self, c: int, raw=None, act=None, f32=None):
         self.c = c
@@ -29,6 +29,7 @@ class Node:
         self.act = act
         self.f32 = f32
         self.g: Optional[Tuple[torch.Tensor, int]] = None
+        self.g32: Optional[torch.Tensor] = None      # gradient already in fp32 NCHW (image-side input of the LPIPS trunk)
 
     @property
     def any(self) -> torch.Tensor:

@@ -162,6 +162,8 @@ class vgg16(nn.Module):
                         h["g"] = g.to(torch.float32).contiguous()
 
             def input_grad():
+                if xin.g32 is not None:
+                    return xin.g32
                 return ops.unpack_nchw(xin.g[0], 3) if xin.g is not None else None
 
             return outs, {"seed": seed, "input_grad": input_grad}
@@ -209,7 +211,14 @@ def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, t
             def first_bwd(node=cur, w=w):
                 if node.g is None:
                     return
-                dx, _, _ = ops.conv(FORM_S1_DGRAD, 2, 3, [(node.g[0], node.c, node.g[1])], w, 1, 3, out_cs=16)
+                gt, g_off = node.g
+                if node.c == 64 and g_off == 0 and gt.shape[-1] == 64 and gt.is_contiguous() and w.is_contiguous():
+                    # taps on the N axis + in-tile shift-add, fp32 NCHW out with the ScalingLayer's division folded in
+                    # (csrc/small_cin.cu vgg_first_dgrad_kernel)
+                    sc = None if scale is None else scale.detach().reshape(-1).to(torch.float32).contiguous()
+                    xin.g32 = ops.vgg_first_dgrad(gt, w.detach(), sc)
+                    return
+                dx, _, _ = ops.conv(FORM_S1_DGRAD, 2, 3, [(gt, node.c, g_off)], w, 1, 3, out_cs=16)
                 xin.g = (dx, 0)
 
             tape.record(first_bwd)
@@ -352,6 +361,8 @@ class LPIPS(nn.Module):
                                  else g.reshape(n).to(torch.float32).contiguous())
 
             def input_grad():
+                if xin.g32 is not None:
+                    return xin.g32           # already divided by the ScalingLayer's scale
                 if xin.g is None:
                     return None
                 return ops.unpack_nchw(xin.g[0], 3) / model.scaling_layer.scale

@@ -485,6 +485,22 @@ def vgg_first_conv(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, sh
     return out
 
 
+def vgg_first_dgrad(dy: torch.Tensor, weight: torch.Tensor, scale: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Data gradient of conv3x3(3 -> 64): dy bf16 channels-last [N, H, W, 64] -> fp32 NCHW [N, 3, H, W], divided by
+    ``scale`` ([3], the ScalingLayer's) if given."""
+    lib = L.load()
+    assert dy.dtype == torch.bfloat16 and dy.dim() == 4 and dy.shape[-1] == 64 and dy.is_contiguous()
+    assert tuple(weight.shape) == (64, 3, 3, 3) and weight.dtype == torch.float32 and weight.is_contiguous()
+    assert scale is None or (scale.dtype == torch.float32 and scale.numel() == 3 and scale.is_contiguous())
+    n, h, w, _ = dy.shape
+    dx = torch.empty((n, 3, h, w), dtype=torch.float32, device=dy.device)
+    with _Timed("hbm/vgg_first_dgrad", n * h * w * (128.0 + 12.0)):
+        L.check(lib.fo_vgg_first_dgrad(dy.data_ptr(), n, h, w, weight.data_ptr(), _p(scale), dx.data_ptr(), _stream()),
+                "fo_vgg_first_dgrad")
+    _count(1)
+    return dx
+
+
 def s2conv(x: torch.Tensor, c: int, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
            mask: Optional[torch.Tensor] = None, addend: Optional[torch.Tensor] = None, relu: bool = False) -> torch.Tensor:
     """Conv2d(c -> 64, 4, stride 2, pad 1) of the fp32 NCHW tensor x [N, Ca, H, W] (first c channels) without an im2col

@@ -163,6 +163,12 @@ int fo_im2col3x3(const float* x, void* out, int n, int c, int h, int w, const fl
  * matrix reaches HBM. */
 int fo_vgg_first_conv(const float* x, int n, int h, int w, const float* weight, const float* bias, const float* shift,
                       const float* scale, void* out_relu, fo_stream_t stream);
+/* Data gradient of that convolution (the gradient leaving the LPIPS trunk): dy bf16 channels-last [n,h,w,64] (gradient
+ * w.r.t. the pre-ReLU output), weight fp32 [64,3,3,3] -> dx fp32 NCHW [n,3,h,w], divided by scale[c] if scale != NULL
+ * (ScalingLayer backward, models/lpips.py:96-103).  One K = 64 GEMM per pixel tile with the nine taps on the N axis + an
+ * in-tile shift-add (csrc/small_cin.cu). */
+int fo_vgg_first_dgrad(const void* dy, int n, int h, int w, const float* weight, const float* scale, float* dx,
+                       fo_stream_t stream);
 /* Image-side layers of the VQVAE without an im2col matrix (csrc/small_cin.cu; reference models/vqvae_conv3d_latent.py:109
  * first Conv2d(c -> 64, 4, stride 2, pad 1), :154-156 last ConvTranspose2d(64 -> c, 4, stride 2, pad 1)); c in {3, 6}.
  * x: fp32 NCHW [n, ca, H, W] (first c channels used), H and W even; all bf16 tensors are channels-last [n, H/2, W/2, 64].

@@ -1,6 +1,5 @@
-F="--set full --clock-control none --import-source on"
-ncu $F -k regex:vgg_first_conv --launch-skip 3 --launch-count 1 -f -o gpurun_out/r2c_vggfirst python tests/gpu_profile_conv.py vgg 8 > /dev/null 2>&1
-ncu $F -k regex:s2conv --launch-skip 3 --launch-count 1 -f -o gpurun_out/r2c_s2conv python tests/gpu_profile_conv.py s2 8 > /dev/null 2>&1
-ncu $F -k regex:s2wgrad_kernel --launch-skip 3 --launch-count 1 -f -o gpurun_out/r2c_s2wgrad python tests/gpu_profile_conv.py s2 8 > /dev/null 2>&1
-timeout 200 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q -k "wgrad_accum" -s 2>&1 | tail -5
-ls -la gpurun_out/*.ncu-rep
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "lpips" 2>&1 | tail -5
+Q="--no-lpips-step --no-cpu-baseline --no-eager --no-disc-step --no-e2e"
+timeout 300 python bench.py --lpips 1 $Q > gpurun_out/d_c32l.json 2>> gpurun_out/d_err.log
+python -c "import json;d=json.load(open('gpurun_out/d_c32l.json'));print('c32 lpips', d['ms_per_step'], d['clocks']['sm_mhz'], {k:v['ms_per_step'] for k,v in d['hbm_kernels'].items()}, d['roofline_by_layer_class'].get('conv3x3_64to3'))"
+tail -3 gpurun_out/d_err.log

@@ -118,7 +118,10 @@ def main():
         print(f"vgg first conv fused (3 -> 64) @256: {ms:.3f} ms  {gb / ms * 1e3:.0f} GB/s")
         del img
         ms = timeit(lambda: ops.conv(ops.FORM_S1_DGRAD, 2, 3, [(x, 64, 0)], w3, 1, 3, f32="nchw"))
-        print(f"vgg first conv dgrad 64->3 @256: {ms:.3f} ms")
+        print(f"vgg first conv dgrad 64->3 @256 (implicit GEMM, N = 16, bf16 channels-last out): {ms:.3f} ms")
+        ms = timeit(lambda: ops.vgg_first_dgrad(x, w3, sc3))
+        print(f"vgg first conv dgrad 64->3 @256 (taps on N + shift-add, fp32 NCHW out): {ms:.3f} ms  "
+              f"{(x.numel() * 2 + F_ * 3 * 65536 * 4) / 1e9 / ms * 1e3:.0f} GB/s")
         del x, col
         x2 = torch.randn(F_, 128, 128, 64, device=dev).to(torch.bfloat16).relu_()
         w2 = torch.randn(128, 64, 3, 3, device=dev) * 0.03

@@ -348,3 +348,25 @@ def test_wgrad_accumulation_chain_is_bounded(clips):
     print(f"wgrad3d {clips} clips: max-normalised err {e_max:.3e}, norm rel err {e_norm:+.3e}")
     assert e_max < 1e-4 and abs(e_norm) < 1e-4
     assert ((db.double() - bref).abs().max() / bref.abs().max()).item() < 1e-4
+
+
+@pytest.mark.parametrize("n,h,w,scaled", [(2, 12, 64, True), (1, 7, 33, True), (3, 5, 200, False), (1, 256, 256, True), (2, 1, 30, False)])
+def test_vgg_first_dgrad_taps_on_n_axis(n, h, w, scaled):
+    """Data gradient of Conv2d(3 -> 64, 3x3, pad 1) (csrc/small_cin.cu vgg_first_dgrad_kernel: one K = 64 GEMM per pixel tile
+    with the taps on the N axis + in-tile shift-add, fp32 NCHW out, ScalingLayer division folded in) against fp64 on the
+    operands the tensor core sees (dy bf16, weights rounded to bf16): products exact, fp32 accumulation.  Sizes that are not
+    multiples of the 6 x 30 output tile included."""
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(n * 1000 + h * 10 + w)
+    dy = (torch.randn(n, h, w, 64, generator=gen) * 0.1).bfloat16()
+    wt = torch.randn(64, 3, 3, 3, generator=gen) * 0.2
+    scale = torch.tensor([.458, .448, .450])
+    got = ops.vgg_first_dgrad(dy.cuda(), wt.cuda(), scale.cuda() if scaled else None)
+    ref = F.conv_transpose2d(dy.double().permute(0, 3, 1, 2), wt.bfloat16().double(), padding=1)
+    if scaled:
+        ref = ref / scale.double().view(1, 3, 1, 1)
+    assert got.shape == (n, 3, h, w) and got.dtype == torch.float32
+    err = (got.double().cpu() - ref).abs().max().item() / ref.abs().max().item()
+    print(f"vgg_first_dgrad {n}x{h}x{w}: max-normalised err {err:.3e}")
+    assert err < 2e-6
