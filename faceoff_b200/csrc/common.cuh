@@ -321,6 +321,35 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// ---- 2x2 max pool on packed bf16 pairs (elementwise.cu maxpool2*, lpips.cu fused tap + pool backward)
+// 0xFFFF per bf16 half where a == b / a > b (value comparison; post-ReLU data: no NaN)
+__device__ __forceinline__ uint32_t bf16x2_eq_mask(uint32_t a, uint32_t b) {
+  return __heq2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+__device__ __forceinline__ uint32_t bf16x2_gt_mask(uint32_t a, uint32_t b) {
+  return __hgt2_mask(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+}
+__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
+  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
+  return *reinterpret_cast<uint32_t*>(&r);
+}
+// dx[pos] = (x[pos] == y && first such position in (row-major) window order && x[pos] > 0) ? dy : 0
+// 8 channels (one 16-byte vector) per thread.  x is a post-ReLU activation: x == 0 means the gate is closed.
+__device__ __forceinline__ uint32_t pool_bwd_pair(uint32_t x, uint32_t y, uint32_t g, uint32_t& taken) {
+  // per bf16 half: hit = !taken && x == y ; out = hit && x > 0 ? g : 0
+  uint32_t out = 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const uint32_t sh = 16 * h;
+    const uint32_t xv = (x >> sh) & 0xFFFFu, yv = (y >> sh) & 0xFFFFu;
+    const bool tk = (taken >> h) & 1u;
+    const bool hit = !tk && xv == yv;     // post-ReLU values: no -0 / NaN, bit equality == value equality
+    if (hit) taken |= (1u << h);
+    if (hit && xv != 0u && !(xv & 0x8000u)) out |= ((g >> sh) & 0xFFFFu) << sh;
+  }
+  return out;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -302,10 +302,6 @@ colsum_final_kernel(const float* __restrict__ part, int nblocks, int cs, int c_o
 }
 
 // ---------------------------------------------------------------- 2x2 max pool, channels-last bf16
-__device__ __forceinline__ uint32_t bf16x2_max(uint32_t a, uint32_t b) {
-  __nv_bfloat162 r = __hmax2(*reinterpret_cast<__nv_bfloat162*>(&a), *reinterpret_cast<__nv_bfloat162*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
-}
 __global__ void maxpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n, int h, int w, int vecs) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
@@ -328,22 +324,7 @@ __global__ void maxpool2_kernel(const uint4* __restrict__ x, uint4* __restrict__
     y[i] = o;
   }
 }
-// dx[pos] = (x[pos] == y && first such position in (row-major) window order && x[pos] > 0) ? dy : 0
-// 8 channels (one 16-byte vector) per thread.  x is a post-ReLU activation: x == 0 means the gate is closed.
-__device__ __forceinline__ uint32_t pool_bwd_pair(uint32_t x, uint32_t y, uint32_t g, uint32_t& taken) {
-  // per bf16 half: hit = !taken && x == y ; out = hit && x > 0 ? g : 0
-  uint32_t out = 0;
-#pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const uint32_t sh = 16 * h;
-    const uint32_t xv = (x >> sh) & 0xFFFFu, yv = (y >> sh) & 0xFFFFu;
-    const bool tk = (taken >> h) & 1u;
-    const bool hit = !tk && xv == yv;     // post-ReLU values: no -0 / NaN, bit equality == value equality
-    if (hit) taken |= (1u << h);
-    if (hit && xv != 0u && !(xv & 0x8000u)) out |= ((g >> sh) & 0xFFFFu) << sh;
-  }
-  return out;
-}
+// dx[pos] = (x[pos] == y && first such position in (row-major) window order && x[pos] > 0) ? dy : 0  (pool_bwd_pair, common.cuh)
 __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ y, const uint4* __restrict__ dy,
                                     uint4* __restrict__ dx, int n, int h, int w, int vecs) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
@@ -357,18 +338,33 @@ __global__ void maxpool2_bwd_kernel(const uint4* __restrict__ x, const uint4* __
     const int oy = (int)(r % ho);
     const size_t nn = r / ho;
     const uint4 yo = __ldg(y + i), g = __ldg(dy + i);
-    uint32_t tk[4] = {0u, 0u, 0u, 0u};
+    // packed form of pool_bwd_pair (common.cuh): m_k = (x_k == y) and no earlier window position matched; x_k > 0 is y > 0
+    // there (the per-half scalar form was instruction bound: 4.6 TB/s)
+    size_t idx[4];
+    uint4 xv[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const size_t idx = ((nn * h + 2 * oy + (k >> 1)) * w + 2 * ox + (k & 1)) * vecs + v;
-      const uint4 xv = __ldg(x + idx);
-      uint4 o;
-      o.x = pool_bwd_pair(xv.x, yo.x, g.x, tk[0]);
-      o.y = pool_bwd_pair(xv.y, yo.y, g.y, tk[1]);
-      o.z = pool_bwd_pair(xv.z, yo.z, g.z, tk[2]);
-      o.w = pool_bwd_pair(xv.w, yo.w, g.w, tk[3]);
-      dx[idx] = o;
+      idx[k] = ((nn * h + 2 * oy + (k >> 1)) * w + 2 * ox + (k & 1)) * vecs + v;
+      xv[k] = __ldg(x + idx[k]);
     }
+    const uint32_t yw[4] = {yo.x, yo.y, yo.z, yo.w}, gw[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4][4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint32_t x0 = e == 0 ? xv[0].x : e == 1 ? xv[0].y : e == 2 ? xv[0].z : xv[0].w;
+      const uint32_t x1 = e == 0 ? xv[1].x : e == 1 ? xv[1].y : e == 2 ? xv[1].z : xv[1].w;
+      const uint32_t x2 = e == 0 ? xv[2].x : e == 1 ? xv[2].y : e == 2 ? xv[2].z : xv[2].w;
+      const uint32_t x3 = e == 0 ? xv[3].x : e == 1 ? xv[3].y : e == 2 ? xv[3].z : xv[3].w;
+      const uint32_t gated = gw[e] & bf16x2_gt_mask(yw[e], 0u);
+      const uint32_t m0 = bf16x2_eq_mask(x0, yw[e]);
+      const uint32_t m1 = bf16x2_eq_mask(x1, yw[e]) & ~m0;
+      const uint32_t m01 = m0 | m1;
+      const uint32_t m2 = bf16x2_eq_mask(x2, yw[e]) & ~m01;
+      const uint32_t m3 = bf16x2_eq_mask(x3, yw[e]) & ~(m01 | m2);
+      o[0][e] = gated & m0; o[1][e] = gated & m1; o[2][e] = gated & m2; o[3][e] = gated & m3;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) dx[idx[k]] = make_uint4(o[k][0], o[k][1], o[k][2], o[k][3]);
   }
 }
 

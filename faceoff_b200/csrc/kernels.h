@@ -108,6 +108,9 @@ cudaError_t launch_lpips_tap(const void* f0, const void* f1, const float* w, int
 cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c,
                                  void* d_f0, const void* addend, int num_sms, cudaStream_t st, int split = 0);
 
+cudaError_t launch_lpips_tap_bwd_pool(const void* f0, const void* f1, const float* w, const float* g, int n, int h, int wd,
+                                      int c, void* d_f0, const void* pool_dy, int num_sms, cudaStream_t st);
+
 // disc.cu (MoCoGAN-HD discriminators): fp32 NCDHW direct convolution + norm / pool / loss kernels
 struct DConvParams {
   int n, cin, id, ih, iw;       // input  [n, cin, id, ih, iw]   (2-D: id = 1)

@@ -239,7 +239,11 @@ def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, t
                 if pooled.g is None:
                     return
                 assert src.g is None
-                src.g = (ops.maxpool2_bwd(src.act, pooled.raw, pooled.g[0]), 0)
+                pg, p_off = pooled.g
+                if src.fuse_pool and p_off == 0 and pg.shape == pooled.raw.shape and pg.is_contiguous():
+                    src.pool_dy = pg      # the tap's backward (recorded just before this pool) folds the pool gradient in
+                    return
+                src.g = (ops.maxpool2_bwd(src.act, pooled.raw, pg), 0)
 
             tape.record(pool_bwd)
             cur, cur_relu = pooled, False
@@ -346,8 +350,16 @@ class LPIPS(nn.Module):
             def tap_hook(k, node):
                 f1, w = feats1[k], ws[k]
                 ops.lpips_tap(node.act, f1, w, val)
+                # a tap that feeds a max pool takes over the pool's backward (one pass over the feature maps instead of
+                # two: ops.lpips_tap_bwd_pool); the verification mode keeps the two kernels
+                node.fuse_pool = (not tape.precise and node.act.shape[1] % 2 == 0 and node.act.shape[2] % 2 == 0)
 
                 def tap_bwd():
+                    if node.pool_dy is not None:
+                        assert node.g is None
+                        node.g = (ops.lpips_tap_bwd_pool(node.act, f1, w, g_holder["g"], node.pool_dy), 0)
+                        node.pool_dy = None
+                        return
                     addend = node.g[0] if node.g is not None else None
                     node.g = (ops.lpips_tap_bwd(node.act, f1, w, g_holder["g"], addend), 0)
 

@@ -747,6 +747,20 @@ def lpips_tap_bwd(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.
     return d
 
 
+def lpips_tap_bwd_pool(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.Tensor,
+                       pool_dy: torch.Tensor) -> torch.Tensor:
+    """lpips_tap_bwd for a tap that feeds a 2x2 max pool, with maxpool2_bwd(f0, ., pool_dy) folded in (product mode only)."""
+    lib = L.load()
+    n, h, wd, c = f0.shape
+    assert not PRECISE and tuple(pool_dy.shape) == (n, h // 2, wd // 2, c) and pool_dy.is_contiguous() and f0.is_contiguous()
+    d = torch.empty_like(f0)
+    with _Timed("hbm/lpips_tap_bwd_pool", 6.5 * f0.numel()):
+        L.check(lib.fo_lpips_tap_bwd_pool(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), g.data_ptr(), n, h, wd, c, d.data_ptr(),
+                                          pool_dy.data_ptr(), _stream()), "fo_lpips_tap_bwd_pool")
+    _count(1)
+    return d
+
+
 # ------------------------------------------------------------------------------------------------
 # reconstruction loss
 # ------------------------------------------------------------------------------------------------

@@ -244,6 +244,11 @@ int fo_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, 
 /* Gradient wrt f0: d_f0 (bf16, same layout), scaled by g[n] (fp32 per image), masked by f0 > 0 (ReLU tap). */
 int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c, void* d_f0,
                      const void* addend, fo_stream_t stream);
+/* The same gradient for a tap that feeds a 2x2/2 max pool (relu1_2 .. relu4_3), with the pool's backward folded in:
+ * f0, f1, d_f0 channels-last bf16 [n, h, w, c]; pool_dy = gradient w.r.t. the pooled tensor [n, h/2, w/2, c].
+ * Bit-identical to fo_maxpool2_bwd followed by fo_lpips_tap_bwd(addend = its result), half the HBM traffic. */
+int fo_lpips_tap_bwd_pool(const void* f0, const void* f1, const float* w, const float* g, int n, int h, int wd, int c,
+                          void* d_f0, const void* pool_dy, fo_stream_t stream);
 /* Verification mode (tests only; see fo_conv_t.split_out): the same two kernels on hi|lo pair tensors [n, hw, 2c]
  * (feature = hi + lo; d_f0 and addend are pairs too). */
 int fo_lpips_tap_split(const void* f0, const void* f1, const float* w, int n, int hw, int c, float* out,

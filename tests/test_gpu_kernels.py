@@ -78,6 +78,28 @@ def test_lpips_tap_forward_and_backward(n, h, w, c):
         _one_ulp_close(d, want, extra=1e-9)
 
 
+@pytest.mark.parametrize("n,h,w,c", [(3, 16, 16, 64), (2, 8, 12, 128), (2, 6, 4, 256), (1, 4, 4, 512), (5, 2, 2, 512), (2, 64, 64, 64)])
+def test_lpips_tap_backward_with_the_pool_folded_in(n, h, w, c):
+    """fo_lpips_tap_bwd_pool == fo_maxpool2_bwd followed by fo_lpips_tap_bwd(addend = its result), bit for bit: coarse
+    features (many exact ties inside a pooling window, closed gates) exercise the first-maximum rule."""
+    from faceoff_b200 import ops
+
+    gen = torch.Generator().manual_seed(c + n + h)
+    f0 = (torch.randn(n, h, w, c, generator=gen).relu() * 4).round().div(4).bfloat16().cuda()    # multiples of 1/4: ties
+    f1 = _bf16(n, h, w, c, gen=gen, relu=True).cuda()
+    lw = (torch.rand(c, generator=gen) * 0.1).cuda()
+    g = torch.randn(n, generator=gen).cuda()
+    pool_dy = _bf16(n, h // 2, w // 2, c, gen=gen, scale=0.01).cuda()
+    y = ops.maxpool2(f0)
+    want = ops.lpips_tap_bwd(f0, f1, lw, g, ops.maxpool2_bwd(f0, y, pool_dy))
+    got = ops.lpips_tap_bwd_pool(f0, f1, lw, g, pool_dy)
+    torch.cuda.synchronize()
+    ties = (f0.view(n, h // 2, 2, w // 2, 2, c).amax((2, 4), keepdim=True) == f0.view(n, h // 2, 2, w // 2, 2, c)).sum((2, 4)) > 1
+    assert ties.any(), "the test data must contain ties"
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16)), \
+        f"{(got.view(torch.int16) != want.view(torch.int16)).sum().item()} elements differ"
+
+
 # ------------------------------------------------------------------------------------------------ pooling / layout
 @pytest.mark.parametrize("n,h,w,cs", [(2, 8, 8, 64), (1, 4, 6, 128), (3, 2, 2, 16)])
 def test_maxpool2_and_backward_bit_exact(n, h, w, cs):
