@@ -29,7 +29,8 @@ struct FirstConvParams {
   __nv_bfloat16* out;    // relu(conv) bf16 channels-last [n, h, w, 64]
   int n, h, w;
   int tiles_x;           // ceil(w / 256)
-  long long total_tiles; // n * h * tiles_x
+  int total_tiles;       // n * h * tiles_x (< 2^31, checked by the launcher)
+  FastDiv fd_tx, fd_h;   // tile -> (image, row, column tile) without integer divisions
 };
 
 __global__ void __launch_bounds__(kFcThreads, 4)
@@ -80,41 +81,55 @@ vgg_first_conv_kernel(const FirstConvParams p) {
   uint32_t phase = 0;
 
   // Image values are fetched into registers one tile ahead: thread t owns column x0 - 1 + t of the nine (channel, row)
-  // lines (threads 0 / 1 also the two right-most columns), no per-element index arithmetic.
+  // lines (threads 0 / 1 also the two right-most columns), no per-element index arithmetic.  The registers hold the RAW
+  // values; the ScalingLayer FMA is applied when they are staged one iteration later -- an FMA right behind the load made
+  // the warp wait for its loads before it could start on the current tile (ncu: long-scoreboard stalls on those FFMAs were
+  // the top stall reason).  Offsets inside an image are 32-bit (3 * h * w < 2^31, checked by the launcher).
   float pre[9], pre_tail[9];
-  auto fetch = [&](long long tile) {
-    const int tx = (int)(tile % p.tiles_x);
-    const long long ty = tile / p.tiles_x;
-    const int y = (int)(ty % p.h);
-    const int n = (int)(ty / p.h);
-    const int x0 = tx * kFcTile;
+  uint32_t pre_ok = 0;      // bit r: pre[r] is inside the image (else the conv's zero padding), bit 9 + r: pre_tail[r]
+  auto decode = [&](int tile, int& n, int& y, int& x0) {
+    int rest, tx;
+    p.fd_tx.divmod(tile, rest, tx);
+    p.fd_h.divmod(rest, n, y);
+    x0 = tx * kFcTile;
+  };
+  auto fetch = [&](int tile) {
+    int n, y, x0;
+    decode(tile, n, y, x0);
     const int ix = x0 - 1 + tid, ixt = x0 + 255 + tid;       // tail: columns 256, 257 of the patch (tid < 2)
     const bool okx = (unsigned)ix < (unsigned)p.w, okt = tid < 2 && (unsigned)ixt < (unsigned)p.w;
+    const float* img = p.x + (size_t)n * 3 * p.h * p.w;
+    const int plane = p.h * p.w;
+    pre_ok = 0;
 #pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      const int ch = r / 3, ky = r - ch * 3;
+    for (int ky = 0; ky < 3; ++ky) {
       const int iy = y - 1 + ky;
       const bool oky = (unsigned)iy < (unsigned)p.h;
-      const float* row = p.x + (((size_t)n * 3 + ch) * p.h + (oky ? iy : 0)) * p.w;
-      pre[r] = (oky && okx) ? fmaf(__ldg(row + ix), sc_a[ch], sc_b[ch]) : 0.f;
-      pre_tail[r] = (oky && okt) ? fmaf(__ldg(row + ixt), sc_a[ch], sc_b[ch]) : 0.f;
+      const int ro = (oky ? iy : 0) * p.w;
+#pragma unroll
+      for (int ch = 0; ch < 3; ++ch) {
+        const int r = ch * 3 + ky;
+        const float* row = img + ch * plane + ro;
+        pre[r] = (oky && okx) ? __ldg(row + ix) : 0.f;
+        pre_tail[r] = (oky && okt) ? __ldg(row + ixt) : 0.f;
+        pre_ok |= (uint32_t)(oky && okx) << r;
+        pre_ok |= (uint32_t)(oky && okt) << (9 + r);
+      }
     }
   };
-  if ((long long)blockIdx.x < p.total_tiles) fetch(blockIdx.x);
-  for (long long tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-    const int tx = (int)(tile % p.tiles_x);
-    const long long ty = tile / p.tiles_x;
-    const int y = (int)(ty % p.h);
-    const int n = (int)(ty / p.h);
-    const int x0 = tx * kFcTile;
+  if ((int)blockIdx.x < p.total_tiles) fetch(blockIdx.x);
+  for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+    int n, y, x0;
+    decode(tile, n, y, x0);
     // ---- the 3 x 3 image rows of the tile (258 columns each) -> shared memory; then start on the next tile's values
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
-      sStage[r * kFcStagePitch + tid] = pre[r];
-      if (tid < 2) sStage[r * kFcStagePitch + 256 + tid] = pre_tail[r];
+      const int ch = r / 3;
+      sStage[r * kFcStagePitch + tid] = (pre_ok >> r) & 1u ? fmaf(pre[r], sc_a[ch], sc_b[ch]) : 0.f;
+      if (tid < 2) sStage[r * kFcStagePitch + 256 + tid] = (pre_ok >> (9 + r)) & 1u ? fmaf(pre_tail[r], sc_a[ch], sc_b[ch]) : 0.f;
     }
     __syncthreads();
-    if (tile + gridDim.x < p.total_tiles) fetch(tile + gridDim.x);
+    if (tile + (int)gridDim.x < p.total_tiles) fetch(tile + gridDim.x);
     // ---- A tiles: thread = pixel, all 32 k values (four 16-byte chunks)
     {
       const int px = tid;
@@ -166,9 +181,10 @@ vgg_first_conv_kernel(const FirstConvParams p) {
           const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           float f[8];
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[e] = fmaxf(__uint_as_float(v[q * 8 + e]) + bb[e], 0.f);
-          uint4 o;
-          o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[q * 8 + e]) + bb[e];
+          uint4 o;   // ReLU inside the packed conversion (cvt.rn.relu.bf16x2.f32)
+          o.x = pack_bf16x2_relu(f[0], f[1]); o.y = pack_bf16x2_relu(f[2], f[3]);
+          o.z = pack_bf16x2_relu(f[4], f[5]); o.w = pack_bf16x2_relu(f[6], f[7]);
           const int chunk = hcol * 4 + q;
           *reinterpret_cast<uint4*>(sOut + row * 128 + ((chunk ^ (row & 7)) << 4)) = o;
         }
@@ -833,7 +849,10 @@ cudaError_t launch_vgg_first_conv(const float* x, int n, int h, int w, const flo
   p.x = x; p.weight = weight; p.bias = bias; p.shift = shift; p.scale = scale; p.out = (__nv_bfloat16*)out;
   p.n = n; p.h = h; p.w = w;
   p.tiles_x = (w + kFcTile - 1) / kFcTile;
-  p.total_tiles = (long long)n * h * p.tiles_x;
+  if ((long long)n * h * p.tiles_x > 0x7fffffffLL || 3LL * h * w > 0x7fffffffLL) return cudaErrorInvalidValue;
+  p.total_tiles = n * h * p.tiles_x;
+  p.fd_tx = make_fastdiv(p.tiles_x);
+  p.fd_h = make_fastdiv(h);
   const size_t smem = kFcTile * 128 + 64 * 64 + 64 * sizeof(float) + 64 + 1024;
   static_assert(2 * 128 * 64 + 9 * kFcStagePitch * sizeof(float) <= kFcTile * 128, "A tiles + staged rows fit under sOut");
   static bool configured = false;
