@@ -72,7 +72,7 @@ def peaks():
 
 def ncu_evidence():
     """Static pointer to the committed ncu captures (profiles/), not a live measurement."""
-    for name in ("r2b_roofline_evidence.json", "r2_roofline_evidence.json", "r1_roofline_evidence.json"):
+    for name in ("r2c_roofline_evidence.json", "r2b_roofline_evidence.json", "r2_roofline_evidence.json", "r1_roofline_evidence.json"):
         path = os.path.join(ROOT, "profiles", name)
         if os.path.exists(path):
             return json.load(open(path))
