@@ -143,6 +143,78 @@ __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __n
   }
 }
 
+// The same tap for a feature map that feeds a 2x2 max pool: the unit of work is a pooling window, and the window maximum of
+// f0 is written as the pooled tensor (bit-identical to maxpool2) -- the pool kernel's re-read of f0 goes away.
+template <int VPL>
+__global__ void __launch_bounds__(256)
+lpips_tap_pool_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1, const float* __restrict__ w,
+                      int h, int wd, int c, int lpp, float* __restrict__ out, __nv_bfloat16* __restrict__ pooled) {
+  pdl_trigger();   // programmatic dependent launch: see common.cuh
+  pdl_wait();
+  __shared__ float red[32];
+  const int n = blockIdx.y;
+  const int ppw = 32 / lpp;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int sub = lane % lpp, pw = lane / lpp;
+  const int hw = h * wd, wo = wd / 2, nwin = (h / 2) * wo;
+  float2 wv[VPL * 4];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      wv[i * 4 + e] = make_float2(__ldg(w + (i * lpp + sub) * 8 + 2 * e), __ldg(w + (i * lpp + sub) * 8 + 2 * e + 1));
+  float2 acc2 = make_float2(0.f, 0.f);
+  const int win_per_block = (blockDim.x >> 5) * ppw;
+  for (int w0 = blockIdx.x * win_per_block; w0 < nwin; w0 += gridDim.x * win_per_block) {
+    const int win = w0 + warp * ppw + pw;
+    const bool ok = win < nwin;
+    const int wvn = ok ? win : 0;
+    const int wy = wvn / wo, wx = wvn - wy * wo;
+    PixRaw<VPL, false> ra[4], rb[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int pix = (2 * wy + (u >> 1)) * wd + 2 * wx + (u & 1);
+      const size_t off = ((size_t)n * hw + pix) * c;
+      load_raw<VPL, false>(f0 + off, lpp, sub, c, ra[u]);
+      load_raw<VPL, false>(f1 + off, lpp, sub, c, rb[u]);
+    }
+    if (ok) {
+      uint4* dst = reinterpret_cast<uint4*>(pooled + ((size_t)n * nwin + win) * c);
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        uint4 y;
+        y.x = bf16x2_max(bf16x2_max(ra[0].hi[i].x, ra[1].hi[i].x), bf16x2_max(ra[2].hi[i].x, ra[3].hi[i].x));
+        y.y = bf16x2_max(bf16x2_max(ra[0].hi[i].y, ra[1].hi[i].y), bf16x2_max(ra[2].hi[i].y, ra[3].hi[i].y));
+        y.z = bf16x2_max(bf16x2_max(ra[0].hi[i].z, ra[1].hi[i].z), bf16x2_max(ra[2].hi[i].z, ra[3].hi[i].z));
+        y.w = bf16x2_max(bf16x2_max(ra[0].hi[i].w, ra[1].hi[i].w), bf16x2_max(ra[2].hi[i].w, ra[3].hi[i].w));
+        dst[i * lpp + sub] = y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      float2 a[VPL * 4], b[VPL * 4];
+      unpack_raw<VPL, false>(ra[u], a);
+      unpack_raw<VPL, false>(rb[u], b);
+      const float s0 = group_sum(sum_sq(a), lpp), s1 = group_sum(sum_sq(b), lpp);
+      const float i0 = rcp_fast(sqrt_fast(s0) + kLpipsEps), i1 = ok ? -rcp_fast(sqrt_fast(s1) + kLpipsEps) : 0.f;
+      const float2 i0v = make_float2(ok ? i0 : 0.f, ok ? i0 : 0.f), i1v = make_float2(i1, i1);
+#pragma unroll
+      for (int j = 0; j < VPL * 4; ++j) {
+        const float2 t = __ffma2_rn(a[j], i0v, __fmul2_rn(b[j], i1v));   // a/n0 - b/n1 (0 for windows past the end)
+        acc2 = __ffma2_rn(__fmul2_rn(wv[j], t), t, acc2);
+      }
+    }
+  }
+  float acc = warp_sum(acc2.x + acc2.y);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) s += red[i];
+    atomicAdd(out + n, s / (float)hw);
+  }
+}
+
 // d/df0 of the tap value, times g[n], gated by the ReLU that produced f0, plus optional addend (pool gradient).
 //   a = f0/n0, n0 = |f0| + eps ;  u_c = (2/hw) w_c (a_c - b_c)
 //   dL/df0_j = u_j / n0 - (sum_c u_c f0_c) f0_j / (n0^2 |f0|)
@@ -393,6 +465,24 @@ cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w,
   return cudaGetLastError();
 }
 
+cudaError_t launch_lpips_tap_pool(const void* f0, const void* f1, const float* w, int n, int h, int wd, int c, float* out,
+                                  void* pooled, int num_sms, cudaStream_t st) {
+  int lpp, vpl;
+  lpips_geometry(c, lpp, vpl);
+  const int threads = 256;
+  const int win_per_block = (threads / 32) * (32 / lpp);
+  const int nwin = (h / 2) * (wd / 2);
+  int bx = (nwin + win_per_block - 1) / win_per_block;
+  const int cap = (num_sms * 8 + n - 1) / n;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  dim3 grid(bx, n);
+  const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
+  __nv_bfloat16* y = (__nv_bfloat16*)pooled;
+  if (vpl == 1) return launch_k(lpips_tap_pool_kernel<1>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, lpp, out, y);
+  if (vpl == 2) return launch_k(lpips_tap_pool_kernel<2>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, lpp, out, y);
+  return cudaErrorInvalidValue;
+}
 cudaError_t launch_lpips_tap_bwd_pool(const void* f0, const void* f1, const float* w, const float* g, int n, int h, int wd,
                                       int c, void* d_f0, const void* pool_dy, int num_sms, cudaStream_t st) {
   int lpp, vpl;

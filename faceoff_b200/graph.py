@@ -21,7 +21,7 @@ from .ops import FORM_DOWN, FORM_S1, FORM_S1_DGRAD, FORM_UP, pad16
 
 
 class Node:
-    __slots__ = ("raw", "act", "c", "g", "f32", "gdec", "g32", "fuse_pool", "pool_dy")
+    __slots__ = ("raw", "act", "c", "g", "f32", "gdec", "g32", "fuse_pool", "pool_dy", "pool_follows", "pooled")
 
     def __init__(self, c: int, raw=None, act=None, f32=None):
         self.c = c
@@ -32,6 +32,8 @@ class Node:
         self.g32: Optional[torch.Tensor] = None      # gradient already in fp32 NCHW (image-side input of the LPIPS trunk)
         self.fuse_pool = False                       # LPIPS tap whose backward also does the following max pool's (lpips.py)
         self.pool_dy: Optional[torch.Tensor] = None  # ... the pooled gradient left for it by the pool's backward
+        self.pool_follows = False                    # set by the VGG trunk on a tap node whose next layer is a max pool
+        self.pooled: Optional[torch.Tensor] = None   # maxpool2(act) if the tap's forward kernel already produced it
 
     @property
     def any(self) -> torch.Tensor:

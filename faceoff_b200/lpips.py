@@ -183,7 +183,7 @@ def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, t
     cur, cur_relu = xin, False
     taps = []
     first = True
-    for kind, key, ch in layout:
+    for li, (kind, key, ch) in enumerate(layout):
         if kind == "conv" and first and tape.precise:
             # verification mode: the plain implicit-GEMM path on the 3-channel (hi|lo pair) input
             first = False
@@ -228,12 +228,14 @@ def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, t
                           param_grad=False)
             cur_relu = True
         elif kind == "tap":
+            cur.pool_follows = li + 1 < len(layout) and layout[li + 1][0] == "pool"
             if tap_hook is not None:
                 tap_hook(len(taps), cur)
             taps.append(cur)
-        else:  # 2x2 max pool
+        else:  # 2x2 max pool (the tap's forward kernel may have produced it already: ops.lpips_tap_pool)
             src = cur
-            pooled = Node(ch, raw=ops.maxpool2(src.act))
+            pooled = Node(ch, raw=src.pooled if src.pooled is not None else ops.maxpool2(src.act))
+            src.pooled = None
 
             def pool_bwd(src=src, pooled=pooled):
                 if pooled.g is None:
@@ -349,10 +351,15 @@ class LPIPS(nn.Module):
 
             def tap_hook(k, node):
                 f1, w = feats1[k], ws[k]
-                ops.lpips_tap(node.act, f1, w, val)
-                # a tap that feeds a max pool takes over the pool's backward (one pass over the feature maps instead of
-                # two: ops.lpips_tap_bwd_pool); the verification mode keeps the two kernels
-                node.fuse_pool = (not tape.precise and node.act.shape[1] % 2 == 0 and node.act.shape[2] % 2 == 0)
+                # a tap that feeds a max pool takes over the pool, forward (ops.lpips_tap_pool writes the pooled tensor)
+                # and backward (ops.lpips_tap_bwd_pool): one pass over the feature maps instead of two each way; the
+                # verification mode keeps the separate kernels
+                node.fuse_pool = (node.pool_follows and not tape.precise and node.act.shape[1] % 2 == 0
+                                  and node.act.shape[2] % 2 == 0 and node.act.is_contiguous() and f1.is_contiguous())
+                if node.fuse_pool:
+                    node.pooled = ops.lpips_tap_pool(node.act, f1, w, val)
+                else:
+                    ops.lpips_tap(node.act, f1, w, val)
 
                 def tap_bwd():
                     if node.pool_dy is not None:

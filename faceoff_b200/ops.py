@@ -730,6 +730,19 @@ def lpips_tap(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, out: torch.Te
     _count(1)
 
 
+def lpips_tap_pool(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
+    """lpips_tap that also returns maxpool2(f0) (the tap feeds a 2x2 max pool; product mode only)."""
+    lib = L.load()
+    n, h, wd, c = f0.shape
+    assert not PRECISE and h % 2 == 0 and wd % 2 == 0 and f0.is_contiguous() and f1.is_contiguous()
+    pooled = torch.empty((n, h // 2, wd // 2, c), dtype=f0.dtype, device=f0.device)
+    with _Timed("hbm/lpips_tap_pool", 4.5 * f0.numel()):
+        L.check(lib.fo_lpips_tap_pool(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), n, h, wd, c, out.data_ptr(),
+                                      pooled.data_ptr(), _stream()), "fo_lpips_tap_pool")
+    _count(1)
+    return pooled
+
+
 def lpips_tap_bwd(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.Tensor,
                   addend: Optional[torch.Tensor] = None) -> torch.Tensor:
     lib = L.load()

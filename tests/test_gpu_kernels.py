@@ -98,6 +98,14 @@ def test_lpips_tap_backward_with_the_pool_folded_in(n, h, w, c):
     assert ties.any(), "the test data must contain ties"
     assert torch.equal(got.view(torch.int16), want.view(torch.int16)), \
         f"{(got.view(torch.int16) != want.view(torch.int16)).sum().item()} elements differ"
+    # forward: the tap that also writes the pooled tensor
+    out_a = torch.zeros(n, device="cuda")
+    out_b = torch.zeros(n, device="cuda")
+    ops.lpips_tap(f0, f1, lw, out_a)
+    pooled = ops.lpips_tap_pool(f0, f1, lw, out_b)
+    torch.cuda.synchronize()
+    assert torch.equal(pooled.view(torch.int16), y.view(torch.int16)), "pooled tensor differs from maxpool2"
+    torch.testing.assert_close(out_b, out_a, rtol=1e-5, atol=1e-8)
 
 
 # ------------------------------------------------------------------------------------------------ pooling / layout
