@@ -1066,11 +1066,11 @@ extern "C" int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, 
   return FO_OK;
 }
 extern "C" int fo_lpips_tap_pool(const void* f0, const void* f1, const float* w, int n, int h, int wd, int c, float* out,
-                                 void* pooled, fo_stream_t stream) {
+                                 void* pooled, void* pooled1, fo_stream_t stream) {
   REQUIRE_INIT();
   if (c % 64 != 0 || c > 512) return fail(FO_ERR_INVALID, "lpips_tap_pool: c must be 64..512, multiple of 64");
   if (h < 2 || wd < 2 || ((h | wd) & 1)) return fail(FO_ERR_INVALID, "lpips_tap_pool: even h, w required");
-  CUDA_TRY(launch_lpips_tap_pool(f0, f1, w, n, h, wd, c, out, pooled, g_num_sms, (cudaStream_t)stream));
+  CUDA_TRY(launch_lpips_tap_pool(f0, f1, w, n, h, wd, c, out, pooled, pooled1, g_num_sms, (cudaStream_t)stream));
   return FO_OK;
 }
 extern "C" int fo_lpips_tap_bwd_pool(const void* f0, const void* f1, const float* w, const float* g, int n, int h, int wd,

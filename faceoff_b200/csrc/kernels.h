@@ -109,7 +109,7 @@ cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w,
                                  void* d_f0, const void* addend, int num_sms, cudaStream_t st, int split = 0);
 
 cudaError_t launch_lpips_tap_pool(const void* f0, const void* f1, const float* w, int n, int h, int wd, int c, float* out,
-                                  void* pooled, int num_sms, cudaStream_t st);
+                                  void* pooled, void* pooled1, int num_sms, cudaStream_t st);
 cudaError_t launch_lpips_tap_bwd_pool(const void* f0, const void* f1, const float* w, const float* g, int n, int h, int wd,
                                       int c, void* d_f0, const void* pool_dy, int num_sms, cudaStream_t st);
 

@@ -148,7 +148,8 @@ __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __n
 template <int VPL>
 __global__ void __launch_bounds__(256)
 lpips_tap_pool_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1, const float* __restrict__ w,
-                      int h, int wd, int c, int lpp, float* __restrict__ out, __nv_bfloat16* __restrict__ pooled) {
+                      int h, int wd, int c, int lpp, float* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
+                      __nv_bfloat16* __restrict__ pooled1) {
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
   __shared__ float red[32];
@@ -188,6 +189,18 @@ lpips_tap_pool_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16*
         y.z = bf16x2_max(bf16x2_max(ra[0].hi[i].z, ra[1].hi[i].z), bf16x2_max(ra[2].hi[i].z, ra[3].hi[i].z));
         y.w = bf16x2_max(bf16x2_max(ra[0].hi[i].w, ra[1].hi[i].w), bf16x2_max(ra[2].hi[i].w, ra[3].hi[i].w));
         dst[i * lpp + sub] = y;
+      }
+      if (pooled1 != nullptr) {   // the other side's pool (the fixed side's trunk runs in lockstep: lpips.py)
+        uint4* dst1 = reinterpret_cast<uint4*>(pooled1 + ((size_t)n * nwin + win) * c);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+          uint4 y;
+          y.x = bf16x2_max(bf16x2_max(rb[0].hi[i].x, rb[1].hi[i].x), bf16x2_max(rb[2].hi[i].x, rb[3].hi[i].x));
+          y.y = bf16x2_max(bf16x2_max(rb[0].hi[i].y, rb[1].hi[i].y), bf16x2_max(rb[2].hi[i].y, rb[3].hi[i].y));
+          y.z = bf16x2_max(bf16x2_max(rb[0].hi[i].z, rb[1].hi[i].z), bf16x2_max(rb[2].hi[i].z, rb[3].hi[i].z));
+          y.w = bf16x2_max(bf16x2_max(rb[0].hi[i].w, rb[1].hi[i].w), bf16x2_max(rb[2].hi[i].w, rb[3].hi[i].w));
+          dst1[i * lpp + sub] = y;
+        }
       }
     }
 #pragma unroll
@@ -466,7 +479,7 @@ cudaError_t launch_lpips_tap_bwd(const void* f0, const void* f1, const float* w,
 }
 
 cudaError_t launch_lpips_tap_pool(const void* f0, const void* f1, const float* w, int n, int h, int wd, int c, float* out,
-                                  void* pooled, int num_sms, cudaStream_t st) {
+                                  void* pooled, void* pooled1, int num_sms, cudaStream_t st) {
   int lpp, vpl;
   lpips_geometry(c, lpp, vpl);
   const int threads = 256;
@@ -478,9 +491,9 @@ cudaError_t launch_lpips_tap_pool(const void* f0, const void* f1, const float* w
   if (bx < 1) bx = 1;
   dim3 grid(bx, n);
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
-  __nv_bfloat16* y = (__nv_bfloat16*)pooled;
-  if (vpl == 1) return launch_k(lpips_tap_pool_kernel<1>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, lpp, out, y);
-  if (vpl == 2) return launch_k(lpips_tap_pool_kernel<2>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, lpp, out, y);
+  __nv_bfloat16 *y = (__nv_bfloat16*)pooled, *y1 = (__nv_bfloat16*)pooled1;
+  if (vpl == 1) return launch_k(lpips_tap_pool_kernel<1>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, lpp, out, y, y1);
+  if (vpl == 2) return launch_k(lpips_tap_pool_kernel<2>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, lpp, out, y, y1);
   return cudaErrorInvalidValue;
 }
 cudaError_t launch_lpips_tap_bwd_pool(const void* f0, const void* f1, const float* w, const float* g, int n, int h, int wd,

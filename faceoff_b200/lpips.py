@@ -174,10 +174,29 @@ class vgg16(nn.Module):
         return vgg_outputs(*outs)
 
 
+# Experiments only: FO_LPIPS_FUSE=0 keeps the separate kernels (maxpool2 / maxpool2_bwd next to the tap kernels, the first
+# conv's data gradient as an implicit GEMM) for same-box A/B timing.
+_FUSE = os.environ.get("FO_LPIPS_FUSE", "1") != "0"
+
+
 def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, tap_hook=None):
     """(Optional scaling layer +) VGG16 trunk on channels-last bf16.  ``tap_hook(k, node)`` is called at each of the
     five taps, at the tape position of the tap (so whatever it records is replayed after the following pool's
     backward).  Returns (input node, tap nodes)."""
+    gen = _vgg_trunk_gen(tape, layout, prefix, x, shift, scale)
+    try:
+        while True:
+            k, node = next(gen)
+            if tap_hook is not None:
+                tap_hook(k, node)
+    except StopIteration as stop:
+        return stop.value
+
+
+def _vgg_trunk_gen(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale):
+    """The trunk as a generator: yields (k, node) at each tap and resumes with the layer after it, so that two trunks (the
+    two sides of LPIPS) can run in lockstep and one kernel can serve the tap and both following pools.  Its return value
+    (StopIteration.value) is (input node, tap nodes)."""
     x = x.to(torch.float32).contiguous()
     xin = Node(3)
     cur, cur_relu = xin, False
@@ -212,7 +231,7 @@ def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, t
                 if node.g is None:
                     return
                 gt, g_off = node.g
-                if node.c == 64 and g_off == 0 and gt.shape[-1] == 64 and gt.is_contiguous() and w.is_contiguous():
+                if _FUSE and node.c == 64 and g_off == 0 and gt.shape[-1] == 64 and gt.is_contiguous() and w.is_contiguous():
                     # taps on the N axis + in-tile shift-add, fp32 NCHW out with the ScalingLayer's division folded in
                     # (csrc/small_cin.cu vgg_first_dgrad_kernel)
                     sc = None if scale is None else scale.detach().reshape(-1).to(torch.float32).contiguous()
@@ -229,8 +248,7 @@ def _vgg_trunk(tape: Tape, layout, prefix: str, x: torch.Tensor, shift, scale, t
             cur_relu = True
         elif kind == "tap":
             cur.pool_follows = li + 1 < len(layout) and layout[li + 1][0] == "pool"
-            if tap_hook is not None:
-                tap_hook(len(taps), cur)
+            yield len(taps), cur
             taps.append(cur)
         else:  # 2x2 max pool (the tap's forward kernel may have produced it already: ops.lpips_tap_pool)
             src = cur
@@ -315,6 +333,12 @@ class LPIPS(nn.Module):
             model._load_checkpoint(ckpt)
         return model
 
+    def _trunk_gen(self, tape: Tape, x: torch.Tensor):
+        """The trunk as a generator over its taps (see ``_vgg_trunk_gen``)."""
+        shift = self.scaling_layer.shift.reshape(-1).contiguous()
+        scale = self.scaling_layer.scale.reshape(-1).contiguous()
+        return _vgg_trunk_gen(tape, self.net.layout, "net.", x, shift, scale)
+
     def _trunk(self, tape: Tape, x: torch.Tensor, tap_hook=None):
         """Scaling layer + VGG16 trunk on channels-last bf16 (see ``_vgg_trunk``)."""
         shift = self.scaling_layer.shift.reshape(-1).contiguous()
@@ -342,22 +366,25 @@ class LPIPS(nn.Module):
 
         def runner(tape: Tape, x: torch.Tensor):
             n = x.shape[0]
-            # fixed side: no gradient, nothing kept but the five taps
+            # fixed side: no gradient, nothing kept but the five taps.  Its trunk runs in lockstep with the differentiated
+            # side's (a generator advanced to tap k inside the other side's tap hook), so that ONE kernel computes the tap
+            # and both sides' following max pools.
             t_tape = Tape(tape.params, need_grad=False)
-            _, taps1 = model._trunk(t_tape, fixed_side.detach())
-            feats1 = [t.act for t in taps1]
+            fixed = model._trunk_gen(t_tape, fixed_side.detach())
             val = torch.zeros(n, dtype=torch.float32, device=x.device)
             g_holder = {}
 
             def tap_hook(k, node):
-                f1, w = feats1[k], ws[k]
-                # a tap that feeds a max pool takes over the pool, forward (ops.lpips_tap_pool writes the pooled tensor)
+                k1, node1 = next(fixed)
+                assert k1 == k
+                f1, w = node1.act, ws[k]
+                # a tap that feeds a max pool takes over the pools, forward (ops.lpips_tap_pool writes both pooled tensors)
                 # and backward (ops.lpips_tap_bwd_pool): one pass over the feature maps instead of two each way; the
                 # verification mode keeps the separate kernels
-                node.fuse_pool = (node.pool_follows and not tape.precise and node.act.shape[1] % 2 == 0
+                node.fuse_pool = (_FUSE and node.pool_follows and not tape.precise and node.act.shape[1] % 2 == 0
                                   and node.act.shape[2] % 2 == 0 and node.act.is_contiguous() and f1.is_contiguous())
                 if node.fuse_pool:
-                    node.pooled = ops.lpips_tap_pool(node.act, f1, w, val)
+                    node.pooled, node1.pooled = ops.lpips_tap_pool(node.act, f1, w, val, pool_f1=node1.pool_follows)
                 else:
                     ops.lpips_tap(node.act, f1, w, val)
 
@@ -373,6 +400,7 @@ class LPIPS(nn.Module):
                 tape.record(tap_bwd)
 
             xin, _ = model._trunk(tape, x, tap_hook)
+            fixed.close()
 
             def seed(tape_, gouts):
                 g = gouts[0]

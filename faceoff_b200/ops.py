@@ -730,17 +730,19 @@ def lpips_tap(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, out: torch.Te
     _count(1)
 
 
-def lpips_tap_pool(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, out: torch.Tensor) -> torch.Tensor:
-    """lpips_tap that also returns maxpool2(f0) (the tap feeds a 2x2 max pool; product mode only)."""
+def lpips_tap_pool(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, out: torch.Tensor, pool_f1: bool = False):
+    """lpips_tap that also returns maxpool2(f0) (and maxpool2(f1) if ``pool_f1``, else None): the taps feed 2x2 max pools
+    (product mode only)."""
     lib = L.load()
     n, h, wd, c = f0.shape
-    assert not PRECISE and h % 2 == 0 and wd % 2 == 0 and f0.is_contiguous() and f1.is_contiguous()
+    assert not PRECISE and h % 2 == 0 and wd % 2 == 0 and f0.is_contiguous() and f1.is_contiguous() and f1.shape == f0.shape
     pooled = torch.empty((n, h // 2, wd // 2, c), dtype=f0.dtype, device=f0.device)
-    with _Timed("hbm/lpips_tap_pool", 4.5 * f0.numel()):
+    pooled1 = torch.empty_like(pooled) if pool_f1 else None
+    with _Timed("hbm/lpips_tap_pool", (4.5 + (0.5 if pool_f1 else 0.0)) * f0.numel()):
         L.check(lib.fo_lpips_tap_pool(f0.data_ptr(), f1.data_ptr(), w.data_ptr(), n, h, wd, c, out.data_ptr(),
-                                      pooled.data_ptr(), _stream()), "fo_lpips_tap_pool")
+                                      pooled.data_ptr(), _p(pooled1), _stream()), "fo_lpips_tap_pool")
     _count(1)
-    return pooled
+    return pooled, pooled1
 
 
 def lpips_tap_bwd(f0: torch.Tensor, f1: torch.Tensor, w: torch.Tensor, g: torch.Tensor,

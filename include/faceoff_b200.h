@@ -244,10 +244,11 @@ int fo_lpips_tap(const void* f0, const void* f1, const float* w, int n, int hw, 
 /* Gradient wrt f0: d_f0 (bf16, same layout), scaled by g[n] (fp32 per image), masked by f0 > 0 (ReLU tap). */
 int fo_lpips_tap_bwd(const void* f0, const void* f1, const float* w, const float* g, int n, int hw, int c, void* d_f0,
                      const void* addend, fo_stream_t stream);
-/* fo_lpips_tap for a feature map f0 [n, h, w, c] that feeds a 2x2/2 max pool: also writes pooled = maxpool2(f0)
- * [n, h/2, w/2, c] (bit-identical to fo_maxpool2), so the pool does not read f0 again. */
+/* fo_lpips_tap for feature maps [n, h, w, c] that feed a 2x2/2 max pool: also writes pooled = maxpool2(f0) and, if
+ * pooled1 != NULL, pooled1 = maxpool2(f1) ([n, h/2, w/2, c], bit-identical to fo_maxpool2): the pools do not read the
+ * feature maps again. */
 int fo_lpips_tap_pool(const void* f0, const void* f1, const float* w, int n, int h, int wd, int c, float* out, void* pooled,
-                      fo_stream_t stream);
+                      void* pooled1, fo_stream_t stream);
 /* The same gradient for a tap that feeds a 2x2/2 max pool (relu1_2 .. relu4_3), with the pool's backward folded in:
  * f0, f1, d_f0 channels-last bf16 [n, h, w, c]; pool_dy = gradient w.r.t. the pooled tensor [n, h/2, w/2, c].
  * Bit-identical to fo_maxpool2_bwd followed by fo_lpips_tap_bwd(addend = its result), half the HBM traffic. */

@@ -102,10 +102,16 @@ def test_lpips_tap_backward_with_the_pool_folded_in(n, h, w, c):
     out_a = torch.zeros(n, device="cuda")
     out_b = torch.zeros(n, device="cuda")
     ops.lpips_tap(f0, f1, lw, out_a)
-    pooled = ops.lpips_tap_pool(f0, f1, lw, out_b)
+    pooled, none1 = ops.lpips_tap_pool(f0, f1, lw, out_b)
+    out_c = torch.zeros(n, device="cuda")
+    pooled_c, pooled1 = ops.lpips_tap_pool(f0, f1, lw, out_c, pool_f1=True)
     torch.cuda.synchronize()
+    assert none1 is None
     assert torch.equal(pooled.view(torch.int16), y.view(torch.int16)), "pooled tensor differs from maxpool2"
+    assert torch.equal(pooled_c.view(torch.int16), y.view(torch.int16))
+    assert torch.equal(pooled1.view(torch.int16), ops.maxpool2(f1).view(torch.int16)), "pooled f1 differs from maxpool2"
     torch.testing.assert_close(out_b, out_a, rtol=1e-5, atol=1e-8)
+    torch.testing.assert_close(out_c, out_a, rtol=1e-5, atol=1e-8)
 
 
 # ------------------------------------------------------------------------------------------------ pooling / layout
