@@ -68,7 +68,9 @@ __device__ __forceinline__ void unpack_raw(const PixRaw<VPL, SPLIT>& r, float2 (
   }
 }
 __device__ __forceinline__ float group_sum(float s, int lpp) {
-  for (int o = lpp >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+    if (o < lpp) s += __shfl_xor_sync(0xffffffffu, s, o);   // (a compile-time lpp leaves straight-line shuffles)
   return s;
 }
 __device__ __forceinline__ float sqrt_fast(float x) {
@@ -145,11 +147,14 @@ __global__ void lpips_tap_kernel(const __nv_bfloat16* __restrict__ f0, const __n
 
 // The same tap for a feature map that feeds a 2x2 max pool: the unit of work is a pooling window, and the window maximum of
 // f0 is written as the pooled tensor (bit-identical to maxpool2) -- the pool kernel's re-read of f0 goes away.
-template <int VPL>
-__global__ void __launch_bounds__(256)
+// (LPP = lanes per pixel is a template parameter here: with a run-time value the three shuffle reductions per pixel stay
+// loops -- SHFL + FADD + SHF + ISETP + BRA per step, ~12 % of the instructions of these issue-bound kernels)
+template <int VPL, int LPP>
+__global__ void __launch_bounds__(256, VPL == 1 ? 3 : 1)
 lpips_tap_pool_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1, const float* __restrict__ w,
-                      int h, int wd, int c, int lpp, float* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
+                      int h, int wd, int c, float* __restrict__ out, __nv_bfloat16* __restrict__ pooled,
                       __nv_bfloat16* __restrict__ pooled1) {
+  constexpr int lpp = LPP;
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
   __shared__ float red[32];
@@ -326,11 +331,12 @@ __global__ void lpips_tap_bwd_kernel(const __nv_bfloat16* __restrict__ f0, const
 // position in row-major window order wins, closed gate at 0 -- exactly maxpool2_bwd), and adds that gradient where the
 // unfused path read it back as `addend`.  Results are bit-identical to maxpool2_bwd + lpips_tap_bwd(addend); the traffic per
 // pixel drops from 6.5 to 3.25 feature-map units (no dx write + read-back, no re-read of f0, no pooled y).
-template <int VPL>
-__global__ void __launch_bounds__(256)
+template <int VPL, int LPP>
+__global__ void __launch_bounds__(256, VPL == 1 ? 3 : 1)
 lpips_tap_bwd_pool_kernel(const __nv_bfloat16* __restrict__ f0, const __nv_bfloat16* __restrict__ f1,
-                          const float* __restrict__ w, const float* __restrict__ g, int h, int wd, int c, int lpp,
+                          const float* __restrict__ w, const float* __restrict__ g, int h, int wd, int c,
                           __nv_bfloat16* __restrict__ d_f0, const __nv_bfloat16* __restrict__ pool_dy) {
+  constexpr int lpp = LPP;
   pdl_trigger();   // programmatic dependent launch: see common.cuh
   pdl_wait();
   const int n = blockIdx.y;
@@ -492,8 +498,10 @@ cudaError_t launch_lpips_tap_pool(const void* f0, const void* f1, const float* w
   dim3 grid(bx, n);
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1;
   __nv_bfloat16 *y = (__nv_bfloat16*)pooled, *y1 = (__nv_bfloat16*)pooled1;
-  if (vpl == 1) return launch_k(lpips_tap_pool_kernel<1>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, lpp, out, y, y1);
-  if (vpl == 2) return launch_k(lpips_tap_pool_kernel<2>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, lpp, out, y, y1);
+  if (vpl == 1 && lpp == 8) return launch_k(lpips_tap_pool_kernel<1, 8>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, out, y, y1);
+  if (vpl == 1 && lpp == 16) return launch_k(lpips_tap_pool_kernel<1, 16>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, out, y, y1);
+  if (vpl == 1 && lpp == 32) return launch_k(lpips_tap_pool_kernel<1, 32>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, out, y, y1);
+  if (vpl == 2 && lpp == 32) return launch_k(lpips_tap_pool_kernel<2, 32>, grid, dim3(threads), 0, st, 1, a, b, w, h, wd, c, out, y, y1);
   return cudaErrorInvalidValue;
 }
 cudaError_t launch_lpips_tap_bwd_pool(const void* f0, const void* f1, const float* w, const float* g, int n, int h, int wd,
@@ -510,8 +518,10 @@ cudaError_t launch_lpips_tap_bwd_pool(const void* f0, const void* f1, const floa
   dim3 grid(bx, n);
   const __nv_bfloat16 *a = (const __nv_bfloat16*)f0, *b = (const __nv_bfloat16*)f1, *pd = (const __nv_bfloat16*)pool_dy;
   __nv_bfloat16* d = (__nv_bfloat16*)d_f0;
-  if (vpl == 1) return launch_k(lpips_tap_bwd_pool_kernel<1>, grid, dim3(threads), 0, st, 1, a, b, w, g, h, wd, c, lpp, d, pd);
-  if (vpl == 2) return launch_k(lpips_tap_bwd_pool_kernel<2>, grid, dim3(threads), 0, st, 1, a, b, w, g, h, wd, c, lpp, d, pd);
+  if (vpl == 1 && lpp == 8) return launch_k(lpips_tap_bwd_pool_kernel<1, 8>, grid, dim3(threads), 0, st, 1, a, b, w, g, h, wd, c, d, pd);
+  if (vpl == 1 && lpp == 16) return launch_k(lpips_tap_bwd_pool_kernel<1, 16>, grid, dim3(threads), 0, st, 1, a, b, w, g, h, wd, c, d, pd);
+  if (vpl == 1 && lpp == 32) return launch_k(lpips_tap_bwd_pool_kernel<1, 32>, grid, dim3(threads), 0, st, 1, a, b, w, g, h, wd, c, d, pd);
+  if (vpl == 2 && lpp == 32) return launch_k(lpips_tap_bwd_pool_kernel<2, 32>, grid, dim3(threads), 0, st, 1, a, b, w, g, h, wd, c, d, pd);
   return cudaErrorInvalidValue;
 }
 
