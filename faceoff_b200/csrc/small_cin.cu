@@ -33,12 +33,14 @@ struct FirstConvParams {
   FastDiv fd_tx, fd_h;   // tile -> (image, row, column tile) without integer divisions
 };
 
-__global__ void __launch_bounds__(kFcThreads, 4)
+__global__ void __launch_bounds__(kFcThreads, 3)
 vgg_first_conv_kernel(const FirstConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   // the output staging tile (32 KB) overlays the A tiles and the staged image rows, which are dead by the time the
-  // epilogue runs (one extra barrier per tile buys a fourth CTA per SM)
+  // epilogue runs.  Three CTAs per SM, not four: at 64 registers per thread the nine prefetched image values of the next
+  // tile were spilled to local memory right behind their loads (ncu: STL on the long scoreboard was the top stall);
+  // 80 registers keep them in flight: 2.88 -> 2.48 ms per 960 frames
   uint8_t* sA = smem;                       // 2 x [128 x 64 B]  pixels x k (27 valid), 64B swizzle
   float* sStage = reinterpret_cast<float*>(sA + 2 * 128 * 64);      // [3 ch x 3 rows][kFcStagePitch] (9.3 KB of 16 KB)
   uint8_t* sOut = smem;                     // [256 x 128 B]     pixels x 64 bf16, 16-byte chunks XOR-ed with (row & 7)
@@ -862,7 +864,7 @@ cudaError_t launch_vgg_first_conv(const float* x, int n, int h, int w, const flo
     configured = true;
   }
   long long grid = p.total_tiles;
-  const long long cap = (long long)num_sms * 4;
+  const long long cap = (long long)num_sms * 3;
   if (grid > cap) grid = cap;
   return launch_k(vgg_first_conv_kernel, dim3((int)grid), dim3(kFcThreads), smem, st, 1, p);
 }
