@@ -738,12 +738,7 @@ static int plan_wgrad(const fo_wgrad_t* g, WgradPlan* out, bool need_maps) {
     const char* e = getenv("FO_WG_CHAIN");   // experiments: 0 = one chain per CTA
     if (e != nullptr) chain_mmas = atoi(e);
     const int per = (p.total_ptiles + splits - 1) / splits;
-    const int mmas_per_tile = p.kpix / 16;
-    int n_flush = chain_mmas > 0 ? (per * mmas_per_tile + chain_mmas - 1) / chain_mmas : 1;
-    if (n_flush < 1) n_flush = 1;
-    p.n_flush = n_flush;
-    p.chain_tiles = (per + n_flush - 1) / n_flush;   // balanced chunks
-    if (p.chain_tiles < 1) p.chain_tiles = 1;
+    wgrad_plan_chains(per, p.kpix, chain_mmas, &p.n_flush, &p.chain_tiles);
   }
   p.partial = (float*)g->workspace;
   {

@@ -138,6 +138,19 @@ struct WgradParams {
   float* bias_partial;   // [passes][splits * n_flush][MC] partial column sums of P (= bias gradient) or null
   WgTap taps[64];        // passes * taps_per_pass entries (padded entries have map = 255)
 };
+// Accumulation chains of the weight gradient (wgrad_igemm.cu): a split's range of `per` pixel tiles (kpix / 16 accumulating
+// MMAs each) is cut into n_flush balanced chunks of chain_tiles tiles so that no TMEM accumulator sums more than chain_mmas
+// MMAs (0 = unbounded).  Chunk c of a CTA with n_my tiles covers [min(n_my, c * chain_tiles), min(n_my, (c + 1) * chain_tiles)).
+inline void wgrad_plan_chains(int per, int kpix, int chain_mmas, int* n_flush, int* chain_tiles) {
+  const int mmas_per_tile = kpix / 16;
+  int nf = chain_mmas > 0 ? (int)(((long long)per * mmas_per_tile + chain_mmas - 1) / chain_mmas) : 1;
+  if (nf < 1) nf = 1;
+  int ct = (per + nf - 1) / nf;
+  if (ct < 1) ct = 1;
+  *n_flush = nf;
+  *chain_tiles = ct;
+}
+
 struct WgradMaps {
   CUtensorMap p;
   CUtensorMap q[kMaxAMaps];

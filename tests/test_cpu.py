@@ -142,6 +142,17 @@ def test_fastdiv_magic_numbers(tmp_path):
     assert res.returncode == 0 and "bad=0" in res.stdout, res.stdout
 
 
+def test_wgrad_accumulation_chain_plan(tmp_path):
+    """Host logic of the weight-gradient kernel's bounded accumulation chains (csrc/igemm.cuh wgrad_plan_chains + the chunk
+    arithmetic of csrc/wgrad_igemm.cu, modelled in tests/wgrad_chain_check.cpp): chunks cover every split's tile range once,
+    respect the MMA bound, enumerate the partial slots once, and the bias-column predicate matches a direct search."""
+    exe = str(tmp_path / "wgrad_chain_check")
+    cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+    subprocess.run(["g++", "-O2", "-I", cuda_inc, os.path.join(ROOT, "tests", "wgrad_chain_check.cpp"), "-o", exe], check=True)
+    res = subprocess.run([exe], stdout=subprocess.PIPE, text=True, timeout=300)
+    assert res.returncode == 0 and "bad=0" in res.stdout, res.stdout
+
+
 def test_no_cpu_fallback_fails_loudly():
     """Without a GPU every op must raise (no silent eager/CPU path)."""
     if torch.cuda.is_available():
