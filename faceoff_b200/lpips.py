@@ -149,6 +149,14 @@ class vgg16(nn.Module):
                     if g is None:
                         return
                     g = ops.pack_nchw(g, cs=node.act.shape[-1])
+                    # the gradient arrives w.r.t. the tap = relu(raw), node.g is w.r.t. raw: close the tap's own ReLU gate
+                    # (the pool gradient it meets in add_grads is gated already); rare stand-alone path, plain torch
+                    t = node.act
+                    if tape.precise:
+                        m = t[..., :t.shape[-1] // 2] > 0
+                        g = g * torch.cat([m, m], -1)
+                    else:
+                        g = g * (t > 0)
                     node.g = (g if node.g is None else ops.add_grads(node.g[0], g), 0)
 
                 tape.record(tap_bwd)

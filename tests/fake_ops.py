@@ -1,0 +1,142 @@
+"""CPU stand-ins (plain torch, fp32) for the C-ABI ops the LPIPS path calls -- TEST INFRASTRUCTURE ONLY.
+
+They let ``pytest -m "not gpu"`` drive the PRODUCT's host logic (faceoff_b200/lpips.py + graph.py: the autograd tape, the
+order of the recorded backward closures, the lockstep of the two VGG trunks, the hand-over of the pool gradient to the fused
+tap kernel, the fp32 NCHW input gradient) without a GPU, and compare the result with the oracle.  Nothing under
+faceoff_b200/ imports this file; ``install(monkeypatch)`` swaps the functions in for the duration of one test and counts the
+calls per op.  Each stand-in restates what the CUDA kernel of the same name is documented to compute (include/faceoff_b200.h).
+"""
+import collections
+
+import torch
+import torch.nn.functional as F
+
+from faceoff_b200 import ops
+
+CALLS = collections.Counter()
+EPS = 1e-10
+
+
+def _nchw(t, c=None):
+    t = t.permute(0, 3, 1, 2)
+    return t if c is None else t[:, :c]
+
+
+def _nhwc(t, cs=None):
+    t = t.permute(0, 2, 3, 1).contiguous()
+    if cs is not None and cs > t.shape[-1]:
+        t = F.pad(t, (0, cs - t.shape[-1]))
+    return t
+
+
+def vgg_first_conv(x, weight, bias, shift=None, scale=None):
+    CALLS["vgg_first_conv"] += 1
+    if shift is not None:
+        x = (x - shift.view(1, 3, 1, 1)) / scale.view(1, 3, 1, 1)
+    return _nhwc(F.conv2d(x, weight, bias[:64], padding=1).relu())
+
+
+def vgg_first_dgrad(dy, weight, scale=None):
+    CALLS["vgg_first_dgrad"] += 1
+    dx = F.conv_transpose2d(_nchw(dy), weight, padding=1)
+    return (dx / scale.view(1, 3, 1, 1) if scale is not None else dx).contiguous()
+
+
+def conv(form, ndim, ksize, srcs, weight, n_axis, cout, bias=None, mask=None, addend=None, want_raw=True, want_relu=False,
+         f32=None, out_cs=None, **kw):
+    """FORM_S1 (forward, weight [cout, cin, k, k], n_axis 0) and FORM_S1_DGRAD (weight of the FORWARD conv, n_axis 1)."""
+    CALLS["conv"] += 1
+    assert ndim == 2 and f32 is None and form in (ops.FORM_S1, ops.FORM_S1_DGRAD)
+    x = torch.cat([t[..., off:off + c] for (t, c, off) in srcs], -1)
+    w = weight.detach()
+    if form == ops.FORM_S1:
+        assert n_axis == 0
+        y = F.conv2d(_nchw(x), w, None if bias is None else bias[:cout], padding=ksize // 2)
+    else:
+        assert n_axis == 1 and bias is None
+        y = F.conv_transpose2d(_nchw(x), w, padding=ksize // 2)
+    y = _nhwc(y, out_cs if out_cs is not None else ops.pad16(cout))
+    if mask is not None:
+        y = torch.where(mask > 0, y, torch.zeros_like(y))
+    if addend is not None:
+        y = y + addend
+    return (y if want_raw else None), (y.relu() if want_relu else None), None
+
+
+def maxpool2(x):
+    CALLS["maxpool2"] += 1
+    return _nhwc(F.max_pool2d(_nchw(x), 2, 2))
+
+
+def maxpool2_bwd(x, y, dy):
+    """Gradient to the FIRST maximum of each window (row-major), only where x > 0 (x is post-ReLU)."""
+    CALLS["maxpool2_bwd"] += 1
+    n, h, w, c = x.shape
+    win = x.view(n, h // 2, 2, w // 2, 2, c).permute(0, 1, 3, 5, 2, 4).reshape(n, h // 2, w // 2, c, 4)
+    first = win.argmax(-1)    # torch.argmax returns the first maximal index on CPU
+    onehot = F.one_hot(first, 4).to(x.dtype) * dy.unsqueeze(-1)
+    dx = onehot.view(n, h // 2, w // 2, c, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(n, h, w, c)
+    return torch.where(x > 0, dx, torch.zeros_like(dx))
+
+
+def _tap_value(f0, f1, w):
+    a = f0 / (f0.pow(2).sum(-1, keepdim=True).sqrt() + EPS)
+    b = f1 / (f1.pow(2).sum(-1, keepdim=True).sqrt() + EPS)
+    return ((a - b).pow(2) * w).sum(-1).mean((1, 2))
+
+
+def lpips_tap(f0, f1, w, out):
+    CALLS["lpips_tap"] += 1
+    out += _tap_value(f0, f1, w)
+
+
+def lpips_tap_pool(f0, f1, w, out, pool_f1=False):
+    CALLS["lpips_tap_pool"] += 1
+    out += _tap_value(f0, f1, w)
+    return _nhwc(F.max_pool2d(_nchw(f0), 2, 2)), (_nhwc(F.max_pool2d(_nchw(f1), 2, 2)) if pool_f1 else None)
+
+
+def lpips_tap_bwd(f0, f1, w, g, addend=None):
+    CALLS["lpips_tap_bwd"] += 1
+    with torch.enable_grad():
+        a = f0.detach().clone().requires_grad_(True)
+        (_tap_value(a, f1, w) * g).sum().backward()
+    d = torch.nan_to_num(a.grad)
+    if addend is not None:
+        d = d + addend
+    return torch.where(f0 > 0, d, torch.zeros_like(d))
+
+
+def lpips_tap_bwd_pool(f0, f1, w, g, pool_dy):
+    CALLS["lpips_tap_bwd_pool"] += 1
+    n = CALLS["lpips_tap_bwd"], CALLS["maxpool2_bwd"], CALLS["maxpool2"]
+    d = lpips_tap_bwd(f0, f1, w, g, maxpool2_bwd(f0, maxpool2(f0), pool_dy))
+    CALLS["lpips_tap_bwd"], CALLS["maxpool2_bwd"], CALLS["maxpool2"] = n
+    return d
+
+
+def add_grads(a, b):
+    CALLS["add_grads"] += 1
+    return a + b
+
+
+def pack_nchw(x, cs=None, shift=None, scale=None):
+    CALLS["pack_nchw"] += 1
+    if shift is not None:
+        x = (x - shift.view(1, -1, 1, 1)) / scale.view(1, -1, 1, 1)
+    return _nhwc(x, cs if cs is not None else ops.pad16(x.shape[1]))
+
+
+def unpack_nchw(x, c):
+    CALLS["unpack_nchw"] += 1
+    return _nchw(x, c).contiguous()
+
+
+_ALL = ("vgg_first_conv", "vgg_first_dgrad", "conv", "maxpool2", "maxpool2_bwd", "lpips_tap", "lpips_tap_pool", "lpips_tap_bwd",
+        "lpips_tap_bwd_pool", "add_grads", "pack_nchw", "unpack_nchw")
+
+
+def install(monkeypatch):
+    CALLS.clear()
+    for name in _ALL:
+        monkeypatch.setattr(ops, name, globals()[name])

@@ -153,6 +153,83 @@ def test_wgrad_accumulation_chain_plan(tmp_path):
     assert res.returncode == 0 and "bad=0" in res.stdout, res.stdout
 
 
+@pytest.mark.parametrize("fuse", [True, False])
+def test_lpips_tape_logic_with_cpu_stand_in_kernels(monkeypatch, fuse):
+    """Host logic of the LPIPS path (faceoff_b200/lpips.py + graph.py) on CPU: the product's tape -- two VGG trunks in
+    lockstep, taps that take over the max pools next to them (forward and backward), the recorded backward order, the
+    fp32 NCHW input gradient -- runs over plain-torch stand-ins of the kernels (tests/fake_ops.py) and must reproduce the
+    oracle's value and input gradient; the op counts show which kernels the tape chose."""
+    import warnings
+
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import fake_ops
+    from faceoff_b200 import lpips as L_
+    from oracle import faceoff_oracle as O
+
+    fake_ops.install(monkeypatch)
+    monkeypatch.setattr(L_, "_FUSE", fuse)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        model = L_.LPIPS().eval()
+    p = O.init_lpips_params(seed=3)
+    model.load_state_dict(p)
+    g = torch.Generator().manual_seed(7)
+    target = torch.rand(2, 3, 32, 32, generator=g) * 2 - 1
+    x = (torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).requires_grad_(True)
+    val = model(target, x)                       # gradient flows to the second argument, as in the reference trainer
+    assert val.shape == (2, 1, 1, 1)
+    (val * torch.tensor([1.0, -0.5]).view(2, 1, 1, 1)).sum().backward()
+    xo = x.detach().clone().requires_grad_(True)
+    ref = O.lpips_forward(p, target, xo)
+    (ref * torch.tensor([1.0, -0.5]).view(2, 1, 1, 1)).sum().backward()
+    torch.testing.assert_close(val.detach(), ref.detach(), rtol=1e-4, atol=1e-6)
+    err = ((x.grad - xo.grad).abs().max() / xo.grad.abs().max()).item()
+    assert err < 1e-4, err
+    c = fake_ops.CALLS
+    if fuse:    # four pooled taps fused both ways, the last tap plain; no stand-alone pool kernels at all
+        assert (c["lpips_tap_pool"], c["lpips_tap"], c["lpips_tap_bwd_pool"], c["lpips_tap_bwd"]) == (4, 1, 4, 1)
+        assert c["maxpool2"] == 0 and c["maxpool2_bwd"] == 0 and c["vgg_first_dgrad"] == 1 and c["unpack_nchw"] == 0
+    else:
+        assert (c["lpips_tap_pool"], c["lpips_tap"], c["lpips_tap_bwd_pool"], c["lpips_tap_bwd"]) == (0, 5, 0, 5)
+        assert c["maxpool2"] == 8 and c["maxpool2_bwd"] == 4 and c["vgg_first_dgrad"] == 0
+    assert c["vgg_first_conv"] == 2
+
+
+def test_vgg16_forward_tape_logic_with_cpu_stand_in_kernels(monkeypatch):
+    """The stand-alone trunk (vgg16.forward, reference models/lpips.py:139-152) over the same stand-ins: five taps and the
+    gradient of a weighted sum of them w.r.t. the input equal the oracle's (tap gradients enter through pack_nchw and meet
+    the pool gradients in add_grads; the pools keep their own kernels here)."""
+    import warnings
+
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import fake_ops
+    from faceoff_b200 import lpips as L_
+    from oracle import faceoff_oracle as O
+
+    fake_ops.install(monkeypatch)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        net = L_.vgg16(pretrained=False).eval()
+    p = {k[len("net."):]: v for k, v in O.init_lpips_params(seed=5).items() if k.startswith("net.")}
+    net.load_state_dict(p)
+    g = torch.Generator().manual_seed(9)
+    x = (torch.rand(2, 3, 32, 32, generator=g) * 2 - 1).requires_grad_(True)
+    outs = net(x)
+    assert outs._fields == ("relu1_2", "relu2_2", "relu3_3", "relu4_3", "relu5_3")
+    sum(((k + 1) * t).sum() for k, t in enumerate(outs)).backward()
+    xo = x.detach().clone().requires_grad_(True)
+    ref = O.vgg_taps({"net." + k: v for k, v in p.items()}, xo)
+    sum(((k + 1) * t).sum() for k, t in enumerate(ref)).backward()
+    for a, b in zip(outs, ref):
+        torch.testing.assert_close(a.detach(), b.detach(), rtol=1e-4, atol=1e-5)
+    err = ((x.grad - xo.grad).abs().max() / xo.grad.abs().max()).item()
+    assert err < 1e-4, err
+    c = fake_ops.CALLS
+    assert c["maxpool2"] == 4 and c["maxpool2_bwd"] == 4 and c["lpips_tap_pool"] == 0 and c["add_grads"] == 4
+
+
 def test_no_cpu_fallback_fails_loudly():
     """Without a GPU every op must raise (no silent eager/CPU path)."""
     if torch.cuda.is_available():
