@@ -42,25 +42,89 @@ def vgg_first_dgrad(dy, weight, scale=None):
     return (dx / scale.view(1, 3, 1, 1) if scale is not None else dx).contiguous()
 
 
+def _to_nc(t, ndim):
+    """channels-last [N, (D,) H, W, C] -> channels-first"""
+    return t.permute(0, 3, 1, 2) if ndim == 2 else t.permute(0, 4, 1, 2, 3)
+
+
+def _to_cl(t, ndim, cs=None):
+    t = (t.permute(0, 2, 3, 1) if ndim == 2 else t.permute(0, 2, 3, 4, 1)).contiguous()
+    if cs is not None and cs > t.shape[-1]:
+        t = F.pad(t, (0, cs - t.shape[-1]))
+    return t
+
+
 def conv(form, ndim, ksize, srcs, weight, n_axis, cout, bias=None, mask=None, addend=None, want_raw=True, want_relu=False,
          f32=None, out_cs=None, **kw):
-    """FORM_S1 (forward, weight [cout, cin, k, k], n_axis 0) and FORM_S1_DGRAD (weight of the FORWARD conv, n_axis 1)."""
+    """One convolution of the planner's vocabulary on channels-last tensors ([N,H,W,Cs], or [B,T,H,W,Cs] for ndim 3):
+    FORM_S1 / FORM_S1_DGRAD = stride 1, pad k//2; FORM_DOWN = Conv2d(4, stride 2, pad 1); FORM_UP = ConvTranspose2d(4, 2, 1).
+    ``n_axis`` says which weight axis is the OUTPUT channel: 0 = a Conv weight [out, in, ...] used as a correlation, 1 = a
+    weight [in, out, ...] used as its transpose (ConvTranspose / the data gradient of a Conv)."""
     CALLS["conv"] += 1
-    assert ndim == 2 and f32 is None and form in (ops.FORM_S1, ops.FORM_S1_DGRAD)
-    x = torch.cat([t[..., off:off + c] for (t, c, off) in srcs], -1)
+    assert f32 is None, "fp32 side outputs are not needed by the stand-in tests"
+    x = _to_nc(torch.cat([t[..., off:off + c] for (t, c, off) in srcs], -1), ndim)
     w = weight.detach()
-    if form == ops.FORM_S1:
-        assert n_axis == 0
-        y = F.conv2d(_nchw(x), w, None if bias is None else bias[:cout], padding=ksize // 2)
+    b = None if bias is None else bias[:cout]
+    fwd = F.conv2d if ndim == 2 else F.conv3d
+    tr = F.conv_transpose2d if ndim == 2 else F.conv_transpose3d
+    if form in (ops.FORM_S1, ops.FORM_S1_DGRAD):
+        y = fwd(x, w, b, padding=ksize // 2) if n_axis == 0 else tr(x, w, b, padding=ksize // 2)
+    elif form == ops.FORM_DOWN:
+        assert n_axis == 0 and ndim == 2 and ksize == 4
+        y = F.conv2d(x, w, b, stride=2, padding=1)
     else:
-        assert n_axis == 1 and bias is None
-        y = F.conv_transpose2d(_nchw(x), w, padding=ksize // 2)
-    y = _nhwc(y, out_cs if out_cs is not None else ops.pad16(cout))
+        assert form == ops.FORM_UP and n_axis == 1 and ndim == 2 and ksize == 4
+        y = F.conv_transpose2d(x, w, b, stride=2, padding=1)
+    assert y.shape[1] == cout, (y.shape, cout)
+    y = _to_cl(y, ndim, out_cs if out_cs is not None else ops.pad16(cout))
     if mask is not None:
         y = torch.where(mask > 0, y, torch.zeros_like(y))
     if addend is not None:
         y = y + addend
     return (y if want_raw else None), (y.relu() if want_relu else None), None
+
+
+def wgrad(form, ndim, ksize, p, q, dweight, m_axis, q_w_off=0, accumulate=False, dbias=None, dbias_accumulate=False,
+          q_shift_sign=1, **kw):
+    """dweight[m][q_w_off + n][tap] (m_axis 0; transposed for m_axis 1) (+)= sum_pix P[pix][m] * Q[s * pix + sign * (tap - pad)][n]
+    with s = 1, pad = k // 2 (FORM_S1) or s = 2, pad = 1 (FORM_DOWN); dbias (+)= column sums of P."""
+    CALLS["wgrad"] += 1
+    pt = _to_nc(p[0][..., p[2]:p[2] + p[1]], ndim)
+    qt = _to_nc(q[0][..., q[2]:q[2] + q[1]], ndim)
+    stride, pad = (1, ksize // 2) if form == ops.FORM_S1 else (2, 1)
+    size = (p[1], q[1]) + (ksize,) * ndim
+    fn = torch.nn.grad.conv2d_weight if ndim == 2 else torch.nn.grad.conv3d_weight
+    dw = fn(qt, size, pt, stride=stride, padding=pad)          # [m][n][taps]: Q is the "input", P the "grad_output"
+    if q_shift_sign < 0:
+        dw = dw.flip(tuple(range(2, 2 + ndim)))
+    if m_axis == 0:
+        view = dweight[:, q_w_off:q_w_off + q[1]]
+    else:
+        view, dw = dweight[q_w_off:q_w_off + q[1], :], dw.transpose(0, 1)
+    if accumulate:
+        view += dw
+    else:
+        view.copy_(dw)
+    if dbias is not None:
+        s_ = pt.transpose(0, 1).reshape(p[1], -1).sum(1)
+        if dbias_accumulate:
+            dbias[:p[1]] += s_
+        else:
+            dbias[:p[1]] = s_
+
+
+def colsum(x, c, out, c_off=0, accumulate=False, **kw):
+    CALLS["colsum"] += 1
+    s_ = x.reshape(-1, x.shape[-1])[:, c_off:c_off + c].sum(0)
+    if accumulate:
+        out[:c] += s_
+    else:
+        out[:c] = s_
+
+
+def relu(x):
+    CALLS["relu"] += 1
+    return x.relu()
 
 
 def maxpool2(x):
@@ -132,7 +196,7 @@ def unpack_nchw(x, c):
     return _nchw(x, c).contiguous()
 
 
-_ALL = ("vgg_first_conv", "vgg_first_dgrad", "conv", "maxpool2", "maxpool2_bwd", "lpips_tap", "lpips_tap_pool", "lpips_tap_bwd",
+_ALL = ("wgrad", "colsum", "relu", "vgg_first_conv", "vgg_first_dgrad", "conv", "maxpool2", "maxpool2_bwd", "lpips_tap", "lpips_tap_pool", "lpips_tap_bwd",
         "lpips_tap_bwd_pool", "add_grads", "pack_nchw", "unpack_nchw")
 
 

@@ -230,6 +230,60 @@ def test_vgg16_forward_tape_logic_with_cpu_stand_in_kernels(monkeypatch):
     assert c["maxpool2"] == 4 and c["maxpool2_bwd"] == 4 and c["lpips_tap_pool"] == 0 and c["add_grads"] == 4
 
 
+def _stack_case(name):
+    """(product module, oracle function of (params, x), input) for one stand-alone conv stack."""
+    from faceoff_b200 import vqvae as V
+    from oracle import faceoff_oracle as O
+
+    g = torch.Generator().manual_seed(11)
+    if name == "resblock":
+        m = V.ResBlock(32, 16)
+        return m, (lambda p, x: O.resblock(p, "m", x)), torch.randn(2, 32, 6, 8, generator=g)
+    if name.startswith("encoder"):
+        stride, nres = (4, 2) if name == "encoder4" else (2, 1) if name == "encoder2" else (2, 0)
+        m = V.Encoder(16, 32, nres, 16, stride)
+        return m, (lambda p, x: O.encoder(p, "m", x, stride, nres)), torch.randn(2, 16, 16, 8, generator=g)
+    if name.startswith("decoder"):
+        stride, nres = (4, 2) if name == "decoder4" else (2, 1)
+        m = V.Decoder(16, 16, 32, nres, 16, stride)
+        return m, (lambda p, x: O.decoder(p, "m", x, stride, nres)), torch.randn(2, 16, 4, 6, generator=g)
+    m = V.Conv3dLatentPostnet(16)
+    return m, (lambda p, x: O.conv3d_postnet(p, "m", x)), torch.randn(2, 16, 3, 4, 6, generator=g)
+
+
+@pytest.mark.parametrize("name", ["resblock", "encoder4", "encoder2", "encoder2_nores", "decoder4", "decoder2", "conv3d"])
+def test_conv_stack_tape_logic_with_cpu_stand_in_kernels(monkeypatch, name):
+    """Host logic of the conv stacks (faceoff_b200/graph.py conv_op / resblock_op + the graph builders of vqvae.py) on CPU:
+    forward value, input gradient and EVERY parameter gradient of the stand-alone drop-in modules over plain-torch stand-ins
+    of fo_conv_run / fo_wgrad_run / fo_colsum (tests/fake_ops.py) against the oracle's autograd -- ReLU views, residual
+    pass-through, fused / column-sum bias gradients, swapped weight-gradient roles of the narrow layers, transposed-conv
+    weight layout, the 3-D views.  (``encoder2_nores``: the n_res_block = 0 configuration of the advisor's note.)"""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import fake_ops
+
+    fake_ops.install(monkeypatch)
+    torch.manual_seed(3)
+    m, ref_fn, x = _stack_case(name)
+    m.train()
+    p = {"m." + k: v.detach().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    x1 = x.clone().requires_grad_(True)
+    y = m(x1)
+    x2 = x.clone().requires_grad_(True)
+    yr = ref_fn(p, x2)
+    assert y.shape == yr.shape
+    gy = torch.randn(yr.shape, generator=torch.Generator().manual_seed(5))
+    (y * gy).sum().backward()
+    (yr * gy).sum().backward()
+    torch.testing.assert_close(y.detach(), yr.detach(), rtol=1e-4, atol=1e-5)
+    assert ((x1.grad - x2.grad).abs().max() / x2.grad.abs().max()).item() < 1e-4
+    for k, v in m.named_parameters():
+        gr = p["m." + k].grad
+        assert v.grad is not None, k
+        err = ((v.grad - gr).abs().max() / (gr.abs().max() + 1e-30)).item()
+        assert err < 1e-4, (k, err)
+
+
 def test_no_cpu_fallback_fails_loudly():
     """Without a GPU every op must raise (no silent eager/CPU path)."""
     if torch.cuda.is_available():
