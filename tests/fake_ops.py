@@ -61,7 +61,6 @@ def conv(form, ndim, ksize, srcs, weight, n_axis, cout, bias=None, mask=None, ad
     ``n_axis`` says which weight axis is the OUTPUT channel: 0 = a Conv weight [out, in, ...] used as a correlation, 1 = a
     weight [in, out, ...] used as its transpose (ConvTranspose / the data gradient of a Conv)."""
     CALLS["conv"] += 1
-    assert f32 is None, "fp32 side outputs are not needed by the stand-in tests"
     x = _to_nc(torch.cat([t[..., off:off + c] for (t, c, off) in srcs], -1), ndim)
     w = weight.detach()
     b = None if bias is None else bias[:cout]
@@ -76,12 +75,15 @@ def conv(form, ndim, ksize, srcs, weight, n_axis, cout, bias=None, mask=None, ad
         assert form == ops.FORM_UP and n_axis == 1 and ndim == 2 and ksize == 4
         y = F.conv_transpose2d(x, w, b, stride=2, padding=1)
     assert y.shape[1] == cout, (y.shape, cout)
+    if f32 == "nchw":          # fp32 NCHW result next to (or instead of) the channels-last ones; no mask / addend there
+        assert mask is None and addend is None and ndim == 2
+        return None, None, y.contiguous()
     y = _to_cl(y, ndim, out_cs if out_cs is not None else ops.pad16(cout))
     if mask is not None:
         y = torch.where(mask > 0, y, torch.zeros_like(y))
     if addend is not None:
         y = y + addend
-    return (y if want_raw else None), (y.relu() if want_relu else None), None
+    return (y if want_raw else None), (y.relu() if want_relu else None), (y if f32 == "cl" else None)
 
 
 def wgrad(form, ndim, ksize, p, q, dweight, m_axis, q_w_off=0, accumulate=False, dbias=None, dbias_accumulate=False,
@@ -125,6 +127,105 @@ def colsum(x, c, out, c_off=0, accumulate=False, **kw):
 def relu(x):
     CALLS["relu"] += 1
     return x.relu()
+
+
+# ---- image-side stride-2 layers (csrc/small_cin.cu) and the GEMM + col2im form of the last ConvTranspose2d
+def s2conv(x, c, weight, bias=None, mask=None, addend=None, relu=False):
+    CALLS["s2conv"] += 1
+    y = _nhwc(F.conv2d(x[:, :c], weight, bias, stride=2, padding=1))
+    if mask is not None:
+        y = torch.where(mask > 0, y, torch.zeros_like(y))
+    if addend is not None:
+        y = y + addend
+    return y.relu() if relu else y
+
+
+def s2wgrad(x, c, y, dweight, accumulate=False, dbias=None, dbias_accumulate=False):
+    CALLS["s2wgrad"] += 1
+    dw = torch.nn.grad.conv2d_weight(x[:, :c], (64, c, 4, 4), _nchw(y), stride=2, padding=1)
+    if accumulate:
+        dweight += dw
+    else:
+        dweight.copy_(dw)
+    if dbias is not None:
+        s_ = y.reshape(-1, 64).sum(0)
+        if dbias_accumulate:
+            dbias[:64] += s_
+        else:
+            dbias[:64] = s_
+
+
+def im2col4x4s2(x, c):
+    CALLS["im2col4x4s2"] += 1
+    n, _, h, w = x.shape
+    cols = F.unfold(x[:, :c], 4, stride=2, padding=1).view(n, c, 16, h // 2, w // 2)     # [N, ch, tap, ho, wo]
+    out = torch.zeros(n, h // 2, w // 2, 16, 8)
+    out[..., :c] = cols.permute(0, 3, 4, 2, 1)
+    return out.view(n, h // 2, w // 2, 128)
+
+
+def col2im4x4s2(col, bias, c):
+    CALLS["col2im4x4s2"] += 1
+    n, hi, wi, _ = col.shape
+    wid = torch.zeros(16, 8, c, 16)
+    for tap in range(16):
+        for co in range(c):
+            wid[tap, co, co, tap] = 1.0
+    out = F.conv_transpose2d(_nchw(col), wid.view(128, c, 4, 4), stride=2, padding=1)
+    return (out + bias.view(1, c, 1, 1) if bias is not None else out).contiguous()
+
+
+def chansum_nchw(x, c, out, accumulate=False):
+    CALLS["chansum_nchw"] += 1
+    s_ = x[:, :c].sum((0, 2, 3))
+    if accumulate:
+        out[:c] += s_
+    else:
+        out[:c] = s_
+
+
+# ---- vector quantiser (csrc/vq.cu)
+def vq_prep(embed):
+    CALLS["vq_prep"] += 1
+    e_t = embed.t().contiguous()
+    return None, e_t, torch.cat([e_t.pow(2).sum(1), e_t.pow(2).sum(1).max().view(1)])
+
+
+def vq_assign(x, e_t, e_split, e_norm2, n_flagged=None):
+    CALLS["vq_assign"] += 1
+    d = x.double().pow(2).sum(1, keepdim=True) - 2 * x.double() @ e_t.double().t() + e_t.double().pow(2).sum(1)
+    return d.argmin(1)
+
+
+def vq_gather_stats(x, ind, e_t, diff_sum, counts, embed_sum, want_f32=True, want_bf16=False):
+    CALLS["vq_gather_stats"] += 1
+    q = e_t[ind]
+    diff_sum += (q - x).pow(2).sum()
+    if counts is not None:
+        counts += torch.bincount(ind, minlength=e_t.shape[0]).to(counts.dtype)
+        embed_sum += x.t() @ F.one_hot(ind, e_t.shape[0]).to(x.dtype)
+    st = x + (q - x)
+    return (st if want_f32 else None), (st.clone() if want_bf16 else None)
+
+
+def vq_ema(embed, cluster_size, embed_avg, counts, embed_sum, decay, eps):
+    CALLS["vq_ema"] += 1
+    cluster_size.mul_(decay).add_(counts, alpha=1 - decay)
+    embed_avg.mul_(decay).add_(embed_sum, alpha=1 - decay)
+    n = cluster_size.sum()
+    cs = (cluster_size + eps) / (n + embed.shape[1] * eps) * n
+    embed.copy_(embed_avg / cs.unsqueeze(0))
+
+
+def vq_backward(g_q, g_c_off, g_diff, x, ind, e_t, want_f32=True, want_bf16=False):
+    """d/dx of the straight-through output (identity) + g_diff * d/dx mean((q - x)^2)."""
+    CALLS["vq_backward"] += 1
+    g = torch.zeros_like(x)
+    if g_q is not None:
+        g = g + g_q[:, g_c_off:g_c_off + x.shape[1]]
+    if g_diff is not None:
+        g = g + g_diff * 2.0 * (x - e_t[ind]) / x.numel()
+    return (g if want_f32 else None), (g.clone() if want_bf16 else None)
 
 
 def maxpool2(x):
@@ -196,7 +297,8 @@ def unpack_nchw(x, c):
     return _nchw(x, c).contiguous()
 
 
-_ALL = ("wgrad", "colsum", "relu", "vgg_first_conv", "vgg_first_dgrad", "conv", "maxpool2", "maxpool2_bwd", "lpips_tap", "lpips_tap_pool", "lpips_tap_bwd",
+_ALL = ("s2conv", "s2wgrad", "im2col4x4s2", "col2im4x4s2", "chansum_nchw", "vq_prep", "vq_assign", "vq_gather_stats", "vq_ema",
+        "vq_backward", "wgrad", "colsum", "relu", "vgg_first_conv", "vgg_first_dgrad", "conv", "maxpool2", "maxpool2_bwd", "lpips_tap", "lpips_tap_pool", "lpips_tap_bwd",
         "lpips_tap_bwd_pool", "add_grads", "pack_nchw", "unpack_nchw")
 
 

@@ -284,6 +284,60 @@ def test_conv_stack_tape_logic_with_cpu_stand_in_kernels(monkeypatch, name):
         assert err < 1e-4, (k, err)
 
 
+@pytest.mark.parametrize("clips,with_lpips", [(1, False), (2, False), (1, True)])
+def test_vqvae_train_step_tape_logic_with_cpu_stand_in_kernels(monkeypatch, clips, with_lpips):
+    """The whole fused training graph of the product VQVAE (faceoff_b200/vqvae.py:_runner + graph.py: both encoders, the Conv3d
+    latent blocks on the clip views, the two quantisers with their straight-through / commitment gradients and EMA update,
+    torch.cat folded into K loops, both decoders, the image-side layers) on CPU over the stand-in kernels: loss, reconstruction,
+    code indices, EVERY parameter gradient and the six codebook buffers after the step against the oracle's train step;
+    ``with_lpips``: the north-star target step (+ VQLPIPS(gt, out), train_faceoff_perceptual.py:32-47) -- two gradient sources
+    meet at the reconstruction."""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import fake_ops
+    from faceoff_b200.vqvae import VQVAE
+    from oracle import faceoff_oracle as O
+
+    fake_ops.install(monkeypatch)
+    p = O.init_vqvae_params(seed=2)
+    img, gt = O.synthetic_clip(clips, 2, 32, 32, seed=8)
+    model = VQVAE(in_channel=6)
+    model.load_state_dict(p)
+    model.train()
+    out, latent, id_t, id_b = model.forward_with_ids(img, clips)
+    loss = torch.nn.functional.mse_loss(out[:, :3], gt) + latent.mean()
+    lp = None
+    if with_lpips:
+        from faceoff_b200.lpips import VQLPIPS
+
+        lp = O.init_lpips_params(seed=4)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            vql = VQLPIPS()
+        vql.load_state_dict({"perceptual_loss." + k: v for k, v in lp.items()})
+        loss = loss + vql(gt, out[:, :3])
+    loss.backward()
+    o = O.train_step(p, img, gt, n_clips=clips, lp=lp)
+    assert torch.equal(id_t, o["id_t"]) and torch.equal(id_b, o["id_b"])
+    torch.testing.assert_close(out.detach(), o["dec"], rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(loss.detach(), o["loss"], rtol=1e-5, atol=1e-7)
+    worst = ("", 0.0)
+    for k, v in model.named_parameters():
+        gr = o["grads"][k]
+        assert v.grad is not None, k
+        err = ((v.grad - gr).abs().max() / (gr.abs().max() + 1e-30)).item()
+        if err > worst[1]:
+            worst = (k, err)
+    assert worst[1] < 2e-4, worst
+    for q in ("quantize_t", "quantize_b"):       # (embed, cluster_size, embed_avg) after the EMA update
+        for i, name in enumerate(("embed", "cluster_size", "embed_avg")):
+            torch.testing.assert_close(getattr(getattr(model, q), name), o["new_buffers"][q][i], rtol=1e-5, atol=1e-6)
+    c = fake_ops.CALLS
+    # the image-side layers took the direct kernels (no im2col matrix), the cat of (dec_t, enc_b) never materialised
+    assert c["s2conv"] == 2 and c["s2wgrad"] == 2 and c["im2col4x4s2"] == 0 and c["col2im4x4s2"] == 1
+    assert c["vq_assign"] == 2 and c["vq_ema"] == 2 and c["vq_backward"] == 2
+
+
 def test_no_cpu_fallback_fails_loudly():
     """Without a GPU every op must raise (no silent eager/CPU path)."""
     if torch.cuda.is_available():
