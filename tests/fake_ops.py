@@ -306,3 +306,10 @@ def install(monkeypatch):
     CALLS.clear()
     for name in _ALL:
         monkeypatch.setattr(ops, name, globals()[name])
+
+
+def install_for_process():
+    """The same without a pytest fixture: for worker processes that live only for one check (tests/gpu_dp_check.py --cpu)."""
+    CALLS.clear()
+    for name in _ALL:
+        setattr(ops, name, globals()[name])

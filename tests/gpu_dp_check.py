@@ -14,6 +14,10 @@ tests run.
    DDP averages over ranks only), ONE EMA update from the summed statistics.
 3. a train-mode forward under ``torch.no_grad()`` with world > 1 (used to raise KeyError) behaves like the reference:
    statistics all-reduced and EMA applied inside forward.
+
+``--cpu`` (used by ``pytest -m "not gpu"``, tests/test_cpu.py): the same three checks with the ranks on the CPU over gloo and
+the kernels replaced by the plain-torch stand-ins of tests/fake_ops.py -- the PRODUCT's host logic (FusedDataParallel: flat
+bucket, ready frontier, chunked all-reduce, deferred statistics / EMA, no_sync; the fused VQVAE + LPIPS tapes) without a GPU.
 """
 import os
 import sys
@@ -33,15 +37,26 @@ from oracle import faceoff_oracle as O  # noqa: E402
 def main():
     rank = int(os.environ["RANK"])
     world = int(os.environ["WORLD_SIZE"])
-    multi_gpu = torch.cuda.device_count() >= world
-    dev = torch.device("cuda", rank if multi_gpu else 0)
-    torch.cuda.set_device(dev)
-    if multi_gpu:
-        dist.init_process_group("nccl", device_id=dev)
-    else:
+    cpu = "--cpu" in sys.argv
+    if cpu:
+        sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+        import fake_ops
+
+        fake_ops.install_for_process()
+        torch.cuda.synchronize = lambda *a, **k: None     # nothing asynchronous on this path
+        multi_gpu = False
+        dev = torch.device("cpu")
         dist.init_process_group("gloo")
+    else:
+        multi_gpu = torch.cuda.device_count() >= world
+        dev = torch.device("cuda", rank if multi_gpu else 0)
+        torch.cuda.set_device(dev)
+        if multi_gpu:
+            dist.init_process_group("nccl", device_id=dev)
+        else:
+            dist.init_process_group("gloo")
     p = O.init_vqvae_params(seed=0)
-    T, R = 4, 64
+    T, R = (2, 32) if cpu else (4, 64)
     img, gt = O.synthetic_clip(2 * world, T, R, R, seed=77)
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")

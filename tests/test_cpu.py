@@ -532,6 +532,28 @@ def test_gloo_world2_collectives_and_fused_data_parallel(tmp_path):
         assert p.returncode == 0, o
 
 
+def test_two_rank_data_parallel_step_on_cpu_stand_in_kernels():
+    """Reference data-parallel semantics (distributed/distributed.py:64-72 + DDP, train_faceoff_perceptual.py:164-169) of the
+    PRODUCT's FusedDataParallel with the real VQVAE + LPIPS tapes, two ranks over gloo on the CPU (kernels = tests/fake_ops.py):
+    one clip per rank == the same two clips in one process (every gradient, codebooks; replicas bit-identical), no_sync
+    micro-batches == one batch with ONE EMA update, train-mode forward under no_grad applies the EMA in forward
+    (tests/gpu_dp_check.py --cpu; the same script runs on GPUs under ``pytest -m gpu``)."""
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), OMP_NUM_THREADS="2")
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "gpu_dp_check.py"), "--cpu"], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+    assert "DP CHECK PASS" in outs[0], outs[0]
+
+
 def test_launch_spawns_world2(tmp_path):
     """distributed.launch (reference distributed/launch.py:22-92) with n_gpu_per_machine=2: spawn, tcp rendezvous on
     127.0.0.1, per-machine LOCAL_PROCESS_GROUP, helpers -- exercised with the gloo backend (no GPU here)."""
