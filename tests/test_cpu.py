@@ -338,6 +338,91 @@ def test_vqvae_train_step_tape_logic_with_cpu_stand_in_kernels(monkeypatch, clip
     assert c["vq_assign"] == 2 and c["vq_ema"] == 2 and c["vq_backward"] == 2
 
 
+@pytest.mark.parametrize("dim,K", [(64, 512), (32, 40)])
+def test_quantize_module_autograd_with_cpu_stand_in_kernels(monkeypatch, dim, K):
+    """The stand-alone Quantize module (its own autograd Function: straight-through + commitment gradient, EMA in train
+    mode only, reference :47-83) over the stand-ins against the oracle."""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import fake_ops
+    from faceoff_b200.vqvae import Quantize
+    from oracle import faceoff_oracle as O
+
+    fake_ops.install(monkeypatch)
+    g = torch.Generator().manual_seed(dim + K)
+    q = Quantize(dim, K)
+    with torch.no_grad():
+        q.embed.copy_(torch.randn(dim, K, generator=g))
+        q.embed_avg.copy_(q.embed)
+        q.cluster_size.copy_(torch.rand(K, generator=g))
+    e0, c0, a0 = q.embed.clone(), q.cluster_size.clone(), q.embed_avg.clone()
+    x = torch.randn(2, 5, 3, dim, generator=g)
+    gq = torch.randn(2, 5, 3, dim, generator=g)
+    x1 = x.clone().requires_grad_(True)
+    quant, diff, ind = q.train()(x1)
+    (quant * gq).sum().add(diff * 3.0).backward()
+    x2 = x.clone().requires_grad_(True)
+    oq, odiff, oind, obuf, _ = O.quantize_forward(x2, e0, c0, a0, training=True)
+    (oq * gq).sum().add(odiff * 3.0).backward()
+    assert torch.equal(ind, oind) and not ind.requires_grad
+    torch.testing.assert_close(quant.detach(), oq.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(diff.detach(), odiff.detach(), rtol=1e-5, atol=1e-7)
+    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-5, atol=1e-7)
+    for got, want in zip((q.embed, q.cluster_size, q.embed_avg), obuf):
+        torch.testing.assert_close(got, want, rtol=1e-5, atol=1e-6)
+    # eval mode: same outputs from the updated codebook, buffers untouched
+    e1 = q.embed.clone()
+    quant_e, _, ind_e = q.eval()(x)
+    assert torch.equal(q.embed, e1) and fake_ops.CALLS["vq_ema"] == 1
+    torch.testing.assert_close(quant_e, q.embed_code(ind_e), rtol=1e-5, atol=1e-6)
+
+
+def test_vqvae_eval_sub_methods_with_cpu_stand_in_kernels(monkeypatch):
+    """The reference's eager sub-methods (only_encode / encode_quantized / decode / decode_code,
+    models/vqvae_conv3d_latent.py:261-295) compose the drop-in modules one by one; in eval mode they must give the oracle's
+    indices and reconstruction, and decode_code(id_t, id_b) must reproduce decode(quant_t, quant_b).  (The reference's
+    own ``forward`` also runs the Conv3d latent blocks between encode and quantise; the sub-method chain does not, so the
+    oracle is evaluated the same way: encoder -> quantise -> decode.)"""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import fake_ops
+    from faceoff_b200.vqvae import VQVAE
+    from oracle import faceoff_oracle as O
+
+    fake_ops.install(monkeypatch)
+    p = O.init_vqvae_params(seed=6)
+    img, _ = O.synthetic_clip(1, 2, 32, 32, seed=3)
+    model = VQVAE(in_channel=6)
+    model.load_state_dict(p)
+    model.eval()
+    with torch.no_grad():
+        enc_b, enc_t = model.only_encode(img)
+        quant_t, quant_b, diff, id_t, id_b = model.encode_quantized(enc_b, enc_t)
+        dec = model.decode(quant_t, quant_b)
+        dec_c = model.decode_code(id_t, id_b)
+        # the same chain from the oracle's pieces
+        ob = O.encoder(p, "enc_b", img, 4)
+        ot = O.encoder(p, "enc_t", ob, 2)
+        qt_in = O._c2(p, "quantize_conv_t", ot).permute(0, 2, 3, 1)
+        oqt, dt, oid_t, _, _ = O.quantize_forward(qt_in, p["quantize_t.embed"], p["quantize_t.cluster_size"],
+                                                  p["quantize_t.embed_avg"], training=False)
+        oqt = oqt.permute(0, 3, 1, 2)
+        odt = O.decoder(p, "dec_t", oqt, 2)
+        qb_in = O._c2(p, "quantize_conv_b", torch.cat([odt, ob], 1)).permute(0, 2, 3, 1)
+        oqb, db, oid_b, _, _ = O.quantize_forward(qb_in, p["quantize_b.embed"], p["quantize_b.cluster_size"],
+                                                  p["quantize_b.embed_avg"], training=False)
+        oqb = oqb.permute(0, 3, 1, 2)
+        odec = O.decoder(p, "dec", torch.cat([O._ct2(p, "upsample_t", oqt), oqb], 1), 4)
+    torch.testing.assert_close(enc_b, ob, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(enc_t, ot, rtol=1e-4, atol=1e-5)
+    assert torch.equal(id_t, oid_t) and torch.equal(id_b, oid_b)
+    torch.testing.assert_close(diff.reshape(-1), (dt + db).reshape(-1), rtol=1e-4, atol=1e-7)
+    torch.testing.assert_close(dec, odec, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dec_c, dec, rtol=1e-5, atol=1e-6)
+    for k, v in model.named_buffers():
+        assert torch.equal(v, p[k]), f"eval mode touched {k}"
+
+
 def test_no_cpu_fallback_fails_loudly():
     """Without a GPU every op must raise (no silent eager/CPU path)."""
     if torch.cuda.is_available():
