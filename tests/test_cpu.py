@@ -377,6 +377,51 @@ def test_quantize_module_autograd_with_cpu_stand_in_kernels(monkeypatch, dim, K)
     torch.testing.assert_close(quant_e, q.embed_code(ind_e), rtol=1e-5, atol=1e-6)
 
 
+@pytest.mark.parametrize("in_channel", [3, 16])
+def test_vqvae_other_input_widths_with_cpu_stand_in_kernels(monkeypatch, in_channel):
+    """in_channel = 3 takes the direct image-side kernels with 3 channels; in_channel = 16 the generic path (packed
+    channels-last input, FORM_DOWN first conv without an input gradient, fp32 NCHW output from the last transposed conv's
+    epilogue).  Also: the 5-D input [B, T, C, H, W] (B clips in one call) and a validation-style eval / no_grad forward that
+    must leave the codebooks untouched and record nothing."""
+    if HERE not in sys.path:
+        sys.path.insert(0, HERE)
+    import fake_ops
+    from faceoff_b200.vqvae import VQVAE
+    from oracle import faceoff_oracle as O
+
+    fake_ops.install(monkeypatch)
+    p = O.init_vqvae_params(seed=4, in_channel=in_channel)
+    img, gt = O.synthetic_clip(2, 2, 32, 32, seed=9, in_channel=in_channel)
+    model = VQVAE(in_channel=in_channel)
+    model.load_state_dict(p)
+    model.train()
+    out, latent = model(img.view(2, 2, in_channel, 32, 32))          # 5-D: two clips of two frames
+    assert out.shape == (2, 2, in_channel, 32, 32)
+    loss = torch.nn.functional.mse_loss(out.reshape(4, in_channel, 32, 32)[:, :3], gt) + latent.mean()
+    loss.backward()
+    o = O.train_step(p, img, gt, n_clips=2)
+    torch.testing.assert_close(loss.detach(), o["loss"], rtol=1e-5, atol=1e-7)
+    for k, v in model.named_parameters():
+        gr = o["grads"][k]
+        err = ((v.grad - gr).abs().max() / (gr.abs().max() + 1e-30)).item()
+        assert err < 2e-4, (k, err)
+    c = fake_ops.CALLS
+    assert (c["s2conv"] > 0) == (in_channel <= 8) and (c["pack_nchw"] > 0) == (in_channel > 8)
+    # validation: eval + no_grad, codebooks untouched, output of the UPDATED codebooks == oracle with the new buffers
+    model.eval()
+    before = {k: v.clone() for k, v in model.named_buffers()}
+    n_ema = c["vq_ema"]
+    with torch.no_grad():
+        out_e, _ = model(img)
+    assert c["vq_ema"] == n_ema and all(torch.equal(v, before[k]) for k, v in model.named_buffers())
+    p2 = dict(p)
+    for q in ("quantize_t", "quantize_b"):
+        for i, name in enumerate(("embed", "cluster_size", "embed_avg")):
+            p2[f"{q}.{name}"] = o["new_buffers"][q][i]
+    ref = O.vqvae_forward(p2, img, n_clips=1, training=False)       # 4-D input: ONE clip of four frames (reference :247)
+    torch.testing.assert_close(out_e, ref["dec"], rtol=1e-4, atol=1e-5)
+
+
 def test_vqvae_eval_sub_methods_with_cpu_stand_in_kernels(monkeypatch):
     """The reference's eager sub-methods (only_encode / encode_quantized / decode / decode_code,
     models/vqvae_conv3d_latent.py:261-295) compose the drop-in modules one by one; in eval mode they must give the oracle's
